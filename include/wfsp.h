@@ -1,0 +1,176 @@
+/*
+ * wfsp.h -- C ABI of libwfsp.so: the B200 (sm_100a) sparse-convolution hot path of WaveformML.
+ *
+ * This is the drop-in boundary.  The reference (pure Python) reaches its sparse convolutions
+ * through the third-party package spconv~=1.2.1 (/root/reference/requirements.txt:15); the entry
+ * points below are what a binding for that path calls instead of upstream's
+ * torch.ops.spconv.{get_indice_pairs, indice_conv, indice_conv_backward}.  Each entry cites the
+ * reference call site (file:line under /root/reference) whose work it carries out.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), performs no
+ *     allocation and no implicit synchronisation; scratch memory is passed in by the caller and
+ *     sized with the matching *_workspace_bytes query;
+ *   - return value 0 = success, negative = error (WFSP_E*); wfsp_last_error() gives the text of
+ *     the calling thread's last failure;
+ *   - row-major everywhere; `indices` rows are (batch, x, y) int32 as spconv requires
+ *     (src/models/SPConvNet.py:51-52,63-64); features are [rows, channels];
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns WFSP_ECUDA.
+ */
+#ifndef WFSP_H_
+#define WFSP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wfsp_stream_t; /* cudaStream_t */
+
+enum wfsp_status {
+  WFSP_OK = 0,
+  WFSP_EINVAL = -1,       /* bad argument */
+  WFSP_ECUDA = -2,        /* CUDA runtime error (text in wfsp_last_error) */
+  WFSP_EWORKSPACE = -3,   /* workspace too small */
+  WFSP_EUNSUPPORTED = -4  /* shape outside what the kernels cover */
+};
+
+enum wfsp_dtype { WFSP_F32 = 0, WFSP_BF16 = 1, WFSP_I16 = 2 };
+
+/* arithmetic of the channel contraction */
+enum wfsp_math {
+  WFSP_MATH_FP32 = 0, /* fp32 FMA on CUDA cores, exact fp32 products                      */
+  WFSP_MATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (kind::f16)  */
+};
+
+#define WFSP_VERSION 100
+#define WFSP_MAX_KVOL 1024
+
+int wfsp_version(void);
+const char* wfsp_last_error(void);
+/* sm count and compute capability of the current device */
+int wfsp_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* tuning / test knobs; "rulebook_force_hash" = 1 forces the open-addressing coordinate hash even
+ * when the dense grid table would be used */
+int wfsp_set_option(const char* name, int value);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Sparse-tensor batcher.
+ * Replaces collate_fn (src/engineering/PSDDataModule.py:10-20: add the running event offset to
+ * coords[:,2] of every item after the first, concatenate), the dtype / normalisation part of
+ * HDF5Dataset._concat_range (src/datasets/HDF5Dataset.py:282-302 coords->int32, :227,290
+ * waveform->float, :345-346 `vals *= 1/(2^14-1)`), and the batch-first column permute of
+ * SPConvNet.forward (src/models/SPConvNet.py:63-64, `x[0][:, [2,0,1]]`).
+ *
+ *   coords_xye   int32 [n_rows,3] = (x, y, event id local to its item), items concatenated
+ *   wave         [n_rows, n_chan] of wave_dtype (WFSP_I16 as stored on disk,
+ *                src/datasets/H5CompoundTypes.py:105-120, or WFSP_F32)
+ *   item_rows    int64 [n_items+1] row offset of each item
+ *   item_offset  int64 [n_items]   event offset added to each item (0 for item 0)
+ *   indices_bxy  int32 [n_rows,3] = (global event, x, y)                       (output)
+ *   feats        [n_rows, feats_pitch] of feats_dtype, value = wave * scale    (output)
+ */
+int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype, int64_t n_rows,
+                    int n_chan, const int64_t* item_rows, const int64_t* item_offset,
+                    int64_t n_items, float scale, int32_t* indices_bxy, void* feats,
+                    int feats_dtype, int64_t feats_pitch, wfsp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) Rulebook builder.  Bit-exact with the CPU path of upstream ops.get_indice_pairs, which
+ * every spconv.SparseConv2d / SubMConv2d with kernel volume > 1 reaches
+ * (src/models/SPConvBlocks.py:75,134,191,249,298,370,498-502,575-579,643-647,710-714,803,809,
+ * 868,877,930,939): output rows in first-touch order, pairs of one offset in ascending input
+ * order, pairs tensor [2, kvol, n_in] padded with -1, pair_num [kvol].
+ */
+/* out = (in + 2p - d(k-1) - 1)/s + 1 per dim (same as src/utils/ModelValidation.py:119-126) */
+int wfsp_conv_out_shape(const int* in_shape_host, const int* ksize_host, const int* stride_host,
+                        const int* pad_host, const int* dil_host, int* out_shape_host);
+
+size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const int* out_shape_host,
+                                     const int* ksize_host);
+
+/* Regular (strided / padded / dilated) convolution.  out_indices must hold out_cap >=
+ * min(n_in*kvol, batch*out_h*out_w) rows; the number of rows actually produced is written to the
+ * device scalar *n_out (the caller copies it to pinned host memory -- the single readback per
+ * rulebook).  stride>1 together with dilation>1 is rejected as upstream does. */
+int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batch, const int* in_shape_host,
+                       const int* ksize_host, const int* stride_host, const int* pad_host,
+                       const int* dil_host, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
+                       int32_t* pair_num, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                       wfsp_stream_t stream);
+
+/* Submanifold convolution: output rows == input rows, padding forced to k/2, stride to 1. */
+int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, int batch, const int* shape_host,
+                       const int* ksize_host, const int* dil_host, int32_t* pairs,
+                       int32_t* pair_num, void* workspace, size_t workspace_bytes,
+                       wfsp_stream_t stream);
+
+/* Derived, output-stationary view of a rulebook used by the forward / dgrad kernels:
+ *   nbr_out [n_out, kvol]: input row that feeds output row o through offset k, or -1
+ *   nbr_in  [n_in,  kvol]: output row that input row i feeds through offset k, or -1
+ * *dup_flag (device int32, caller zero-fills) is set to 1 if two pairs of one offset share an
+ * output row (duplicate input coordinates), which the output-stationary kernels do not cover. */
+int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol,
+                         int64_t pair_pitch, int64_t n_in, int64_t n_out, int32_t* nbr_out,
+                         int32_t* nbr_in, int32_t* dup_flag, wfsp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Gather-GEMM forward / dgrad / wgrad.  Replaces upstream indice_conv /
+ * indice_conv_backward reached from spconv.SparseConv2d / SubMConv2d / SparseInverseConv2d
+ * .forward and their autograd backward (same call sites as (2), plus the 1x1 shortcut
+ * `torch.mm(features, weight.view(Cin,Cout))` of every pointwise layer,
+ * src/models/SPConvBlocks.py:335,498).
+ *
+ * wfsp_conv_apply computes, for every destination row r,
+ *     dst[r, :] = bias + sum_k  src[ nbr[r,k], : ] @ Wk          (rows with nbr = -1 contribute 0)
+ * where Wk = weight[k] ([c_red, c_dst]) if transpose_w == 0, or weight[k]^T if transpose_w == 1
+ * (weight[k] is then [c_dst, c_red]).  The four uses:
+ *     forward            nbr = nbr_out, src = features, weight [kvol,Cin,Cout], transpose_w = 0
+ *     dgrad              nbr = nbr_in,  src = dOut,     weight [kvol,Cin,Cout], transpose_w = 1
+ *     inverse forward    nbr = nbr_in,  src = features, weight [kvol,Cin,Cout], transpose_w = 0
+ *     inverse dgrad      nbr = nbr_out, src = dOut,     weight [kvol,Cin,Cout], transpose_w = 1
+ * nbr == NULL means kvol == 1 with the identity map (the 1x1 shortcut, n_dst == n_src).
+ * src and dst are fp32 [rows, channels] with row pitch == channels; weight and bias are fp32.
+ */
+size_t wfsp_conv_apply_workspace_bytes(int kvol, int c_red, int c_dst, int math);
+
+int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* weight,
+                    int transpose_w, const float* bias, const int32_t* nbr, int kvol, float* dst,
+                    int64_t n_dst, int c_dst, int math, void* workspace, size_t workspace_bytes,
+                    wfsp_stream_t stream);
+
+/* wgrad: d_weight[k] (+)= sum over pairs p of offset k of  a[pa[k,p], :]^T (outer) b[pb[k,p], :]
+ * with a = features [n_a, c_a], b = dOut [n_b, c_b], d_weight fp32 [kvol, c_a, c_b]
+ * (pair_a = pairs[0], pair_b = pairs[1]; for the inverse convolution the roles swap:
+ * pair_a = pairs[1], pair_b = pairs[0]).  pair_a / pair_b are [kvol, pair_pitch], only the first
+ * pair_num[k] entries of row k are read.  d_weight is overwritten (accumulate == 0) or added to
+ * (accumulate == 1).  pair_a == pair_b == pair_num == NULL selects the identity pair list of the
+ * 1x1 shortcut (kvol == 1, n_a == n_b pairs). */
+size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int c_a, int c_b, int64_t pair_pitch, int math);
+
+int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
+                    const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
+                    int64_t pair_pitch, float* d_weight, int accumulate, int math, void* workspace,
+                    size_t workspace_bytes, wfsp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) Dense scatter.  Replaces spconv.ToDense / SparseConvTensor.dense()
+ * (src/models/SPConvBlocks.py:81,726; src/engineering/LitBase.py:138-146): zeros
+ * [B, C, H, W], dense[b, :, x, y] = features[row] (last row wins on duplicate coordinates), and
+ * its backward, the gather d_features[row, :] = d_dense[b, :, x, y].
+ * cell_table: int32 scratch [batch*h*w].
+ */
+int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, int n_chan,
+                  int batch, int h, int w, float* dense, int32_t* cell_table,
+                  wfsp_stream_t stream);
+
+int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows, int n_chan,
+                      int batch, int h, int w, float* d_feats, wfsp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFSP_H_ */

@@ -1,0 +1,164 @@
+"""GPU sparse-conv layers (forward, dgrad, wgrad, bias grad) vs the CPU oracle on the same seeded
+inputs and weights.
+
+Tolerances (stated per north_star):
+  fp32 mode  (CUDA-core FMA, exact fp32 products): rtol 1e-4, atol 1e-5 * max|ref|
+  bf16 mode  (tcgen05, bf16 operands, fp32 accumulate): rtol 2e-2, atol 2e-2 * max|ref|
+"""
+import pytest
+import torch
+
+from oracle import mirror
+from oracle import spconv_cpu as osp
+from waveformml_b200 import spconv
+from waveformml_b200.synth import make_events
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (1e-4, 1e-5), "bf16": (2e-2, 2e-2)}
+
+
+def close(got, ref, mode, what=""):
+    rtol, afrac = TOL[mode]
+    got = got.detach().float().cpu()
+    ref = ref.detach().float()
+    atol = afrac * max(float(ref.abs().max()), 1e-30)
+    torch.testing.assert_close(got, ref, rtol=rtol, atol=atol, msg=lambda m: "%s [%s]: %s" % (what, mode, m))
+
+
+def events(B, seed, C, full=False):
+    ev = make_events(B, n_samples=1, seed=seed, full_grid=full)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous()
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.rand(idx.shape[0], C, generator=g)  # waveform-like: non-negative
+    return idx, feats
+
+
+def run_pair(layers, idx, feats, B, dev, mode, dense=False):
+    """Runs the same stack on the GPU and through the oracle; returns outputs and all grads."""
+    gnet = spconv.SparseSequential(*layers).to(dev)
+    onet = mirror.to_oracle(gnet)
+    for m in gnet.modules():
+        if isinstance(m, spconv.SparseConvolution):
+            m.math = mode
+    fg = feats.clone().to(dev).requires_grad_(True)
+    fo = feats.clone().requires_grad_(True)
+    yg = gnet(spconv.SparseConvTensor(fg, idx.to(dev), [14, 11], B))
+    yo = onet(osp.SparseConvTensor(fo, idx, [14, 11], B))
+    if not dense:
+        assert torch.equal(yg.indices.cpu(), yo.indices) and list(yg.spatial_shape) == list(yo.spatial_shape)
+        yg, yo = yg.features, yo.features
+    assert tuple(yg.shape) == tuple(yo.shape)
+    gen = torch.Generator().manual_seed(7)
+    w = torch.randn(yo.shape, generator=gen)
+    (yg * w.to(dev)).sum().backward()
+    (yo * w).sum().backward()
+    gp = [p for p in gnet.parameters()]
+    op = [p for p in onet.parameters()]
+    return yg, yo, fg.grad, fo.grad, gp, op
+
+
+CASES = [
+    # (name, layer factory, Cin)
+    ("conv3_p0", lambda: [spconv.SparseConv2d(20, 24, 3, 1, 0, 1, 1, False)], 20),
+    ("conv3_p1_bias", lambda: [spconv.SparseConv2d(12, 17, 3, 1, 1)], 12),
+    ("conv3_s2", lambda: [spconv.SparseConv2d(10, 6, 3, 2, 1, 1, 1, True)], 10),
+    ("conv2_even", lambda: [spconv.SparseConv2d(9, 5, 2, 1, 0, 1, 1, False)], 9),
+    ("conv3_dil2", lambda: [spconv.SparseConv2d(8, 8, 3, 1, 2, 2)], 8),
+    ("conv1x1", lambda: [spconv.SparseConv2d(30, 7, 1, 1, 0, 1, 1, True)], 30),
+    ("conv1x1_cout1", lambda: [spconv.SparseConv2d(15, 1, 1, 1, 0)], 15),
+    ("subm3", lambda: [spconv.SubMConv2d(16, 12, 3, 1, 1, indice_key="subm0")], 16),
+    ("subm5_cout2", lambda: [spconv.SubMConv2d(11, 2, 5, 1, 2, indice_key="subm5")], 11),
+    ("subm_chain_shared_key", lambda: [spconv.SubMConv2d(8, 8, 3, indice_key="subm0"),
+                                       spconv.SubMConv2d(8, 4, 3, indice_key="subm0")], 8),
+    ("conv_inverse", lambda: [spconv.SparseConv2d(6, 10, 3, 1, 1, 1, 1, False, indice_key="ind_0"),
+                              spconv.SparseInverseConv2d(10, 10, 3, "ind_0", bias=False)], 6),
+    ("conv_inverse_k2", lambda: [spconv.SparseConv2d(7, 5, 2, 1, 0, 1, 1, False, indice_key="ind_2"),
+                                 spconv.SparseInverseConv2d(5, 5, 2, "ind_2", bias=True)], 7),
+    ("wide_odd_channels", lambda: [spconv.SparseConv2d(158, 64, 3, 1, 0, 1, 1, False)], 158),
+    ("cout_gt_256", lambda: [spconv.SparseConv2d(36, 300, 3, 1, 1, 1, 1, True)], 36),
+    ("cin_300_k1", lambda: [spconv.SparseConv2d(300, 252, 1, 1, 0, 1, 1, False)], 300),
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,factory,cin", CASES, ids=[c[0] for c in CASES])
+def test_layer_parity(cuda_device, name, factory, cin, mode):
+    torch.manual_seed(sum(name.encode()))
+    B = 19
+    idx, feats = events(B, 21, cin)
+    yg, yo, dfg, dfo, gp, op = run_pair(factory(), idx, feats, B, cuda_device, mode)
+    close(yg, yo, mode, name + " out")
+    close(dfg, dfo, mode, name + " d_features")
+    for a, b in zip(gp, op):
+        close(a.grad, b.grad, mode, name + " d_param %s" % (tuple(a.shape),))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_gep_conv_stack_dense(cuda_device, mode):
+    """The three convolutions of the GEP stack + ToDense (no BN so the comparison isolates our kernels)."""
+    torch.manual_seed(3)
+    B = 64
+    ev = make_events(B, n_samples=150, seed=1234)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous()
+    feats = torch.from_numpy(ev["wave"]).float() / 16383.0
+    layers = [spconv.SparseConv2d(300, 252, 1, 1, 0, 1, 1, False), torch.nn.ReLU(),
+              spconv.SparseConv2d(252, 158, 3, 1, 0, 1, 1, False), torch.nn.ReLU(),
+              spconv.SparseConv2d(158, 64, 3, 1, 0, 1, 1, False), spconv.ToDense()]
+    yg, yo, dfg, dfo, gp, op = run_pair(layers, idx, feats, B, cuda_device, mode, dense=True)
+    assert tuple(yg.shape) == (64, 64, 10, 7)
+    close(yg, yo, mode, "dense out")
+    close(dfg, dfo, mode, "d_features")
+    for a, b in zip(gp, op):
+        close(a.grad, b.grad, mode, "d_weight %s" % (tuple(a.shape),))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_multi_tile_rows(cuda_device, mode):
+    """More than one 128-row tile, many CTAs, split wgrad reduction."""
+    torch.manual_seed(5)
+    B = 300
+    idx, feats = events(B, 31, 40)
+    yg, yo, dfg, dfo, gp, op = run_pair([spconv.SparseConv2d(40, 48, 3, 1, 1, 1, 1, True)], idx, feats, B,
+                                        cuda_device, mode)
+    close(yg, yo, mode, "out")
+    close(dfg, dfo, mode, "d_features")
+    for a, b in zip(gp, op):
+        close(a.grad, b.grad, mode, "d_param")
+
+
+def test_linearity_full_size(cuda_device):
+    """Size-independent property at BASELINE full size (C5, 1024 full-grid events): the layer is
+    linear in its input, conv(a + 2b) == conv(a) + 2 conv(b), and 1x1 == dense matmul."""
+    B = 1024
+    ev = make_events(B, n_samples=1, seed=2, full_grid=True)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous().to(cuda_device)
+    N = idx.shape[0]
+    torch.manual_seed(0)
+    a = torch.rand(N, 64, device=cuda_device)
+    b = torch.rand(N, 64, device=cuda_device)
+    conv = spconv.SparseConv2d(64, 32, 3, 1, 0, 1, 1, False).to(cuda_device)
+    for mode, tol in (("fp32", 1e-4), ("bf16", 3e-2)):
+        conv.math = mode
+        with torch.no_grad():
+            ya = conv(spconv.SparseConvTensor(a, idx, [14, 11], B)).features
+            yb = conv(spconv.SparseConvTensor(b, idx, [14, 11], B)).features
+            yab = conv(spconv.SparseConvTensor(a + 2 * b, idx, [14, 11], B)).features
+        assert ya.shape == (1024 * 108, 32)
+        err = (yab - (ya + 2 * yb)).abs().max() / yab.abs().max()
+        assert float(err) < tol, (mode, float(err))
+    pw = spconv.SparseConv2d(64, 48, 1, 1, 0, 1, 1, False).to(cuda_device)
+    pw.math = "fp32"
+    with torch.no_grad():
+        y = pw(spconv.SparseConvTensor(a, idx, [14, 11], B)).features
+        ref = a @ pw.weight.view(64, 48)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_half_precision_features(cuda_device):
+    """system_config.half_precision feeds fp16 features (src/datasets/HDF5Dataset.py:227): accepted,
+    computed in fp32/bf16 internally, returned in the input dtype."""
+    idx, feats = events(5, 3, 8)
+    conv = spconv.SubMConv2d(8, 4, 3, indice_key="subm0").to(cuda_device)
+    y = conv(spconv.SparseConvTensor(feats.half().to(cuda_device), idx.to(cuda_device), [14, 11], 5))
+    assert y.features.dtype == torch.float16 and y.features.shape == (idx.shape[0], 4)

@@ -1,0 +1,82 @@
+"""GPU batcher (wfsp_batch_pack) and dense scatter / gather (wfsp_to_dense[_bwd]) vs the oracle and
+vs golden vectors produced by the reference's own collate_fn (tests/golden/batcher_golden.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spconv_cpu as osp
+from waveformml_b200 import batcher, spconv
+from waveformml_b200.synth import MAX_RANGE_INV, make_events
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "batcher_golden.npz")
+
+
+def _items():
+    g = np.load(GOLD)
+    n = int(g["n_items"])
+    coords = [g["coords%d" % i] for i in range(n)]
+    wave = [g["wave%d" % i] for i in range(n)]
+    labels = [g["labels%d" % i] for i in range(n)]
+    return g, coords, wave, labels
+
+
+def test_pack_matches_reference_collate_fn(cuda_device):
+    g, coords, wave, labels = _items()
+    rows = np.cumsum([0] + [c.shape[0] for c in coords]).tolist()
+    evs = [l.shape[0] for l in labels]
+    c = torch.from_numpy(np.concatenate(coords)).to(cuda_device)
+    w = torch.from_numpy(np.concatenate(wave)).to(cuda_device)
+    idx, feats = batcher.pack_batch(c, w, rows, evs)
+    assert torch.equal(idx.cpu()[:, [1, 2, 0]], torch.from_numpy(g["out_coords"]))  # reference keeps (x, y, event)
+    assert torch.equal(feats.cpu(), torch.from_numpy(g["out_feats"]))  # bit-exact fp32
+    # bf16 output variant == rounding of the fp32 result
+    _, fb = batcher.pack_batch(c, w, rows, evs, out_dtype=torch.bfloat16)
+    assert torch.equal(fb.cpu(), torch.from_numpy(g["out_feats"]).bfloat16())
+    # the collate_fn mirror (same call shape as the reference's)
+    items = [([torch.from_numpy(ci).to(cuda_device), torch.from_numpy(wi).to(cuda_device)],
+              torch.from_numpy(li).to(cuda_device)) for ci, wi, li in zip(coords, wave, labels)]
+    (cc, ff), yy = batcher.collate_fn(items, scale=MAX_RANGE_INV)
+    assert torch.equal(cc.cpu(), torch.from_numpy(g["out_coords"]))
+    assert torch.equal(ff.cpu(), torch.from_numpy(g["out_feats"]))
+    assert torch.equal(yy.cpu(), torch.from_numpy(g["out_labels"]))
+
+
+@pytest.mark.parametrize("C", [300, 130, 7])
+def test_pack_matches_oracle(cuda_device, C):
+    ev = make_events(50, n_samples=1, seed=4)
+    n = ev["coords"].shape[0]
+    wave = torch.from_numpy(np.random.default_rng(1).integers(0, 2 ** 14, size=(n, C), dtype=np.int16))
+    coords = torch.from_numpy(ev["coords"])
+    oi, of, bs = osp.batch_pack(coords, wave, [0, n], [50], MAX_RANGE_INV)
+    gi, gf = batcher.pack_batch(coords.to(cuda_device), wave.to(cuda_device))
+    assert bs == 50 and torch.equal(gi.cpu(), oi) and torch.equal(gf.cpu(), of)
+
+
+@pytest.mark.parametrize("shape,C", [((14, 11), 64), ((10, 7), 64), ((14, 11), 1), ((12, 9), 33)])
+def test_to_dense_fwd_bwd(cuda_device, shape, C):
+    B = 21
+    ev = make_events(B, n_samples=1, seed=9)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous()
+    keep = (idx[:, 1] < shape[0]) & (idx[:, 2] < shape[1])
+    idx = idx[keep].contiguous()
+    feats = torch.randn(idx.shape[0], C)
+    ref = osp.to_dense_c(feats, idx, B, shape)
+    assert torch.equal(ref, osp.SparseConvTensor(feats, idx, shape, B).dense())
+    fg = feats.to(cuda_device).requires_grad_(True)
+    d = spconv.SparseConvTensor(fg, idx.to(cuda_device), list(shape), B).dense()
+    assert torch.equal(d.cpu(), ref)
+    g = torch.randn(ref.shape)
+    (d * g.to(cuda_device)).sum().backward()
+    li = idx.long()
+    assert torch.equal(fg.grad.cpu(), g[li[:, 0], :, li[:, 1], li[:, 2]])
+    nhwc = spconv.SparseConvTensor(fg.detach(), idx.to(cuda_device), list(shape), B).dense(channels_first=False)
+    assert torch.equal(nhwc.cpu(), ref.permute(0, 2, 3, 1))
+
+
+def test_to_dense_empty(cuda_device):
+    d = spconv.SparseConvTensor(torch.zeros(0, 3, device=cuda_device), torch.zeros(0, 3, dtype=torch.int32, device=cuda_device),
+                                [14, 11], 2).dense()
+    assert d.shape == (2, 3, 14, 11) and float(d.abs().sum()) == 0.0

@@ -1,0 +1,118 @@
+"""Whole-model parity on the GPU: the reference's layer stacks forward + backward
+through the training-step harness vs the same stacks run through the CPU oracle with shared
+weights.  BatchNorm1d / ReLU / Linear are stock torch on both sides."""
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import mirror
+from oracle import spconv_cpu as osp
+from waveformml_b200 import batcher, harness, spconv, stacks
+from waveformml_b200.synth import make_events
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(B, ns, seed, dev, full=False):
+    ev = make_events(B, n_samples=ns, seed=seed, full_grid=full)
+    coords, wave = torch.from_numpy(ev["coords"]), torch.from_numpy(ev["wave"])
+    idx, feats = batcher.pack_batch(coords.to(dev), wave.to(dev))
+    return ev, idx, feats
+
+
+def _rel(a, b):
+    return float((a.detach().float().cpu() - b.detach().float()).abs().max() / b.detach().float().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("mode,tol,ltol", [("fp32", 2e-3, 1e-3), ("bf16", 5e-2, 1e-2)])
+def test_psd_classifier_step_c1(cuda_device, mode, tol, ltol):
+    """Config C1/C2: GEP stack, 64 events, CE loss; loss, logits and every parameter gradient."""
+    torch.manual_seed(0)
+    spconv.set_math_mode(mode)
+    try:
+        model = stacks.PSDClassifier().to(cuda_device).train()
+        ev, idx, feats = _batch(64, 150, 1234, cuda_device)
+        labels = torch.from_numpy(ev["labels"])
+        step = harness.TrainStep(model, "psd")
+        loss = step.forward_backward(idx, feats, labels.to(cuda_device), 64)
+        # oracle twin
+        osparse = mirror.to_oracle(model.sparseModel).train()
+        olinear = copy.deepcopy(model.linear).cpu()
+        for p in list(osparse.parameters()) + list(olinear.parameters()):
+            p.grad = None
+        d = mirror.run_stack(osparse, idx.cpu(), feats.cpu(), [14, 11], 64)
+        ologits = olinear(d.view(-1, model.n_linear))
+        oloss = nn.CrossEntropyLoss()(ologits, labels)
+        oloss.backward()
+        assert abs(float(loss) - float(oloss)) / abs(float(oloss)) < ltol
+        gparams = dict(model.named_parameters())
+        oparams = {"sparseModel." + k: v for k, v in osparse.named_parameters()}
+        oparams.update({"linear." + k: v for k, v in olinear.named_parameters()})
+        assert set(gparams) == set(oparams)
+        for k in gparams:
+            assert _rel(gparams[k].grad, oparams[k].grad) < tol, (k, _rel(gparams[k].grad, oparams[k].grad))
+    finally:
+        spconv.set_math_mode("bf16")
+
+
+@pytest.mark.parametrize("mode,tol,ltol", [("fp32", 2e-3, 1e-3), ("bf16", 5e-2, 1e-2)])
+def test_z_regressor_step(cuda_device, mode, tol, ltol):
+    """Config C3 model (SingleEndedZCNN) with the masked-L1 segment loss of LitBase._calc_segment_loss."""
+    torch.manual_seed(1)
+    spconv.set_math_mode(mode)
+    try:
+        B = 96
+        model = stacks.ZRegressor().to(cuda_device).train()
+        ev, idx, feats = _batch(B, 150, 77, cuda_device)
+        z = torch.from_numpy(ev["z"])
+        step = harness.TrainStep(model, "z")
+        loss = step.forward_backward(idx, feats, z.to(cuda_device), B)
+        onet = mirror.to_oracle(model.model.network).train()
+        pred = mirror.run_stack(onet, idx.cpu(), feats.cpu(), [14, 11], B)
+        mask = osp.SparseConvTensor(torch.ones(idx.shape[0], 1), idx.cpu(), [14, 11], B).dense()
+        tgt = osp.SparseConvTensor(z.unsqueeze(1), idx.cpu(), [14, 11], B).dense()
+        oloss = nn.functional.l1_loss(mask * pred, tgt, reduction="sum") / idx.shape[0]
+        oloss.backward()
+        assert abs(float(loss) - float(oloss)) / abs(float(oloss)) < ltol
+        for (k, a), (_, b) in zip(model.model.network.named_parameters(), onet.named_parameters()):
+            assert a.shape == b.shape
+            assert _rel(a.grad, b.grad) < tol, (k, _rel(a.grad, b.grad))
+    finally:
+        spconv.set_math_mode("bf16")
+
+
+@pytest.mark.parametrize("name", ["ez_subm", "ioni_preserve"])
+def test_other_stacks_forward(cuda_device, name):
+    """SubM k5 with a shared rulebook key, and six conv/inverse-conv pairs (k3 and even k2)."""
+    torch.manual_seed(2)
+    spconv.set_math_mode("fp32")
+    try:
+        B = 40
+        if name == "ez_subm":
+            model, ns = stacks.EZSubM().to(cuda_device).eval(), 150
+            net = model.network
+        else:
+            model, ns = stacks.IoniPreserve().to(cuda_device).eval(), 65
+            net = model.model.func
+        ev, idx, feats = _batch(B, ns, 5, cuda_device)
+        with torch.no_grad():
+            got = model([idx, feats, B])
+            ref = mirror.run_stack(mirror.to_oracle(net).eval(), idx.cpu(), feats.cpu(), [14, 11], B)
+        ref = ref.features if isinstance(ref, osp.SparseConvTensor) else ref
+        assert got.shape == ref.shape
+        assert _rel(got, ref) < 2e-3, _rel(got, ref)
+    finally:
+        spconv.set_math_mode("bf16")
+
+
+def test_training_reduces_loss(cuda_device):
+    """A few SGD steps on one batch reduce the loss (end-to-end sanity of fwd+bwd+update)."""
+    torch.manual_seed(3)
+    model = stacks.PSDClassifier().to(cuda_device).train()
+    ev, idx, feats = _batch(64, 150, 1234, cuda_device)
+    labels = torch.from_numpy(ev["labels"]).to(cuda_device)
+    step = harness.TrainStep(model, "psd", lr=0.01, momentum=0.9)
+    losses = [float(step.step(idx, feats, labels, 64)) for _ in range(8)]
+    assert losses[-1] < losses[0], losses

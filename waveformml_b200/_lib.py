@@ -1,0 +1,90 @@
+"""ctypes binding of libwfsp.so (include/wfsp.h).  There is no fallback: if the library cannot be
+loaded, importing the compute path raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwfsp.so")
+
+F32, BF16, I16 = 0, 1, 2
+MATH_FP32, MATH_BF16 = 0, 1
+
+_c = ctypes
+_vp, _i64, _int, _sz, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_size_t, _c.c_float
+_intp = _c.POINTER(_c.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/wfsp.h declares
+SIGNATURES = {
+    "wfsp_version": (_int, []),
+    "wfsp_last_error": (_c.c_char_p, []),
+    "wfsp_device_info": (_int, [_intp, _intp, _intp]),
+    "wfsp_set_option": (_int, [_c.c_char_p, _int]),
+    "wfsp_batch_pack": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _i64, _f32, _vp, _vp, _int, _i64, _vp]),
+    "wfsp_conv_out_shape": (_int, [_intp] * 6),
+    "wfsp_rulebook_workspace_bytes": (_sz, [_i64, _int, _intp, _intp]),
+    "wfsp_rulebook_conv": (_int, [_vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _vp, _i64, _vp, _vp, _vp,
+                                  _vp, _sz, _vp]),
+    "wfsp_rulebook_subm": (_int, [_vp, _i64, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
+    "wfsp_rulebook_tables": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "wfsp_conv_apply_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "wfsp_conv_apply": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _int, _int, _vp, _sz, _vp]),
+    "wfsp_conv_wgrad_workspace_bytes": (_sz, [_int, _int, _int, _i64, _int]),
+    "wfsp_conv_wgrad": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _int, _i64, _vp, _int, _int, _vp,
+                               _sz, _vp]),
+    "wfsp_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "wfsp_to_dense_bwd": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
+}
+
+_lib = None
+
+
+class WfspError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libwfsp.so (building it with nvcc first if the .so is absent).  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise WfspError("libwfsp error %d: %s" % (rc, load().wfsp_last_error().decode(errors="replace")))
+
+
+def ints(v, n=2):
+    try:
+        v = [int(x) for x in v]
+    except TypeError:
+        v = [int(v)] * n
+    if len(v) != n:
+        raise ValueError("expected %d values, got %r" % (n, v))
+    return (ctypes.c_int * n)(*v)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("waveformml_b200 has no CPU path: tensor on %s (the sparse-conv kernels are CUDA "
+                               "sm_100a only)" % t.device)

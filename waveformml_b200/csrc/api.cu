@@ -1,0 +1,112 @@
+// C-ABI glue of libwfsp.so: error text, device queries, math-mode dispatch (include/wfsp.h).
+#include "common.cuh"
+
+#include <string.h>
+
+namespace wfsp {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+void set_force_hash(int v);
+
+// conv_simt.cu
+int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
+                    const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
+                    cudaStream_t st);
+int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
+                    const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
+                    float* d_weight, int accumulate, cudaStream_t st);
+// conv_umma.cu
+size_t conv_apply_umma_workspace(int kvol, int c_red, int c_dst);
+int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
+                    const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
+size_t conv_wgrad_umma_workspace(int kvol, int c_a, int c_b, int64_t pitch);
+int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
+                    const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
+                    float* d_weight, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace wfsp
+
+using namespace wfsp;
+
+extern "C" int wfsp_version(void) { return WFSP_VERSION; }
+
+extern "C" const char* wfsp_last_error(void) { return error_buffer(); }
+
+extern "C" int wfsp_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  WFSP_CHECK_CUDA(cudaGetDevice(&dev));
+  WFSP_CHECK_CUDA(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+  WFSP_CHECK_CUDA(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+  WFSP_CHECK_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return WFSP_OK;
+}
+
+// test hook: force the open-addressing hash table in the rulebook builder even for small grids
+extern "C" int wfsp_set_option(const char* name, int value) {
+  if (strcmp(name, "rulebook_force_hash") == 0) { set_force_hash(value); return WFSP_OK; }
+  return set_error(WFSP_EINVAL, "unknown option %s", name);
+}
+
+extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int c_red, int c_dst, int math) {
+  return math == WFSP_MATH_BF16 ? conv_apply_umma_workspace(kvol, c_red, c_dst) : 0;
+}
+
+extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
+                               const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst,
+                               int c_dst, int math, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_src >= 0 && n_dst >= 0 && c_red >= 1 && c_dst >= 1, "bad conv sizes");
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  WFSP_REQUIRE(nbr != nullptr || (kvol == 1 && n_src == n_dst), "identity map needs kvol == 1 and n_src == n_dst");
+  if (math == WFSP_MATH_FP32)
+    return conv_apply_simt(src, n_src, c_red, weight, transpose_w, bias, nbr, kvol, dst, n_dst, c_dst,
+                           as_stream(stream));
+  if (math == WFSP_MATH_BF16)
+    return conv_apply_umma(src, n_src, c_red, weight, transpose_w, bias, nbr, kvol, dst, n_dst, c_dst, workspace,
+                           workspace_bytes, as_stream(stream));
+  return set_error(WFSP_EINVAL, "unknown math mode %d", math);
+}
+
+extern "C" size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int c_a, int c_b, int64_t pair_pitch, int math) {
+  return math == WFSP_MATH_BF16 ? conv_wgrad_umma_workspace(kvol, c_a, c_b, pair_pitch) : 0;
+}
+
+extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
+                               const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
+                               int64_t pair_pitch, float* d_weight, int accumulate, int math, void* workspace,
+                               size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_a >= 0 && n_b >= 0 && c_a >= 1 && c_b >= 1 && pair_pitch >= 0, "bad wgrad sizes");
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  if (math == WFSP_MATH_FP32)
+    return conv_wgrad_simt(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
+                           accumulate, as_stream(stream));
+  if (math == WFSP_MATH_BF16)
+    return conv_wgrad_umma(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
+                           accumulate, workspace, workspace_bytes, as_stream(stream));
+  return set_error(WFSP_EINVAL, "unknown math mode %d", math);
+}

@@ -1,0 +1,227 @@
+// Batcher (pack) and dense scatter / gather kernels: pure copy / convert work, HBM-bound.
+//
+//  * wfsp_batch_pack   : collate_fn (src/engineering/PSDDataModule.py:10-20) + int16 -> float
+//                        normalisation (src/datasets/HDF5Dataset.py:345-346) + batch-first permute
+//                        (src/models/SPConvNet.py:63-64) in one pass: 2 B read + 4 B written / sample.
+//  * wfsp_to_dense     : SparseConvTensor.dense() / spconv.ToDense (src/models/SPConvBlocks.py:81):
+//                        [N,C] rows -> [B,C,H,W]; a 32x32 shared-memory transpose so that both the
+//                        row reads (channel-contiguous) and the NCHW writes (cell-contiguous) are
+//                        coalesced; every dense element is written exactly once (no memset pass).
+//  * wfsp_to_dense_bwd : the gather back, same transpose in the other direction.
+#include "common.cuh"
+
+namespace wfsp {
+namespace {
+
+__global__ void __launch_bounds__(256) pack_indices_kernel(const int32_t* __restrict__ coords, int64_t n,
+                                                           const int64_t* __restrict__ item_rows,
+                                                           const int64_t* __restrict__ item_offset, int64_t n_items,
+                                                           int32_t* __restrict__ indices) {
+  int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  // item of row j: last it with item_rows[it] <= j
+  int64_t lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    int64_t mid = (lo + hi + 1) >> 1;
+    if (item_rows[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  int32_t off = n_items > 0 ? int32_t(item_offset[lo]) : 0;
+  indices[3 * j + 0] = coords[3 * j + 2] + off;
+  indices[3 * j + 1] = coords[3 * j + 0];
+  indices[3 * j + 2] = coords[3 * j + 1];
+}
+
+template <typename In>
+__device__ __forceinline__ float to_f32(In v) { return float(v); }
+
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) pack_feats_kernel(const In* __restrict__ wave, int64_t n, int c, float scale,
+                                                         Out* __restrict__ feats, int64_t pitch) {
+  // one thread per 4 consecutive channels (c % 4 == 0 fast path), grid-stride
+  const int c4 = c >> 2;
+  const int64_t total = n * c4;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t row = i / c4;
+    int col = int(i - row * c4) << 2;
+    const In* s = wave + row * c + col;
+    float v0, v1, v2, v3;
+    if (sizeof(In) == 2) {
+      const short4 q = *reinterpret_cast<const short4*>(s);
+      v0 = float(q.x); v1 = float(q.y); v2 = float(q.z); v3 = float(q.w);
+    } else {
+      const float4 q = *reinterpret_cast<const float4*>(s);
+      v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
+    }
+    v0 *= scale; v1 *= scale; v2 *= scale; v3 *= scale;
+    Out* d = feats + row * pitch + col;
+    if (sizeof(Out) == 4) {
+      *reinterpret_cast<float4*>(d) = make_float4(v0, v1, v2, v3);
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(d) = u;
+    }
+  }
+}
+
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) pack_feats_scalar_kernel(const In* __restrict__ wave, int64_t n, int c,
+                                                                float scale, Out* __restrict__ feats, int64_t pitch) {
+  const int64_t total = n * c;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    int64_t row = i / c;
+    int col = int(i - row * c);
+    float v = float(wave[i]) * scale;
+    if (sizeof(Out) == 4) reinterpret_cast<float*>(feats)[row * pitch + col] = v;
+    else reinterpret_cast<__nv_bfloat16*>(feats)[row * pitch + col] = __float2bfloat16_rn(v);
+  }
+}
+
+template <typename In, typename Out>
+int launch_pack_feats(const void* wave, int64_t n, int c, float scale, void* feats, int64_t pitch, cudaStream_t st) {
+  if (n == 0 || c == 0) return WFSP_OK;
+  const bool vec = (c % 4 == 0) && (pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(wave) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(feats) % 16 == 0);
+  const int64_t work = vec ? n * (c / 4) : n * int64_t(c);
+  int64_t blocks = ceil_div<int64_t>(work, 256);
+  const int64_t cap = int64_t(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (vec)
+    pack_feats_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, c, scale,
+                                                                 static_cast<Out*>(feats), pitch);
+  else
+    pack_feats_scalar_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, c, scale,
+                                                                        static_cast<Out*>(feats), pitch);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+// ---- dense ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dense_mark_kernel(const int32_t* __restrict__ indices, int64_t n, int batch,
+                                                         int h, int w, int32_t* __restrict__ cell_table) {
+  int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
+  if (b < 0 || b >= batch || x < 0 || x >= h || y < 0 || y >= w) return;
+  atomicMax(&cell_table[(int64_t(b) * h + x) * w + y], int(j));  // last row wins, as index assignment does
+}
+
+// grid: (ceil(cells/32), ceil(C/32)), block (32, 8)
+__global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict__ feats, int c,
+                                                        const int32_t* __restrict__ cell_table, int64_t cells,
+                                                        int hw, float* __restrict__ dense) {
+  __shared__ float tile[32][33];
+  __shared__ int s_row[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t cell0 = int64_t(blockIdx.x) * 32;
+  const int ch0 = blockIdx.y * 32;
+  if (ty == 0) s_row[tx] = (cell0 + tx < cells) ? cell_table[cell0 + tx] : -1;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int i = ty + 8 * q;  // cell within tile
+    int row = s_row[i];
+    tile[i][tx] = (row >= 0 && ch0 + tx < c) ? feats[int64_t(row) * c + ch0 + tx] : 0.f;
+  }
+  __syncthreads();
+  const int64_t cell = cell0 + tx;
+  if (cell >= cells) return;
+  const int64_t b = cell / hw;
+  const int xy = int(cell - b * hw);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int ch = ch0 + ty + 8 * q;
+    if (ch < c) dense[(b * c + ch) * hw + xy] = tile[tx][ty + 8 * q];
+  }
+}
+
+// grid: (ceil(N/32), ceil(C/32)), block (32, 8)
+__global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ d_dense,
+                                                        const int32_t* __restrict__ indices, int64_t n, int c,
+                                                        int batch, int h, int w, float* __restrict__ d_feats) {
+  __shared__ float tile[32][33];
+  __shared__ int64_t s_base[32];
+  __shared__ int s_xy[32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t row0 = int64_t(blockIdx.x) * 32;
+  const int ch0 = blockIdx.y * 32;
+  const int hw = h * w;
+  if (ty == 0) {
+    int64_t j = row0 + tx;
+    int64_t base = -1;
+    int xy = 0;
+    if (j < n) {
+      int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
+      if (b >= 0 && b < batch && x >= 0 && x < h && y >= 0 && y < w) { base = int64_t(b) * c * hw; xy = x * w + y; }
+    }
+    s_base[tx] = base;
+    s_xy[tx] = xy;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int ch = ch0 + ty + 8 * q;  // tx indexes the row: neighbouring rows are neighbouring cells
+    int64_t base = s_base[tx];
+    tile[ty + 8 * q][tx] = (base >= 0 && ch < c) ? d_dense[base + int64_t(ch) * hw + s_xy[tx]] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int i = ty + 8 * q;  // row within tile
+    int64_t j = row0 + i;
+    if (j < n && ch0 + tx < c) d_feats[j * c + ch0 + tx] = tile[tx][i];
+  }
+}
+
+}  // namespace
+}  // namespace wfsp
+
+using namespace wfsp;
+
+extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype, int64_t n_rows,
+                               int n_chan, const int64_t* item_rows, const int64_t* item_offset, int64_t n_items,
+                               float scale, int32_t* indices_bxy, void* feats, int feats_dtype, int64_t feats_pitch,
+                               wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && n_chan >= 0 && feats_pitch >= n_chan, "bad pack sizes");
+  WFSP_REQUIRE(wave_dtype == WFSP_I16 || wave_dtype == WFSP_F32, "wave dtype must be int16 or f32");
+  WFSP_REQUIRE(feats_dtype == WFSP_F32 || feats_dtype == WFSP_BF16, "feats dtype must be f32 or bf16");
+  cudaStream_t st = as_stream(stream);
+  if (n_rows == 0) return WFSP_OK;
+  pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, item_rows,
+                                                                               item_offset, n_items, indices_bxy);
+  WFSP_CHECK_LAUNCH();
+  if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_F32)
+    return launch_pack_feats<int16_t, float>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+  if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_BF16)
+    return launch_pack_feats<int16_t, __nv_bfloat16>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+  if (wave_dtype == WFSP_F32 && feats_dtype == WFSP_F32)
+    return launch_pack_feats<float, float>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+  return launch_pack_feats<float, __nv_bfloat16>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+}
+
+extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, int n_chan, int batch,
+                             int h, int w, float* dense, int32_t* cell_table, wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0 && n_rows >= 0, "bad dense sizes");
+  cudaStream_t st = as_stream(stream);
+  const int64_t cells = int64_t(batch) * h * w;
+  if (cells == 0 || n_chan == 0) return WFSP_OK;
+  WFSP_CHECK_CUDA(cudaMemsetAsync(cell_table, 0xff, size_t(cells) * 4, st));
+  if (n_rows > 0)
+    dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, batch, h, w, cell_table);
+  dim3 grid(unsigned(ceil_div<int64_t>(cells, 32)), unsigned(ceil_div(n_chan, 32)));
+  dense_fwd_kernel<<<grid, dim3(32, 8), 0, st>>>(feats, n_chan, cell_table, cells, h * w, dense);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows, int n_chan, int batch,
+                                 int h, int w, float* d_feats, wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0 && n_rows >= 0, "bad dense sizes");
+  if (n_rows == 0 || n_chan == 0) return WFSP_OK;
+  dim3 grid(unsigned(ceil_div<int64_t>(n_rows, 32)), unsigned(ceil_div(n_chan, 32)));
+  dense_bwd_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(d_dense, indices, n_rows, n_chan, batch, h, w, d_feats);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}

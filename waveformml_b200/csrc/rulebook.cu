@@ -1,0 +1,476 @@
+// Rulebook builder for sm_100a: deterministic, bit-exact with the CPU path of upstream
+// spconv-1.2.1 get_indice_pairs, which the reference reaches from every
+// spconv.SparseConv2d / SubMConv2d with kernel volume > 1 (src/models/SPConvBlocks.py:498-502 ...).
+//
+// CPU semantics to reproduce on a GPU:
+//   * regular conv: walk inputs j in order, their candidate outputs in ascending kernel offset k;
+//     the first (j,k) that touches an output cell creates the next output row.  Every candidate
+//     gets rank r = j*K + k; phase 1 does atomicMin(rank) into a coordinate table (direct-addressed
+//     when batch*out_h*out_w is small, else an open-addressing hash), so the winner of each cell is
+//     its first toucher.  Output row id = number of first touchers with a smaller rank = an
+//     exclusive scan in (j,k) order (block scan + scan over per-block totals).
+//   * pairs of one offset are in ascending input order and each input occurs at most once per
+//     offset, so the slot of pair (j,k) = #inputs j' < j valid at k: K independent compactions,
+//     done with warp ballots + popc inside a block and the same per-block-total scan across blocks.
+//   * submanifold conv: table[cell] = row (largest j wins, "later duplicates overwrite"), then the
+//     same per-offset compaction with validity = "neighbour cell is occupied".
+//
+// HBM traffic is tiny (12 B/row read, 8 B/pair written); these kernels are latency / atomic bound
+// and the tables live in L2.
+#include "common.cuh"
+
+namespace wfsp {
+
+static int g_force_hash = 0;
+void set_force_hash(int v) { g_force_hash = v; }
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr uint32_t kEmptyKey = 0xffffffffu;
+constexpr int kRankInf = 0x7f7f7f7f;  // memset(0x7f) pattern
+constexpr int64_t kDirectMaxCells = int64_t(1) << 24;
+
+struct Geom {
+  int in_h, in_w, out_h, out_w;
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int kvol, batch;
+};
+
+struct Table {
+  int32_t* vals;
+  uint32_t* keys;  // hash mode only
+  uint32_t mask;   // hash mode only
+};
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+template <bool HASH>
+__device__ __forceinline__ int table_insert(const Table& t, uint32_t key) {
+  if (!HASH) return int(key);
+  uint32_t s = mix32(key) & t.mask;
+  while (true) {
+    uint32_t prev = atomicCAS(&t.keys[s], kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) return int(s);
+    s = (s + 1) & t.mask;
+  }
+}
+
+// slot holding `key`, or -1 (hash mode, key absent).  Direct mode always returns the cell itself.
+template <bool HASH>
+__device__ __forceinline__ int table_find(const Table& t, uint32_t key) {
+  if (!HASH) return int(key);
+  uint32_t s = mix32(key) & t.mask;
+  while (true) {
+    uint32_t k = t.keys[s];
+    if (k == key) return int(s);
+    if (k == kEmptyKey) return -1;
+    s = (s + 1) & t.mask;
+  }
+}
+
+// bit kk of the result is set iff kernel tap kk along one dimension maps input coordinate `c`
+// onto an existing output coordinate:  c = o*s - p + kk*d  with 0 <= o < out
+__device__ __forceinline__ uint32_t tap_mask(int c, int k, int s, int p, int d, int out) {
+  uint32_t m = 0;
+  for (int kk = 0; kk < k; ++kk) {
+    int num = c + p - kk * d;
+    if (num >= 0 && (num % s) == 0 && (num / s) < out) m |= 1u << kk;
+  }
+  return m;
+}
+
+struct Row {
+  int b, x, y;
+  uint32_t mx, my;
+  bool ok;
+};
+
+__device__ __forceinline__ Row load_row(const int32_t* __restrict__ indices, int64_t n, int64_t j,
+                                        const Geom& g) {
+  Row r;
+  r.ok = j < n;
+  r.b = r.x = r.y = 0;
+  r.mx = r.my = 0;
+  if (r.ok) {
+    r.b = indices[3 * j + 0];
+    r.x = indices[3 * j + 1];
+    r.y = indices[3 * j + 2];
+    r.ok = r.b >= 0 && r.b < g.batch && r.x >= 0 && r.x < g.in_h && r.y >= 0 && r.y < g.in_w;
+    if (r.ok) {
+      r.mx = tap_mask(r.x, g.kh, g.sh, g.ph, g.dh, g.out_h);
+      r.my = tap_mask(r.y, g.kw, g.sw, g.pw, g.dw, g.out_w);
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ uint32_t out_key(const Row& r, const Geom& g, int kx, int ky, int& ox, int& oy) {
+  ox = (r.x + g.ph - kx * g.dh) / g.sh;
+  oy = (r.y + g.pw - ky * g.dw) / g.sw;
+  return uint32_t((r.b * g.out_h + ox) * g.out_w + oy);
+}
+
+// ---- regular conv, phase 1: atomicMin(rank) per touched output cell ---------------------------
+template <bool HASH>
+__global__ void __launch_bounds__(kBlock) rb_conv_mark(const int32_t* __restrict__ indices, int64_t n,
+                                                       Geom g, Table t) {
+  int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  Row r = load_row(indices, n, j, g);
+  if (!r.ok) return;
+  for (int kx = 0; kx < g.kh; ++kx) {
+    if (!((r.mx >> kx) & 1)) continue;
+    for (int ky = 0; ky < g.kw; ++ky) {
+      if (!((r.my >> ky) & 1)) continue;
+      int ox, oy;
+      uint32_t key = out_key(r, g, kx, ky, ox, oy);
+      int slot = table_insert<HASH>(t, key);
+      atomicMin(&t.vals[slot], int(j) * g.kvol + kx * g.kw + ky);
+    }
+  }
+}
+
+// ---- submanifold, phase 1: table[cell] = row (largest row id wins) ----------------------------
+template <bool HASH>
+__global__ void __launch_bounds__(kBlock) rb_subm_insert(const int32_t* __restrict__ indices, int64_t n,
+                                                         Geom g, Table t) {
+  int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (j >= n) return;
+  int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
+  if (b < 0 || b >= g.batch || x < 0 || x >= g.in_h || y < 0 || y >= g.in_w) return;
+  uint32_t key = uint32_t((b * g.in_h + x) * g.in_w + y);
+  int slot = table_insert<HASH>(t, key);
+  atomicMax(&t.vals[slot], int(j));
+}
+
+// validity of candidate (row, kx, ky); for SUBM also returns the output row in `val`,
+// for CONV the table slot in `slot`.
+template <bool HASH, bool SUBM>
+__device__ __forceinline__ bool candidate(const Row& r, const Geom& g, const Table& t, int kx, int ky,
+                                          int& slot, int& val, int& ox, int& oy) {
+  if (!(r.ok && ((r.mx >> kx) & 1) && ((r.my >> ky) & 1))) return false;
+  uint32_t key = out_key(r, g, kx, ky, ox, oy);
+  slot = table_find<HASH>(t, key);
+  if (SUBM) {
+    if (slot < 0) return false;
+    val = t.vals[slot];
+    return val >= 0;
+  }
+  return true;
+}
+
+// ---- phase 2: per-block totals: K per-offset pair counts (+ first-touch count for CONV) -------
+template <bool HASH, bool SUBM>
+__global__ void __launch_bounds__(kBlock) rb_count(const int32_t* __restrict__ indices, int64_t n, Geom g,
+                                                   Table t, int32_t* __restrict__ blk_cnt) {
+  extern __shared__ int s_cnt[];  // kvol + 1
+  const int K = g.kvol;
+  for (int i = threadIdx.x; i <= K; i += kBlock) s_cnt[i] = 0;
+  __syncthreads();
+  int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  Row r = load_row(indices, n, j, g);
+  const int lane = threadIdx.x & 31;
+  int first = 0;
+  for (int kx = 0; kx < g.kh; ++kx) {
+    for (int ky = 0; ky < g.kw; ++ky) {
+      int slot = 0, val = 0, ox, oy;
+      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+      const int k = kx * g.kw + ky;
+      if (!SUBM && v && t.vals[slot] == int(j) * K + k) ++first;
+      unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (lane == 0 && bal) atomicAdd(&s_cnt[k], __popc(bal));
+    }
+  }
+  if (!SUBM) {
+    for (int o = 16; o > 0; o >>= 1) first += __shfl_xor_sync(0xffffffffu, first, o);
+    if (lane == 0 && first) atomicAdd(&s_cnt[K], first);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= K; i += kBlock) blk_cnt[int64_t(blockIdx.x) * (K + 1) + i] = s_cnt[i];
+}
+
+// ---- phase 3: exclusive scan of every counter across blocks; totals -> pair_num / n_out -------
+__global__ void __launch_bounds__(32) rb_scan(const int32_t* __restrict__ blk_cnt, int nblk, int K,
+                                              int32_t* __restrict__ blk_base, int32_t* __restrict__ pair_num,
+                                              int32_t* __restrict__ n_out) {
+  const int c = blockIdx.x;  // counter id, 0..K
+  const int lane = threadIdx.x;
+  int running = 0;
+  for (int base = 0; base < nblk; base += 32) {
+    int i = base + lane;
+    int v = i < nblk ? blk_cnt[int64_t(i) * (K + 1) + c] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (i < nblk) blk_base[int64_t(i) * (K + 1) + c] = running + incl - v;
+    running += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    if (c < K) pair_num[c] = running;
+    else if (n_out) *n_out = running;
+  }
+}
+
+// ---- phase 4 (CONV): first touchers get output row ids in rank order --------------------------
+template <bool HASH>
+__global__ void __launch_bounds__(kBlock) rb_conv_assign(const int32_t* __restrict__ indices, int64_t n,
+                                                         Geom g, Table t, const int32_t* __restrict__ blk_base,
+                                                         int32_t* __restrict__ out_indices, int64_t out_cap) {
+  __shared__ int s_warp[kWarps];
+  const int K = g.kvol;
+  int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  Row r = load_row(indices, n, j, g);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int first = 0;
+  for (int kx = 0; kx < g.kh; ++kx)
+    for (int ky = 0; ky < g.kw; ++ky) {
+      int slot = 0, val, ox, oy;
+      if (candidate<HASH, false>(r, g, t, kx, ky, slot, val, ox, oy) &&
+          t.vals[slot] == int(j) * K + kx * g.kw + ky)
+        ++first;
+    }
+  // block-wide exclusive scan of `first`
+  int incl = first;
+  for (int o = 1; o < 32; o <<= 1) {
+    int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int off = blk_base[int64_t(blockIdx.x) * (K + 1) + K] + incl - first;
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  if (first == 0) return;
+  for (int kx = 0; kx < g.kh; ++kx)
+    for (int ky = 0; ky < g.kw; ++ky) {
+      int slot = 0, val, ox, oy;
+      if (candidate<HASH, false>(r, g, t, kx, ky, slot, val, ox, oy) &&
+          t.vals[slot] == int(j) * K + kx * g.kw + ky) {
+        if (off < out_cap) {
+          out_indices[3 * int64_t(off) + 0] = r.b;
+          out_indices[3 * int64_t(off) + 1] = ox;
+          out_indices[3 * int64_t(off) + 2] = oy;
+        }
+        t.vals[slot] = -off - 1;  // only the first toucher ever rewrites its cell
+        ++off;
+      }
+    }
+}
+
+// ---- phase 5: write the pairs in (offset, ascending input) order ------------------------------
+template <bool HASH, bool SUBM>
+__global__ void __launch_bounds__(kBlock) rb_pairs(const int32_t* __restrict__ indices, int64_t n, Geom g,
+                                                   Table t, const int32_t* __restrict__ blk_base,
+                                                   int32_t* __restrict__ pairs) {
+  extern __shared__ int s_wcnt[];  // kvol * kWarps
+  const int K = g.kvol;
+  int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  Row r = load_row(indices, n, j, g);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int kx = 0; kx < g.kh; ++kx)
+    for (int ky = 0; ky < g.kw; ++ky) {
+      int slot = 0, val = 0, ox, oy;
+      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+      unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_wcnt[(kx * g.kw + ky) * kWarps + warp] = __popc(bal);
+    }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int kx = 0; kx < g.kh; ++kx)
+    for (int ky = 0; ky < g.kw; ++ky) {
+      const int k = kx * g.kw + ky;
+      int slot = 0, val = 0, ox, oy;
+      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+      unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        int pos = blk_base[int64_t(blockIdx.x) * (K + 1) + k] + __popc(bal & lt);
+        for (int w = 0; w < warp; ++w) pos += s_wcnt[k * kWarps + w];
+        int o = SUBM ? val : -t.vals[slot] - 1;
+        pairs[(int64_t(0) * K + k) * n + pos] = int32_t(j);
+        pairs[(int64_t(1) * K + k) * n + pos] = o;
+      }
+    }
+}
+
+// ---- output-stationary tables from the pair lists ---------------------------------------------
+__global__ void __launch_bounds__(kBlock) rb_tables(const int32_t* __restrict__ pairs,
+                                                    const int32_t* __restrict__ pair_num, int K, int64_t pitch,
+                                                    int64_t n_in, int64_t n_out, int32_t* __restrict__ nbr_out,
+                                                    int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag) {
+  const int k = blockIdx.y;
+  int64_t s = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+  if (s >= pair_num[k]) return;
+  int i = pairs[(int64_t(0) * K + k) * pitch + s];
+  int o = pairs[(int64_t(1) * K + k) * pitch + s];
+  if (i < 0 || i >= n_in || o < 0 || o >= n_out) { *dup_flag = 2; return; }
+  nbr_in[int64_t(i) * K + k] = o;
+  int prev = atomicExch(&nbr_out[int64_t(o) * K + k], i);
+  if (prev != -1) *dup_flag = 1;
+}
+
+struct Plan {
+  bool hash;
+  int64_t table_slots;
+  int nblk;
+  size_t off_vals, off_keys, off_cnt, off_base, total;
+};
+
+Plan make_plan(int64_t n_in, int batch, int out_h, int out_w, int kvol) {
+  Plan p;
+  int64_t cells = int64_t(batch) * out_h * out_w;
+  if (cells < 1) cells = 1;
+  p.hash = g_force_hash || cells > kDirectMaxCells;
+  if (p.hash) {
+    int64_t want = n_in * int64_t(kvol);
+    if (want > cells) want = cells;
+    int64_t cap = 64;
+    while (cap < 2 * want + 2) cap <<= 1;
+    p.table_slots = cap;
+  } else {
+    p.table_slots = cells;
+  }
+  p.nblk = int(ceil_div<int64_t>(n_in > 0 ? n_in : 1, kBlock));
+  size_t o = 0;
+  p.off_vals = o; o += align_up(size_t(p.table_slots) * 4, 256);
+  p.off_keys = o; o += p.hash ? align_up(size_t(p.table_slots) * 4, 256) : 0;
+  p.off_cnt = o;  o += align_up(size_t(p.nblk) * (kvol + 1) * 4, 256);
+  p.off_base = o; o += align_up(size_t(p.nblk) * (kvol + 1) * 4, 256);
+  p.total = o;
+  return p;
+}
+
+int check_geom(const int* ksize, const int* stride, const int* pad, const int* dil) {
+  for (int i = 0; i < 2; ++i) {
+    WFSP_REQUIRE(ksize[i] >= 1 && ksize[i] <= 32, "kernel size %d outside [1,32]", ksize[i]);
+    WFSP_REQUIRE(stride[i] >= 1 && dil[i] >= 1 && pad[i] >= 0, "bad stride/dilation/padding");
+    WFSP_REQUIRE(stride[i] == 1 || dil[i] == 1, "don't support this: stride>1 with dilation>1");
+  }
+  return WFSP_OK;
+}
+
+template <bool HASH>
+int run_conv(const int32_t* indices, int64_t n, const Geom& g, const Table& t, const Plan& p, char* ws,
+             int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num, int32_t* n_out,
+             cudaStream_t st) {
+  const int K = g.kvol;
+  int32_t* blk_cnt = reinterpret_cast<int32_t*>(ws + p.off_cnt);
+  int32_t* blk_base = reinterpret_cast<int32_t*>(ws + p.off_base);
+  rb_conv_mark<HASH><<<p.nblk, kBlock, 0, st>>>(indices, n, g, t);
+  rb_count<HASH, false><<<p.nblk, kBlock, (K + 1) * sizeof(int), st>>>(indices, n, g, t, blk_cnt);
+  rb_scan<<<K + 1, 32, 0, st>>>(blk_cnt, p.nblk, K, blk_base, pair_num, n_out);
+  rb_conv_assign<HASH><<<p.nblk, kBlock, 0, st>>>(indices, n, g, t, blk_base, out_indices, out_cap);
+  rb_pairs<HASH, false><<<p.nblk, kBlock, K * kWarps * sizeof(int), st>>>(indices, n, g, t, blk_base, pairs);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+template <bool HASH>
+int run_subm(const int32_t* indices, int64_t n, const Geom& g, const Table& t, const Plan& p, char* ws,
+             int32_t* pairs, int32_t* pair_num, cudaStream_t st) {
+  const int K = g.kvol;
+  int32_t* blk_cnt = reinterpret_cast<int32_t*>(ws + p.off_cnt);
+  int32_t* blk_base = reinterpret_cast<int32_t*>(ws + p.off_base);
+  rb_subm_insert<HASH><<<p.nblk, kBlock, 0, st>>>(indices, n, g, t);
+  rb_count<HASH, true><<<p.nblk, kBlock, (K + 1) * sizeof(int), st>>>(indices, n, g, t, blk_cnt);
+  rb_scan<<<K, 32, 0, st>>>(blk_cnt, p.nblk, K, blk_base, pair_num, nullptr);
+  rb_pairs<HASH, true><<<p.nblk, kBlock, K * kWarps * sizeof(int), st>>>(indices, n, g, t, blk_base, pairs);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+}  // namespace
+}  // namespace wfsp
+
+using namespace wfsp;
+
+extern "C" int wfsp_conv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* pad,
+                                   const int* dil, int* out_shape) {
+  for (int i = 0; i < 2; ++i) {
+    WFSP_REQUIRE(stride[i] >= 1, "stride must be >= 1");
+    int num = in_shape[i] + 2 * pad[i] - dil[i] * (ksize[i] - 1) - 1;
+    int q = num >= 0 ? num / stride[i] : -((-num + stride[i] - 1) / stride[i]);  // floor
+    out_shape[i] = q + 1;
+  }
+  return WFSP_OK;
+}
+
+extern "C" size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const int* out_shape, const int* ksize) {
+  return make_plan(n_in, batch, out_shape[0], out_shape[1], ksize[0] * ksize[1]).total;
+}
+
+extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batch, const int* in_shape,
+                                  const int* ksize, const int* stride, const int* pad, const int* dil,
+                                  int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
+                                  int32_t* n_out, void* workspace, size_t workspace_bytes,
+                                  wfsp_stream_t stream) {
+  if (int rc = check_geom(ksize, stride, pad, dil)) return rc;
+  int out_shape[2];
+  wfsp_conv_out_shape(in_shape, ksize, stride, pad, dil, out_shape);
+  WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
+  Geom g{in_shape[0], in_shape[1], out_shape[0] > 0 ? out_shape[0] : 0, out_shape[1] > 0 ? out_shape[1] : 0,
+         ksize[0], ksize[1], stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ksize[0] * ksize[1], batch};
+  WFSP_REQUIRE(n_in * int64_t(g.kvol) < int64_t(kRankInf), "n_in * kvol too large for 31-bit ranks");
+  WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * out_h * out_w too large");
+  cudaStream_t st = as_stream(stream);
+  Plan p = make_plan(n_in, batch, g.out_h, g.out_w, g.kvol);
+  if (workspace_bytes < p.total) return set_error(WFSP_EWORKSPACE, "rulebook workspace %zu < %zu", workspace_bytes, p.total);
+  char* ws = static_cast<char*>(workspace);
+  Table t{reinterpret_cast<int32_t*>(ws + p.off_vals), reinterpret_cast<uint32_t*>(ws + p.off_keys),
+          uint32_t(p.table_slots - 1)};
+  WFSP_CHECK_CUDA(cudaMemsetAsync(t.vals, 0x7f, size_t(p.table_slots) * 4, st));
+  if (p.hash) WFSP_CHECK_CUDA(cudaMemsetAsync(t.keys, 0xff, size_t(p.table_slots) * 4, st));
+  if (n_in > 0) WFSP_CHECK_CUDA(cudaMemsetAsync(pairs, 0xff, size_t(2) * g.kvol * n_in * 4, st));
+  if (n_in == 0) {
+    WFSP_CHECK_CUDA(cudaMemsetAsync(pair_num, 0, size_t(g.kvol) * 4, st));
+    WFSP_CHECK_CUDA(cudaMemsetAsync(n_out, 0, 4, st));
+    return WFSP_OK;
+  }
+  return p.hash ? run_conv<true>(indices, n_in, g, t, p, ws, out_indices, out_cap, pairs, pair_num, n_out, st)
+                : run_conv<false>(indices, n_in, g, t, p, ws, out_indices, out_cap, pairs, pair_num, n_out, st);
+}
+
+extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, int batch, const int* shape,
+                                  const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num,
+                                  void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  const int one[2] = {1, 1};
+  const int pad[2] = {ksize[0] / 2, ksize[1] / 2};
+  if (int rc = check_geom(ksize, one, pad, dil)) return rc;
+  WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
+  Geom g{shape[0], shape[1], shape[0], shape[1], ksize[0], ksize[1], 1, 1, pad[0], pad[1], dil[0], dil[1],
+         ksize[0] * ksize[1], batch};
+  WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * h * w too large");
+  cudaStream_t st = as_stream(stream);
+  Plan p = make_plan(n_in, batch, g.out_h, g.out_w, g.kvol);
+  if (workspace_bytes < p.total) return set_error(WFSP_EWORKSPACE, "rulebook workspace %zu < %zu", workspace_bytes, p.total);
+  char* ws = static_cast<char*>(workspace);
+  Table t{reinterpret_cast<int32_t*>(ws + p.off_vals), reinterpret_cast<uint32_t*>(ws + p.off_keys),
+          uint32_t(p.table_slots - 1)};
+  WFSP_CHECK_CUDA(cudaMemsetAsync(t.vals, 0xff, size_t(p.table_slots) * 4, st));
+  if (p.hash) WFSP_CHECK_CUDA(cudaMemsetAsync(t.keys, 0xff, size_t(p.table_slots) * 4, st));
+  if (n_in == 0) {
+    WFSP_CHECK_CUDA(cudaMemsetAsync(pair_num, 0, size_t(g.kvol) * 4, st));
+    return WFSP_OK;
+  }
+  WFSP_CHECK_CUDA(cudaMemsetAsync(pairs, 0xff, size_t(2) * g.kvol * n_in * 4, st));
+  return p.hash ? run_subm<true>(indices, n_in, g, t, p, ws, pairs, pair_num, st)
+                : run_subm<false>(indices, n_in, g, t, p, ws, pairs, pair_num, st);
+}
+
+extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol, int64_t pair_pitch,
+                                    int64_t n_in, int64_t n_out, int32_t* nbr_out, int32_t* nbr_in,
+                                    int32_t* dup_flag, wfsp_stream_t stream) {
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  cudaStream_t st = as_stream(stream);
+  if (n_out > 0) WFSP_CHECK_CUDA(cudaMemsetAsync(nbr_out, 0xff, size_t(n_out) * kvol * 4, st));
+  if (n_in > 0) WFSP_CHECK_CUDA(cudaMemsetAsync(nbr_in, 0xff, size_t(n_in) * kvol * 4, st));
+  if (pair_pitch == 0 || n_in == 0 || n_out == 0) return WFSP_OK;
+  dim3 grid(unsigned(ceil_div<int64_t>(pair_pitch, kBlock)), unsigned(kvol));
+  rb_tables<<<grid, kBlock, 0, st>>>(pairs, pair_num, kvol, pair_pitch, n_in, n_out, nbr_out, nbr_in, dup_flag);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}

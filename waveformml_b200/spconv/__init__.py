@@ -1,0 +1,262 @@
+"""Drop-in for the `spconv` (v1.2.x) layer API that WaveformML's models construct
+(src/models/SPConvBlocks.py, SPConvNet.py:63-64, SingleEndedZConv.py:41-45, LitBase.py:138-146),
+backed by the sm_100a kernels in libwfsp.so.  Constructing modules needs no GPU; running them needs
+CUDA tensors -- there is no CPU path.
+
+Kept from upstream: constructor signatures incl. the 8 positional arguments the
+reference passes (nin, nout, kernel, stride, padding, dilation, groups, bias); weight shape
+[kH, kW, Cin, Cout] with kaiming_uniform_(a=sqrt(5)) init, bias [Cout]; kernel volume 1 takes the
+`features @ weight` shortcut and ignores stride / padding; SubMConv2d ignores stride / padding
+(pad := k//2, stride := 1); rulebooks are cached in the tensor's shared `indice_dict` under
+`indice_key` (also under None); SparseInverseConv2d reuses its partner's rulebook with the roles
+swapped; bias is added to active rows only; SparseSequential applies non-sparse modules to
+`.features` when there is at least one row.
+"""
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import functional as Fsp
+from . import ops
+from .ops import Rulebook, get_conv_output_size, get_indice_pairs  # noqa: F401
+
+__all__ = ["SparseConvTensor", "SparseModule", "SparseConvolution", "SparseConv2d", "SubMConv2d",
+           "SparseInverseConv2d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode"]
+
+_math_mode = os.environ.get("WFSP_MATH", "bf16")
+assert _math_mode in ("bf16", "fp32")
+
+
+def set_math_mode(mode):
+    """'bf16': tcgen05 tensor cores, bf16 operands / fp32 accumulate.  'fp32': exact fp32 CUDA-core path."""
+    global _math_mode
+    assert mode in ("bf16", "fp32")
+    _math_mode = mode
+
+
+def get_math_mode():
+    return _math_mode
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+        """features [N, C]; indices int32 [N, 3] = (batch, x, y); spatial_shape e.g. [14, 11]
+        (list / numpy array); batch_size int or 0-dim tensor (as the reference passes,
+        src/models/SPConvNet.py:51,63)."""
+        self.features = features
+        self.indices = indices
+        if self.indices.dtype != torch.int32:
+            self.indices = self.indices.int()
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.indice_dict = {}
+        self.grid = grid
+
+    @property
+    def spatial_size(self):
+        return int(np.prod(self.spatial_shape))
+
+    def find_indice_pair(self, key):
+        if key is None:
+            return None
+        if key in self.indice_dict:
+            return self.indice_dict[key]
+        return None
+
+    def dense(self, channels_first=True):
+        h, w = self.spatial_shape
+        out = Fsp.ToDenseFunction.apply(self.features, self.indices, self.batch_size, h, w)
+        if not channels_first:
+            return out.permute(0, 2, 3, 1).contiguous()
+        return out
+
+    @property
+    def sparity(self):
+        return self.indices.shape[0] / max(1, self.spatial_size * self.batch_size)
+
+
+class SparseModule(nn.Module):
+    """Marker base class: modules that consume / produce a SparseConvTensor."""
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None,
+                 fused_bn=False, use_hash=False):
+        super().__init__()
+        assert groups == 1
+        if ndim != 2:
+            raise NotImplementedError("only 2-d sparse convolutions are implemented (the 14x11 segment grid)")
+        if transposed:
+            raise NotImplementedError("SparseConvTranspose is not used by the reference models")
+
+        def tup(v):
+            return [int(v)] * ndim if isinstance(v, (int, np.integer)) else [int(x) for x in v]
+
+        self.ndim = ndim
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.kernel_size, self.stride, self.padding = tup(kernel_size), tup(stride), tup(padding)
+        self.dilation, self.output_padding = tup(dilation), tup(output_padding)
+        self.conv1x1 = int(np.prod(self.kernel_size)) == 1
+        self.transposed, self.inverse, self.groups, self.subm = transposed, inverse, groups, subm
+        self.indice_key, self.fused_bn, self.use_hash = indice_key, fused_bn, use_hash
+        self.math = None  # None -> follow the global math mode
+        self.weight = nn.Parameter(torch.empty(*self.kernel_size, self.in_channels, self.out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(self.out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in, _ = nn.init._calculate_fan_in_and_fan_out(self.weight)
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        return "{}, {}, kernel_size={}, stride={}, padding={}, dilation={}, subm={}, inverse={}, indice_key={}".format(
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.dilation,
+            self.subm, self.inverse, self.indice_key)
+
+    def forward(self, input):
+        assert isinstance(input, SparseConvTensor)
+        features, indices = input.features, input.indices
+        mode = self.math or _math_mode
+        if self.conv1x1:
+            out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, None, False, mode)
+            out = SparseConvTensor(out_features, indices, input.spatial_shape, input.batch_size)
+            out.indice_dict, out.grid = input.indice_dict, input.grid
+            return out
+        datas = input.find_indice_pair(self.indice_key)
+        if self.inverse:
+            assert datas is not None and self.indice_key is not None
+            rb = datas
+            assert rb.kvol == int(np.prod(self.kernel_size)), \
+                "inverse conv must have same kernel size as its couple conv"
+            outids, out_spatial_shape = rb.indices, rb.spatial_shape
+        else:
+            if self.indice_key is not None and datas is not None:
+                rb = datas
+            else:
+                pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
+                stride = [1] * self.ndim if self.subm else self.stride
+                rb = ops.build_rulebook(indices, input.batch_size, input.spatial_shape, self.kernel_size, stride,
+                                        pad, self.dilation, self.subm)
+                input.indice_dict[self.indice_key] = rb
+            outids = rb.outids
+            out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
+        out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, rb, self.inverse, mode)
+        out = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size)
+        out.indice_dict, out.grid = input.indice_dict, input.grid
+        return out
+
+
+class SparseConv2d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, use_hash=False):
+        super().__init__(2, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         indice_key=indice_key, use_hash=use_hash)
+
+
+class SubMConv2d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, use_hash=False):
+        super().__init__(2, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key, use_hash=use_hash)
+
+
+class SparseInverseConv2d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key, bias=True):
+        super().__init__(2, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key)
+
+
+def _not_implemented(name):
+    class _Stub(SparseModule):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(
+                "%s is listed by src/utils/ModelValidation.py:24-31 but constructed by no shipped config; "
+                "only the 2-d layers of the 14x11 grid are implemented" % name)
+    _Stub.__name__ = name
+    return _Stub
+
+
+SparseConv1d = _not_implemented("SparseConv1d")
+SparseConv3d = _not_implemented("SparseConv3d")
+SparseConv4d = _not_implemented("SparseConv4d")
+SubMConv3d = _not_implemented("SubMConv3d")
+SparseConvTranspose2d = _not_implemented("SparseConvTranspose2d")
+SparseConvTranspose3d = _not_implemented("SparseConvTranspose3d")
+
+
+class ToDense(SparseModule):
+    """SparseConvTensor -> dense [B, C, H, W]."""
+
+    def forward(self, x):
+        return x.dense()
+
+
+def is_spconv_module(module):
+    return isinstance(module, SparseModule)
+
+
+class SparseSequential(SparseModule):
+    """nn.Sequential that hands the SparseConvTensor to sparse modules and `.features` to the
+    rest (BatchNorm1d / ReLU / Dropout), as upstream spconv/modules.py does."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], OrderedDict):
+            for key, module in args[0].items():
+                self.add_module(key, module)
+        else:
+            for idx, module in enumerate(args):
+                self.add_module(str(idx), module)
+        for name, module in kwargs.items():
+            if name in self._modules:
+                raise ValueError("name exists.")
+            self.add_module(name, module)
+        self._sparity_dict = {}
+
+    def __getitem__(self, idx):
+        if not (-len(self) <= idx < len(self)):
+            raise IndexError("index {} is out of range".format(idx))
+        if idx < 0:
+            idx += len(self)
+        it = iter(self._modules.values())
+        for _ in range(idx):
+            next(it)
+        return next(it)
+
+    def __len__(self):
+        return len(self._modules)
+
+    @property
+    def sparity_dict(self):
+        return self._sparity_dict
+
+    def add(self, module, name=None):
+        if name is None:
+            name = str(len(self._modules))
+            if name in self._modules:
+                raise KeyError("name exists")
+        self.add_module(name, module)
+
+    def forward(self, input):
+        for k, module in self._modules.items():
+            if is_spconv_module(module):
+                assert isinstance(input, SparseConvTensor)
+                self._sparity_dict[k] = input.sparity
+                input = module(input)
+            else:
+                if isinstance(input, SparseConvTensor):
+                    if input.indices.shape[0] != 0:
+                        input.features = module(input.features)
+                else:
+                    input = module(input)
+        return input

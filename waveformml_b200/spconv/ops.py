@@ -1,0 +1,118 @@
+"""Rulebook ops (mirror of upstream spconv/ops.py: get_conv_output_size, get_indice_pairs) on top
+of libwfsp.so.  Reference call sites: every spconv.SparseConv2d / SubMConv2d with kernel volume > 1
+in src/models/SPConvBlocks.py (e.g. :498-502)."""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _list2(v):
+    if isinstance(v, (int, np.integer)):
+        return [int(v), int(v)]
+    v = [int(x) for x in v]
+    assert len(v) == 2, "only 2-d sparse convolutions are implemented"
+    return v
+
+
+def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
+    """(i + 2p - d(k-1) - 1)//s + 1 per dimension; the same arithmetic as the reference's
+    ModelValidation.calc_output_size_1d (src/utils/ModelValidation.py:119-126)."""
+    out = []
+    for i, k, s, p, d in zip(input_size, kernel_size, stride, padding, dilation):
+        out.append((int(i) + 2 * int(p) - int(d) * (int(k) - 1) - 1) // int(s) + 1)
+    return out
+
+
+class Rulebook:
+    """Geometry of one sparse convolution, cached in SparseConvTensor.indice_dict under the layer's
+    indice_key.  Unpacks like upstream's 5-tuple (outids, indices, indice_pairs, indice_pair_num,
+    spatial_shape) and additionally carries the output-stationary neighbour tables."""
+
+    def __init__(self, outids, indices, pairs, pair_num, spatial_shape, out_spatial_shape, nbr_out, nbr_in, dup_flag):
+        self.outids, self.indices, self.pairs, self.pair_num = outids, indices, pairs, pair_num
+        self.spatial_shape, self.out_spatial_shape = spatial_shape, out_spatial_shape
+        self.nbr_out, self.nbr_in, self.dup_flag = nbr_out, nbr_in, dup_flag
+
+    def _tuple(self):
+        return (self.outids, self.indices, self.pairs, self.pair_num, self.spatial_shape)
+
+    def __iter__(self):
+        return iter(self._tuple())
+
+    def __getitem__(self, i):
+        return self._tuple()[i]
+
+    def __len__(self):
+        return 5
+
+    @property
+    def kvol(self):
+        return self.pairs.shape[1]
+
+
+def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=False,
+                   check_duplicates=False):
+    """Builds pairs + neighbour tables on the GPU.  One host readback (n_out) for a regular conv,
+    none for a submanifold conv."""
+    lib = _lib.load()
+    _lib.require_cuda(indices)
+    if indices.dtype != torch.int32:
+        raise RuntimeError("indices must be int32 (got %s)" % indices.dtype)
+    assert indices.dim() == 2 and indices.shape[1] == 3, "indices must be [N, 3] = (batch, x, y)"
+    indices = indices.contiguous()
+    ksize, stride, padding, dilation = _list2(ksize), _list2(stride), _list2(padding), _list2(dilation)
+    spatial_shape = [int(s) for s in spatial_shape]
+    for s, d in zip(stride, dilation):
+        assert s == 1 or d == 1, "don't support this."
+    batch_size = int(batch_size)
+    dev = indices.device
+    N, K = indices.shape[0], ksize[0] * ksize[1]
+    if subm:
+        out_shape = list(spatial_shape)
+    else:
+        out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
+    pairs = torch.empty((2, K, N), dtype=torch.int32, device=dev)
+    pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
+    oshape_c = _lib.ints([max(o, 0) for o in out_shape])
+    ws_bytes = lib.wfsp_rulebook_workspace_bytes(N, batch_size, oshape_c, _lib.ints(ksize))
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        if subm:
+            _lib.check(lib.wfsp_rulebook_subm(_lib.ptr(indices), N, batch_size, _lib.ints(spatial_shape),
+                                              _lib.ints(ksize), _lib.ints(dilation), _lib.ptr(pairs),
+                                              _lib.ptr(pair_num), _lib.ptr(ws), ws.numel(), _lib.stream()))
+            outids, n_out = indices, N
+        else:
+            cells = batch_size * max(out_shape[0], 0) * max(out_shape[1], 0)
+            cap = max(1, min(N * K, cells))
+            outbuf = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+            n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+            _lib.check(lib.wfsp_rulebook_conv(_lib.ptr(indices), N, batch_size, _lib.ints(spatial_shape),
+                                              _lib.ints(ksize), _lib.ints(stride), _lib.ints(padding),
+                                              _lib.ints(dilation), _lib.ptr(outbuf), cap, _lib.ptr(pairs),
+                                              _lib.ptr(pair_num), _lib.ptr(n_out_dev), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream()))
+            n_out = int(n_out_dev.item())  # the one readback per rulebook (output tensor shapes need it)
+            outids = outbuf[:n_out]
+        nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
+        nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
+        dup = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.wfsp_rulebook_tables(_lib.ptr(pairs), _lib.ptr(pair_num), K, N, N, n_out, _lib.ptr(nbr_out),
+                                            _lib.ptr(nbr_in), _lib.ptr(dup), _lib.stream()))
+    if check_duplicates and int(dup.item()) != 0:
+        raise RuntimeError("duplicate (batch, x, y) coordinates in the input: not supported by the "
+                           "output-stationary kernels")
+    return Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup)
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
+                     subm=False, transpose=False, grid=None, use_hash=False):
+    """Upstream-compatible signature; returns (outids, indice_pairs [2,K,N], indice_pair_num [K])."""
+    if transpose:
+        raise NotImplementedError("transposed sparse convolution is not used by the reference models")
+    ks = _list2(ksize)
+    pad = [k // 2 for k in ks] if subm else _list2(padding)
+    st = [1, 1] if subm else _list2(stride)
+    rb = build_rulebook(indices, batch_size, spatial_shape, ks, st, pad, dilation, subm)
+    return rb.outids, rb.pairs, rb.pair_num
