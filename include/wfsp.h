@@ -56,6 +56,8 @@ int wfsp_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host)
 /* tuning / test knobs; "rulebook_force_hash" = 1 forces the open-addressing coordinate hash even
  * when the dense grid table would be used */
 int wfsp_set_option(const char* name, int value);
+/* number of CUDA kernels this library has launched in the calling process (monotonic) */
+unsigned long long wfsp_kernel_launches(void);
 
 /* ---------------------------------------------------------------------------------------------
  * (1) Sparse-tensor batcher.

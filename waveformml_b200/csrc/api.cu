@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <string.h>
+#include <atomic>
 
 namespace wfsp {
 
@@ -33,6 +34,9 @@ int sm_count() {
 
 void set_force_hash(int v);
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 // conv_simt.cu
 int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
@@ -57,6 +61,8 @@ using namespace wfsp;
 extern "C" int wfsp_version(void) { return WFSP_VERSION; }
 
 extern "C" const char* wfsp_last_error(void) { return error_buffer(); }
+
+extern "C" unsigned long long wfsp_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int wfsp_device_info(int* sm, int* major, int* minor) {
   int dev = 0;

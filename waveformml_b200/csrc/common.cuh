@@ -38,4 +38,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 int sm_count();
 
+// number of kernels libwfsp.so has launched in this process (wfsp_kernel_launches)
+void count_launches(int n);
+
 }  // namespace wfsp

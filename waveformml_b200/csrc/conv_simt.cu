@@ -176,6 +176,7 @@ int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* wei
   const int w_ns = transpose_w ? c_red : 1;
   conv_apply_simt_kernel<<<grid, 256, 0, st>>>(src, n_src, c_red, weight, w_ks, w_cs, w_ns, bias, nbr, kvol, dst,
                                                n_dst, c_dst);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -201,6 +202,7 @@ int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_
   dim3 grid(unsigned(ceil_div(c_a, BM)), unsigned(ceil_div(c_b, BN)), unsigned(kvol * nsplit));
   conv_wgrad_simt_kernel<<<grid, 256, 0, st>>>(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch,
                                                nsplit, chunk, d_weight, use_atomic);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }

@@ -422,6 +422,7 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     int64_t blocks = ceil_div<int64_t>(total, 256);
     if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
     prep_weight_kernel<<<unsigned(blocks), 256, 0, st>>>(weight, kvol, c_red, c_dst, transpose_w, wt, a.n_pad, a.kc_pad);
+    count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
   ApplyParams p{src, n_src, c_red, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2};
@@ -434,6 +435,7 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
   auto launch = [&](auto kern) -> int {
     WFSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     kern<<<grid, kThreads, smem, st>>>(p);
+    count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   };
@@ -478,6 +480,7 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   auto launch = [&](auto kern) -> int {
     WFSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     kern<<<grid, kThreads, smem, st>>>(p);
+    count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   };

@@ -94,6 +94,7 @@ int launch_pack_feats(const void* wave, int64_t n, int c, float scale, void* fea
   else
     pack_feats_scalar_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, c, scale,
                                                                         static_cast<Out*>(feats), pitch);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -191,6 +192,7 @@ extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int 
   if (n_rows == 0) return WFSP_OK;
   pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, item_rows,
                                                                                item_offset, n_items, indices_bxy);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_F32)
     return launch_pack_feats<int16_t, float>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
@@ -212,6 +214,7 @@ extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t
     dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, batch, h, w, cell_table);
   dim3 grid(unsigned(ceil_div<int64_t>(cells, 32)), unsigned(ceil_div(n_chan, 32)));
   dense_fwd_kernel<<<grid, dim3(32, 8), 0, st>>>(feats, n_chan, cell_table, cells, h * w, dense);
+  count_launches(n_rows > 0 ? 2 : 1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -222,6 +225,7 @@ extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, i
   if (n_rows == 0 || n_chan == 0) return WFSP_OK;
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, 32)), unsigned(ceil_div(n_chan, 32)));
   dense_bwd_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(d_dense, indices, n_rows, n_chan, batch, h, w, d_feats);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }

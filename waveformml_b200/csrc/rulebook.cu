@@ -365,6 +365,7 @@ int run_conv(const int32_t* indices, int64_t n, const Geom& g, const Table& t, c
   rb_scan<<<K + 1, 32, 0, st>>>(blk_cnt, p.nblk, K, blk_base, pair_num, n_out);
   rb_conv_assign<HASH><<<p.nblk, kBlock, 0, st>>>(indices, n, g, t, blk_base, out_indices, out_cap);
   rb_pairs<HASH, false><<<p.nblk, kBlock, K * kWarps * sizeof(int), st>>>(indices, n, g, t, blk_base, pairs);
+  count_launches(5);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -379,6 +380,7 @@ int run_subm(const int32_t* indices, int64_t n, const Geom& g, const Table& t, c
   rb_count<HASH, true><<<p.nblk, kBlock, (K + 1) * sizeof(int), st>>>(indices, n, g, t, blk_cnt);
   rb_scan<<<K, 32, 0, st>>>(blk_cnt, p.nblk, K, blk_base, pair_num, nullptr);
   rb_pairs<HASH, true><<<p.nblk, kBlock, K * kWarps * sizeof(int), st>>>(indices, n, g, t, blk_base, pairs);
+  count_launches(4);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -471,6 +473,7 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
   if (pair_pitch == 0 || n_in == 0 || n_out == 0) return WFSP_OK;
   dim3 grid(unsigned(ceil_div<int64_t>(pair_pitch, kBlock)), unsigned(kvol));
   rb_tables<<<grid, kBlock, 0, st>>>(pairs, pair_num, kvol, pair_pitch, n_in, n_out, nbr_out, nbr_in, dup_flag);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
