@@ -137,7 +137,7 @@ int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol
  * nbr == NULL means kvol == 1 with the identity map (the 1x1 shortcut, n_dst == n_src).
  * src and dst are fp32 [rows, channels] with row pitch == channels; weight and bias are fp32.
  */
-size_t wfsp_conv_apply_workspace_bytes(int kvol, int c_red, int c_dst, int math);
+size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math);
 
 int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* weight,
                     int transpose_w, const float* bias, const int32_t* nbr, int kvol, float* dst,
@@ -151,7 +151,8 @@ int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* wei
  * pair_num[k] entries of row k are read.  d_weight is overwritten (accumulate == 0) or added to
  * (accumulate == 1).  pair_a == pair_b == pair_num == NULL selects the identity pair list of the
  * 1x1 shortcut (kvol == 1, n_a == n_b pairs). */
-size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int c_a, int c_b, int64_t pair_pitch, int math);
+size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b,
+                                       int64_t pair_pitch, int math);
 
 int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,

@@ -116,11 +116,27 @@ def _scatter_add(out, idx, n, buf):
                                _p(buf, ctypes.c_float))
 
 
+_OPERAND_ROUNDING = None
+
+
+def set_operand_rounding(mode):
+    """None: plain fp32 (the reference arithmetic).  'bf16': round both GEMM operands to bf16 before
+    every product (fp32 accumulate) -- emulates the tensor-core arithmetic of the GPU's bf16 mode so
+    a test can separate rounding of the operands from kernel bugs."""
+    global _OPERAND_ROUNDING
+    assert mode in (None, "bf16")
+    _OPERAND_ROUNDING = mode
+
+
+def _r(t):
+    return t.bfloat16().float() if _OPERAND_ROUNDING == "bf16" else t
+
+
 def indice_conv(features, filters, pairs, pair_num, num_act_out, inverse=False, subm=False):
     """Upstream indiceConv: for each offset gather -> mm -> scatter-add."""
-    features = features.contiguous().float()
+    features = _r(features.contiguous().float())
     K = pairs.shape[1]
-    W = filters.reshape(K, filters.shape[-2], filters.shape[-1]).float()
+    W = _r(filters.reshape(K, filters.shape[-2], filters.shape[-1]).float())
     nums = pair_num.tolist()
     kmax = int(np.argmax(nums)) if K > 0 else 0
     if subm:
@@ -139,10 +155,10 @@ def indice_conv(features, filters, pairs, pair_num, num_act_out, inverse=False, 
 
 def indice_conv_backward(features, filters, out_bp, pairs, pair_num, inverse=False, subm=False):
     """Upstream indiceConvBackward."""
-    features = features.contiguous().float()
-    out_bp = out_bp.contiguous().float()
+    features = _r(features.contiguous().float())
+    out_bp = _r(out_bp.contiguous().float())
     K = pairs.shape[1]
-    W = filters.reshape(K, filters.shape[-2], filters.shape[-1]).float()
+    W = _r(filters.reshape(K, filters.shape[-2], filters.shape[-1]).float())
     nums = pair_num.tolist()
     kmax = int(np.argmax(nums)) if K > 0 else 0
     dW = torch.zeros_like(W)
@@ -235,7 +251,12 @@ class SparseConvolution(nn.Module):
     def forward(self, x):
         assert isinstance(x, SparseConvTensor)
         if self.conv1x1:
-            f = torch.mm(x.features, self.weight.view(self.in_channels, self.out_channels))
+            if _OPERAND_ROUNDING is None:
+                f = torch.mm(x.features, self.weight.view(self.in_channels, self.out_channels))
+            else:  # same product through the rounding-aware function (identity pair list)
+                n = x.features.shape[0]
+                ident = torch.arange(n, dtype=torch.int32).repeat(2, 1, 1)
+                f = _ConvFn.apply(x.features, self.weight, ident, torch.tensor([n], dtype=torch.int32), n, False, False)
             if self.bias is not None:
                 f = f + self.bias
             out = SparseConvTensor(f, x.indices, x.spatial_shape, x.batch_size)

@@ -35,8 +35,8 @@ def test_host_only_helpers():
                                        _lib.ints([1, 1]), out))
     assert list(out) == [6, 5]
     assert lib.wfsp_rulebook_workspace_bytes(185, 64, _lib.ints([12, 9]), _lib.ints([3, 3])) > 64 * 108 * 4
-    assert lib.wfsp_conv_apply_workspace_bytes(9, 252, 158, _lib.MATH_BF16) >= 9 * 160 * 256 * 2
-    assert lib.wfsp_conv_apply_workspace_bytes(9, 252, 158, _lib.MATH_FP32) == 0
+    assert lib.wfsp_conv_apply_workspace_bytes(9, 100, 252, 158, _lib.MATH_BF16) >= 9 * 160 * 256 * 2 + 100 * 256 * 2
+    assert lib.wfsp_conv_apply_workspace_bytes(9, 100, 252, 158, _lib.MATH_FP32) == 0
 
 
 def test_bad_arguments_report_errors():

@@ -45,11 +45,11 @@ int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, cudaStream_t st);
 // conv_umma.cu
-size_t conv_apply_umma_workspace(int kvol, int c_red, int c_dst);
+size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst);
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
                     void* ws, size_t ws_bytes, cudaStream_t st);
-size_t conv_wgrad_umma_workspace(int kvol, int c_a, int c_b, int64_t pitch);
+size_t conv_wgrad_umma_workspace(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t pitch);
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -79,8 +79,8 @@ extern "C" int wfsp_set_option(const char* name, int value) {
   return set_error(WFSP_EINVAL, "unknown option %s", name);
 }
 
-extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int c_red, int c_dst, int math) {
-  return math == WFSP_MATH_BF16 ? conv_apply_umma_workspace(kvol, c_red, c_dst) : 0;
+extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math) {
+  return math == WFSP_MATH_BF16 ? conv_apply_umma_workspace(kvol, n_src, c_red, c_dst) : 0;
 }
 
 extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
@@ -98,8 +98,9 @@ extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
 }
 
-extern "C" size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int c_a, int c_b, int64_t pair_pitch, int math) {
-  return math == WFSP_MATH_BF16 ? conv_wgrad_umma_workspace(kvol, c_a, c_b, pair_pitch) : 0;
+extern "C" size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b,
+                                                  int64_t pair_pitch, int math) {
+  return math == WFSP_MATH_BF16 ? conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pair_pitch) : 0;
 }
 
 extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,

@@ -2,22 +2,29 @@
 // accumulation in tensor memory.  They replace upstream indiceConv / indiceConvBackward
 // (reference call sites src/models/SPConvBlocks.py:498-502 etc.).
 //
+// Both kernels are warp-specialised (160 threads):
+//   warps 0-3  producers: issue 16-byte cp.async copies of gathered bf16 rows and of the weight /
+//              gradient slice straight into 128-byte-swizzled shared-memory tiles, then
+//              cp.async.mbarrier.arrive.noinc on the stage's "full" barrier and move on -- they
+//              never wait for data, so up to `stages` slices are in flight per CTA;
+//   warp 4     one elected lane waits on "full", issues 4 tcgen05.mma (K=16 each) accumulating in
+//              TMEM and tcgen05.commit's to the stage's "free" barrier;
+//   warps 0-3  epilogue after the last commit: tcgen05.ld -> registers -> global.
+//
 // apply kernel (forward, dgrad, inverse forward, inverse dgrad) -- output-stationary implicit GEMM:
-//   a CTA owns 128 destination rows.  For every kernel offset k that is active in the tile and
-//   every 64-channel slice of the reduction dimension it
-//     - gathers the fp32 source rows nbr[r][k] (zeros for -1), converts to bf16 and stores them
-//       into shared memory in the 128-byte-swizzled K-major layout UMMA expects (A tile, 16 KB),
-//     - copies the matching slice of the pre-transposed bf16 weights (B tile, N x 64),
-//     - one thread issues 4 tcgen05.mma (M=128, N=n_tile, K=16) accumulating into TMEM and commits
-//       them to the stage's mbarrier, which frees the stage for the gather two/three steps later.
-//   The MMAs are asynchronous, so the gather of step i+1 overlaps the tensor work of step i.
-//   One epilogue: TMEM -> registers (tcgen05.ld) -> + bias -> coalesced fp32 row stores.
-//   No scatter-add, no atomics, fixed summation order.
+//   a CTA owns 128 destination rows and walks (active kernel offset k) x (64-channel slice):
+//   A tile = rows nbr[r][k] of the bf16 activation copy (zero-filled for -1 through cp.async
+//   src-size 0), B tile = slice of the pre-transposed bf16 weights.  No scatter-add, no atomics,
+//   fixed summation order.
 //
 // wgrad kernel: d_weight[k] = A_k^T B_k over the pair list of offset k.  The gathered rows are
-//   [pairs][channels] = MN-major operands for UMMA (the reduction index is the pair), so the very
-//   same swizzled row layout is used with the MN-major bits set in the instruction descriptor.
-//   CTAs split the pair list; partial tiles are reduced with fp32 atomics (red.global.add.f32).
+//   [pairs][channels] = MN-major operands for UMMA (the reduction index is the pair), so the same
+//   swizzled row layout is used with the MN-major bits set in the instruction descriptor.
+//   CTAs split the pair list; partial tiles are reduced with fp32 atomics.
+//
+// Activations arrive as fp32 [rows, C] from the torch modules between the convolutions; a small
+// cast kernel makes the bf16 copy (row pitch padded to 8 elements so every row is 16-byte aligned)
+// that the K gathers then read at half the bytes.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -26,12 +33,22 @@ namespace {
 
 using namespace umma;
 
-constexpr int kThreads = 128;
-constexpr int kTileM = 128;      // destination rows (apply) / a-channels (wgrad) per CTA
-constexpr int kSliceK = 64;      // reduction elements per pipeline stage (one 128 B swizzle row of bf16)
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;
+constexpr int kTileM = 128;   // destination rows (apply) / a-channels (wgrad) per CTA
+constexpr int kSliceK = 64;   // reduction elements per stage (one 128 B swizzle row of bf16)
 constexpr int kABytes = kTileM * 128;
-constexpr int kMaxStages = 4;
-constexpr int kSmemBudget = 110 * 1024;  // keeps two CTAs resident per SM
+constexpr int kMaxStages = 8;
+constexpr int kNbrStageK = 32;  // kernel volumes up to this keep the CTA's neighbour tile in smem
+constexpr int kSmemMax = 200 * 1024;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ---- weight preparation: fp32 [kvol][c_red][c_dst] (or transposed) -> bf16 [kvol][n_pad][kc_pad]
 __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ w, int kvol, int c_red,
@@ -52,42 +69,66 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
   }
 }
 
-// load 4 consecutive floats of a row (guarded), VEC = alignment the row pitch guarantees
-template <int VEC>
-__device__ __forceinline__ void load4(const float* __restrict__ row, int col, int c_max, float (&v)[4]) {
-  if (VEC == 4 && col + 3 < c_max) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(row + col));
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-  } else if (VEC == 2 && col + 3 < c_max) {
-    const float2 q0 = __ldg(reinterpret_cast<const float2*>(row + col));
-    const float2 q1 = __ldg(reinterpret_cast<const float2*>(row + col + 2));
-    v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-  } else {
+// ---- activation cast: fp32 [n][c] -> bf16 [n][c_pad], zero padded; one 16-byte chunk per thread
+struct CastJob { const float* src; __nv_bfloat16* dst; int64_t n; int c, c_pad; };
+
+__global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1, int64_t chunks0, int64_t chunks_total) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < chunks_total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const CastJob& j = i < chunks0 ? j0 : j1;
+    const int64_t ii = i < chunks0 ? i : i - chunks0;
+    const int cpr = j.c_pad >> 3;
+    const int64_t row = ii / cpr;
+    const int col = int(ii - row * cpr) << 3;
+    const float* s = j.src + row * j.c + col;
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = (col + e < c_max) ? __ldg(row + col + e) : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = (col + e < j.c) ? __ldg(s + e) : 0.f;
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(j.dst + row * j.c_pad + col) = u;
   }
 }
 
-__device__ __forceinline__ void store_bf16x4(uint8_t* base, uint32_t off, const float (&v)[4]) {
-  uint2 u;
-  u.x = pack_bf16x2(v[0], v[1]);
-  u.y = pack_bf16x2(v[2], v[3]);
-  *reinterpret_cast<uint2*>(base + off) = u;
+int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
+  CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8};
+  const int64_t c0 = a.n * (a.c_pad >> 3), c1 = j1.n * (j1.c_pad >> 3);
+  if (c0 + c1 == 0) return WFSP_OK;
+  int64_t blocks = ceil_div<int64_t>(c0 + c1, 256);
+  if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+  cast_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(a, j1, c0, c0 + c1);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+struct PipeBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t free_[kMaxStages];
+  uint64_t done;
+};
+
+__device__ __forceinline__ void init_pipe(PipeBarriers& b) {
+  for (int s = 0; s < kMaxStages; ++s) {
+    mbar_init(&b.full[s], kProducerThreads);
+    mbar_init(&b.free_[s], 1);
+  }
+  mbar_init(&b.done, 1);
+  fence_mbar_init();
 }
 
 struct ApplyParams {
-  const float* src; int64_t n_src; int c_red;
+  const __nv_bfloat16* src; int64_t n_src; int c_pad;
   const __nv_bfloat16* wt; int n_pad, kc_pad;
   const float* bias; const int32_t* nbr; int kvol;
   float* dst; int64_t n_dst; int c_dst;
   int n_tile, stages;
 };
 
-template <int VEC>
 __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_free[kMaxStages];
-  __shared__ uint64_t bar_done;
+  __shared__ PipeBarriers bars;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_active[WFSP_MAX_KVOL / 32];
 
@@ -96,15 +137,13 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   const int n0 = blockIdx.y * p.n_tile;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = kABytes + uint32_t(p.n_tile) * 128u;
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + uint32_t(p.stages) * stage_bytes);
   const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(p.n_tile));
+  const bool staged = p.nbr != nullptr && p.kvol <= kNbrStageK;
 
   for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kThreads) s_active[i] = 0;
-  if (tid == 0) {
-    for (int s = 0; s < kMaxStages; ++s) mbar_init(&bar_free[s], 1);
-    mbar_init(&bar_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
+  if (tid == 0) init_pipe(bars);
+  if (warp == 4) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
   }
@@ -113,98 +152,89 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  // which kernel offsets have at least one neighbour in this tile
-  {
-    const int64_t r = row0 + tid;
-    for (int k = 0; k < p.kvol; ++k) {
-      bool v = r < p.n_dst && (p.nbr ? p.nbr[r * p.kvol + k] >= 0 : true);
-      unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (lane == 0 && bal) atomicOr(&s_active[k >> 5], 1u << (k & 31));
+  // neighbour tile of this CTA: which kernel offsets are active, and (small kernels) a smem copy
+  if (p.nbr) {
+    const int total = kTileM * p.kvol;
+    int64_t rows_left = p.n_dst - row0;
+    if (rows_left > kTileM) rows_left = kTileM;
+    const int limit = int(rows_left) * p.kvol;
+    const int32_t* base = p.nbr + row0 * p.kvol;
+    for (int i = tid; i < total; i += kThreads) {
+      int v = i < limit ? __ldg(base + i) : -1;
+      if (v >= p.n_src) v = -1;
+      if (staged) s_nbr[i] = v;
+      if (v >= 0) {
+        const int k = i % p.kvol;
+        atomicOr(&s_active[k >> 5], 1u << (k & 31));
+      }
     }
+  } else if (tid == 0) {
+    s_active[0] = 1u;
   }
   __syncthreads();
 
-  const int sub = tid & 15;  // 4-float column group inside the 64-wide slice
-  const int r8 = tid >> 4;   // this thread covers tile rows r8 + 8*i
   const int num_kb = p.kc_pad / kSliceK;
-  const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
-  int it = 0;
+  int n_active = 0;
+  for (int w = 0; w < (p.kvol + 31) / 32; ++w) n_active += __popc(s_active[w]);
+  const int total_iters = n_active * num_kb;
 
-  for (int kw = 0; kw < (p.kvol + 31) / 32; ++kw) {
-    uint32_t mask = s_active[kw];
-    while (mask) {
-      const int k = kw * 32 + __ffs(mask) - 1;
-      mask &= mask - 1;
-      int my_rows[16];
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int c16 = tid & 7;    // 16-byte chunk inside the 128-byte slice row
+    const int rsub = tid >> 3;  // this thread covers tile rows rsub + 16*i
+    int it = 0;
+    for (int kw = 0; kw < (p.kvol + 31) / 32; ++kw) {
+      uint32_t mask = s_active[kw];
+      while (mask) {
+        const int k = kw * 32 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        int rows[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int64_t r = row0 + r8 + 8 * i;
-        int v = -1;
-        if (r < p.n_dst) v = p.nbr ? __ldg(p.nbr + r * p.kvol + k) : int(r);
-        if (v >= p.n_src) v = -1;
-        my_rows[i] = v;
-      }
-      const __nv_bfloat16* wk = p.wt + (int64_t(k) * p.n_pad + n0) * p.kc_pad;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % p.stages;
-        if (it >= p.stages) mbar_wait(&bar_free[s], uint32_t((it / p.stages - 1) & 1));
-        uint8_t* sa = smem + uint32_t(s) * stage_bytes;
-        uint8_t* sb = sa + kABytes;
-        const int c0 = kb * kSliceK + sub * 4;
-        // A tile: gather + convert
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float v[8][4];
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 16 * i;
+          int v;
+          if (!p.nbr) {
+            v = (row0 + r < p.n_dst) ? int(row0 + r) : -1;
+          } else if (staged) {
+            v = s_nbr[r * p.kvol + k];
+          } else {
+            v = (row0 + r < p.n_dst) ? __ldg(p.nbr + (row0 + r) * p.kvol + k) : -1;
+            if (v >= p.n_src) v = -1;
+          }
+          rows[i] = v;
+        }
+        const __nv_bfloat16* wk = p.wt + (int64_t(k) * p.n_pad + n0) * p.kc_pad;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          if (it >= p.stages) mbar_wait(&bars.free_[s], uint32_t((it / p.stages - 1) & 1));
+          const uint32_t sa = smem_u32(smem + uint32_t(s) * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const int col = kb * kSliceK + c16 * 8;
+          const bool col_ok = col < p.c_pad;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = my_rows[h * 8 + i];
-            if (row >= 0) load4<VEC>(p.src + int64_t(row) * p.c_red, c0, p.c_red, v[i]);
-            else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+            const bool ok = col_ok && rows[i] >= 0;
+            const __nv_bfloat16* g = ok ? p.src + int64_t(rows[i]) * p.c_pad + col : p.src;
+            cp_async16(sa + sw128_offset(uint32_t(rsub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t trow = uint32_t(r8 + 8 * (h * 8 + i));
-            store_bf16x4(sa, sw128_offset(trow, uint32_t(sub >> 1)) + uint32_t(sub & 1) * 8u, v[i]);
-          }
-        }
-        // B tile: n_tile rows x 128 B of the prepared weights
-        {
-          const int c16 = tid & 7;
-          for (int n = tid >> 3; n < p.n_tile; n += kThreads / 8) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(wk + int64_t(n) * p.kc_pad + kb * kSliceK) + c16);
-            *reinterpret_cast<uint4*>(sb + sw128_offset(uint32_t(n), uint32_t(c16))) = q;
-          }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
-#pragma unroll
-          for (int kk = 0; kk < kSliceK / 16; ++kk) {
-            const uint64_t adesc = make_desc_sw128(a_addr + kk * 32, 16, 1024);
-            const uint64_t bdesc = make_desc_sw128(b_addr + kk * 32, 16, 1024);
-            mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          }
-          mma_commit(&bar_free[s]);
+          const __nv_bfloat16* wb = wk + kb * kSliceK + c16 * 8;
+          for (int n = rsub; n < p.n_tile; n += 16)
+            cp_async16(sb + sw128_offset(uint32_t(n), uint32_t(c16)), wb + int64_t(n) * p.kc_pad, 16u);
+          cp_async_arrive_noinc(&bars.full[s]);
         }
       }
     }
-  }
-
-  if (it > 0) {
-    if (tid == 0) mma_commit(&bar_done);
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-  }
-  // epilogue: thread (warp, lane) owns tile row 32*warp + lane
-  {
+    // ------------------------------------------------------------------ epilogue
+    if (total_iters > 0) {
+      mbar_wait(&bars.done, 0);
+      tc_fence_after();
+    }
     const int64_t r = row0 + warp * 32 + lane;
     float* out = p.dst + r * p.c_dst;
     const bool vec_ok = (p.c_dst % 4) == 0;
     for (int col = 0; col < p.n_tile; col += 16) {
       uint32_t acc[16];
-      if (it > 0) {
+      if (total_iters > 0) {
         tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), acc);
         tmem_ld_wait();
       } else {
@@ -232,15 +262,34 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
         }
       }
     }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % p.stages;
+      mbar_wait(&bars.full[s], uint32_t((it / p.stages) & 1));
+      fence_proxy_async_smem();
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + uint32_t(s) * stage_bytes), b_addr = a_addr + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < kSliceK / 16; ++kk) {
+        const uint64_t adesc = make_desc_sw128(a_addr + kk * 32, 16, 1024);
+        const uint64_t bdesc = make_desc_sw128(b_addr + kk * 32, 16, 1024);
+        mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+      }
+      mma_commit(&bars.free_[s]);
+    }
+    if (total_iters > 0) mma_commit(&bars.done);
   }
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
 }
 
 struct WgradParams {
-  const float* a; int64_t n_a; int c_a;
-  const float* b; int64_t n_b; int c_b;
+  const __nv_bfloat16* a; int64_t n_a; int c_a, ca_pad;
+  const __nv_bfloat16* b; int64_t n_b; int c_b, cb_pad;
   const int32_t* pair_a; const int32_t* pair_b; const int32_t* pair_num;
   int kvol; int64_t pitch;
   float* dw;
@@ -248,11 +297,9 @@ struct WgradParams {
   int64_t chunk;
 };
 
-template <int VEC_A, int VEC_B>
 __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_free[kMaxStages];
-  __shared__ uint64_t bar_done;
+  __shared__ PipeBarriers bars;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -272,12 +319,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const uint32_t stage_bytes = a_bytes + uint32_t(b_panels) * 8192u;
   const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(p.n_tile));
 
-  if (tid == 0) {
-    for (int s = 0; s < kMaxStages; ++s) mbar_init(&bar_free[s], 1);
-    mbar_init(&bar_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
+  if (tid == 0) init_pipe(bars);
+  if (warp == 4) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
   }
@@ -286,76 +329,65 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  const int sub = tid & 15, r8 = tid >> 4;
-  const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 1, 1);
-  const int32_t* pa = p.pair_a ? p.pair_a + int64_t(k) * p.pitch : nullptr;
-  const int32_t* pb = p.pair_b ? p.pair_b + int64_t(k) * p.pitch : nullptr;
-
-  for (int it = 0; it < iters; ++it) {
-    const int s = it % p.stages;
-    if (it >= p.stages) mbar_wait(&bar_free[s], uint32_t((it / p.stages - 1) & 1));
-    uint8_t* sa = smem + uint32_t(s) * stage_bytes;
-    uint8_t* sb = sa + a_bytes;
-    int ia[8], ib[8];
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int c16 = tid & 7;    // 16-byte chunk inside a 64-channel panel row
+    const int psub = tid >> 3;  // this thread covers pairs psub + 16*i of the 64-pair slice
+    const int32_t* pa = p.pair_a ? p.pair_a + int64_t(k) * p.pitch : nullptr;
+    const int32_t* pb = p.pair_b ? p.pair_b + int64_t(k) * p.pitch : nullptr;
+    auto load_idx = [&](int it, int (&ia)[4], int (&ib)[4]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t q = begin + int64_t(it) * kSliceK + r8 + 8 * i;
-      int va = -1, vb = -1;
-      if (q < end) {
-        va = pa ? __ldg(pa + q) : int(q);
-        vb = pb ? __ldg(pb + q) : int(q);
+      for (int i = 0; i < 4; ++i) {
+        const int64_t q = begin + int64_t(it) * kSliceK + psub + 16 * i;
+        int va = -1, vb = -1;
+        if (q < end) {
+          va = pa ? __ldg(pa + q) : int(q);
+          vb = pb ? __ldg(pb + q) : int(q);
+        }
+        if (va < 0 || vb < 0 || va >= p.n_a || vb >= p.n_b) { va = -1; vb = -1; }
+        ia[i] = va; ib[i] = vb;
       }
-      if (va < 0 || vb < 0 || va >= p.n_a || vb >= p.n_b) { va = -1; vb = -1; }
-      ia[i] = va; ib[i] = vb;
-    }
-    // A: [64 pairs][128 channels of a] as two 64-channel swizzled panels
+    };
+    int ia[4], ib[4], na[4], nb[4];
+    if (iters > 0) load_idx(0, ia, ib);
+    for (int it = 0; it < iters; ++it) {
+      if (it + 1 < iters) load_idx(it + 1, na, nb);  // prefetch the next slice's pair indices
+      const int s = it % p.stages;
+      if (it >= p.stages) mbar_wait(&bars.free_[s], uint32_t((it / p.stages - 1) & 1));
+      const uint32_t sa = smem_u32(smem + uint32_t(s) * stage_bytes);
+      const uint32_t sb = sa + a_bytes;
+      // A: [64 pairs][128 channels of a] as two 64-channel swizzled panels
 #pragma unroll
-    for (int panel = 0; panel < 2; ++panel) {
-      float v[8][4];
-      const int col = a_c0 + panel * 64 + sub * 4;
+      for (int panel = 0; panel < 2; ++panel) {
+        const int col = a_c0 + panel * 64 + c16 * 8;
+        const bool col_ok = col < p.ca_pad;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (ia[i] >= 0) load4<VEC_A>(p.a + int64_t(ia[i]) * p.c_a, col, p.c_a, v[i]);
-        else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = col_ok && ia[i] >= 0;
+          const __nv_bfloat16* g = ok ? p.a + int64_t(ia[i]) * p.ca_pad + col : p.a;
+          cp_async16(sa + panel * 8192 + sw128_offset(uint32_t(psub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
+        }
       }
+      // B: [64 pairs][n_tile channels of b]
+      for (int panel = 0; panel < b_panels; ++panel) {
+        const int col = b_c0 + panel * 64 + c16 * 8;
+        const bool col_ok = col < p.cb_pad;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        store_bf16x4(sa + panel * 8192, sw128_offset(uint32_t(r8 + 8 * i), uint32_t(sub >> 1)) + uint32_t(sub & 1) * 8u, v[i]);
-    }
-    // B: [64 pairs][n_tile channels of b]
-    for (int panel = 0; panel < b_panels; ++panel) {
-      float v[8][4];
-      const int col = b_c0 + panel * 64 + sub * 4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (ib[i] >= 0) load4<VEC_B>(p.b + int64_t(ib[i]) * p.c_b, col, p.c_b, v[i]);
-        else { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = col_ok && ib[i] >= 0;
+          const __nv_bfloat16* g = ok ? p.b + int64_t(ib[i]) * p.cb_pad + col : p.b;
+          cp_async16(sb + panel * 8192 + sw128_offset(uint32_t(psub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
+        }
       }
+      cp_async_arrive_noinc(&bars.full[s]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        store_bf16x4(sb + panel * 8192, sw128_offset(uint32_t(r8 + 8 * i), uint32_t(sub >> 1)) + uint32_t(sub & 1) * 8u, v[i]);
+      for (int i = 0; i < 4; ++i) { ia[i] = na[i]; ib[i] = nb[i]; }
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+    // ------------------------------------------------------------------ epilogue
+    if (iters > 0) {
+      mbar_wait(&bars.done, 0);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
-#pragma unroll
-      for (int kk = 0; kk < kSliceK / 16; ++kk) {
-        // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
-        const uint64_t adesc = make_desc_sw128(a_addr + kk * 2048, 8192, 1024);
-        const uint64_t bdesc = make_desc_sw128(b_addr + kk * 2048, 8192, 1024);
-        mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-      }
-      mma_commit(&bar_free[s]);
     }
-  }
-  if (iters > 0) {
-    if (tid == 0) mma_commit(&bar_done);
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-  }
-  {
     const int ca = a_c0 + warp * 32 + lane;
     float* out = p.dw + (int64_t(k) * p.c_a + ca) * p.c_b;
     for (int col = 0; col < p.n_tile; col += 16) {
@@ -378,45 +410,68 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
         }
       }
     }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 1, 1);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % p.stages;
+      mbar_wait(&bars.full[s], uint32_t((it / p.stages) & 1));
+      fence_proxy_async_smem();
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + uint32_t(s) * stage_bytes), b_addr = a_addr + a_bytes;
+#pragma unroll
+      for (int kk = 0; kk < kSliceK / 16; ++kk) {
+        // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
+        const uint64_t adesc = make_desc_sw128(a_addr + kk * 2048, 8192, 1024);
+        const uint64_t bdesc = make_desc_sw128(b_addr + kk * 2048, 8192, 1024);
+        mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+      }
+      mma_commit(&bars.free_[s]);
+    }
+    if (iters > 0) mma_commit(&bars.done);
   }
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct ApplyPlan { int n_tiles, n_tile, n_pad, kc_pad; };
-ApplyPlan apply_plan(int c_red, int c_dst) {
+struct ApplyPlan { int n_tiles, n_tile, n_pad, kc_pad, c_pad; size_t off_act, total; };
+ApplyPlan apply_plan(int kvol, int64_t n_src, int c_red, int c_dst) {
   ApplyPlan a;
   a.n_tiles = (c_dst + 255) / 256;
   a.n_tile = round_up((c_dst + a.n_tiles - 1) / a.n_tiles, 16);
   a.n_pad = a.n_tiles * a.n_tile;
   a.kc_pad = round_up(c_red, kSliceK);
+  a.c_pad = round_up(c_red, 8);
+  a.off_act = align_up(size_t(kvol) * a.n_pad * a.kc_pad * sizeof(__nv_bfloat16), 256);
+  a.total = a.off_act + align_up(size_t(n_src) * a.c_pad * sizeof(__nv_bfloat16), 256);
   return a;
 }
 
-inline int vec_of(int c, const void* ptr) {
-  if (reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && c % 4 == 0) return 4;
-  if (reinterpret_cast<uintptr_t>(ptr) % 8 == 0 && c % 2 == 0) return 2;
-  return 1;
+// stages that fit: prefer two resident CTAs per SM when a 4-deep ring fits in ~110 KB
+int pick_stages(int stage_bytes, int extra_bytes) {
+  if (4 * stage_bytes + extra_bytes <= 110 * 1024) return 4;
+  int s = (kSmemMax - extra_bytes) / stage_bytes;
+  return s < 2 ? 2 : (s > 6 ? 6 : s);
 }
 
 }  // namespace
 
-size_t conv_apply_umma_workspace(int kvol, int c_red, int c_dst) {
-  ApplyPlan a = apply_plan(c_red, c_dst);
-  return align_up(size_t(kvol) * a.n_pad * a.kc_pad * sizeof(__nv_bfloat16), 256);
+size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) {
+  return apply_plan(kvol, n_src, c_red, c_dst).total;
 }
 
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
                     size_t ws_bytes, cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
-  ApplyPlan a = apply_plan(c_red, c_dst);
-  const size_t need = conv_apply_umma_workspace(kvol, c_red, c_dst);
-  if (ws == nullptr || ws_bytes < need) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, need);
+  ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
+  if (ws == nullptr || ws_bytes < a.total) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, a.total);
   __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + a.off_act);
   {
     const int64_t total = int64_t(kvol) * a.n_pad * a.kc_pad;
     int64_t blocks = ceil_div<int64_t>(total, 256);
@@ -425,32 +480,40 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
-  ApplyParams p{src, n_src, c_red, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2};
+  CastJob job{src, act, n_src, c_red, a.c_pad};
+  if (int rc = launch_cast(job, nullptr, st)) return rc;
+
+  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2};
   const int stage_bytes = kABytes + a.n_tile * 128;
-  int stages = kSmemBudget / stage_bytes;
-  p.stages = stages < 2 ? 2 : (stages > kMaxStages ? kMaxStages : stages);
-  const size_t smem = size_t(p.stages) * stage_bytes + 1024;
+  const int nbr_bytes = (nbr != nullptr && kvol <= kNbrStageK) ? kTileM * kvol * 4 : 0;
+  p.stages = pick_stages(stage_bytes, nbr_bytes + 1024);
+  const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + 1024;
   dim3 grid(unsigned(ceil_div<int64_t>(n_dst, kTileM)), unsigned(a.n_tiles));
-  const int vec = vec_of(c_red, src);
-  auto launch = [&](auto kern) -> int {
-    WFSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<grid, kThreads, smem, st>>>(p);
-    count_launches(1);
-    WFSP_CHECK_LAUNCH();
-    return WFSP_OK;
-  };
-  if (vec == 4) return launch(conv_apply_umma_kernel<4>);
-  if (vec == 2) return launch(conv_apply_umma_kernel<2>);
-  return launch(conv_apply_umma_kernel<1>);
+  WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  conv_apply_umma_kernel<<<grid, kThreads, smem, st>>>(p);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
 }
 
-size_t conv_wgrad_umma_workspace(int, int, int, int64_t) { return 0; }
+size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t) {
+  return align_up(size_t(n_a) * round_up(c_a, 8) * 2, 256) + align_up(size_t(n_b) * round_up(c_b, 8) * 2, 256);
+}
 
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
-                    float* d_weight, int accumulate, void*, size_t, cudaStream_t st) {
+                    float* d_weight, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch);
+  if (need > 0 && (ws == nullptr || ws_bytes < need))
+    return set_error(WFSP_EWORKSPACE, "conv_wgrad workspace %zu < %zu", ws_bytes, need);
   WgradParams p{};
-  p.a = a; p.n_a = n_a; p.c_a = c_a; p.b = b; p.n_b = n_b; p.c_b = c_b;
+  p.ca_pad = round_up(c_a, 8);
+  p.cb_pad = round_up(c_b, 8);
+  __nv_bfloat16* a16 = static_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + align_up(size_t(n_a) * p.ca_pad * 2, 256));
+  CastJob ja{a, a16, n_a, c_a, p.ca_pad}, jb{b, b16, n_b, c_b, p.cb_pad};
+  if (int rc = launch_cast(ja, &jb, st)) return rc;
+  p.a = a16; p.n_a = n_a; p.c_a = c_a; p.b = b16; p.n_b = n_b; p.c_b = c_b;
   p.pair_a = pair_a; p.pair_b = pair_b; p.pair_num = pair_num; p.kvol = kvol; p.pitch = pitch; p.dw = d_weight;
   const int n_tiles = (c_b + 255) / 256;
   p.n_tile = round_up((c_b + n_tiles - 1) / n_tiles, 16);
@@ -460,7 +523,7 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   int nsplit = 1;
   if (rows > 0) {
     int64_t want = ceil_div<int64_t>(int64_t(2) * sm_count(), int64_t(tiles) * kvol);
-    int64_t maxs = ceil_div<int64_t>(rows, 512);
+    int64_t maxs = ceil_div<int64_t>(rows, 256);
     nsplit = int(want < 1 ? 1 : (want > maxs ? maxs : want));
     if (int64_t(kvol) * nsplit > 65535) nsplit = 65535 / kvol;
     if (nsplit < 1) nsplit = 1;
@@ -472,21 +535,14 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
   const int b_panels = (p.n_tile + 63) / 64;
   const int stage_bytes = 2 * 8192 + b_panels * 8192;
-  int stages = kSmemBudget / stage_bytes;
-  p.stages = stages < 2 ? 2 : (stages > kMaxStages ? kMaxStages : stages);
+  p.stages = pick_stages(stage_bytes, 1024);
   const size_t smem = size_t(p.stages) * stage_bytes + 1024;
   dim3 grid(unsigned(tiles), unsigned(kvol * nsplit));
-  const int va = vec_of(c_a, a), vb = vec_of(c_b, b);
-  auto launch = [&](auto kern) -> int {
-    WFSP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<grid, kThreads, smem, st>>>(p);
-    count_launches(1);
-    WFSP_CHECK_LAUNCH();
-    return WFSP_OK;
-  };
-  if (va == 4 && vb == 4) return launch(conv_wgrad_umma_kernel<4, 4>);
-  if (va >= 2 && vb >= 2) return launch(conv_wgrad_umma_kernel<2, 2>);
-  return launch(conv_wgrad_umma_kernel<1, 1>);
+  WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  conv_wgrad_umma_kernel<<<grid, kThreads, smem, st>>>(p);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
 }
 
 }  // namespace wfsp

@@ -24,7 +24,7 @@ def conv_apply(src, weight3, transpose_w, bias, nbr, n_dst, c_dst, math):
     if n_dst == 0:
         return dst
     m = _MATH[math]
-    ws_bytes = lib.wfsp_conv_apply_workspace_bytes(kvol, c_red, c_dst, m)
+    ws_bytes = lib.wfsp_conv_apply_workspace_bytes(kvol, src.shape[0], c_red, c_dst, m)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=src.device) if ws_bytes else None
     with torch.cuda.device(src.device):
         _lib.check(lib.wfsp_conv_apply(_lib.ptr(src), src.shape[0], c_red, _lib.ptr(weight3), int(transpose_w),
@@ -40,7 +40,7 @@ def conv_wgrad(a, b, pair_a, pair_b, pair_num, kvol, math):
     dw = torch.empty((kvol, c_a, c_b), dtype=torch.float32, device=a.device)
     pitch = pair_a.shape[-1] if pair_a is not None else a.shape[0]
     m = _MATH[math]
-    ws_bytes = lib.wfsp_conv_wgrad_workspace_bytes(kvol, c_a, c_b, pitch, m)
+    ws_bytes = lib.wfsp_conv_wgrad_workspace_bytes(kvol, a.shape[0], c_a, b.shape[0], c_b, pitch, m)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=a.device) if ws_bytes else None
     with torch.cuda.device(a.device):
         _lib.check(lib.wfsp_conv_wgrad(_lib.ptr(a), a.shape[0], c_a, _lib.ptr(b), b.shape[0], c_b, _lib.ptr(pair_a),
