@@ -16,6 +16,11 @@
  *     the calling thread's last failure;
  *   - row-major everywhere; `indices` rows are (batch, x, y) int32 as spconv requires
  *     (src/models/SPConvNet.py:51-52,63-64); features are [rows, channels];
+ *   - DEVICE-SIDE ROW COUNTS: every row count `n_x` has a companion `const int32_t* n_x_dev`.
+ *     NULL: `n_x` is the exact count (the eager, reference-shaped path).  Non-NULL: `n_x` is only
+ *     the CAPACITY of the buffers / the launch bound and the kernels read the live count from
+ *     *n_x_dev, so a whole training step can be enqueued without any host readback and replayed
+ *     from a CUDA graph; rows past the live count are neither read nor written;
  *   - there is NO CPU fallback: without a CUDA device every compute entry returns WFSP_ECUDA.
  */
 #ifndef WFSP_H_
@@ -76,9 +81,9 @@ unsigned long long wfsp_kernel_launches(void);
  *   feats        [n_rows, feats_pitch] of feats_dtype, value = wave * scale    (output)
  */
 int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype, int64_t n_rows,
-                    int n_chan, const int64_t* item_rows, const int64_t* item_offset,
-                    int64_t n_items, float scale, int32_t* indices_bxy, void* feats,
-                    int feats_dtype, int64_t feats_pitch, wfsp_stream_t stream);
+                    const int32_t* n_rows_dev, int n_chan, const int64_t* item_rows,
+                    const int64_t* item_offset, int64_t n_items, float scale, int32_t* indices_bxy,
+                    void* feats, int feats_dtype, int64_t feats_pitch, wfsp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) Rulebook builder.  Bit-exact with the CPU path of upstream ops.get_indice_pairs, which
@@ -96,23 +101,25 @@ size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const int* out_sha
 
 /* Regular (strided / padded / dilated) convolution.  out_indices must hold out_cap >=
  * min(n_in*kvol, batch*out_h*out_w) rows; the number of rows actually produced is written to the
- * device scalar *n_out (the caller copies it to pinned host memory -- the single readback per
- * rulebook).  stride>1 together with dilation>1 is rejected as upstream does. */
-int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batch, const int* in_shape_host,
-                       const int* ksize_host, const int* stride_host, const int* pad_host,
-                       const int* dil_host, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
-                       int32_t* pair_num, int32_t* n_out, void* workspace, size_t workspace_bytes,
-                       wfsp_stream_t stream);
+ * device scalar *n_out (in the eager path the caller copies it to the host -- the single readback
+ * per rulebook; in the graph path it feeds the next call's n_*_dev).  stride>1 together with
+ * dilation>1 is rejected as upstream does.  The pair arrays always have pitch n_in. */
+int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                       const int* in_shape_host, const int* ksize_host, const int* stride_host,
+                       const int* pad_host, const int* dil_host, int32_t* out_indices,
+                       int64_t out_cap, int32_t* pairs, int32_t* pair_num, int32_t* n_out,
+                       void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
 
 /* Submanifold convolution: output rows == input rows, padding forced to k/2, stride to 1. */
-int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, int batch, const int* shape_host,
-                       const int* ksize_host, const int* dil_host, int32_t* pairs,
-                       int32_t* pair_num, void* workspace, size_t workspace_bytes,
+int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                       const int* shape_host, const int* ksize_host, const int* dil_host,
+                       int32_t* pairs, int32_t* pair_num, void* workspace, size_t workspace_bytes,
                        wfsp_stream_t stream);
 
 /* Derived, output-stationary view of a rulebook used by the forward / dgrad kernels:
  *   nbr_out [n_out, kvol]: input row that feeds output row o through offset k, or -1
  *   nbr_in  [n_in,  kvol]: output row that input row i feeds through offset k, or -1
+ * n_in / n_out may be capacities (only pair_num[k] pairs per offset are read).
  * *dup_flag (device int32, caller zero-fills) is set to 1 if two pairs of one offset share an
  * output row (duplicate input coordinates), which the output-stationary kernels do not cover. */
 int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol,
@@ -139,10 +146,10 @@ int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol
  */
 size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math);
 
-int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* weight,
-                    int transpose_w, const float* bias, const int32_t* nbr, int kvol, float* dst,
-                    int64_t n_dst, int c_dst, int math, void* workspace, size_t workspace_bytes,
-                    wfsp_stream_t stream);
+int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n_src_dev, int c_red,
+                    const float* weight, int transpose_w, const float* bias, const int32_t* nbr,
+                    int kvol, float* dst, int64_t n_dst, const int32_t* n_dst_dev, int c_dst,
+                    int math, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
 
 /* wgrad: d_weight[k] (+)= sum over pairs p of offset k of  a[pa[k,p], :]^T (outer) b[pb[k,p], :]
  * with a = features [n_a, c_a], b = dOut [n_b, c_b], d_weight fp32 [kvol, c_a, c_b]
@@ -154,9 +161,10 @@ int wfsp_conv_apply(const float* src, int64_t n_src, int c_red, const float* wei
 size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b,
                                        int64_t pair_pitch, int math);
 
-int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
-                    const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
-                    int64_t pair_pitch, float* d_weight, int accumulate, int math, void* workspace,
+int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_dev, int c_a, const float* b,
+                    int64_t n_b, const int32_t* n_b_dev, int c_b, const int32_t* pair_a,
+                    const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pair_pitch,
+                    float* d_weight, int accumulate, int math, void* workspace,
                     size_t workspace_bytes, wfsp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -166,12 +174,38 @@ int wfsp_conv_wgrad(const float* a, int64_t n_a, int c_a, const float* b, int64_
  * its backward, the gather d_features[row, :] = d_dense[b, :, x, y].
  * cell_table: int32 scratch [batch*h*w].
  */
-int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, int n_chan,
-                  int batch, int h, int w, float* dense, int32_t* cell_table,
-                  wfsp_stream_t stream);
+int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows,
+                  const int32_t* n_rows_dev, int n_chan, int batch, int h, int w, float* dense,
+                  int32_t* cell_table, wfsp_stream_t stream);
 
-int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows, int n_chan,
-                      int batch, int h, int w, float* d_feats, wfsp_stream_t stream);
+int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows,
+                      const int32_t* n_rows_dev, int n_chan, int batch, int h, int w,
+                      float* d_feats, wfsp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) BatchNorm1d (+ReLU) over the active rows -- the modules the reference's SparseSequential
+ * applies to `.features` between convolutions (src/models/SPConvBlocks.py:505-508:
+ * nn.BatchNorm1d(c), nn.ReLU()).  Needed natively only by the graph path, where the row count
+ * lives on the device; same arithmetic as torch.nn.BatchNorm1d in training mode (biased batch
+ * variance for normalisation, unbiased for the running estimate).
+ *   forward : y = relu?((x - mean) * invstd * gamma + beta); saves mean / invstd [c];
+ *             running_mean / running_var (may be NULL) updated with `momentum`.
+ *             training == 0 normalises with the running statistics instead.
+ *   backward: dx, d_gamma, d_beta from dy (ReLU mask recomputed from x).
+ * workspace: wfsp_bn_workspace_bytes(n_rows, c) bytes.
+ */
+size_t wfsp_bn_workspace_bytes(int64_t n_rows, int c);
+
+int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                     const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int training, int relu,
+                     float* y, float* save_mean, float* save_invstd, void* workspace,
+                     size_t workspace_bytes, wfsp_stream_t stream);
+
+int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
+                     int c, const float* gamma, const float* beta, const float* save_mean,
+                     const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
+                     void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ def test_host_only_helpers():
 
 def test_bad_arguments_report_errors():
     lib = _lib.load()
-    rc = lib.wfsp_rulebook_conv(None, 0, 1, _lib.ints([14, 11]), _lib.ints([3, 3]), _lib.ints([2, 2]),
+    rc = lib.wfsp_rulebook_conv(None, 0, None, 1, _lib.ints([14, 11]), _lib.ints([3, 3]), _lib.ints([2, 2]),
                                 _lib.ints([0, 0]), _lib.ints([2, 2]), None, 0, None, None, None, None, 0, None)
     assert rc == -1 and b"stride>1 with dilation>1" in lib.wfsp_last_error()
     assert lib.wfsp_set_option(b"no_such_option", 1) == -1

@@ -22,20 +22,25 @@ SIGNATURES = {
     "wfsp_device_info": (_int, [_intp, _intp, _intp]),
     "wfsp_set_option": (_int, [_c.c_char_p, _int]),
     "wfsp_kernel_launches": (_c.c_ulonglong, []),
-    "wfsp_batch_pack": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp, _i64, _f32, _vp, _vp, _int, _i64, _vp]),
+    "wfsp_batch_pack": (_int, [_vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _i64, _f32, _vp, _vp, _int, _i64, _vp]),
     "wfsp_conv_out_shape": (_int, [_intp] * 6),
     "wfsp_rulebook_workspace_bytes": (_sz, [_i64, _int, _intp, _intp]),
-    "wfsp_rulebook_conv": (_int, [_vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _vp, _i64, _vp, _vp, _vp,
+    "wfsp_rulebook_conv": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _intp, _intp, _vp, _i64, _vp, _vp, _vp,
                                   _vp, _sz, _vp]),
-    "wfsp_rulebook_subm": (_int, [_vp, _i64, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
+    "wfsp_rulebook_subm": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_rulebook_tables": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "wfsp_conv_apply_workspace_bytes": (_sz, [_int, _i64, _int, _int, _int]),
-    "wfsp_conv_apply": (_int, [_vp, _i64, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _int, _int, _vp, _sz, _vp]),
+    "wfsp_conv_apply": (_int, [_vp, _i64, _vp, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _vp, _int, _int, _vp, _sz,
+                               _vp]),
     "wfsp_conv_wgrad_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _int, _i64, _int]),
-    "wfsp_conv_wgrad": (_int, [_vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp, _int, _i64, _vp, _int, _int, _vp,
-                               _sz, _vp]),
-    "wfsp_to_dense": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp]),
-    "wfsp_to_dense_bwd": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp]),
+    "wfsp_conv_wgrad": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _vp, _int,
+                               _int, _vp, _sz, _vp]),
+    "wfsp_to_dense": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "wfsp_to_dense_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp]),
+    "wfsp_bn_workspace_bytes": (_sz, [_i64, _int]),
+    "wfsp_bn_relu_fwd": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,
+                                _sz, _vp]),
+    "wfsp_bn_relu_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -9,11 +9,26 @@ from . import _lib
 from .synth import MAX_RANGE_INV
 
 
-def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RANGE_INV, out_dtype=torch.float32):
+def item_tables(item_rows, item_events, device):
+    """Device copies of the per-item row offsets and running event offsets collate_fn needs."""
+    rows = torch.as_tensor(item_rows, dtype=torch.int64)
+    evs = torch.as_tensor(item_events, dtype=torch.int64)
+    offs = torch.zeros_like(evs)
+    if evs.numel() > 1:
+        offs[1:] = torch.cumsum(evs, 0)[:-1]  # running offset; item 0 is left untouched
+    return rows.to(device, non_blocking=True), offs.to(device, non_blocking=True), evs.numel()
+
+
+def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RANGE_INV, out_dtype=torch.float32,
+               n_rows=None, tables=None):
     """coords_xye int32 [N,3] = (x, y, event id local to its item) and wave int16|f32 [N,C], both on
     the GPU, items concatenated.  item_rows [n_items+1] row offsets and item_events [n_items] events
     per item (host lists / tensors); omitted = a single item.  Returns (indices int32 [N,3] =
-    (event, x, y), features [N,C] = wave * scale)."""
+    (event, x, y), features [N,C] = wave * scale).
+
+    Graph path: n_rows = int32 device scalar with the live row count (the inputs are capacity-sized
+    static buffers) and tables = item_tables(...) prepared once, so nothing is copied from the host
+    inside a captured region."""
     lib = _lib.load()
     _lib.require_cuda(coords_xye, wave)
     dev = wave.device
@@ -21,21 +36,18 @@ def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RAN
     if coords_xye.dtype != torch.int32:
         raise RuntimeError("coords must be int32")
     n, c = wave.shape
-    if item_rows is None:
-        item_rows, item_events = [0, n], [0]
-    rows = torch.as_tensor(item_rows, dtype=torch.int64)
-    evs = torch.as_tensor(item_events, dtype=torch.int64)
-    offs = torch.zeros_like(evs)
-    if evs.numel() > 1:
-        offs[1:] = torch.cumsum(evs, 0)[:-1]  # running offset; item 0 is left untouched
-    rows_d, offs_d = rows.to(dev, non_blocking=True), offs.to(dev, non_blocking=True)
+    if tables is None:
+        if item_rows is None:
+            item_rows, item_events = [0, n], [0]
+        tables = item_tables(item_rows, item_events, dev)
+    rows_d, offs_d, n_items = tables
     wdt = {torch.int16: _lib.I16, torch.float32: _lib.F32}[wave.dtype]
     odt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[out_dtype]
     indices = torch.empty((n, 3), dtype=torch.int32, device=dev)
     feats = torch.empty((n, c), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), _lib.ptr(wave), wdt, n, c, _lib.ptr(rows_d),
-                                       _lib.ptr(offs_d), evs.numel(), float(scale), _lib.ptr(indices),
+        _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), _lib.ptr(wave), wdt, n, _lib.ptr(n_rows), c,
+                                       _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), _lib.ptr(indices),
                                        _lib.ptr(feats), odt, c, _lib.stream()))
     return indices, feats
 

@@ -1,0 +1,241 @@
+// BatchNorm1d (+ReLU) over the live rows of a [capacity, C] feature buffer whose row count lives
+// on the device (graph path).  These are the modules the reference's SparseSequential applies to
+// `.features` between the sparse convolutions (src/models/SPConvBlocks.py:505-508).  Arithmetic
+// follows torch.nn.BatchNorm1d in training mode: biased batch variance for the normalisation,
+// unbiased variance for the running estimate, running = (1 - momentum) * running + momentum * new.
+//
+// Pure streaming work (HBM-bound): forward reads x twice (statistics, normalise) and writes y once;
+// statistics are per-(row-chunk, channel) Welford partials (count, mean, M2) merged in double in a
+// fixed order, so the result does not depend on scheduling.
+#include "common.cuh"
+
+namespace wfsp {
+namespace {
+
+constexpr int kRows = 128;  // rows per partial
+constexpr int kCh = 32;     // channels per block (one 128-byte row segment)
+
+__device__ __forceinline__ int64_t live_rows(int64_t n, const int32_t* n_dev) { return n_dev ? int64_t(*n_dev) : n; }
+
+// grid (ceil(cap/kRows), ceil(c/kCh)), block (32, 8)
+__global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict__ x, int64_t n_cap,
+                                                        const int32_t* __restrict__ n_dev, int c,
+                                                        float* __restrict__ part /* [nblk][2][c] mean, M2 */) {
+  __shared__ float red[8][kCh];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t r0 = int64_t(blockIdx.x) * kRows;
+  if (r0 >= n) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.y * kCh + tx;
+  const int rows = int(n - r0 < kRows ? n - r0 : kRows);
+  float s = 0.f;
+  if (ch < c)
+    for (int r = ty; r < rows; r += 8) s += x[(r0 + r) * c + ch];
+  red[ty][tx] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][tx];
+  const float mean = tot / float(rows);
+  __syncthreads();
+  float m2 = 0.f;
+  if (ch < c)
+    for (int r = ty; r < rows; r += 8) {
+      const float d = x[(r0 + r) * c + ch] - mean;
+      m2 += d * d;
+    }
+  red[ty][tx] = m2;
+  __syncthreads();
+  if (ty == 0 && ch < c) {
+    float t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t2 += red[i][tx];
+    part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = mean;
+    part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = t2;
+  }
+}
+
+__global__ void __launch_bounds__(128) bn_finalize_stats(const float* __restrict__ part, int64_t n_cap,
+                                                         const int32_t* __restrict__ n_dev, int c, float eps,
+                                                         float momentum, float* __restrict__ running_mean,
+                                                         float* __restrict__ running_var,
+                                                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int64_t n = live_rows(n_cap, n_dev);
+  if (n <= 0) { save_mean[ch] = 0.f; save_invstd[ch] = 0.f; return; }
+  const int64_t nblk = (n + kRows - 1) / kRows;
+  double cnt = 0.0, mean = 0.0, m2 = 0.0;
+  for (int64_t b = 0; b < nblk; ++b) {  // Chan's parallel-variance merge, fixed order
+    const double nb = double(b + 1 < nblk ? kRows : n - b * kRows);
+    const double mb = part[(b * 2 + 0) * c + ch], m2b = part[(b * 2 + 1) * c + ch];
+    const double delta = mb - mean, tot = cnt + nb;
+    mean += delta * nb / tot;
+    m2 += m2b + delta * delta * cnt * nb / tot;
+    cnt = tot;
+  }
+  const double var = m2 / cnt;
+  save_mean[ch] = float(mean);
+  save_invstd[ch] = float(1.0 / sqrt(var + double(eps)));
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * float(mean);
+  if (running_var && cnt > 1.0) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * float(m2 / (cnt - 1.0));
+}
+
+__global__ void __launch_bounds__(128) bn_eval_stats(int c, float eps, const float* __restrict__ running_mean,
+                                                     const float* __restrict__ running_var,
+                                                     float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  save_mean[ch] = running_mean[ch];
+  save_invstd[ch] = rsqrtf(running_var[ch] + eps);
+}
+
+__global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
+                                                const int32_t* __restrict__ n_dev, int c,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                int relu, float* __restrict__ y) {
+  const int64_t total = live_rows(n_cap, n_dev) * c;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    float v = (x[i] - mean[ch]) * invstd[ch] * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
+    y[i] = (relu && v < 0.f) ? 0.f : v;
+  }
+}
+
+// backward partials: sum(dy') and sum(dy' * xhat) per (row chunk, channel); dy' = dy masked by relu
+__global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      int relu, float* __restrict__ part /* [nblk][2][c] */) {
+  __shared__ float red0[8][kCh], red1[8][kCh];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t r0 = int64_t(blockIdx.x) * kRows;
+  if (r0 >= n) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.y * kCh + tx;
+  const int rows = int(n - r0 < kRows ? n - r0 : kRows);
+  float s0 = 0.f, s1 = 0.f;
+  if (ch < c) {
+    const float m = mean[ch], is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    for (int r = ty; r < rows; r += 8) {
+      const float xh = (x[(r0 + r) * c + ch] - m) * is;
+      float d = dy[(r0 + r) * c + ch];
+      if (relu && xh * g + b <= 0.f) d = 0.f;
+      s0 += d;
+      s1 += d * xh;
+    }
+  }
+  red0[ty][tx] = s0;
+  red1[ty][tx] = s1;
+  __syncthreads();
+  if (ty == 0 && ch < c) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
+    part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = t0;
+    part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = t1;
+  }
+}
+
+__global__ void __launch_bounds__(128) bn_bwd_finalize(const float* __restrict__ part, int64_t n_cap,
+                                                       const int32_t* __restrict__ n_dev, int c,
+                                                       float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t nblk = n > 0 ? (n + kRows - 1) / kRows : 0;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t b = 0; b < nblk; ++b) {
+    s0 += part[(b * 2 + 0) * c + ch];
+    s1 += part[(b * 2 + 1) * c + ch];
+  }
+  d_beta[ch] = float(s0);
+  d_gamma[ch] = float(s1);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
+                                                    int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                    const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
+                                                    int relu, float* __restrict__ dx) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t total = n * c;
+  const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    const float xh = (x[i] - mean[ch]) * is;
+    float d = dy[i];
+    if (relu && xh * g + b <= 0.f) d = 0.f;
+    dx[i] = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
+  }
+}
+
+inline unsigned stream_blocks(int64_t elems) {
+  int64_t b = ceil_div<int64_t>(elems > 0 ? elems : 1, 256);
+  const int64_t cap = int64_t(sm_count()) * 16;
+  return unsigned(b > cap ? cap : b);
+}
+
+}  // namespace
+}  // namespace wfsp
+
+using namespace wfsp;
+
+extern "C" size_t wfsp_bn_workspace_bytes(int64_t n_rows, int c) {
+  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRows)) * 2 * c * sizeof(float), 256);
+}
+
+extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                int training, int relu, float* y, float* save_mean, float* save_invstd,
+                                void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
+  if (n_rows == 0) return WFSP_OK;
+  cudaStream_t st = as_stream(stream);
+  if (training) {
+    if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
+      return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
+    float* part = static_cast<float*>(workspace);
+    dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
+    bn_partial_stats<<<grid, dim3(32, 8), 0, st>>>(x, n_rows, n_rows_dev, c, part);
+    bn_finalize_stats<<<ceil_div(c, 128), 128, 0, st>>>(part, n_rows, n_rows_dev, c, eps, momentum, running_mean,
+                                                        running_var, save_mean, save_invstd);
+    count_launches(2);
+  } else {
+    WFSP_REQUIRE(running_mean && running_var, "eval-mode batch norm needs running statistics");
+    bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(c, eps, running_mean, running_var, save_mean, save_invstd);
+    count_launches(1);
+  }
+  bn_apply<<<stream_blocks(n_rows * c), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                                const float* gamma, const float* beta, const float* save_mean,
+                                const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
+                                void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
+  cudaStream_t st = as_stream(stream);
+  if (n_rows == 0) {
+    WFSP_CHECK_CUDA(cudaMemsetAsync(d_gamma, 0, size_t(c) * 4, st));
+    WFSP_CHECK_CUDA(cudaMemsetAsync(d_beta, 0, size_t(c) * 4, st));
+    return WFSP_OK;
+  }
+  if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
+    return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
+  float* part = static_cast<float*>(workspace);
+  dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
+  bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+  bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
+  bn_bwd_apply<<<stream_blocks(n_rows * c), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+                                                          save_invstd, d_gamma, d_beta, relu, dx);
+  count_launches(3);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}

@@ -20,13 +20,17 @@ constexpr int TM = 4, TN = 4;  // per-thread micro tile; 16x16 threads
 __global__ void __launch_bounds__(256) conv_apply_simt_kernel(
     const float* __restrict__ src, int64_t n_src, int c_red, const float* __restrict__ weight, int64_t w_ks,
     int w_cs, int w_ns, const float* __restrict__ bias, const int32_t* __restrict__ nbr, int kvol,
-    float* __restrict__ dst, int64_t n_dst, int c_dst) {
+    float* __restrict__ dst, int64_t n_dst, int c_dst, const int32_t* __restrict__ n_src_dev,
+    const int32_t* __restrict__ n_dst_dev) {
   __shared__ float As[BK][BM + 1];
   __shared__ float Bs[BK][BN + 1];
   __shared__ int s_nbr[BM];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t r0 = int64_t(blockIdx.x) * BM;
+  if (n_src_dev) n_src = *n_src_dev;
+  if (n_dst_dev) n_dst = *n_dst_dev;
+  if (r0 >= n_dst) return;
   const int n0 = blockIdx.y * BN;
   float acc[TM][TN];
 #pragma unroll
@@ -96,7 +100,8 @@ __global__ void __launch_bounds__(256) conv_apply_simt_kernel(
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(
     const float* __restrict__ a, int64_t n_a, int c_a, const float* __restrict__ b, int64_t n_b, int c_b,
     const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b, const int32_t* __restrict__ pair_num,
-    int kvol, int64_t pitch, int nsplit, int64_t chunk, float* __restrict__ d_weight, int use_atomic) {
+    int kvol, int64_t pitch, int nsplit, int64_t chunk, float* __restrict__ d_weight, int use_atomic,
+    const int32_t* __restrict__ n_a_dev) {
   __shared__ float As[BK][BM + 1];
   __shared__ float Bs[BK][BN + 1];
   __shared__ int s_ia[BK], s_ib[BK];
@@ -104,7 +109,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(
   const int tx = tid & 15, ty = tid >> 4;
   const int k = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
   const int a0 = blockIdx.x * BM, b0 = blockIdx.y * BN;
-  const int64_t n = pair_num ? int64_t(pair_num[k]) : n_a;  // NULL lists = identity (1x1 shortcut)
+  // NULL lists = identity (1x1 shortcut): one pair per live row
+  const int64_t n = pair_num ? int64_t(pair_num[k]) : (n_a_dev ? int64_t(*n_a_dev) : n_a);
   const int64_t p_begin = int64_t(split) * chunk;
   int64_t p_end = p_begin + chunk;
   if (p_end > n) p_end = n;
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(
 
 int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                    cudaStream_t st) {
+                    const int32_t* n_src_dev, const int32_t* n_dst_dev, cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   dim3 grid(unsigned(ceil_div<int64_t>(n_dst, BM)), unsigned(ceil_div(c_dst, BN)));
   const int64_t w_ks = int64_t(c_red) * c_dst;
@@ -175,7 +181,7 @@ int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* wei
   const int w_cs = transpose_w ? 1 : c_dst;
   const int w_ns = transpose_w ? c_red : 1;
   conv_apply_simt_kernel<<<grid, 256, 0, st>>>(src, n_src, c_red, weight, w_ks, w_cs, w_ns, bias, nbr, kvol, dst,
-                                               n_dst, c_dst);
+                                               n_dst, c_dst, n_src_dev, n_dst_dev);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -183,7 +189,7 @@ int conv_apply_simt(const float* src, int64_t n_src, int c_red, const float* wei
 
 int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
-                    float* d_weight, int accumulate, cudaStream_t st) {
+                    float* d_weight, int accumulate, const int32_t* n_a_dev, cudaStream_t st) {
   const int tiles = ceil_div(c_a, BM) * ceil_div(c_b, BN);
   int nsplit = 1;
   if (pitch > 0) {
@@ -201,7 +207,7 @@ int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
   dim3 grid(unsigned(ceil_div(c_a, BM)), unsigned(ceil_div(c_b, BN)), unsigned(kvol * nsplit));
   conv_wgrad_simt_kernel<<<grid, 256, 0, st>>>(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch,
-                                               nsplit, chunk, d_weight, use_atomic);
+                                               nsplit, chunk, d_weight, use_atomic, n_a_dev);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

@@ -70,9 +70,12 @@ __global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restric
 }
 
 // ---- activation cast: fp32 [n][c] -> bf16 [n][c_pad], zero padded; one 16-byte chunk per thread
-struct CastJob { const float* src; __nv_bfloat16* dst; int64_t n; int c, c_pad; };
+struct CastJob { const float* src; __nv_bfloat16* dst; int64_t n; int c, c_pad; const int32_t* n_dev; };
 
-__global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1, int64_t chunks0, int64_t chunks_total) {
+__global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1) {
+  const int64_t n0 = j0.n_dev ? int64_t(*j0.n_dev) : j0.n;
+  const int64_t n1 = j1.n_dev ? int64_t(*j1.n_dev) : j1.n;
+  const int64_t chunks0 = n0 * (j0.c_pad >> 3), chunks_total = chunks0 + n1 * (j1.c_pad >> 3);
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < chunks_total;
        i += int64_t(gridDim.x) * blockDim.x) {
     const CastJob& j = i < chunks0 ? j0 : j1;
@@ -92,12 +95,12 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1, 
 }
 
 int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
-  CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8};
+  CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8, nullptr};
   const int64_t c0 = a.n * (a.c_pad >> 3), c1 = j1.n * (j1.c_pad >> 3);
   if (c0 + c1 == 0) return WFSP_OK;
   int64_t blocks = ceil_div<int64_t>(c0 + c1, 256);
   if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
-  cast_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(a, j1, c0, c0 + c1);
+  cast_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(a, j1);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -124,9 +127,14 @@ struct ApplyParams {
   const float* bias; const int32_t* nbr; int kvol;
   float* dst; int64_t n_dst; int c_dst;
   int n_tile, stages;
+  const int32_t* n_src_dev; const int32_t* n_dst_dev;
 };
 
-__global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyParams pp) {
+  ApplyParams p = pp;
+  if (p.n_src_dev) p.n_src = *p.n_src_dev;
+  if (p.n_dst_dev) p.n_dst = *p.n_dst_dev;
+  if (int64_t(blockIdx.x) * kTileM >= p.n_dst) return;  // capacity-sized grid: nothing live in this tile
   extern __shared__ uint8_t smem_raw[];
   __shared__ PipeBarriers bars;
   __shared__ uint32_t s_tmem;
@@ -295,6 +303,7 @@ struct WgradParams {
   float* dw;
   int n_tile, m_tiles, nsplit, stages, use_atomic;
   int64_t chunk;
+  const int32_t* n_a_dev;
 };
 
 __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradParams p) {
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const int k = blockIdx.y / p.nsplit, split = blockIdx.y % p.nsplit;
   const int mt = blockIdx.x % p.m_tiles, nt = blockIdx.x / p.m_tiles;
   const int a_c0 = mt * kTileM, b_c0 = nt * p.n_tile;
-  const int64_t n_pairs = p.pair_num ? int64_t(p.pair_num[k]) : p.n_a;
+  const int64_t n_pairs = p.pair_num ? int64_t(p.pair_num[k]) : (p.n_a_dev ? int64_t(*p.n_a_dev) : p.n_a);
   const int64_t begin = int64_t(split) * p.chunk;
   int64_t end = begin + p.chunk;
   if (end > n_pairs) end = n_pairs;
@@ -466,7 +475,7 @@ size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) 
 
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
   if (ws == nullptr || ws_bytes < a.total) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, a.total);
@@ -480,10 +489,11 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
-  CastJob job{src, act, n_src, c_red, a.c_pad};
+  CastJob job{src, act, n_src, c_red, a.c_pad, n_src_dev};
   if (int rc = launch_cast(job, nullptr, st)) return rc;
 
-  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2};
+  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2,
+                n_src_dev, n_dst_dev};
   const int stage_bytes = kABytes + a.n_tile * 128;
   const int nbr_bytes = (nbr != nullptr && kvol <= kNbrStageK) ? kTileM * kvol * 4 : 0;
   p.stages = pick_stages(stage_bytes, nbr_bytes + 1024);
@@ -502,7 +512,8 @@ size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b
 
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
-                    float* d_weight, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
+                    const int32_t* n_b_dev, cudaStream_t st) {
   const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch);
   if (need > 0 && (ws == nullptr || ws_bytes < need))
     return set_error(WFSP_EWORKSPACE, "conv_wgrad workspace %zu < %zu", ws_bytes, need);
@@ -511,7 +522,8 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   p.cb_pad = round_up(c_b, 8);
   __nv_bfloat16* a16 = static_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + align_up(size_t(n_a) * p.ca_pad * 2, 256));
-  CastJob ja{a, a16, n_a, c_a, p.ca_pad}, jb{b, b16, n_b, c_b, p.cb_pad};
+  CastJob ja{a, a16, n_a, c_a, p.ca_pad, n_a_dev}, jb{b, b16, n_b, c_b, p.cb_pad, n_b_dev};
+  p.n_a_dev = n_a_dev;
   if (int rc = launch_cast(ja, &jb, st)) return rc;
   p.a = a16; p.n_a = n_a; p.c_a = c_a; p.b = b16; p.n_b = n_b; p.c_b = c_b;
   p.pair_a = pair_a; p.pair_b = pair_b; p.pair_num = pair_num; p.kvol = kvol; p.pitch = pitch; p.dw = d_weight;

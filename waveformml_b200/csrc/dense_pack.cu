@@ -14,10 +14,12 @@ namespace wfsp {
 namespace {
 
 __global__ void __launch_bounds__(256) pack_indices_kernel(const int32_t* __restrict__ coords, int64_t n,
+                                                           const int32_t* __restrict__ n_dev,
                                                            const int64_t* __restrict__ item_rows,
                                                            const int64_t* __restrict__ item_offset, int64_t n_items,
                                                            int32_t* __restrict__ indices) {
   int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   if (j >= n) return;
   // item of row j: last it with item_rows[it] <= j
   int64_t lo = 0, hi = n_items - 1;
@@ -35,9 +37,11 @@ template <typename In>
 __device__ __forceinline__ float to_f32(In v) { return float(v); }
 
 template <typename In, typename Out>
-__global__ void __launch_bounds__(256) pack_feats_kernel(const In* __restrict__ wave, int64_t n, int c, float scale,
+__global__ void __launch_bounds__(256) pack_feats_kernel(const In* __restrict__ wave, int64_t n,
+                                                         const int32_t* __restrict__ n_dev, int c, float scale,
                                                          Out* __restrict__ feats, int64_t pitch) {
   // one thread per 4 consecutive channels (c % 4 == 0 fast path), grid-stride
+  if (n_dev) n = *n_dev;
   const int c4 = c >> 2;
   const int64_t total = n * c4;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -67,8 +71,10 @@ __global__ void __launch_bounds__(256) pack_feats_kernel(const In* __restrict__ 
 }
 
 template <typename In, typename Out>
-__global__ void __launch_bounds__(256) pack_feats_scalar_kernel(const In* __restrict__ wave, int64_t n, int c,
+__global__ void __launch_bounds__(256) pack_feats_scalar_kernel(const In* __restrict__ wave, int64_t n,
+                                                                const int32_t* __restrict__ n_dev, int c,
                                                                 float scale, Out* __restrict__ feats, int64_t pitch) {
+  if (n_dev) n = *n_dev;
   const int64_t total = n * c;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     int64_t row = i / c;
@@ -80,7 +86,8 @@ __global__ void __launch_bounds__(256) pack_feats_scalar_kernel(const In* __rest
 }
 
 template <typename In, typename Out>
-int launch_pack_feats(const void* wave, int64_t n, int c, float scale, void* feats, int64_t pitch, cudaStream_t st) {
+int launch_pack_feats(const void* wave, int64_t n, const int32_t* n_dev, int c, float scale, void* feats,
+                      int64_t pitch, cudaStream_t st) {
   if (n == 0 || c == 0) return WFSP_OK;
   const bool vec = (c % 4 == 0) && (pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(wave) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(feats) % 16 == 0);
@@ -89,10 +96,10 @@ int launch_pack_feats(const void* wave, int64_t n, int c, float scale, void* fea
   const int64_t cap = int64_t(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   if (vec)
-    pack_feats_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, c, scale,
+    pack_feats_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, n_dev, c, scale,
                                                                  static_cast<Out*>(feats), pitch);
   else
-    pack_feats_scalar_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, c, scale,
+    pack_feats_scalar_kernel<In, Out><<<unsigned(blocks), 256, 0, st>>>(static_cast<const In*>(wave), n, n_dev, c, scale,
                                                                         static_cast<Out*>(feats), pitch);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -100,9 +107,11 @@ int launch_pack_feats(const void* wave, int64_t n, int c, float scale, void* fea
 }
 
 // ---- dense ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dense_mark_kernel(const int32_t* __restrict__ indices, int64_t n, int batch,
-                                                         int h, int w, int32_t* __restrict__ cell_table) {
+__global__ void __launch_bounds__(256) dense_mark_kernel(const int32_t* __restrict__ indices, int64_t n,
+                                                         const int32_t* __restrict__ n_dev, int batch, int h, int w,
+                                                         int32_t* __restrict__ cell_table) {
   int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   if (j >= n) return;
   int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
   if (b < 0 || b >= batch || x < 0 || x >= h || y < 0 || y >= w) return;
@@ -140,8 +149,9 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
 
 // grid: (ceil(N/32), ceil(C/32)), block (32, 8)
 __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ d_dense,
-                                                        const int32_t* __restrict__ indices, int64_t n, int c,
-                                                        int batch, int h, int w, float* __restrict__ d_feats) {
+                                                        const int32_t* __restrict__ indices, int64_t n,
+                                                        const int32_t* __restrict__ n_dev, int c, int batch, int h,
+                                                        int w, float* __restrict__ d_feats) {
   __shared__ float tile[32][33];
   __shared__ int64_t s_base[32];
   __shared__ int s_xy[32];
@@ -149,6 +159,8 @@ __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict_
   const int64_t row0 = int64_t(blockIdx.x) * 32;
   const int ch0 = blockIdx.y * 32;
   const int hw = h * w;
+  if (n_dev) n = *n_dev;
+  if (row0 >= n) return;
   if (ty == 0) {
     int64_t j = row0 + tx;
     int64_t base = -1;
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict_
 using namespace wfsp;
 
 extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype, int64_t n_rows,
-                               int n_chan, const int64_t* item_rows, const int64_t* item_offset, int64_t n_items,
+                               const int32_t* n_rows_dev, int n_chan, const int64_t* item_rows, const int64_t* item_offset, int64_t n_items,
                                float scale, int32_t* indices_bxy, void* feats, int feats_dtype, int64_t feats_pitch,
                                wfsp_stream_t stream) {
   WFSP_REQUIRE(n_rows >= 0 && n_chan >= 0 && feats_pitch >= n_chan, "bad pack sizes");
@@ -190,28 +202,29 @@ extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int 
   WFSP_REQUIRE(feats_dtype == WFSP_F32 || feats_dtype == WFSP_BF16, "feats dtype must be f32 or bf16");
   cudaStream_t st = as_stream(stream);
   if (n_rows == 0) return WFSP_OK;
-  pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, item_rows,
+  pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, n_rows_dev, item_rows,
                                                                                item_offset, n_items, indices_bxy);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_F32)
-    return launch_pack_feats<int16_t, float>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+    return launch_pack_feats<int16_t, float>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
   if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_BF16)
-    return launch_pack_feats<int16_t, __nv_bfloat16>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+    return launch_pack_feats<int16_t, __nv_bfloat16>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
   if (wave_dtype == WFSP_F32 && feats_dtype == WFSP_F32)
-    return launch_pack_feats<float, float>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
-  return launch_pack_feats<float, __nv_bfloat16>(wave, n_rows, n_chan, scale, feats, feats_pitch, st);
+    return launch_pack_feats<float, float>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
+  return launch_pack_feats<float, __nv_bfloat16>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
 }
 
-extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, int n_chan, int batch,
-                             int h, int w, float* dense, int32_t* cell_table, wfsp_stream_t stream) {
+extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, const int32_t* n_rows_dev,
+                             int n_chan, int batch, int h, int w, float* dense, int32_t* cell_table,
+                             wfsp_stream_t stream) {
   WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0 && n_rows >= 0, "bad dense sizes");
   cudaStream_t st = as_stream(stream);
   const int64_t cells = int64_t(batch) * h * w;
   if (cells == 0 || n_chan == 0) return WFSP_OK;
   WFSP_CHECK_CUDA(cudaMemsetAsync(cell_table, 0xff, size_t(cells) * 4, st));
   if (n_rows > 0)
-    dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, batch, h, w, cell_table);
+    dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, n_rows_dev, batch, h, w, cell_table);
   dim3 grid(unsigned(ceil_div<int64_t>(cells, 32)), unsigned(ceil_div(n_chan, 32)));
   dense_fwd_kernel<<<grid, dim3(32, 8), 0, st>>>(feats, n_chan, cell_table, cells, h * w, dense);
   count_launches(n_rows > 0 ? 2 : 1);
@@ -219,12 +232,13 @@ extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t
   return WFSP_OK;
 }
 
-extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows, int n_chan, int batch,
-                                 int h, int w, float* d_feats, wfsp_stream_t stream) {
+extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows,
+                                 const int32_t* n_rows_dev, int n_chan, int batch, int h, int w, float* d_feats,
+                                 wfsp_stream_t stream) {
   WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0 && n_rows >= 0, "bad dense sizes");
   if (n_rows == 0 || n_chan == 0) return WFSP_OK;
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, 32)), unsigned(ceil_div(n_chan, 32)));
-  dense_bwd_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(d_dense, indices, n_rows, n_chan, batch, h, w, d_feats);
+  dense_bwd_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(d_dense, indices, n_rows, n_rows_dev, n_chan, batch, h, w, d_feats);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

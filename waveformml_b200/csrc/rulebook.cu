@@ -36,6 +36,7 @@ struct Geom {
   int in_h, in_w, out_h, out_w;
   int kh, kw, sh, sw, ph, pw, dh, dw;
   int kvol, batch;
+  const int32_t* n_dev;  // live row count (graph path); NULL = the host count is exact
 };
 
 struct Table {
@@ -93,7 +94,7 @@ struct Row {
 __device__ __forceinline__ Row load_row(const int32_t* __restrict__ indices, int64_t n, int64_t j,
                                         const Geom& g) {
   Row r;
-  r.ok = j < n;
+  r.ok = j < (g.n_dev ? int64_t(*g.n_dev) : n);
   r.b = r.x = r.y = 0;
   r.mx = r.my = 0;
   if (r.ok) {
@@ -139,7 +140,7 @@ template <bool HASH>
 __global__ void __launch_bounds__(kBlock) rb_subm_insert(const int32_t* __restrict__ indices, int64_t n,
                                                          Geom g, Table t) {
   int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-  if (j >= n) return;
+  if (j >= (g.n_dev ? int64_t(*g.n_dev) : n)) return;
   int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
   if (b < 0 || b >= g.batch || x < 0 || x >= g.in_h || y < 0 || y >= g.in_w) return;
   uint32_t key = uint32_t((b * g.in_h + x) * g.in_w + y);
@@ -405,7 +406,8 @@ extern "C" size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const i
   return make_plan(n_in, batch, out_shape[0], out_shape[1], ksize[0] * ksize[1]).total;
 }
 
-extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batch, const int* in_shape,
+extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                                  const int* in_shape,
                                   const int* ksize, const int* stride, const int* pad, const int* dil,
                                   int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
                                   int32_t* n_out, void* workspace, size_t workspace_bytes,
@@ -415,7 +417,8 @@ extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batc
   wfsp_conv_out_shape(in_shape, ksize, stride, pad, dil, out_shape);
   WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
   Geom g{in_shape[0], in_shape[1], out_shape[0] > 0 ? out_shape[0] : 0, out_shape[1] > 0 ? out_shape[1] : 0,
-         ksize[0], ksize[1], stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ksize[0] * ksize[1], batch};
+         ksize[0], ksize[1], stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ksize[0] * ksize[1], batch,
+         n_in_dev};
   WFSP_REQUIRE(n_in * int64_t(g.kvol) < int64_t(kRankInf), "n_in * kvol too large for 31-bit ranks");
   WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * out_h * out_w too large");
   cudaStream_t st = as_stream(stream);
@@ -436,7 +439,8 @@ extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, int batc
                 : run_conv<false>(indices, n_in, g, t, p, ws, out_indices, out_cap, pairs, pair_num, n_out, st);
 }
 
-extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, int batch, const int* shape,
+extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                                  const int* shape,
                                   const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num,
                                   void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
   const int one[2] = {1, 1};
@@ -444,7 +448,7 @@ extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, int batc
   if (int rc = check_geom(ksize, one, pad, dil)) return rc;
   WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
   Geom g{shape[0], shape[1], shape[0], shape[1], ksize[0], ksize[1], 1, 1, pad[0], pad[1], dil[0], dil[1],
-         ksize[0] * ksize[1], batch};
+         ksize[0] * ksize[1], batch, n_in_dev};
   WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * h * w too large");
   cudaStream_t st = as_stream(stream);
   Plan p = make_plan(n_in, batch, g.out_h, g.out_w, g.kvol);

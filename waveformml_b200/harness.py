@@ -8,12 +8,20 @@ all-reduce per step -- SURVEY.md 8e).
   optimiser              config/examples/GEP.json:56-68 (SGD lr 0.02, momentum 0.98, nesterov)
   data parallel          src/utils/util.py:233-236 (Lightning DDPPlugin; plain BatchNorm1d, so
                          statistics stay rank-local)
+
+Two ways to run a step:
+  TrainStep       eager: exact tensor shapes, stock torch BatchNorm1d / ReLU between our kernels, one
+                  host readback per regular-conv rulebook (as upstream spconv needs for its shapes).
+  GraphTrainStep  the whole step (batcher -> rulebooks -> fwd -> loss -> bwd -> all-reduce -> SGD) is
+                  enqueued without any host readback -- row counts stay on the device, buffers are
+                  capacity-sized -- captured once in a CUDA graph and replayed per batch.
 """
 import torch
 import torch.distributed as dist
 from torch import nn
 
-from . import spconv
+from . import batcher, spconv
+from .synth import MAX_RANGE_INV
 
 
 def shard_events(n_events, rank, world):
@@ -46,16 +54,17 @@ class FlatGrads:
             self.flat.div_(dist.get_world_size(group))
 
 
-def segment_l1_loss(indices, predictions, target, spatial_size, batch_size):
+def segment_l1_loss(indices, predictions, target, spatial_size, batch_size, n_rows=None):
     """LitBase._calc_segment_loss with use_float=True, SE_only=False (LitBase.py:124-174): both the
     ones-mask and the target are densified through SparseConvTensor(...).dense()."""
     n = indices.shape[0]
     mask = spconv.SparseConvTensor(torch.ones((n, predictions.shape[1]), dtype=torch.float32, device=predictions.device),
-                                   indices, spatial_size, batch_size).dense()
+                                   indices, spatial_size, batch_size, n_rows=n_rows).dense()
     tgt = target.unsqueeze(1) if target.dim() == 1 else target
-    target_tensor = spconv.SparseConvTensor(tgt, indices, spatial_size, batch_size).dense()
+    target_tensor = spconv.SparseConvTensor(tgt, indices, spatial_size, batch_size, n_rows=n_rows).dense()
     pred = mask * predictions
-    return nn.functional.l1_loss(pred, target_tensor, reduction="sum") / n
+    denom = n if n_rows is None else n_rows.to(torch.float32)
+    return nn.functional.l1_loss(pred, target_tensor, reduction="sum") / denom
 
 
 class TrainStep:
@@ -66,20 +75,108 @@ class TrainStep:
         self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov, foreach=True)
         self.criterion = nn.CrossEntropyLoss()
 
-    def loss(self, indices, feats, target, batch_size):
-        out = self.model([indices, feats, batch_size])
+    def loss(self, indices, feats, target, batch_size, n_rows=None):
+        x = [indices, feats, batch_size] if n_rows is None else [indices, feats, batch_size, n_rows]
+        out = self.model(x)
         if self.task == "psd":
             return self.criterion(out, target)
-        return segment_l1_loss(indices, out, target, self.model.spatial_size, batch_size)
+        return segment_l1_loss(indices, out, target, self.model.spatial_size, batch_size, n_rows)
 
-    def forward_backward(self, indices, feats, target, batch_size):
+    def forward_backward(self, indices, feats, target, batch_size, n_rows=None):
         self.grads.zero()
-        loss = self.loss(indices, feats, target, batch_size)
+        loss = self.loss(indices, feats, target, batch_size, n_rows)
         loss.backward()
         return loss
 
-    def step(self, indices, feats, target, batch_size):
-        loss = self.forward_backward(indices, feats, target, batch_size)
+    def step(self, indices, feats, target, batch_size, n_rows=None):
+        loss = self.forward_backward(indices, feats, target, batch_size, n_rows)
         self.grads.all_reduce_mean(self.group)
         self.opt.step()
         return loss.detach()
+
+
+class GraphTrainStep(TrainStep):
+    """One CUDA graph per model: static input buffers of `row_capacity` rows and `batch_size` events;
+    `load()` copies a batch in (async from pinned host memory or device to device), `run()` replays
+    the captured step.  Any batch with at most `row_capacity` rows and exactly `batch_size` events
+    reuses the same graph -- the live row count is data, not shape."""
+
+    def __init__(self, model, task, batch_size, row_capacity, n_chan, wave_dtype=torch.int16, scale=MAX_RANGE_INV,
+                 capture_update=True, **kw):
+        super().__init__(model, task, **kw)
+        dev = self.grads.flat.device
+        self.batch_size, self.row_capacity, self.scale = int(batch_size), int(row_capacity), scale
+        self.coords = torch.zeros((row_capacity, 3), dtype=torch.int32, device=dev)
+        self.wave = torch.zeros((row_capacity, n_chan), dtype=wave_dtype, device=dev)
+        tshape = (batch_size,) if task == "psd" else (row_capacity,)
+        self.target = torch.zeros(tshape, dtype=torch.int64 if task == "psd" else torch.float32, device=dev)
+        self.n_rows = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._n_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.tables = batcher.item_tables([0, row_capacity], [0], dev)
+        self.capture_update = capture_update
+        self.graph = None
+        self.loss_out = None
+
+    def load(self, coords, wave, target):
+        """coords int32 [n,3] (x, y, event), wave [n,C], target [B] (psd) or [n] (z); host (pinned for an
+        asynchronous copy) or device tensors."""
+        n = coords.shape[0]
+        if n > self.row_capacity:
+            raise ValueError("batch has %d rows, graph capacity is %d" % (n, self.row_capacity))
+        self.coords[:n].copy_(coords, non_blocking=True)
+        self.wave[:n].copy_(wave, non_blocking=True)
+        self.target[:target.shape[0]].copy_(target, non_blocking=True)
+        self.n_rows.fill_(n)  # the value travels as a kernel argument: no host buffer to race with
+
+    def _body(self):
+        idx, feats = batcher.pack_batch(self.coords, self.wave, scale=self.scale, n_rows=self.n_rows,
+                                        tables=self.tables)
+        loss = self.forward_backward(idx, feats, self.target, self.batch_size, self.n_rows)
+        if self.capture_update:
+            self.grads.all_reduce_mean(self.group)
+            self.opt.step()
+        return loss.detach()
+
+    def _snapshot(self):
+        import copy
+        return (copy.deepcopy(self.model.state_dict()), copy.deepcopy(self.opt.state_dict()))
+
+    def _restore(self, snap):
+        # strictly in place: the captured graph holds the addresses of the parameters, BatchNorm buffers
+        # and momentum buffers
+        self.model.load_state_dict(snap[0])
+        old = snap[1]["state"]
+        for i, p in enumerate(self.grads.params):
+            st = self.opt.state.get(p, {})
+            if "momentum_buffer" in st and st["momentum_buffer"] is not None:
+                prev = old.get(i, {}).get("momentum_buffer")
+                if prev is None:
+                    st["momentum_buffer"].zero_()  # == "no buffer yet" for SGD without dampening
+                else:
+                    st["momentum_buffer"].copy_(prev)
+
+    def capture(self):
+        snap = self._snapshot()  # the warm-up iterations below must not count as training steps
+        self._capture()
+        self._restore(snap)
+
+    def _capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm-up on a side stream (allocator, cuBLAS handles, NCCL) before capture
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss_out = self._body()
+
+    def run(self):
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        if not self.capture_update:
+            self.grads.all_reduce_mean(self.group)
+            self.opt.step()
+        return self.loss_out

@@ -43,10 +43,14 @@ def get_math_mode():
 
 
 class SparseConvTensor:
-    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, n_rows=None):
         """features [N, C]; indices int32 [N, 3] = (batch, x, y); spatial_shape e.g. [14, 11]
         (list / numpy array); batch_size int or 0-dim tensor (as the reference passes,
-        src/models/SPConvNet.py:51,63)."""
+        src/models/SPConvNet.py:51,63).
+
+        n_rows (extension, graph path): int32 device scalar with the live row count; features /
+        indices are then capacity-sized buffers, nothing downstream reads the count back to the host
+        and the whole step can be captured in a CUDA graph."""
         self.features = features
         self.indices = indices
         if self.indices.dtype != torch.int32:
@@ -55,6 +59,7 @@ class SparseConvTensor:
         self.batch_size = int(batch_size)
         self.indice_dict = {}
         self.grid = grid
+        self.n_rows = n_rows
 
     @property
     def spatial_size(self):
@@ -69,7 +74,7 @@ class SparseConvTensor:
 
     def dense(self, channels_first=True):
         h, w = self.spatial_shape
-        out = Fsp.ToDenseFunction.apply(self.features, self.indices, self.batch_size, h, w)
+        out = Fsp.ToDenseFunction.apply(self.features, self.indices, self.batch_size, h, w, self.n_rows)
         if not channels_first:
             return out.permute(0, 2, 3, 1).contiguous()
         return out
@@ -129,8 +134,9 @@ class SparseConvolution(SparseModule):
         features, indices = input.features, input.indices
         mode = self.math or _math_mode
         if self.conv1x1:
-            out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, None, False, mode)
-            out = SparseConvTensor(out_features, indices, input.spatial_shape, input.batch_size)
+            out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, None, False, mode,
+                                                        input.n_rows)
+            out = SparseConvTensor(out_features, indices, input.spatial_shape, input.batch_size, n_rows=input.n_rows)
             out.indice_dict, out.grid = input.indice_dict, input.grid
             return out
         datas = input.find_indice_pair(self.indice_key)
@@ -139,7 +145,7 @@ class SparseConvolution(SparseModule):
             rb = datas
             assert rb.kvol == int(np.prod(self.kernel_size)), \
                 "inverse conv must have same kernel size as its couple conv"
-            outids, out_spatial_shape = rb.indices, rb.spatial_shape
+            outids, out_spatial_shape, out_rows = rb.indices, rb.spatial_shape, rb.n_in_dev
         else:
             if self.indice_key is not None and datas is not None:
                 rb = datas
@@ -147,12 +153,12 @@ class SparseConvolution(SparseModule):
                 pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
                 stride = [1] * self.ndim if self.subm else self.stride
                 rb = ops.build_rulebook(indices, input.batch_size, input.spatial_shape, self.kernel_size, stride,
-                                        pad, self.dilation, self.subm)
+                                        pad, self.dilation, self.subm, n_rows=input.n_rows)
                 input.indice_dict[self.indice_key] = rb
-            outids = rb.outids
+            outids, out_rows = rb.outids, rb.n_out_dev
             out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
-        out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, rb, self.inverse, mode)
-        out = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size)
+        out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, rb, self.inverse, mode, None)
+        out = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size, n_rows=out_rows)
         out.indice_dict, out.grid = input.indice_dict, input.grid
         return out
 
@@ -248,15 +254,30 @@ class SparseSequential(SparseModule):
         self.add_module(name, module)
 
     def forward(self, input):
-        for k, module in self._modules.items():
+        mods = list(self._modules.items())
+        i = 0
+        while i < len(mods):
+            k, module = mods[i]
+            i += 1
             if is_spconv_module(module):
                 assert isinstance(input, SparseConvTensor)
                 self._sparity_dict[k] = input.sparity
                 input = module(input)
-            else:
-                if isinstance(input, SparseConvTensor):
-                    if input.indices.shape[0] != 0:
+            elif isinstance(input, SparseConvTensor):
+                if input.n_rows is not None:
+                    # graph path: row count lives on the device, so BatchNorm1d statistics must be taken
+                    # over the live rows by our own kernel (fused with a directly following ReLU);
+                    # element-wise modules may run over the whole capacity-sized buffer
+                    if isinstance(module, nn.BatchNorm1d):
+                        fuse = i < len(mods) and isinstance(mods[i][1], nn.ReLU)
+                        input.features = Fsp.batch_norm_relu(input.features, input.n_rows, module, fuse)
+                        i += 1 if fuse else 0
+                    elif isinstance(module, (nn.ReLU, nn.Dropout, nn.Identity, nn.LeakyReLU, nn.Sigmoid, nn.Tanh)):
                         input.features = module(input.features)
-                else:
-                    input = module(input)
+                    else:
+                        raise NotImplementedError("graph path: %s between sparse layers" % type(module).__name__)
+                elif input.indices.shape[0] != 0:
+                    input.features = module(input.features)
+            else:
+                input = module(input)
         return input

@@ -27,12 +27,17 @@ def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
 class Rulebook:
     """Geometry of one sparse convolution, cached in SparseConvTensor.indice_dict under the layer's
     indice_key.  Unpacks like upstream's 5-tuple (outids, indices, indice_pairs, indice_pair_num,
-    spatial_shape) and additionally carries the output-stationary neighbour tables."""
+    spatial_shape) and additionally carries the output-stationary neighbour tables.
 
-    def __init__(self, outids, indices, pairs, pair_num, spatial_shape, out_spatial_shape, nbr_out, nbr_in, dup_flag):
+    Graph path: n_in_dev / n_out_dev are int32 device scalars holding the live row counts and every
+    tensor is allocated at capacity; eager path: they are None and all shapes are exact."""
+
+    def __init__(self, outids, indices, pairs, pair_num, spatial_shape, out_spatial_shape, nbr_out, nbr_in, dup_flag,
+                 n_in_dev=None, n_out_dev=None):
         self.outids, self.indices, self.pairs, self.pair_num = outids, indices, pairs, pair_num
         self.spatial_shape, self.out_spatial_shape = spatial_shape, out_spatial_shape
         self.nbr_out, self.nbr_in, self.dup_flag = nbr_out, nbr_in, dup_flag
+        self.n_in_dev, self.n_out_dev = n_in_dev, n_out_dev
 
     def _tuple(self):
         return (self.outids, self.indices, self.pairs, self.pair_num, self.spatial_shape)
@@ -52,9 +57,13 @@ class Rulebook:
 
 
 def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=False,
-                   check_duplicates=False):
-    """Builds pairs + neighbour tables on the GPU.  One host readback (n_out) for a regular conv,
-    none for a submanifold conv."""
+                   check_duplicates=False, n_rows=None):
+    """Builds pairs + neighbour tables on the GPU.
+
+    Eager path (n_rows None): one host readback (n_out) for a regular conv, none for a submanifold
+    conv; all results have exact shapes.  Graph path (n_rows = int32 device scalar, indices at
+    capacity): no readback at all -- outputs are allocated at their upper bound
+    min(N*K, B*H'*W') and the live output count stays on the device."""
     lib = _lib.load()
     _lib.require_cuda(indices)
     if indices.dtype != torch.int32:
@@ -68,6 +77,7 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     batch_size = int(batch_size)
     dev = indices.device
     N, K = indices.shape[0], ksize[0] * ksize[1]
+    static = n_rows is not None
     if subm:
         out_shape = list(spatial_shape)
     else:
@@ -77,33 +87,41 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     oshape_c = _lib.ints([max(o, 0) for o in out_shape])
     ws_bytes = lib.wfsp_rulebook_workspace_bytes(N, batch_size, oshape_c, _lib.ints(ksize))
     ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    n_in_dev = n_rows if static else None
+    n_out_dev = None
     with torch.cuda.device(dev):
         if subm:
-            _lib.check(lib.wfsp_rulebook_subm(_lib.ptr(indices), N, batch_size, _lib.ints(spatial_shape),
-                                              _lib.ints(ksize), _lib.ints(dilation), _lib.ptr(pairs),
-                                              _lib.ptr(pair_num), _lib.ptr(ws), ws.numel(), _lib.stream()))
+            _lib.check(lib.wfsp_rulebook_subm(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+                                              _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(dilation),
+                                              _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream()))
             outids, n_out = indices, N
+            n_out_dev = n_in_dev
         else:
             cells = batch_size * max(out_shape[0], 0) * max(out_shape[1], 0)
             cap = max(1, min(N * K, cells))
             outbuf = torch.empty((cap, 3), dtype=torch.int32, device=dev)
-            n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_conv(_lib.ptr(indices), N, batch_size, _lib.ints(spatial_shape),
-                                              _lib.ints(ksize), _lib.ints(stride), _lib.ints(padding),
-                                              _lib.ints(dilation), _lib.ptr(outbuf), cap, _lib.ptr(pairs),
-                                              _lib.ptr(pair_num), _lib.ptr(n_out_dev), _lib.ptr(ws), ws.numel(),
-                                              _lib.stream()))
-            n_out = int(n_out_dev.item())  # the one readback per rulebook (output tensor shapes need it)
-            outids = outbuf[:n_out]
+            n_out_t = torch.empty((1,), dtype=torch.int32, device=dev)
+            _lib.check(lib.wfsp_rulebook_conv(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+                                              _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
+                                              _lib.ints(padding), _lib.ints(dilation), _lib.ptr(outbuf), cap,
+                                              _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t), _lib.ptr(ws),
+                                              ws.numel(), _lib.stream()))
+            if static:
+                n_out, outids, n_out_dev = cap, outbuf, n_out_t
+            else:
+                n_out = int(n_out_t.item())  # the one readback per rulebook (output tensor shapes need it)
+                outids = outbuf[:n_out]
         nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
         nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
         dup = torch.zeros((1,), dtype=torch.int32, device=dev)
         _lib.check(lib.wfsp_rulebook_tables(_lib.ptr(pairs), _lib.ptr(pair_num), K, N, N, n_out, _lib.ptr(nbr_out),
                                             _lib.ptr(nbr_in), _lib.ptr(dup), _lib.stream()))
-    if check_duplicates and int(dup.item()) != 0:
+    if check_duplicates and not static and int(dup.item()) != 0:
         raise RuntimeError("duplicate (batch, x, y) coordinates in the input: not supported by the "
                            "output-stationary kernels")
-    return Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup)
+    return Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup,
+                    n_in_dev, n_out_dev)
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,

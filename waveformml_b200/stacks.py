@@ -15,6 +15,16 @@ from . import spconv
 SPATIAL = [14, 11]
 
 
+def _wrap(x, spatial_size):
+    """x = [indices (batch, x, y) int32, features] (+ optional batch size, which skips the readback the
+    reference does with `x[0][-1, -1] + 1` (SPConvNet.py:63); + optional int32 device scalar with the
+    live row count = the graph path, see spconv.SparseConvTensor)."""
+    indices, feats = x[0], x[1]
+    batch_size = x[2] if len(x) > 2 else int(indices[-1, 0]) + 1
+    n_rows = x[3] if len(x) > 3 else None
+    return spconv.SparseConvTensor(feats, indices, spatial_size, batch_size, n_rows=n_rows)
+
+
 def _conv_out(size, k, s, p, d):
     return [(i + 2 * p - d * (k - 1) - 1) // s + 1 for i in size]
 
@@ -56,12 +66,7 @@ class PSDClassifier(nn.Module):
         self.spatial_size = SPATIAL
 
     def forward(self, x):
-        """x = [indices (batch, x, y) int32, features] (+ optional batch size to skip the readback
-        the reference does with `x[0][-1, -1] + 1`, SPConvNet.py:63)."""
-        indices, feats = x[0], x[1]
-        batch_size = x[2] if len(x) > 2 else int(indices[-1, 0]) + 1
-        t = spconv.SparseConvTensor(feats, indices, self.spatial_size, batch_size)
-        d = self.sparseModel(t)
+        d = self.sparseModel(_wrap(x, self.spatial_size))
         return self.linear(d.view(-1, self.n_linear))
 
 
@@ -81,10 +86,7 @@ class ZRegressor(nn.Module):
         self.spatial_size = SPATIAL
 
     def forward(self, x):
-        indices, feats = x[0], x[1]
-        batch_size = x[2] if len(x) > 2 else int(indices[-1, 0]) + 1
-        t = spconv.SparseConvTensor(feats, indices, self.spatial_size, batch_size)
-        return self.model.network(t)
+        return self.model.network(_wrap(x, self.spatial_size))
 
 
 class EZSubM(nn.Module):
@@ -118,9 +120,7 @@ class EZSubM(nn.Module):
         self.spatial_size = SPATIAL
 
     def forward(self, x):
-        indices, feats = x[0], x[1]
-        batch_size = x[2] if len(x) > 2 else int(indices[-1, 0]) + 1
-        return self.network(spconv.SparseConvTensor(feats, indices, self.spatial_size, batch_size))
+        return self.network(_wrap(x, self.spatial_size))
 
 
 class IoniPreserve(nn.Module):
@@ -144,9 +144,7 @@ class IoniPreserve(nn.Module):
         self.spatial_size = SPATIAL
 
     def forward(self, x):
-        indices, feats = x[0], x[1]
-        batch_size = x[2] if len(x) > 2 else int(indices[-1, 0]) + 1
-        return self.model.func(spconv.SparseConvTensor(feats, indices, self.spatial_size, batch_size)).features
+        return self.model.func(_wrap(x, self.spatial_size)).features
 
 
 def describe(module):
