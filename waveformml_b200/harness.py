@@ -168,9 +168,13 @@ class GraphTrainStep(TrainStep):
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+        lib = _lib.load()
         self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.wfsp_kernel_launches()
         with torch.cuda.graph(self.graph):
             self.loss_out = self._body()
+        self.launches_per_replay = int(lib.wfsp_kernel_launches() - n0)  # libwfsp kernels in one replay
 
     def run(self):
         if self.graph is None:
