@@ -146,10 +146,13 @@ int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol
  */
 size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math);
 
+/* n_dst_hint (graph path; 0 = none): the number of live destination rows the caller expects, used
+ * only to pick the launch shape (column tiling) -- never for correctness. */
 int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n_src_dev, int c_red,
                     const float* weight, int transpose_w, const float* bias, const int32_t* nbr,
-                    int kvol, float* dst, int64_t n_dst, const int32_t* n_dst_dev, int c_dst,
-                    int math, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+                    int kvol, float* dst, int64_t n_dst, const int32_t* n_dst_dev,
+                    int64_t n_dst_hint, int c_dst, int math, void* workspace,
+                    size_t workspace_bytes, wfsp_stream_t stream);
 
 /* wgrad: d_weight[k] (+)= sum over pairs p of offset k of  a[pa[k,p], :]^T (outer) b[pb[k,p], :]
  * with a = features [n_a, c_a], b = dOut [n_b, c_b], d_weight fp32 [kvol, c_a, c_b]
@@ -161,10 +164,11 @@ int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n_src_dev, i
 size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b,
                                        int64_t pair_pitch, int math);
 
+/* pairs_hint (graph path; 0 = none): expected pairs of the fullest offset, launch shaping only. */
 int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_dev, int c_a, const float* b,
                     int64_t n_b, const int32_t* n_b_dev, int c_b, const int32_t* pair_a,
                     const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pair_pitch,
-                    float* d_weight, int accumulate, int math, void* workspace,
+                    int64_t pairs_hint, float* d_weight, int accumulate, int math, void* workspace,
                     size_t workspace_bytes, wfsp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

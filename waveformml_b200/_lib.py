@@ -30,10 +30,10 @@ SIGNATURES = {
     "wfsp_rulebook_subm": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_rulebook_tables": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "wfsp_conv_apply_workspace_bytes": (_sz, [_int, _i64, _int, _int, _int]),
-    "wfsp_conv_apply": (_int, [_vp, _i64, _vp, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _vp, _int, _int, _vp, _sz,
-                               _vp]),
+    "wfsp_conv_apply": (_int, [_vp, _i64, _vp, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _int, _vp,
+                               _sz, _vp]),
     "wfsp_conv_wgrad_workspace_bytes": (_sz, [_int, _i64, _int, _i64, _int, _i64, _int]),
-    "wfsp_conv_wgrad": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _vp, _int,
+    "wfsp_conv_wgrad": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _i64, _vp, _int,
                                _int, _vp, _sz, _vp]),
     "wfsp_to_dense": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp, _vp]),
     "wfsp_to_dense_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp]),

@@ -48,12 +48,13 @@ int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_
 size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst);
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                    void* ws, size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, cudaStream_t st);
+                    void* ws, size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                    cudaStream_t st);
 size_t conv_wgrad_umma_workspace(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t pitch);
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
-                    const int32_t* n_b_dev, cudaStream_t st);
+                    const int32_t* n_b_dev, int64_t pairs_hint, cudaStream_t st);
 
 }  // namespace wfsp
 
@@ -86,8 +87,8 @@ extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c
 
 extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n_src_dev, int c_red,
                                const float* weight, int transpose_w, const float* bias, const int32_t* nbr,
-                               int kvol, float* dst, int64_t n_dst, const int32_t* n_dst_dev, int c_dst, int math,
-                               void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+                               int kvol, float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                               int c_dst, int math, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
   WFSP_REQUIRE(n_src >= 0 && n_dst >= 0 && c_red >= 1 && c_dst >= 1, "bad conv sizes");
   WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
   WFSP_REQUIRE(nbr != nullptr || (kvol == 1 && n_src == n_dst), "identity map needs kvol == 1 and n_src == n_dst");
@@ -96,7 +97,7 @@ extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n
                            n_dst_dev, as_stream(stream));
   if (math == WFSP_MATH_BF16)
     return conv_apply_umma(src, n_src, c_red, weight, transpose_w, bias, nbr, kvol, dst, n_dst, c_dst, workspace,
-                           workspace_bytes, n_src_dev, n_dst_dev, as_stream(stream));
+                           workspace_bytes, n_src_dev, n_dst_dev, n_dst_hint, as_stream(stream));
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
 }
 
@@ -108,8 +109,8 @@ extern "C" size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a
 extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_dev, int c_a, const float* b,
                                int64_t n_b, const int32_t* n_b_dev, int c_b, const int32_t* pair_a,
                                const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pair_pitch,
-                               float* d_weight, int accumulate, int math, void* workspace, size_t workspace_bytes,
-                               wfsp_stream_t stream) {
+                               int64_t pairs_hint, float* d_weight, int accumulate, int math, void* workspace,
+                               size_t workspace_bytes, wfsp_stream_t stream) {
   WFSP_REQUIRE(n_a >= 0 && n_b >= 0 && c_a >= 1 && c_b >= 1 && pair_pitch >= 0, "bad wgrad sizes");
   WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
   if (math == WFSP_MATH_FP32)
@@ -117,6 +118,6 @@ extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_d
                            accumulate, n_a_dev, as_stream(stream));
   if (math == WFSP_MATH_BF16)
     return conv_wgrad_umma(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
-                           accumulate, workspace, workspace_bytes, n_a_dev, n_b_dev, as_stream(stream));
+                           accumulate, workspace, workspace_bytes, n_a_dev, n_b_dev, pairs_hint, as_stream(stream));
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
 }

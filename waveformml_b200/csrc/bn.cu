@@ -174,6 +174,95 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
   }
 }
 
+// ---- small problems: one launch per direction ----------------------------------------------------
+// A block owns kCh channels for ALL live rows (threads (32, 16): 16 row lanes): statistics, running
+// estimates and the normalise(+ReLU) pass in one kernel; the slab it re-reads stays in L1/L2.  Used
+// when the row capacity is small (a whole C2 step is launch-latency bound).
+constexpr int kSmallRows = 16384;
+constexpr int kRowLanes = 16;
+
+__device__ __forceinline__ float block_col_sum(float v, float (*red)[kCh], int tx, int ty) {
+  red[ty][tx] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRowLanes; ++i) t += red[i][tx];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
+    const float* __restrict__ x, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
+    float* __restrict__ running_var, float momentum, float eps, int training, int relu, float* __restrict__ y,
+    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ float red[kRowLanes][kCh];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * kCh + tx;
+  const bool on = ch < c;
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    if (on) for (int64_t r = ty; r < n; r += kRowLanes) s += x[r * c + ch];
+    mean = n > 0 ? block_col_sum(s, red, tx, ty) / float(n) : 0.f;
+    float m2 = 0.f;
+    if (on) for (int64_t r = ty; r < n; r += kRowLanes) { const float d = x[r * c + ch] - mean; m2 += d * d; }
+    m2 = block_col_sum(m2, red, tx, ty);
+    invstd = n > 0 ? rsqrtf(m2 / float(n) + eps) : 0.f;
+    if (on && ty == 0) {
+      save_mean[ch] = mean;
+      save_invstd[ch] = invstd;
+      if (n > 0 && running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+      if (n > 1 && running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (m2 / float(n - 1));
+    }
+  } else {
+    mean = on ? running_mean[ch] : 0.f;
+    invstd = on ? rsqrtf(running_var[ch] + eps) : 0.f;
+    if (on && ty == 0) { save_mean[ch] = mean; save_invstd[ch] = invstd; }
+  }
+  if (!on) return;
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  for (int64_t r = ty; r < n; r += kRowLanes) {
+    const float v = (x[r * c + ch] - mean) * invstd * g + b;
+    y[r * c + ch] = (relu && v < 0.f) ? 0.f : v;
+  }
+}
+
+__global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
+    const float* __restrict__ x, const float* __restrict__ dy, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_,
+    const float* __restrict__ invstd_, int relu, float* __restrict__ dx, float* __restrict__ d_gamma,
+    float* __restrict__ d_beta) {
+  __shared__ float red[kRowLanes][kCh];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * kCh + tx;
+  const bool on = ch < c;
+  const float m = on ? mean_[ch] : 0.f, is = on ? invstd_[ch] : 0.f;
+  const float g = (on && gamma) ? gamma[ch] : 1.f, b = (on && beta) ? beta[ch] : 0.f;
+  float s0 = 0.f, s1 = 0.f;
+  if (on)
+    for (int64_t r = ty; r < n; r += kRowLanes) {
+      const float xh = (x[r * c + ch] - m) * is;
+      float d = dy[r * c + ch];
+      if (relu && xh * g + b <= 0.f) d = 0.f;
+      s0 += d;
+      s1 += d * xh;
+    }
+  s0 = block_col_sum(s0, red, tx, ty);
+  s1 = block_col_sum(s1, red, tx, ty);
+  if (!on) return;
+  if (ty == 0) { d_beta[ch] = s0; d_gamma[ch] = s1; }
+  const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
+  for (int64_t r = ty; r < n; r += kRowLanes) {
+    const float xh = (x[r * c + ch] - m) * is;
+    float d = dy[r * c + ch];
+    if (relu && xh * g + b <= 0.f) d = 0.f;
+    dx[r * c + ch] = g * is * (d - s0 * inv_n - xh * s1 * inv_n);
+  }
+}
+
 inline unsigned stream_blocks(int64_t elems) {
   int64_t b = ceil_div<int64_t>(elems > 0 ? elems : 1, 256);
   const int64_t cap = int64_t(sm_count()) * 16;
@@ -196,6 +285,15 @@ extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
   if (n_rows == 0) return WFSP_OK;
   cudaStream_t st = as_stream(stream);
+  if (!training) WFSP_REQUIRE(running_mean && running_var, "eval-mode batch norm needs running statistics");
+  if (n_rows <= kSmallRows) {
+    bn_fwd_small<<<ceil_div(c, kCh), dim3(kCh, kRowLanes), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, running_mean,
+                                                                    running_var, momentum, eps, training, relu, y,
+                                                                    save_mean, save_invstd);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return WFSP_OK;
+  }
   if (training) {
     if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
       return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
@@ -225,6 +323,13 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
   if (n_rows == 0) {
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_gamma, 0, size_t(c) * 4, st));
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_beta, 0, size_t(c) * 4, st));
+    return WFSP_OK;
+  }
+  if (n_rows <= kSmallRows) {
+    bn_bwd_small<<<ceil_div(c, kCh), dim3(kCh, kRowLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+                                                                    save_invstd, relu, dx, d_gamma, d_beta);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   }
   if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))

@@ -94,6 +94,45 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1) 
   }
 }
 
+// weight preparation and activation cast of one conv_apply call in a single launch: the first
+// `prep_blocks` CTAs transpose / pad the weights, the rest cast the activation rows
+__global__ void __launch_bounds__(256) prep_and_cast_kernel(const float* __restrict__ w, int kvol, int c_red, int c_dst,
+                                                            int transpose_w, __nv_bfloat16* __restrict__ wt, int n_pad,
+                                                            int kc_pad, int prep_blocks, CastJob job) {
+  if (int(blockIdx.x) < prep_blocks) {
+    const int64_t total = int64_t(kvol) * n_pad * kc_pad;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(prep_blocks) * blockDim.x) {
+      int c = int(i % kc_pad);
+      int64_t t = i / kc_pad;
+      int n = int(t % n_pad);
+      int k = int(t / n_pad);
+      float v = 0.f;
+      if (c < c_red && n < c_dst) {
+        const float* wk = w + int64_t(k) * c_red * c_dst;
+        v = transpose_w ? wk[int64_t(n) * c_red + c] : wk[int64_t(c) * c_dst + n];
+      }
+      wt[i] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const int64_t n = job.n_dev ? int64_t(*job.n_dev) : job.n;
+  const int cpr = job.c_pad >> 3;
+  const int64_t chunks = n * cpr;
+  const int64_t nb = int64_t(gridDim.x) - prep_blocks;
+  for (int64_t i = (int64_t(blockIdx.x) - prep_blocks) * blockDim.x + threadIdx.x; i < chunks; i += nb * blockDim.x) {
+    const int64_t row = i / cpr;
+    const int col = int(i - row * cpr) << 3;
+    const float* s = job.src + row * job.c + col;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (col + e < job.c) ? __ldg(s + e) : 0.f;
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(job.dst + row * job.c_pad + col) = u;
+  }
+}
+
 int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
   CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8, nullptr};
   const int64_t c0 = a.n * (a.c_pad >> 3), c1 = j1.n * (j1.c_pad >> 3);
@@ -226,8 +265,11 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
             cp_async16(sa + sw128_offset(uint32_t(rsub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
           }
           const __nv_bfloat16* wb = wk + kb * kSliceK + c16 * 8;
-          for (int n = rsub; n < p.n_tile; n += 16)
-            cp_async16(sb + sw128_offset(uint32_t(n), uint32_t(c16)), wb + int64_t(n) * p.kc_pad, 16u);
+          for (int n = rsub; n < p.n_tile; n += 16) {
+            const bool ok = n0 + n < p.n_pad;  // the last column tile may overhang the padded weights
+            cp_async16(sb + sw128_offset(uint32_t(n), uint32_t(c16)), ok ? wb + int64_t(n) * p.kc_pad : wb,
+                       ok ? 16u : 0u);
+          }
           cp_async_arrive_noinc(&bars.full[s]);
         }
       }
@@ -447,12 +489,23 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct ApplyPlan { int n_tiles, n_tile, n_pad, kc_pad, c_pad; size_t off_act, total; };
+// column tiling of the destination channels: as few tiles as possible (<= 256 columns each) when
+// there are enough row tiles to fill the machine, narrower tiles (down to 32 columns) when there are
+// not -- a small problem is bound by the serial k-loop of its few CTAs, so spreading the columns over
+// idle SMs shortens it; the price (the A tile is gathered once per column tile) is negligible there.
+void choose_column_tiles(int n_pad, int64_t live_row_tiles, int& n_tile, int& n_tiles) {
+  const int t_min = (n_pad + 255) / 256;
+  const int t_max = (n_pad + 31) / 32;
+  int64_t want = ceil_div<int64_t>(sm_count(), live_row_tiles > 0 ? live_row_tiles : 1);
+  int t = int(want < t_min ? t_min : (want > t_max ? t_max : want));
+  n_tile = round_up((n_pad + t - 1) / t, 16);
+  n_tiles = (n_pad + n_tile - 1) / n_tile;
+}
+
+struct ApplyPlan { int n_pad, kc_pad, c_pad; size_t off_act, total; };
 ApplyPlan apply_plan(int kvol, int64_t n_src, int c_red, int c_dst) {
   ApplyPlan a;
-  a.n_tiles = (c_dst + 255) / 256;
-  a.n_tile = round_up((c_dst + a.n_tiles - 1) / a.n_tiles, 16);
-  a.n_pad = a.n_tiles * a.n_tile;
+  a.n_pad = round_up(c_dst, 16);
   a.kc_pad = round_up(c_red, kSliceK);
   a.c_pad = round_up(c_red, 8);
   a.off_act = align_up(size_t(kvol) * a.n_pad * a.kc_pad * sizeof(__nv_bfloat16), 256);
@@ -475,30 +528,36 @@ size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) 
 
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
-                    size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, cudaStream_t st) {
+                    size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                    cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
+  const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
+  int n_tile, n_tiles;
+  choose_column_tiles(a.n_pad, ceil_div<int64_t>(live, kTileM), n_tile, n_tiles);
   if (ws == nullptr || ws_bytes < a.total) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, a.total);
   __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + a.off_act);
   {
     const int64_t total = int64_t(kvol) * a.n_pad * a.kc_pad;
-    int64_t blocks = ceil_div<int64_t>(total, 256);
-    if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
-    prep_weight_kernel<<<unsigned(blocks), 256, 0, st>>>(weight, kvol, c_red, c_dst, transpose_w, wt, a.n_pad, a.kc_pad);
+    int64_t prep_blocks = ceil_div<int64_t>(total, 256);
+    if (prep_blocks > int64_t(sm_count()) * 8) prep_blocks = int64_t(sm_count()) * 8;
+    CastJob job{src, act, n_src, c_red, a.c_pad, n_src_dev};
+    int64_t cast_blocks = ceil_div<int64_t>(n_src * (a.c_pad >> 3) > 0 ? n_src * (a.c_pad >> 3) : 1, 256);
+    if (cast_blocks > int64_t(sm_count()) * 16) cast_blocks = int64_t(sm_count()) * 16;
+    prep_and_cast_kernel<<<unsigned(prep_blocks + cast_blocks), 256, 0, st>>>(
+        weight, kvol, c_red, c_dst, transpose_w, wt, a.n_pad, a.kc_pad, int(prep_blocks), job);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
-  CastJob job{src, act, n_src, c_red, a.c_pad, n_src_dev};
-  if (int rc = launch_cast(job, nullptr, st)) return rc;
 
-  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, a.n_tile, 2,
+  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, n_tile, 2,
                 n_src_dev, n_dst_dev};
-  const int stage_bytes = kABytes + a.n_tile * 128;
+  const int stage_bytes = kABytes + n_tile * 128;
   const int nbr_bytes = (nbr != nullptr && kvol <= kNbrStageK) ? kTileM * kvol * 4 : 0;
   p.stages = pick_stages(stage_bytes, nbr_bytes + 1024);
   const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + 1024;
-  dim3 grid(unsigned(ceil_div<int64_t>(n_dst, kTileM)), unsigned(a.n_tiles));
+  dim3 grid(unsigned(ceil_div<int64_t>(n_dst, kTileM)), unsigned(n_tiles));
   WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   conv_apply_umma_kernel<<<grid, kThreads, smem, st>>>(p);
   count_launches(1);
@@ -513,7 +572,7 @@ size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
-                    const int32_t* n_b_dev, cudaStream_t st) {
+                    const int32_t* n_b_dev, int64_t pairs_hint, cudaStream_t st) {
   const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch);
   if (need > 0 && (ws == nullptr || ws_bytes < need))
     return set_error(WFSP_EWORKSPACE, "conv_wgrad workspace %zu < %zu", ws_bytes, need);
@@ -531,7 +590,10 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   p.n_tile = round_up((c_b + n_tiles - 1) / n_tiles, 16);
   p.m_tiles = (c_a + kTileM - 1) / kTileM;
   const int tiles = p.m_tiles * n_tiles;
-  const int64_t rows = pair_a ? pitch : n_a;
+  // pairs per offset that bound the split of the reduction: the caller's hint (graph path, where only
+  // capacities are known on the host) or the capacity itself
+  int64_t rows = pair_a ? pitch : n_a;
+  if (pairs_hint > 0 && pairs_hint < rows) rows = pairs_hint;
   int nsplit = 1;
   if (rows > 0) {
     int64_t want = ceil_div<int64_t>(int64_t(2) * sm_count(), int64_t(tiles) * kvol);

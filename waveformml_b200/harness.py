@@ -72,7 +72,10 @@ class TrainStep:
         assert task in ("psd", "z")
         self.model, self.task, self.group = model, task, group
         self.grads = FlatGrads(model.parameters())
-        self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov, foreach=True)
+        # fused=True: one multi-tensor kernel for the whole update instead of four foreach passes
+        on_gpu = self.grads.flat.is_cuda
+        self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov,
+                                   fused=True if on_gpu else None, foreach=None if on_gpu else True)
         self.criterion = nn.CrossEntropyLoss()
 
     def loss(self, indices, feats, target, batch_size, n_rows=None):
@@ -163,17 +166,25 @@ class GraphTrainStep(TrainStep):
     def _capture(self):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        from . import _lib
+        from .spconv.functional import hints
         with torch.cuda.stream(side):
-            for _ in range(3):  # warm-up on a side stream (allocator, cuBLAS handles, NCCL) before capture
+            # warm-up on a side stream (allocator, cuBLAS handles, NCCL) before capture; the first pass also
+            # records the live row counts of the loaded batch as launch-shape hints (see LaunchHints)
+            for i in range(3):
+                hints.start("record" if i == 0 else "replay")
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
         lib = _lib.load()
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.wfsp_kernel_launches()
-        with torch.cuda.graph(self.graph):
-            self.loss_out = self._body()
+        hints.start("replay")
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss_out = self._body()
+        finally:
+            hints.stop()
         self.launches_per_replay = int(lib.wfsp_kernel_launches() - n0)  # libwfsp kernels in one replay
 
     def run(self):

@@ -17,6 +17,40 @@ def _f32c(t):
     return t.contiguous()
 
 
+class LaunchHints:
+    """Graph path only.  The host never learns the live row counts there, yet launch shapes (how the
+    columns are tiled, how the wgrad reduction is split) should follow them rather than the buffer
+    capacities.  During one eager warm-up pass (`record`) every kernel call reads its live count back
+    and appends it; the captured pass (`replay`) consumes the same numbers in the same call order.
+    They only shape launches; correctness never depends on them."""
+
+    def __init__(self):
+        self.mode, self.values, self.pos = None, [], 0
+
+    def start(self, mode):
+        self.mode, self.pos = mode, 0
+        if mode == "record":
+            self.values = []
+
+    def stop(self):
+        self.mode = None
+
+    def get(self, count):
+        """count: device tensor (its max is taken), or None."""
+        if count is None or self.mode is None:
+            return 0
+        if self.mode == "record":
+            v = int(count.max().item())
+            self.values.append(v)
+            return v
+        v = self.values[self.pos] if self.pos < len(self.values) else 0
+        self.pos += 1
+        return v
+
+
+hints = LaunchHints()
+
+
 def conv_apply(src, weight3, transpose_w, bias, nbr, n_dst, c_dst, math, n_src_dev=None, n_dst_dev=None):
     """dst[r] = bias + sum_k src[nbr[r,k]] @ (weight3[k] or weight3[k]^T)   (wfsp_conv_apply)"""
     lib = _lib.load()
@@ -27,12 +61,13 @@ def conv_apply(src, weight3, transpose_w, bias, nbr, n_dst, c_dst, math, n_src_d
     if n_dst == 0:
         return dst
     m = _MATH[math]
+    hint = hints.get(n_dst_dev)
     ws_bytes = lib.wfsp_conv_apply_workspace_bytes(kvol, src.shape[0], c_red, c_dst, m)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=src.device) if ws_bytes else None
     with torch.cuda.device(src.device):
         _lib.check(lib.wfsp_conv_apply(_lib.ptr(src), src.shape[0], _lib.ptr(n_src_dev), c_red, _lib.ptr(weight3),
                                        int(transpose_w), _lib.ptr(bias), _lib.ptr(nbr), kvol, _lib.ptr(dst), n_dst,
-                                       _lib.ptr(n_dst_dev), c_dst, m, _lib.ptr(ws), ws_bytes, _lib.stream()))
+                                       _lib.ptr(n_dst_dev), hint, c_dst, m, _lib.ptr(ws), ws_bytes, _lib.stream()))
     return dst
 
 
@@ -45,10 +80,13 @@ def conv_wgrad(a, b, pair_a, pair_b, pair_num, kvol, math, n_a_dev=None, n_b_dev
     m = _MATH[math]
     ws_bytes = lib.wfsp_conv_wgrad_workspace_bytes(kvol, a.shape[0], c_a, b.shape[0], c_b, pitch, m)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=a.device) if ws_bytes else None
+    hint = 0
+    if n_a_dev is not None:  # graph path: expected pairs of the fullest offset
+        hint = hints.get(pair_num if pair_num is not None else n_a_dev)
     with torch.cuda.device(a.device):
         _lib.check(lib.wfsp_conv_wgrad(_lib.ptr(a), a.shape[0], _lib.ptr(n_a_dev), c_a, _lib.ptr(b), b.shape[0],
                                        _lib.ptr(n_b_dev), c_b, _lib.ptr(pair_a), _lib.ptr(pair_b), _lib.ptr(pair_num),
-                                       kvol, pitch, _lib.ptr(dw), 0, m, _lib.ptr(ws), ws_bytes, _lib.stream()))
+                                       kvol, pitch, hint, _lib.ptr(dw), 0, m, _lib.ptr(ws), ws_bytes, _lib.stream()))
     return dw
 
 
