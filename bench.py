@@ -424,8 +424,16 @@ def run_ours(args):
                                           "CPU algorithm, oracle/)" % (len(times), B)}
     if rank == 0:
         print(json.dumps(line))
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graph holds NCCL kernels; tearing the communicator down under it hung the 2-GPU run
+        # at exit (the JSON line was already out).  Drain the device, meet the other ranks once, and leave
+        # without NCCL teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
     return 0
 
 

@@ -214,3 +214,28 @@ def test_half_precision_features(cuda_device):
     conv = spconv.SubMConv2d(8, 4, 3, indice_key="subm0").to(cuda_device)
     y = conv(spconv.SparseConvTensor(feats.half().to(cuda_device), idx.to(cuda_device), [14, 11], 5))
     assert y.features.dtype == torch.float16 and y.features.shape == (idx.shape[0], 4)
+
+
+def test_wgrad_launch_hint_never_drops_pairs(cuda_device):
+    """Graph path: the launch-shape hint (pairs of the fullest offset seen while warming up) may be far
+    below the live pair count of a later batch; the split of the pair list must still cover every pair."""
+    from waveformml_b200.spconv import functional as Fsp
+    from waveformml_b200.spconv import ops
+    B = 300
+    idx, feats = events(B, 41, 24)
+    idx_d = idx.to(cuda_device)
+    n = idx.shape[0]
+    out_idx, pairs, pair_num = ops.get_indice_pairs(idx_d, B, [14, 11], [3, 3], [1, 1], [1, 1], [1, 1], subm=True)
+    g = torch.Generator().manual_seed(1)
+    dout = torch.randn(n, 16, generator=g).to(cuda_device)
+    fd = feats.to(cuda_device)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=cuda_device)
+    ref = Fsp.conv_wgrad(fd, dout, pairs[0], pairs[1], pair_num, 9, "bf16")
+    Fsp.hints.start("replay")
+    Fsp.hints.values = [64]  # "expect 64 pairs per offset": the real count is ~10x that
+    try:
+        got = Fsp.conv_wgrad(fd, dout, pairs[0], pairs[1], pair_num, 9, "bf16", n_dev, n_dev)
+    finally:
+        Fsp.hints.stop()
+    assert int(pair_num.max()) > 256
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))

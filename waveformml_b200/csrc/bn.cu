@@ -55,23 +55,43 @@ __global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(128) bn_finalize_stats(const float* __restrict__ part, int64_t n_cap,
+// One block per 32 channels; 32 row lanes each merge every 32nd partial (Chan's parallel-variance merge, in
+// double), then lane 0 merges the 32 lane results in lane order: a fixed order, so the statistics do
+// not depend on scheduling, and nblk/32 dependent steps instead of nblk.
+constexpr int kFinLanes = 32;
+
+__global__ void __launch_bounds__(kCh * kFinLanes) bn_finalize_stats(const float* __restrict__ part, int64_t n_cap,
                                                          const int32_t* __restrict__ n_dev, int c, float eps,
                                                          float momentum, float* __restrict__ running_mean,
                                                          float* __restrict__ running_var,
                                                          float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ double s_cnt[kFinLanes][kCh], s_mean[kFinLanes][kCh], s_m2[kFinLanes][kCh];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * kCh + tx;
   const int64_t n = live_rows(n_cap, n_dev);
-  if (n <= 0) { save_mean[ch] = 0.f; save_invstd[ch] = 0.f; return; }
-  const int64_t nblk = (n + kRows - 1) / kRows;
+  const int64_t nblk = n > 0 ? (n + kRows - 1) / kRows : 0;
   double cnt = 0.0, mean = 0.0, m2 = 0.0;
-  for (int64_t b = 0; b < nblk; ++b) {  // Chan's parallel-variance merge, fixed order
-    const double nb = double(b + 1 < nblk ? kRows : n - b * kRows);
-    const double mb = part[(b * 2 + 0) * c + ch], m2b = part[(b * 2 + 1) * c + ch];
-    const double delta = mb - mean, tot = cnt + nb;
+  if (ch < c) {
+#pragma unroll 4
+    for (int64_t b = ty; b < nblk; b += kFinLanes) {
+      const double nb = double(b + 1 < nblk ? kRows : n - b * kRows);
+      const double mb = part[(b * 2 + 0) * c + ch], m2b = part[(b * 2 + 1) * c + ch];
+      const double delta = mb - mean, tot = cnt + nb;
+      mean += delta * nb / tot;
+      m2 += m2b + delta * delta * cnt * nb / tot;
+      cnt = tot;
+    }
+  }
+  s_cnt[ty][tx] = cnt; s_mean[ty][tx] = mean; s_m2[ty][tx] = m2;
+  __syncthreads();
+  if (ty != 0 || ch >= c) return;
+  if (n <= 0) { save_mean[ch] = 0.f; save_invstd[ch] = 0.f; return; }
+  for (int l = 1; l < kFinLanes; ++l) {
+    const double nb = s_cnt[l][tx];
+    if (nb <= 0.0) continue;
+    const double delta = s_mean[l][tx] - mean, tot = cnt + nb;
     mean += delta * nb / tot;
-    m2 += m2b + delta * delta * cnt * nb / tot;
+    m2 += s_m2[l][tx] + delta * delta * cnt * nb / tot;
     cnt = tot;
   }
   const double var = m2 / cnt;
@@ -139,18 +159,26 @@ __global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(128) bn_bwd_finalize(const float* __restrict__ part, int64_t n_cap,
+__global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* __restrict__ part, int64_t n_cap,
                                                        const int32_t* __restrict__ n_dev, int c,
                                                        float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ double r0[kFinLanes][kCh], r1[kFinLanes][kCh];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * kCh + tx;
   const int64_t n = live_rows(n_cap, n_dev);
   const int64_t nblk = n > 0 ? (n + kRows - 1) / kRows : 0;
   double s0 = 0.0, s1 = 0.0;
-  for (int64_t b = 0; b < nblk; ++b) {
-    s0 += part[(b * 2 + 0) * c + ch];
-    s1 += part[(b * 2 + 1) * c + ch];
+  if (ch < c) {
+#pragma unroll 4
+    for (int64_t b = ty; b < nblk; b += kFinLanes) {
+      s0 += part[(b * 2 + 0) * c + ch];
+      s1 += part[(b * 2 + 1) * c + ch];
+    }
   }
+  r0[ty][tx] = s0; r1[ty][tx] = s1;
+  __syncthreads();
+  if (ty != 0 || ch >= c) return;
+  for (int l = 1; l < kFinLanes; ++l) { s0 += r0[l][tx]; s1 += r1[l][tx]; }
   d_beta[ch] = float(s0);
   d_gamma[ch] = float(s1);
 }
@@ -300,7 +328,7 @@ extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n
     float* part = static_cast<float*>(workspace);
     dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
     bn_partial_stats<<<grid, dim3(32, 8), 0, st>>>(x, n_rows, n_rows_dev, c, part);
-    bn_finalize_stats<<<ceil_div(c, 128), 128, 0, st>>>(part, n_rows, n_rows_dev, c, eps, momentum, running_mean,
+    bn_finalize_stats<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, eps, momentum, running_mean,
                                                         running_var, save_mean, save_invstd);
     count_launches(2);
   } else {
@@ -337,7 +365,7 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
   float* part = static_cast<float*>(workspace);
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
   bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
-  bn_bwd_finalize<<<ceil_div(c, 128), 128, 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
+  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
   bn_bwd_apply<<<stream_blocks(n_rows * c), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                           save_invstd, d_gamma, d_beta, relu, dx);
   count_launches(3);

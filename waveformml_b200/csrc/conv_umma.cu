@@ -41,6 +41,7 @@ constexpr int kABytes = kTileM * 128;
 constexpr int kMaxStages = 8;
 constexpr int kNbrStageK = 32;  // kernel volumes up to this keep the CTA's neighbour tile in smem
 constexpr int kSmemMax = 200 * 1024;
+constexpr int kEpiPitch = 36;  // words per row of a warp's 32 x 32 epilogue tile (16-byte aligned, conflict-free)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -227,15 +228,27 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
+    // Everything that does not change along the reduction is hoisted: the swizzled shared-memory
+    // offset of this thread's chunk (rows rsub + 16 i are 2048 B apart), the global row pointers of
+    // the current offset, the number of slices in which the chunk lies inside the padded row.
     const int c16 = tid & 7;    // 16-byte chunk inside the 128-byte slice row
     const int rsub = tid >> 3;  // this thread covers tile rows rsub + 16*i
-    int it = 0;
+    const uint32_t off0 = sw128_offset(uint32_t(rsub), uint32_t(c16));
+    const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;
+    int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
+    if (n_lim > p.n_tile) n_lim = p.n_tile;
+    const size_t a_row_bytes = size_t(p.c_pad) * 2, w_row_bytes = size_t(p.kc_pad) * 2;
+    const char* src_c = reinterpret_cast<const char*>(p.src) + c16 * 16;
+    const uint32_t smem0 = smem_u32(smem);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
     for (int kw = 0; kw < (p.kvol + 31) / 32; ++kw) {
       uint32_t mask = s_active[kw];
       while (mask) {
         const int k = kw * 32 + __ffs(mask) - 1;
         mask &= mask - 1;
-        int rows[8];
+        const char* ga[8];
+        uint32_t asz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = rsub + 16 * i;
@@ -248,79 +261,93 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
             v = (row0 + r < p.n_dst) ? __ldg(p.nbr + (row0 + r) * p.kvol + k) : -1;
             if (v >= p.n_src) v = -1;
           }
-          rows[i] = v;
+          asz[i] = v >= 0 ? 16u : 0u;
+          ga[i] = src_c + (v >= 0 ? size_t(v) * a_row_bytes : size_t(0));
         }
-        const __nv_bfloat16* wk = p.wt + (int64_t(k) * p.n_pad + n0) * p.kc_pad;
+        const char* wk = reinterpret_cast<const char*>(p.wt + (int64_t(k) * p.n_pad + n0 + rsub) * p.kc_pad) + c16 * 16;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          if (it >= p.stages) mbar_wait(&bars.free_[s], uint32_t((it / p.stages - 1) & 1));
-          const uint32_t sa = smem_u32(smem + uint32_t(s) * stage_bytes);
+          if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
+          const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
           const uint32_t sb = sa + kABytes;
-          const int col = kb * kSliceK + c16 * 8;
-          const bool col_ok = col < p.c_pad;
+          const uint32_t colm = kb < kb_lim ? 16u : 0u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = col_ok && rows[i] >= 0;
-            const __nv_bfloat16* g = ok ? p.src + int64_t(rows[i]) * p.c_pad + col : p.src;
-            cp_async16(sa + sw128_offset(uint32_t(rsub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
-          }
-          const __nv_bfloat16* wb = wk + kb * kSliceK + c16 * 8;
-          for (int n = rsub; n < p.n_tile; n += 16) {
-            const bool ok = n0 + n < p.n_pad;  // the last column tile may overhang the padded weights
-            cp_async16(sb + sw128_offset(uint32_t(n), uint32_t(c16)), ok ? wb + int64_t(n) * p.kc_pad : wb,
-                       ok ? 16u : 0u);
-          }
+          for (int i = 0; i < 8; ++i) cp_async16(sa + i * 2048, ga[i] + kb * 128, asz[i] & colm);
+          const char* wb = wk + kb * 128;
+          int n = rsub;
+          uint32_t sbn = sb;
+          for (; n < n_lim; n += 16, sbn += 2048, wb += 16 * w_row_bytes) cp_async16(sbn, wb, 16u);
+          for (; n < p.n_tile; n += 16, sbn += 2048) cp_async16(sbn, p.wt, 0u);
           cp_async_arrive_noinc(&bars.full[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
     // ------------------------------------------------------------------ epilogue
+    // TMEM -> registers (thread = row) -> this warp's shared-memory tile -> global with a warp writing
+    // whole row segments, so the stores are coalesced whatever the channel count.  The pipeline's
+    // stage memory is free once `done` has fired.
     if (total_iters > 0) {
       mbar_wait(&bars.done, 0);
       tc_fence_after();
     }
-    const int64_t r = row0 + warp * 32 + lane;
-    float* out = p.dst + r * p.c_dst;
-    const bool vec_ok = (p.c_dst % 4) == 0;
-    for (int col = 0; col < p.n_tile; col += 16) {
-      uint32_t acc[16];
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
+    const int64_t wrow0 = row0 + warp * 32;
+    const bool vec_ok = (p.c_dst & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0;
+    for (int col = 0; col < p.n_tile; col += 32) {
+      const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
+      uint32_t acc[32];
       if (total_iters > 0) {
-        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), acc);
+        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        if (ncols > 16)
+          tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col + 16), *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0u;
+        for (int e = 0; e < 32; ++e) acc[e] = 0u;
       }
-      if (r < p.n_dst) {
-        const int c = n0 + col;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = c + 4 * q;
-          float f[4];
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < ncols)
+          *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      __syncwarp();
+      if (vec_ok) {
+        const int c4 = (lane & 7) * 4, cc = n0 + col + c4;
+        if (c4 < ncols && cc < p.c_dst) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = make_float4(__ldg(p.bias + cc), __ldg(p.bias + cc + 1), __ldg(p.bias + cc + 2), __ldg(p.bias + cc + 3));
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            f[e] = __uint_as_float(acc[4 * q + e]);
-            if (p.bias && cc + e < p.c_dst) f[e] += __ldg(p.bias + cc + e);
-          }
-          if (vec_ok && cc + 3 < p.c_dst) {
-            *reinterpret_cast<float4*>(out + cc) = make_float4(f[0], f[1], f[2], f[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (cc + e < p.c_dst) out[cc + e] = f[e];
+          for (int j = 0; j < 8; ++j) {
+            const int r = j * 4 + (lane >> 3);
+            if (wrow0 + r < p.n_dst) {
+              float4 v = *reinterpret_cast<const float4*>(tile + r * kEpiPitch + c4);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              *reinterpret_cast<float4*>(p.dst + (wrow0 + r) * p.c_dst + cc) = v;
+            }
           }
         }
+      } else {
+        const int cc = n0 + col + lane;
+        if (lane < ncols && cc < p.c_dst) {
+          const float bv = p.bias ? __ldg(p.bias + cc) : 0.f;
+          int64_t rmax = p.n_dst - wrow0;
+          if (rmax > 32) rmax = 32;
+          float* o = p.dst + wrow0 * p.c_dst + cc;
+          for (int r = 0; r < int(rmax); ++r) o[int64_t(r) * p.c_dst] = tile[r * kEpiPitch + lane] + bv;
+        }
       }
+      __syncwarp();
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
+    const uint32_t smem0 = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < total_iters; ++it) {
-      const int s = it % p.stages;
-      mbar_wait(&bars.full[s], uint32_t((it / p.stages) & 1));
+      mbar_wait(&bars.full[s], ph);
       fence_proxy_async_smem();
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + uint32_t(s) * stage_bytes), b_addr = a_addr + kABytes;
+      const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + kABytes;
 #pragma unroll
       for (int kk = 0; kk < kSliceK / 16; ++kk) {
         const uint64_t adesc = make_desc_sw128(a_addr + kk * 32, 16, 1024);
@@ -328,6 +355,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
         mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
       }
       mma_commit(&bars.free_[s]);
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
     if (total_iters > 0) mma_commit(&bars.done);
   }
@@ -360,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const int64_t n_pairs = p.pair_num ? int64_t(p.pair_num[k]) : (p.n_a_dev ? int64_t(*p.n_a_dev) : p.n_a);
   const int64_t begin = int64_t(split) * p.chunk;
   int64_t end = begin + p.chunk;
-  if (end > n_pairs) end = n_pairs;
+  if (end > n_pairs || split == p.nsplit - 1) end = n_pairs;  // the last split takes whatever the launch-shape hint missed
   if (begin >= n_pairs && (split > 0 || p.use_atomic)) return;  // nothing to add (uniform per CTA)
   const int iters = begin < end ? int((end - begin + kSliceK - 1) / kSliceK) : 0;
 
@@ -399,77 +427,96 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
         ia[i] = va; ib[i] = vb;
       }
     };
+    // loop invariants: swizzled smem offset of this thread's chunk (pairs psub + 16 i are 2048 B
+    // apart, panels 8192 B apart), which panels' chunks lie inside the padded rows
+    const uint32_t off0 = sw128_offset(uint32_t(psub), uint32_t(c16));
+    const uint32_t smem0 = smem_u32(smem);
+    const size_t a_row_bytes = size_t(p.ca_pad) * 2, b_row_bytes = size_t(p.cb_pad) * 2;
+    const char* a_c = reinterpret_cast<const char*>(p.a) + size_t(a_c0 + c16 * 8) * 2;
+    const char* b_c = reinterpret_cast<const char*>(p.b) + size_t(b_c0 + c16 * 8) * 2;
+    uint32_t a_ok[2], b_ok[4];
+#pragma unroll
+    for (int pn = 0; pn < 2; ++pn) a_ok[pn] = (a_c0 + pn * 64 + c16 * 8 < p.ca_pad) ? 16u : 0u;
+#pragma unroll
+    for (int pn = 0; pn < 4; ++pn) b_ok[pn] = (pn < b_panels && b_c0 + pn * 64 + c16 * 8 < p.cb_pad) ? 16u : 0u;
     int ia[4], ib[4], na[4], nb[4];
     if (iters > 0) load_idx(0, ia, ib);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
       if (it + 1 < iters) load_idx(it + 1, na, nb);  // prefetch the next slice's pair indices
-      const int s = it % p.stages;
-      if (it >= p.stages) mbar_wait(&bars.free_[s], uint32_t((it / p.stages - 1) & 1));
-      const uint32_t sa = smem_u32(smem + uint32_t(s) * stage_bytes);
+      if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
+      const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
       const uint32_t sb = sa + a_bytes;
-      // A: [64 pairs][128 channels of a] as two 64-channel swizzled panels
 #pragma unroll
-      for (int panel = 0; panel < 2; ++panel) {
-        const int col = a_c0 + panel * 64 + c16 * 8;
-        const bool col_ok = col < p.ca_pad;
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t live = ia[i] >= 0 ? 16u : 0u;
+        const char* ga = a_c + (ia[i] >= 0 ? size_t(ia[i]) * a_row_bytes : size_t(0));
+        const char* gb = b_c + (ib[i] >= 0 ? size_t(ib[i]) * b_row_bytes : size_t(0));
+        // A: [64 pairs][128 channels of a] as two 64-channel swizzled panels
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool ok = col_ok && ia[i] >= 0;
-          const __nv_bfloat16* g = ok ? p.a + int64_t(ia[i]) * p.ca_pad + col : p.a;
-          cp_async16(sa + panel * 8192 + sw128_offset(uint32_t(psub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
-        }
-      }
-      // B: [64 pairs][n_tile channels of b]
-      for (int panel = 0; panel < b_panels; ++panel) {
-        const int col = b_c0 + panel * 64 + c16 * 8;
-        const bool col_ok = col < p.cb_pad;
+        for (int pn = 0; pn < 2; ++pn) cp_async16(sa + pn * 8192 + i * 2048, ga + pn * 128, live & a_ok[pn]);
+        // B: [64 pairs][n_tile channels of b]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool ok = col_ok && ib[i] >= 0;
-          const __nv_bfloat16* g = ok ? p.b + int64_t(ib[i]) * p.cb_pad + col : p.b;
-          cp_async16(sb + panel * 8192 + sw128_offset(uint32_t(psub + 16 * i), uint32_t(c16)), g, ok ? 16u : 0u);
-        }
+        for (int pn = 0; pn < 4; ++pn)
+          if (pn < b_panels) cp_async16(sb + pn * 8192 + i * 2048, gb + pn * 128, live & b_ok[pn]);
       }
       cp_async_arrive_noinc(&bars.full[s]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { ia[i] = na[i]; ib[i] = nb[i]; }
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
     // ------------------------------------------------------------------ epilogue
+    // TMEM -> registers (thread = a-channel) -> this warp's smem tile -> global, a warp adding / storing
+    // 32 consecutive b-channels of one a-channel row at a time (coalesced stores / reductions)
     if (iters > 0) {
       mbar_wait(&bars.done, 0);
       tc_fence_after();
     }
-    const int ca = a_c0 + warp * 32 + lane;
-    float* out = p.dw + (int64_t(k) * p.c_a + ca) * p.c_b;
-    for (int col = 0; col < p.n_tile; col += 16) {
-      uint32_t acc[16];
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
+    const int ca0 = a_c0 + warp * 32;
+    float* out = p.dw + (int64_t(k) * p.c_a + ca0) * p.c_b;
+    int rmax = p.c_a - ca0;
+    if (rmax > 32) rmax = 32;
+    for (int col = 0; col < p.n_tile; col += 32) {
+      const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
+      uint32_t acc[32];
       if (iters > 0) {
-        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), acc);
+        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        if (ncols > 16)
+          tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col + 16), *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = 0u;
+        for (int e = 0; e < 32; ++e) acc[e] = 0u;
       }
-      if (ca < p.c_a) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int cb = b_c0 + col + e;
-          if (cb < p.c_b) {
-            if (p.use_atomic) atomicAdd(out + cb, __uint_as_float(acc[e]));
-            else out[cb] = __uint_as_float(acc[e]);
-          }
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < ncols)
+          *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      __syncwarp();
+      const int cb = b_c0 + col + lane;
+      if (lane < ncols && cb < p.c_b) {
+        float* o = out + cb;
+        if (p.use_atomic) {
+          for (int r = 0; r < rmax; ++r) atomicAdd(o + int64_t(r) * p.c_b, tile[r * kEpiPitch + lane]);
+        } else {
+          for (int r = 0; r < rmax; ++r) o[int64_t(r) * p.c_b] = tile[r * kEpiPitch + lane];
         }
       }
+      __syncwarp();
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 1, 1);
+    const uint32_t smem0 = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % p.stages;
-      mbar_wait(&bars.full[s], uint32_t((it / p.stages) & 1));
+      mbar_wait(&bars.full[s], ph);
       fence_proxy_async_smem();
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + uint32_t(s) * stage_bytes), b_addr = a_addr + a_bytes;
+      const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
 #pragma unroll
       for (int kk = 0; kk < kSliceK / 16; ++kk) {
         // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
@@ -478,6 +525,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
         mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
       }
       mma_commit(&bars.free_[s]);
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
     if (iters > 0) mma_commit(&bars.done);
   }
@@ -590,27 +638,35 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   p.n_tile = round_up((c_b + n_tiles - 1) / n_tiles, 16);
   p.m_tiles = (c_a + kTileM - 1) / kTileM;
   const int tiles = p.m_tiles * n_tiles;
+  const int b_panels = (p.n_tile + 63) / 64;
+  const int stage_bytes = 2 * 8192 + b_panels * 8192;
+  p.stages = pick_stages(stage_bytes, 1024);
+  const size_t smem = size_t(p.stages) * stage_bytes + 1024;
   // pairs per offset that bound the split of the reduction: the caller's hint (graph path, where only
   // capacities are known on the host) or the capacity itself
   int64_t rows = pair_a ? pitch : n_a;
   if (pairs_hint > 0 && pairs_hint < rows) rows = pairs_hint;
+  // Split the pair list so that the CTAs fill whole waves of the machine: cost(ns) ~ waves(ns) / ns with
+  // waves = ceil(tiles * kvol * ns / resident CTA slots); the smallest ns among the best is taken (fewer
+  // partial tiles to reduce with atomics).  At least 256 pairs per split.
   int nsplit = 1;
   if (rows > 0) {
-    int64_t want = ceil_div<int64_t>(int64_t(2) * sm_count(), int64_t(tiles) * kvol);
+    const int64_t slots = int64_t(sm_count()) * ((2 * (smem + 2048) <= size_t(227) * 1024) ? 2 : 1);
+    const int64_t units = int64_t(tiles) * kvol;
     int64_t maxs = ceil_div<int64_t>(rows, 256);
-    nsplit = int(want < 1 ? 1 : (want > maxs ? maxs : want));
-    if (int64_t(kvol) * nsplit > 65535) nsplit = 65535 / kvol;
-    if (nsplit < 1) nsplit = 1;
+    if (maxs > 64) maxs = 64;
+    if (maxs * kvol > 65535) maxs = 65535 / kvol;
+    double best = 1e30;
+    for (int64_t ns = 1; ns <= maxs; ++ns) {
+      const double cost = double(ceil_div<int64_t>(units * ns, slots)) / double(ns);
+      if (cost < best * 0.98) { best = cost; nsplit = int(ns); }
+    }
   }
   p.nsplit = nsplit;
   p.chunk = round_up(int(ceil_div<int64_t>(rows > 0 ? rows : 1, nsplit)), kSliceK);
   p.use_atomic = (nsplit > 1 || accumulate) ? 1 : 0;
   if (p.use_atomic && !accumulate)
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
-  const int b_panels = (p.n_tile + 63) / 64;
-  const int stage_bytes = 2 * 8192 + b_panels * 8192;
-  p.stages = pick_stages(stage_bytes, 1024);
-  const size_t smem = size_t(p.stages) * stage_bytes + 1024;
   dim3 grid(unsigned(tiles), unsigned(kvol * nsplit));
   WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   conv_wgrad_umma_kernel<<<grid, kThreads, smem, st>>>(p);
