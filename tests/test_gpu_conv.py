@@ -239,3 +239,19 @@ def test_wgrad_launch_hint_never_drops_pairs(cuda_device):
         Fsp.hints.stop()
     assert int(pair_num.max()) > 256
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("rblk", [1, 2, 3, 4])
+def test_row_blocked_tiles(cuda_device, rblk):
+    """The apply kernel may give one CTA up to four 128-row blocks that share each weight slice.  Force
+    every blocking on a problem with a ragged last block (forward, dgrad and bias), bf16 mode."""
+    from waveformml_b200 import _lib
+    torch.manual_seed(8)
+    B = 420
+    idx, feats = events(B, 35, 72)
+    _lib.load().wfsp_set_option(b"apply_row_blocks", rblk)
+    try:
+        g, refs = run_pair([spconv.SparseConv2d(72, 40, 3, 1, 1, 1, 1, True)], idx, feats, B, cuda_device, "bf16")
+    finally:
+        _lib.load().wfsp_set_option(b"apply_row_blocks", 0)
+    check_all(g, refs, "bf16", "row blocks %d" % rblk)

@@ -33,6 +33,7 @@ int sm_count() {
 }
 
 void set_force_hash(int v);
+void set_force_rblk(int v);
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
@@ -78,6 +79,7 @@ extern "C" int wfsp_device_info(int* sm, int* major, int* minor) {
 // test hook: force the open-addressing hash table in the rulebook builder even for small grids
 extern "C" int wfsp_set_option(const char* name, int value) {
   if (strcmp(name, "rulebook_force_hash") == 0) { set_force_hash(value); return WFSP_OK; }
+  if (strcmp(name, "apply_row_blocks") == 0) { set_force_rblk(value); return WFSP_OK; }
   return set_error(WFSP_EINVAL, "unknown option %s", name);
 }
 

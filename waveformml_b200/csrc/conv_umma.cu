@@ -40,7 +40,8 @@ constexpr int kSliceK = 64;   // reduction elements per stage (one 128 B swizzle
 constexpr int kABytes = kTileM * 128;
 constexpr int kMaxStages = 8;
 constexpr int kNbrStageK = 32;  // kernel volumes up to this keep the CTA's neighbour tile in smem
-constexpr int kSmemMax = 200 * 1024;
+constexpr int kSmemMax = 222 * 1024;
+constexpr int kMaxRowBlocks = 4;  // 128-row blocks per CTA of the apply kernel
 constexpr int kEpiPitch = 36;  // words per row of a warp's 32 x 32 epilogue tile (16-byte aligned, conflict-free)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -51,23 +52,22 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- weight preparation: fp32 [kvol][c_red][c_dst] (or transposed) -> bf16 [kvol][n_pad][kc_pad]
-__global__ void __launch_bounds__(256) prep_weight_kernel(const float* __restrict__ w, int kvol, int c_red,
-                                                          int c_dst, int transpose_w, __nv_bfloat16* __restrict__ wt,
-                                                          int n_pad, int kc_pad) {
-  const int64_t total = int64_t(kvol) * n_pad * kc_pad;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    int c = int(i % kc_pad);
-    int64_t t = i / kc_pad;
-    int n = int(t % n_pad);
-    int k = int(t / n_pad);
-    float v = 0.f;
-    if (c < c_red && n < c_dst) {
-      const float* wk = w + int64_t(k) * c_red * c_dst;
-      v = transpose_w ? wk[int64_t(n) * c_red + c] : wk[int64_t(c) * c_dst + n];
-    }
-    wt[i] = __float2bfloat16_rn(v);
-  }
+// ---- weight preparation: fp32 [kvol][c_red][c_dst] (or transposed) -> bf16 tiles
+// [kvol][kc_pad/64][n_pad][64], zero padded, each row's eight 16-byte chunks already permuted by the
+// 128-byte swizzle (chunk ^ (row & 7)).  Rows n0 .. n0+n_tile of one (offset, 64-channel slice) are then
+// one contiguous block of n_tile * 128 bytes that a single bulk copy (cp.async.bulk) drops into shared
+// memory exactly as the UMMA descriptor expects it.
+__device__ __forceinline__ float prep_weight_value(const float* __restrict__ w, int64_t i, int c_red, int c_dst,
+                                                   int transpose_w, int n_pad, int num_kb) {
+  const int e = int(i & 7), pc = int((i >> 3) & 7);
+  int64_t t = i >> 6;
+  const int n = int(t % n_pad);
+  t /= n_pad;
+  const int kb = int(t % num_kb), k = int(t / num_kb);
+  const int c = kb * 64 + ((pc ^ (n & 7)) << 3) + e;
+  if (c >= c_red || n >= c_dst) return 0.f;
+  const float* wk = w + int64_t(k) * c_red * c_dst;
+  return transpose_w ? wk[int64_t(n) * c_red + c] : wk[int64_t(c) * c_dst + n];
 }
 
 // ---- activation cast: fp32 [n][c] -> bf16 [n][c_pad], zero padded; one 16-byte chunk per thread
@@ -101,19 +101,10 @@ __global__ void __launch_bounds__(256) prep_and_cast_kernel(const float* __restr
                                                             int transpose_w, __nv_bfloat16* __restrict__ wt, int n_pad,
                                                             int kc_pad, int prep_blocks, CastJob job) {
   if (int(blockIdx.x) < prep_blocks) {
+    const int num_kb = kc_pad / 64;
     const int64_t total = int64_t(kvol) * n_pad * kc_pad;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(prep_blocks) * blockDim.x) {
-      int c = int(i % kc_pad);
-      int64_t t = i / kc_pad;
-      int n = int(t % n_pad);
-      int k = int(t / n_pad);
-      float v = 0.f;
-      if (c < c_red && n < c_dst) {
-        const float* wk = w + int64_t(k) * c_red * c_dst;
-        v = transpose_w ? wk[int64_t(n) * c_red + c] : wk[int64_t(c) * c_dst + n];
-      }
-      wt[i] = __float2bfloat16_rn(v);
-    }
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(prep_blocks) * blockDim.x)
+      wt[i] = __float2bfloat16_rn(prep_weight_value(w, i, c_red, c_dst, transpose_w, n_pad, num_kb));
     return;
   }
   const int64_t n = job.n_dev ? int64_t(*job.n_dev) : job.n;
@@ -152,13 +143,49 @@ struct PipeBarriers {
   uint64_t done;
 };
 
-__device__ __forceinline__ void init_pipe(PipeBarriers& b) {
+__device__ __forceinline__ void init_pipe(PipeBarriers& b, uint32_t full_count) {
   for (int s = 0; s < kMaxStages; ++s) {
-    mbar_init(&b.full[s], kProducerThreads);
+    mbar_init(&b.full[s], full_count);
     mbar_init(&b.free_[s], 1);
   }
   mbar_init(&b.done, 1);
   fence_mbar_init();
+}
+
+// one arrival on `bar` that also announces `bytes` of bulk-copy traffic to wait for
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy (no tensor map): `bytes` contiguous bytes global -> shared, completion counted on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// TMEM -> registers (thread = row) -> the warp's shared-memory tile -> global, the warp writing whole row
+// segments so the stores are coalesced whatever the channel count (float4 / float2 / scalar by the
+// alignment the row pitch allows).  acc: 32 columns of this thread's row.
+template <int V>
+__device__ __forceinline__ void store_tile_rows(const float* tile, float* dst, int64_t pitch, int rmax, int ncols,
+                                                int c_left, const float* bias, int lane) {
+  constexpr int kLanesPerRow = 32 / V;  // lanes covering the 32 columns of one row
+  constexpr int kRowsPerIt = 32 / kLanesPerRow;
+  const int c = (lane % kLanesPerRow) * V;
+  if (c >= ncols || c >= c_left) return;  // V divides c_dst, so a vector is never cut by the row end
+  float bv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) bv[e] = bias ? __ldg(bias + c + e) : 0.f;
+#pragma unroll 4
+  for (int r = lane / kLanesPerRow; r < rmax; r += kRowsPerIt) {
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = tile[r * kEpiPitch + c + e] + bv[e];
+    float* o = dst + int64_t(r) * pitch + c;
+    if (V == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (V == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+    else o[0] = v[0];
+  }
 }
 
 struct ApplyParams {
@@ -166,31 +193,39 @@ struct ApplyParams {
   const __nv_bfloat16* wt; int n_pad, kc_pad;
   const float* bias; const int32_t* nbr; int kvol;
   float* dst; int64_t n_dst; int c_dst;
-  int n_tile, stages;
+  int n_tile, stages, rblk, acc_stride, staged;
   const int32_t* n_src_dev; const int32_t* n_dst_dev;
 };
 
+// A CTA owns rblk (1..4) consecutive 128-row blocks of destination rows and one column tile.  Every
+// pipeline stage holds the gathered A slice of each row block plus ONE weight slice shared by all of
+// them, so the weights -- the larger half of the operand traffic when the channel counts are a few
+// hundred -- cross L2 -> SM once per rblk row blocks.  Accumulators: rblk x n_tile fp32 columns of TMEM.
+template <int RB>
 __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyParams pp) {
   ApplyParams p = pp;
   if (p.n_src_dev) p.n_src = *p.n_src_dev;
   if (p.n_dst_dev) p.n_dst = *p.n_dst_dev;
-  if (int64_t(blockIdx.x) * kTileM >= p.n_dst) return;  // capacity-sized grid: nothing live in this tile
+  const int64_t row0 = int64_t(blockIdx.x) * (kTileM * RB);
+  if (row0 >= p.n_dst) return;  // capacity-sized grid: nothing live in this tile
   extern __shared__ uint8_t smem_raw[];
   __shared__ PipeBarriers bars;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_active[WFSP_MAX_KVOL / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row0 = int64_t(blockIdx.x) * kTileM;
   const int n0 = blockIdx.y * p.n_tile;
+  int rows_left = int(p.n_dst - row0 < int64_t(kTileM * RB) ? p.n_dst - row0 : int64_t(kTileM * RB));
+  const int rb_live = (rows_left + kTileM - 1) / kTileM;  // row blocks with at least one live row
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = kABytes + uint32_t(p.n_tile) * 128u;
+  const uint32_t a_bytes = uint32_t(RB) * kABytes;
+  const uint32_t stage_bytes = a_bytes + uint32_t(p.n_tile) * 128u;
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + uint32_t(p.stages) * stage_bytes);
-  const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(p.n_tile));
-  const bool staged = p.nbr != nullptr && p.kvol <= kNbrStageK;
+  const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(RB * p.acc_stride));
+  const bool staged = p.nbr != nullptr && p.staged;
 
   for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kThreads) s_active[i] = 0;
-  if (tid == 0) init_pipe(bars);
+  if (tid == 0) init_pipe(bars, kProducerThreads + 1);
   if (warp == 4) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
@@ -200,20 +235,30 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  // neighbour tile of this CTA: which kernel offsets are active, and (small kernels) a smem copy
+  // neighbour tile of this CTA: which kernel offsets are active, and (small kernels) a smem copy.
+  // Loads are issued eight at a time before any is used: one memory round trip per batch.
   if (p.nbr) {
-    const int total = kTileM * p.kvol;
-    int64_t rows_left = p.n_dst - row0;
-    if (rows_left > kTileM) rows_left = kTileM;
-    const int limit = int(rows_left) * p.kvol;
+    const int total = rb_live * kTileM * p.kvol;
+    const int limit = rows_left * p.kvol;
     const int32_t* base = p.nbr + row0 * p.kvol;
-    for (int i = tid; i < total; i += kThreads) {
-      int v = i < limit ? __ldg(base + i) : -1;
-      if (v >= p.n_src) v = -1;
-      if (staged) s_nbr[i] = v;
-      if (v >= 0) {
-        const int k = i % p.kvol;
-        atomicOr(&s_active[k >> 5], 1u << (k & 31));
+    for (int i0 = tid; i0 < total; i0 += kThreads * 8) {
+      int v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * kThreads;
+        v[j] = i < limit ? __ldg(base + i) : -1;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * kThreads;
+        if (i < total) {
+          const int vv = v[j] >= p.n_src ? -1 : v[j];
+          if (staged) s_nbr[i] = vv;
+          if (vv >= 0) {
+            const int k = i % p.kvol;
+            atomicOr(&s_active[k >> 5], 1u << (k & 31));
+          }
+        }
       }
     }
   } else if (tid == 0) {
@@ -225,21 +270,21 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   int n_active = 0;
   for (int w = 0; w < (p.kvol + 31) / 32; ++w) n_active += __popc(s_active[w]);
   const int total_iters = n_active * num_kb;
+  const uint32_t smem0 = smem_u32(smem);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
-    // Everything that does not change along the reduction is hoisted: the swizzled shared-memory
-    // offset of this thread's chunk (rows rsub + 16 i are 2048 B apart), the global row pointers of
-    // the current offset, the number of slices in which the chunk lies inside the padded row.
+    // A: 16-byte cp.async of this thread's chunk of 8 rows per row block (rows rsub + 16 i are 2048 B
+    // apart in the swizzled tile); B: thread 0 issues one bulk copy of the pre-swizzled weight slice.
     const int c16 = tid & 7;    // 16-byte chunk inside the 128-byte slice row
     const int rsub = tid >> 3;  // this thread covers tile rows rsub + 16*i
     const uint32_t off0 = sw128_offset(uint32_t(rsub), uint32_t(c16));
-    const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;
+    const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;  // slices in which the chunk is inside the row
     int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
     if (n_lim > p.n_tile) n_lim = p.n_tile;
-    const size_t a_row_bytes = size_t(p.c_pad) * 2, w_row_bytes = size_t(p.kc_pad) * 2;
+    const uint32_t b_bytes = uint32_t(n_lim) * 128u;
+    const size_t a_row_bytes = size_t(p.c_pad) * 2;
     const char* src_c = reinterpret_cast<const char*>(p.src) + c16 * 16;
-    const uint32_t smem0 = smem_u32(smem);
     int s = 0, it = 0;
     uint32_t ph = 0;
     for (int kw = 0; kw < (p.kvol + 31) / 32; ++kw) {
@@ -247,112 +292,110 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
       while (mask) {
         const int k = kw * 32 + __ffs(mask) - 1;
         mask &= mask - 1;
-        const char* ga[8];
-        uint32_t asz[8];
+        int rows[RB * 8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 16 * i;
-          int v;
-          if (!p.nbr) {
-            v = (row0 + r < p.n_dst) ? int(row0 + r) : -1;
-          } else if (staged) {
-            v = s_nbr[r * p.kvol + k];
-          } else {
-            v = (row0 + r < p.n_dst) ? __ldg(p.nbr + (row0 + r) * p.kvol + k) : -1;
-            if (v >= p.n_src) v = -1;
+        for (int rb = 0; rb < RB; ++rb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rb * kTileM + rsub + 16 * i;
+            int v = -1;
+            if (rb < rb_live) {
+              if (!p.nbr) {
+                v = r < rows_left ? int(row0 + r) : -1;
+              } else if (staged) {
+                v = s_nbr[r * p.kvol + k];
+              } else if (r < rows_left) {
+                v = __ldg(p.nbr + (row0 + r) * p.kvol + k);
+                if (v >= p.n_src) v = -1;
+              }
+            }
+            rows[rb * 8 + i] = v;
           }
-          asz[i] = v >= 0 ? 16u : 0u;
-          ga[i] = src_c + (v >= 0 ? size_t(v) * a_row_bytes : size_t(0));
         }
-        const char* wk = reinterpret_cast<const char*>(p.wt + (int64_t(k) * p.n_pad + n0 + rsub) * p.kc_pad) + c16 * 16;
+        const char* wk = reinterpret_cast<const char*>(p.wt) + ((size_t(k) * num_kb) * p.n_pad + n0) * 128;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
-          const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
-          const uint32_t sb = sa + kABytes;
-          const uint32_t colm = kb < kb_lim ? 16u : 0u;
+          const uint32_t sa = smem0 + uint32_t(s) * stage_bytes;
+          if (tid == 0) {
+            mbar_arrive_expect_tx(&bars.full[s], b_bytes);
+            bulk_copy_g2s(sa + a_bytes, wk + size_t(kb) * p.n_pad * 128, b_bytes, &bars.full[s]);
+          }
+          const bool col_ok = kb < kb_lim;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cp_async16(sa + i * 2048, ga[i] + kb * 128, asz[i] & colm);
-          const char* wb = wk + kb * 128;
-          int n = rsub;
-          uint32_t sbn = sb;
-          for (; n < n_lim; n += 16, sbn += 2048, wb += 16 * w_row_bytes) cp_async16(sbn, wb, 16u);
-          for (; n < p.n_tile; n += 16, sbn += 2048) cp_async16(sbn, p.wt, 0u);
+          for (int rb = 0; rb < RB; ++rb) {
+            if (rb < rb_live) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int v = rows[rb * 8 + i];
+                const bool ok = col_ok && v >= 0;
+                cp_async16(sa + off0 + rb * kABytes + i * 2048, src_c + (ok ? size_t(v) * a_row_bytes + kb * 128 : size_t(0)),
+                           ok ? 16u : 0u);
+              }
+            }
+          }
           cp_async_arrive_noinc(&bars.full[s]);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
     // ------------------------------------------------------------------ epilogue
-    // TMEM -> registers (thread = row) -> this warp's shared-memory tile -> global with a warp writing
-    // whole row segments, so the stores are coalesced whatever the channel count.  The pipeline's
-    // stage memory is free once `done` has fired.
+    // The pipeline's stage memory is free once `done` has fired: warp w stages its 32 x 32 blocks there.
     if (total_iters > 0) {
       mbar_wait(&bars.done, 0);
       tc_fence_after();
     }
     float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
-    const int64_t wrow0 = row0 + warp * 32;
-    const bool vec_ok = (p.c_dst & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0;
-    for (int col = 0; col < p.n_tile; col += 32) {
-      const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
-      uint32_t acc[32];
-      if (total_iters > 0) {
-        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        if (ncols > 16)
-          tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col + 16), *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tmem_ld_wait();
-      } else {
+    const bool al16 = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(p.dst) & 7) == 0;
+    const int vec = ((p.c_dst & 3) == 0 && al16) ? 4 : (((p.c_dst & 1) == 0 && al8) ? 2 : 1);
+    for (int rb = 0; rb < rb_live; ++rb) {
+      const int wr0 = rb * kTileM + warp * 32;  // first row of this warp's block inside the CTA tile
+      int rmax = rows_left - wr0;
+      if (rmax > 32) rmax = 32;
+      for (int col = 0; col < p.n_tile; col += 32) {
+        const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
+        uint32_t acc[32];
+        if (total_iters > 0) {
+          const uint32_t taddr = tmem + (uint32_t(warp * 32) << 16) + uint32_t(rb * p.acc_stride + col);
+          tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          if (ncols > 16) tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0u;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (4 * q < ncols)
-          *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-      __syncwarp();
-      if (vec_ok) {
-        const int c4 = (lane & 7) * 4, cc = n0 + col + c4;
-        if (c4 < ncols && cc < p.c_dst) {
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bv = make_float4(__ldg(p.bias + cc), __ldg(p.bias + cc + 1), __ldg(p.bias + cc + 2), __ldg(p.bias + cc + 3));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = j * 4 + (lane >> 3);
-            if (wrow0 + r < p.n_dst) {
-              float4 v = *reinterpret_cast<const float4*>(tile + r * kEpiPitch + c4);
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              *reinterpret_cast<float4*>(p.dst + (wrow0 + r) * p.c_dst + cc) = v;
-            }
-          }
+          for (int e = 0; e < 32; ++e) acc[e] = 0u;
         }
-      } else {
-        const int cc = n0 + col + lane;
-        if (lane < ncols && cc < p.c_dst) {
-          const float bv = p.bias ? __ldg(p.bias + cc) : 0.f;
-          int64_t rmax = p.n_dst - wrow0;
-          if (rmax > 32) rmax = 32;
-          float* o = p.dst + wrow0 * p.c_dst + cc;
-          for (int r = 0; r < int(rmax); ++r) o[int64_t(r) * p.c_dst] = tile[r * kEpiPitch + lane] + bv;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (4 * q < ncols)
+            *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        __syncwarp();
+        if (rmax > 0) {
+          const int cc = n0 + col;
+          float* o = p.dst + (row0 + wr0) * p.c_dst + cc;
+          const float* bias = p.bias ? p.bias + cc : nullptr;
+          if (vec == 4) store_tile_rows<4>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
+          else if (vec == 2) store_tile_rows<2>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
+          else store_tile_rows<1>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
-    const uint32_t smem0 = smem_u32(smem);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < total_iters; ++it) {
       mbar_wait(&bars.full[s], ph);
       fence_proxy_async_smem();
       tc_fence_after();
-      const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + kABytes;
+      const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
+      for (int rb = 0; rb < rb_live; ++rb) {
 #pragma unroll
-      for (int kk = 0; kk < kSliceK / 16; ++kk) {
-        const uint64_t adesc = make_desc_sw128(a_addr + kk * 32, 16, 1024);
-        const uint64_t bdesc = make_desc_sw128(b_addr + kk * 32, 16, 1024);
-        mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kSliceK / 16; ++kk) {
+          const uint64_t adesc = make_desc_sw128(a_addr + rb * kABytes + kk * 32, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(b_addr + kk * 32, 16, 1024);
+          mma_bf16(tmem + uint32_t(rb * p.acc_stride), adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
       }
       mma_commit(&bars.free_[s]);
       if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -398,7 +441,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const uint32_t stage_bytes = a_bytes + uint32_t(b_panels) * 8192u;
   const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(p.n_tile));
 
-  if (tid == 0) init_pipe(bars);
+  if (tid == 0) init_pipe(bars, kProducerThreads);
   if (warp == 4) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
@@ -537,6 +580,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+int g_force_rblk = 0;  // tuning knob (wfsp_set_option "apply_row_blocks"): 0 = cost model
+
 // column tiling of the destination channels: as few tiles as possible (<= 256 columns each) when
 // there are enough row tiles to fill the machine, narrower tiles (down to 32 columns) when there are
 // not -- a small problem is bound by the serial k-loop of its few CTAs, so spreading the columns over
@@ -570,6 +615,8 @@ int pick_stages(int stage_bytes, int extra_bytes) {
 
 }  // namespace
 
+void set_force_rblk(int v) { g_force_rblk = v; }
+
 size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) {
   return apply_plan(kvol, n_src, c_red, c_dst).total;
 }
@@ -599,15 +646,49 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     WFSP_CHECK_LAUNCH();
   }
 
-  ApplyParams p{act, n_src, a.c_pad, wt, a.n_pad, a.kc_pad, bias, nbr, kvol, dst, n_dst, c_dst, n_tile, 2,
-                n_src_dev, n_dst_dev};
-  const int stage_bytes = kABytes + n_tile * 128;
-  const int nbr_bytes = (nbr != nullptr && kvol <= kNbrStageK) ? kTileM * kvol * 4 : 0;
+  ApplyParams p{};
+  p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
+  p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst; p.n_tile = n_tile;
+  p.n_src_dev = n_src_dev; p.n_dst_dev = n_dst_dev;
+  p.acc_stride = round_up(n_tile, 32);
+  // Row blocking: rblk 128-row blocks per CTA share every weight slice.  Modelled cost of a launch =
+  // rounds of CTAs over the SMs x (operand KB a CTA moves + a per-CTA prologue / epilogue term); the weight
+  // slice (n_tile * 128 B per stage) is amortised over rblk blocks, the rounds quantise.  Only worth it
+  // when the row blocks exceed one round -- small problems keep rblk = 1 and as many CTAs as possible.
+  const int64_t row_blocks = ceil_div<int64_t>(live, kTileM);
+  const int iters_est = kvol * (a.kc_pad / kSliceK);
+  int best_r = 1;
+  double best_cost = 1e300;
+  for (int r = 1; r <= kMaxRowBlocks; ++r) {
+    if (r * p.acc_stride > 512) break;
+    const int stage_b = r * kABytes + n_tile * 128;
+    const int nbr_b = (nbr != nullptr && kvol <= kNbrStageK) ? r * kTileM * kvol * 4 : 0;
+    if (2 * stage_b + nbr_b + 1024 > kSmemMax) break;
+    const int64_t ctas = ceil_div<int64_t>(row_blocks, r) * n_tiles;
+    const double rounds = double(ceil_div<int64_t>(ctas, sm_count()));
+    const double cost = rounds * (double(iters_est) * (r * 16.0 + n_tile / 8.0) + 48.0 * r + 48.0);
+    if (cost < best_cost * 0.97) { best_cost = cost; best_r = r; }
+  }
+  if (g_force_rblk > 0 && g_force_rblk <= kMaxRowBlocks && g_force_rblk * p.acc_stride <= 512) best_r = g_force_rblk;
+  p.rblk = best_r;
+  const int stage_bytes = p.rblk * kABytes + n_tile * 128;
+  p.staged = (nbr != nullptr && kvol <= kNbrStageK) ? 1 : 0;
+  const int nbr_bytes = p.staged ? p.rblk * kTileM * kvol * 4 : 0;
   p.stages = pick_stages(stage_bytes, nbr_bytes + 1024);
   const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + 1024;
-  dim3 grid(unsigned(ceil_div<int64_t>(n_dst, kTileM)), unsigned(n_tiles));
-  WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  conv_apply_umma_kernel<<<grid, kThreads, smem, st>>>(p);
+  if (smem > size_t(227) * 1024) return set_error(WFSP_EUNSUPPORTED, "conv_apply tile needs %zu B of shared memory", smem);
+  dim3 grid(unsigned(ceil_div<int64_t>(n_dst, int64_t(kTileM) * p.rblk)), unsigned(n_tiles));
+  switch (p.rblk) {
+#define WFSP_LAUNCH_APPLY(RB)                                                                                        \
+    case RB:                                                                                                         \
+      WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           int(smem)));                                                              \
+      conv_apply_umma_kernel<RB><<<grid, kThreads, smem, st>>>(p);                                                   \
+      break;
+    WFSP_LAUNCH_APPLY(1) WFSP_LAUNCH_APPLY(2) WFSP_LAUNCH_APPLY(3) WFSP_LAUNCH_APPLY(4)
+#undef WFSP_LAUNCH_APPLY
+    default: return set_error(WFSP_EINVAL, "bad row blocking %d", p.rblk);
+  }
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
