@@ -211,6 +211,69 @@ int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int3
                      const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
                      void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (6) bf16-resident pipeline.  The entries of (3) and (5) take and return fp32 [rows, channels]
+ * tensors, which is what the torch modules between the reference's sparse layers exchange
+ * (src/models/SPConvBlocks.py:498-508: SparseConv2d, nn.BatchNorm1d, nn.ReLU).  A caller that owns a
+ * whole SparseSequential stack (waveformml_b200/spconv/fused.py) can instead keep the tensor-core
+ * operands resident in bf16 between layers: every activation is cast ONCE, by the kernel that
+ * produces it, the weights of all layers are prepared by one launch per step, and forward /
+ * dgrad / wgrad read those copies directly.  Same arithmetic as WFSP_MATH_BF16 in (3): bf16 operands,
+ * fp32 accumulation, fp32 results.
+ *
+ * bf16 activation format: [rows, WFSP_BF16_PITCH(c)] row-major, channels c .. pitch-1 zero.
+ * Prepared weight format: opaque, wfsp_prepared_weight_bytes() bytes, made by wfsp_prep_weights for
+ * one (weight, direction): transpose_w = 0 for forward / inverse forward, 1 for dgrad.
+ */
+#define WFSP_BF16_PITCH(c) (((c) + 7) / 8 * 8)
+
+typedef struct wfsp_prep_job {
+  const float* weight; /* fp32 [kvol, c_red, c_dst], or [kvol, c_dst, c_red] if transpose_w      */
+  void* out;           /* prepared bf16 weights, wfsp_prepared_weight_bytes(kvol, c_red, c_dst) */
+  int kvol, c_red, c_dst, transpose_w;
+} wfsp_prep_job;
+
+size_t wfsp_prepared_weight_bytes(int kvol, int c_red, int c_dst);
+/* jobs_host: HOST array; one kernel launch per 16 jobs */
+int wfsp_prep_weights(const wfsp_prep_job* jobs_host, int n_jobs, wfsp_stream_t stream);
+
+/* fp32 [n_rows, c] -> bf16 [n_rows, WFSP_BF16_PITCH(c)] */
+int wfsp_cast_rows_bf16(const float* src, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                        void* dst_bf16, wfsp_stream_t stream);
+
+/* wfsp_conv_apply on bf16 activations and prepared weights (no workspace, no cast pass) */
+int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
+                         const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,
+                         float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                         int c_dst, wfsp_stream_t stream);
+
+/* wfsp_conv_wgrad on bf16 rows (a = layer input, b = gradient of the layer output) */
+int wfsp_conv_wgrad_bf16(const void* a_bf16, int64_t n_a, const int32_t* n_a_dev, int c_a,
+                         const void* b_bf16, int64_t n_b, const int32_t* n_b_dev, int c_b,
+                         const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num,
+                         int kvol, int64_t pair_pitch, int64_t pairs_hint, float* d_weight,
+                         int accumulate, wfsp_stream_t stream);
+
+/* BatchNorm1d(+ReLU) as in (5) with optional outputs: y / dx fp32 [rows, c] and / or y_bf16 / dx_bf16
+ * in the bf16 activation format (either may be NULL, not both). */
+int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                       const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int training, int relu,
+                       float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                       void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+
+int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
+                       int c, const float* gamma, const float* beta, const float* save_mean,
+                       const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
+                       float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+
+/* a convolution followed by nn.ReLU (or nothing) without BatchNorm: y = relu?(x), and its backward
+ * dx = dy * (x > 0 or no relu), with the same optional outputs */
+int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, int relu,
+                 float* y, void* y_bf16, wfsp_stream_t stream);
+int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                 int relu, float* dx, void* dx_bf16, wfsp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,14 +131,64 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16_per_layer"])
 @pytest.mark.parametrize("name,factory,cin", CASES, ids=[c[0] for c in CASES])
 def test_layer_parity(cuda_device, name, factory, cin, mode):
+    """bf16: the stack runs as one fused node with bf16-resident operands (spconv/fused.py);
+    bf16_per_layer: the same kernels module by module through the fp32-in / fp32-out C entries."""
     torch.manual_seed(sum(name.encode()))
     B = 19
     idx, feats = events(B, 21, cin)
-    g, refs = run_pair(factory(), idx, feats, B, cuda_device, mode)
+    spconv.set_fused(mode != "bf16_per_layer")
+    try:
+        mode = "bf16" if mode == "bf16_per_layer" else mode
+        g, refs = run_pair(factory(), idx, feats, B, cuda_device, mode)
+    finally:
+        spconv.set_fused(True)
     check_all(g, refs, mode, name)
+
+
+def test_fused_equals_per_layer(cuda_device):
+    """The fused stack rounds the same values to bf16 at the same points as the per-layer path, so
+    a conv-BN-ReLU stack must agree with it closely (outputs, input and parameter gradients, BN buffers)."""
+    B = 40
+    idx, feats = events(B, 23, 30)
+
+    def make():
+        torch.manual_seed(11)
+        return spconv.SparseSequential(
+            spconv.SparseConv2d(30, 26, 1, 1, 0, 1, 1, False), torch.nn.BatchNorm1d(26), torch.nn.ReLU(),
+            spconv.SparseConv2d(26, 20, 3, 1, 1, 1, 1, True, indice_key="k"), torch.nn.ReLU(),
+            spconv.SparseInverseConv2d(20, 12, 3, "k", bias=False),
+            # bias=False before BatchNorm: its gradient is identically zero in exact arithmetic (pure round-off)
+            spconv.SubMConv2d(12, 9, 3, bias=False, indice_key="subm0"), torch.nn.BatchNorm1d(9),
+            spconv.ToDense()).to(cuda_device)
+
+    res = []
+    for fused_on in (True, False):
+        spconv.set_fused(fused_on)
+        try:
+            net = make()
+            f = feats.clone().to(cuda_device).requires_grad_(True)
+            y = net(spconv.SparseConvTensor(f, idx.to(cuda_device), [14, 11], B))
+            gen = torch.Generator().manual_seed(5)
+            w = torch.randn(tuple(y.shape), generator=gen).to(cuda_device)
+            (y * w).sum().backward()
+            res.append((y.detach(), f.grad, [p.grad for p in net.parameters()],
+                        [b.clone() for b in net.buffers()]))
+        finally:
+            spconv.set_fused(True)
+    (ya, fa, pa, ba), (yb, fb, pb, bb) = res
+    # not bit-equal: the eager per-layer path normalises with torch's BatchNorm1d, whose statistics differ
+    # from ours in the last fp32 bits, which can flip an occasional bf16 rounding of an activation
+    def close_(a, b):
+        torch.testing.assert_close(a, b, rtol=5e-3, atol=5e-3 * max(float(b.abs().max()), 1e-6))
+    close_(ya, yb)
+    close_(fa, fb)
+    for a, b in zip(pa, pb):
+        close_(a, b)
+    for a, b in zip(ba, bb):  # BatchNorm running statistics and step counters
+        torch.testing.assert_close(a.float(), b.float(), rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])

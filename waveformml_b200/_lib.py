@@ -41,7 +41,26 @@ SIGNATURES = {
     "wfsp_bn_relu_fwd": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,
                                 _sz, _vp]),
     "wfsp_bn_relu_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    # (6) bf16-resident pipeline
+    "wfsp_prepared_weight_bytes": (_sz, [_int, _int, _int]),
+    "wfsp_prep_weights": (_int, [_vp, _int, _vp]),
+    "wfsp_cast_rows_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp]),
+    "wfsp_conv_apply_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp]),
+    "wfsp_conv_wgrad_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _i64, _vp,
+                                    _int, _vp]),
+    "wfsp_bn_relu_fwd_x": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,
+                                  _vp, _sz, _vp]),
+    "wfsp_bn_relu_bwd_x": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _sz,
+                                  _vp]),
+    "wfsp_act_fwd": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
+    "wfsp_act_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
 }
+
+
+class PrepJob(ctypes.Structure):
+    """struct wfsp_prep_job (include/wfsp.h)"""
+    _fields_ = [("weight", ctypes.c_void_p), ("out", ctypes.c_void_p), ("kvol", ctypes.c_int), ("c_red", ctypes.c_int),
+                ("c_dst", ctypes.c_int), ("transpose_w", ctypes.c_int)]
 
 _lib = None
 

@@ -57,6 +57,17 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
                     const int32_t* n_b_dev, int64_t pairs_hint, cudaStream_t st);
 
+size_t prepared_weight_bytes(int kvol, int c_red, int c_dst);
+int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st);
+int cast_rows_bf16(const float* src, int64_t n, const int32_t* n_dev, int c, void* dst16, cudaStream_t st);
+int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
+                           const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, cudaStream_t st);
+int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const __nv_bfloat16* b16, int64_t n_b, int c_b,
+                           const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
+                           int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
+                           cudaStream_t st);
+
 }  // namespace wfsp
 
 using namespace wfsp;
@@ -122,4 +133,44 @@ extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_d
     return conv_wgrad_umma(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
                            accumulate, workspace, workspace_bytes, n_a_dev, n_b_dev, pairs_hint, as_stream(stream));
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
+}
+
+// ---- (6) bf16-resident pipeline -------------------------------------------------------------------
+extern "C" size_t wfsp_prepared_weight_bytes(int kvol, int c_red, int c_dst) {
+  return prepared_weight_bytes(kvol, c_red, c_dst);
+}
+
+extern "C" int wfsp_prep_weights(const wfsp_prep_job* jobs_host, int n_jobs, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_jobs >= 0 && (n_jobs == 0 || jobs_host != nullptr), "bad job list");
+  return prep_weights_batch(jobs_host, n_jobs, as_stream(stream));
+}
+
+extern "C" int wfsp_cast_rows_bf16(const float* src, int64_t n_rows, const int32_t* n_rows_dev, int c, void* dst_bf16,
+                                   wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1 && src != nullptr && dst_bf16 != nullptr, "bad cast arguments");
+  return cast_rows_bf16(src, n_rows, n_rows_dev, c, dst_bf16, as_stream(stream));
+}
+
+extern "C" int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
+                                    const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,
+                                    float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint, int c_dst,
+                                    wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_src >= 0 && n_dst >= 0 && c_red >= 1 && c_dst >= 1, "bad conv sizes");
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  WFSP_REQUIRE(nbr != nullptr || (kvol == 1 && n_src == n_dst), "identity map needs kvol == 1 and n_src == n_dst");
+  return conv_apply_umma_launch(static_cast<const __nv_bfloat16*>(src_bf16), n_src, c_red,
+                                static_cast<const __nv_bfloat16*>(weight_prepared), bias, nbr, kvol, dst, n_dst, c_dst,
+                                n_src_dev, n_dst_dev, n_dst_hint, as_stream(stream));
+}
+
+extern "C" int wfsp_conv_wgrad_bf16(const void* a_bf16, int64_t n_a, const int32_t* n_a_dev, int c_a, const void* b_bf16,
+                                    int64_t n_b, const int32_t* n_b_dev, int c_b, const int32_t* pair_a,
+                                    const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pair_pitch,
+                                    int64_t pairs_hint, float* d_weight, int accumulate, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_a >= 0 && n_b >= 0 && c_a >= 1 && c_b >= 1 && pair_pitch >= 0, "bad wgrad sizes");
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  (void)n_b_dev;
+  return conv_wgrad_umma_launch(static_cast<const __nv_bfloat16*>(a_bf16), n_a, c_a,
+                                static_cast<const __nv_bfloat16*>(b_bf16), n_b, c_b, pair_a, pair_b, pair_num, kvol,
+                                pair_pitch, d_weight, accumulate, n_a_dev, pairs_hint, as_stream(stream));
 }

@@ -110,16 +110,44 @@ __global__ void __launch_bounds__(128) bn_eval_stats(int c, float eps, const flo
   save_invstd[ch] = rsqrtf(running_var[ch] + eps);
 }
 
+__device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// One thread = 8 consecutive channels of one row.  Outputs (each optional): y fp32 [rows, c] and
+// y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as zero) -- the operand format of
+// the tcgen05 convolution kernels, so the next layer needs no cast pass.
 __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                int relu, float* __restrict__ y) {
-  const int64_t total = live_rows(n_cap, n_dev) * c;
+                                                int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
+  const int cpr = (c + 7) >> 3;
+  const int64_t total = live_rows(n_cap, n_dev) * cpr;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int ch = int(i % c);
-    float v = (x[i] - mean[ch]) * invstd[ch] * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
-    y[i] = (relu && v < 0.f) ? 0.f : v;
+    const int64_t row = i / cpr;
+    const int col = int(i - row * cpr) << 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = col + e;
+      float t = 0.f;
+      if (ch < c) {
+        t = x[row * c + ch];
+        if (mean) t = (t - mean[ch]) * invstd[ch] * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
+        if (relu && t < 0.f) t = 0.f;
+        if (y) y[row * c + ch] = t;
+      }
+      v[e] = t;
+    }
+    if (y16) {
+      uint4 u;
+      u.x = bn_pack_bf16x2(v[0], v[1]); u.y = bn_pack_bf16x2(v[2], v[3]);
+      u.z = bn_pack_bf16x2(v[4], v[5]); u.w = bn_pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(y16 + row * (int64_t(cpr) << 3) + col) = u;
+    }
   }
 }
 
@@ -183,22 +211,45 @@ __global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* 
   d_gamma[ch] = float(s1);
 }
 
+// same thread mapping as bn_apply; mean == nullptr means "no normalisation" (plain ReLU backward)
 __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
                                                     int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                                     const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                                                    int relu, float* __restrict__ dx) {
+                                                    int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16) {
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t total = n * c;
+  const int cpr = (c + 7) >> 3;
+  const int64_t total = n * cpr;
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int ch = int(i % c);
-    const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-    const float xh = (x[i] - mean[ch]) * is;
-    float d = dy[i];
-    if (relu && xh * g + b <= 0.f) d = 0.f;
-    dx[i] = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
+    const int64_t row = i / cpr;
+    const int col = int(i - row * cpr) << 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = col + e;
+      float t = 0.f;
+      if (ch < c) {
+        float d = dy[row * c + ch];
+        if (mean) {
+          const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+          const float xh = (x[row * c + ch] - mean[ch]) * is;
+          if (relu && xh * g + b <= 0.f) d = 0.f;
+          t = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
+        } else {
+          t = (relu && x[row * c + ch] <= 0.f) ? 0.f : d;
+        }
+        if (dx) dx[row * c + ch] = t;
+      }
+      v[e] = t;
+    }
+    if (dx16) {
+      uint4 u;
+      u.x = bn_pack_bf16x2(v[0], v[1]); u.y = bn_pack_bf16x2(v[2], v[3]);
+      u.z = bn_pack_bf16x2(v[4], v[5]); u.w = bn_pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dx16 + row * (int64_t(cpr) << 3) + col) = u;
+    }
   }
 }
 
@@ -223,7 +274,7 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
     const float* __restrict__ x, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
     float* __restrict__ running_var, float momentum, float eps, int training, int relu, float* __restrict__ y,
-    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+    __nv_bfloat16* __restrict__ y16, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   __shared__ float red[kRowLanes][kCh];
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -249,19 +300,26 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
     invstd = on ? rsqrtf(running_var[ch] + eps) : 0.f;
     if (on && ty == 0) { save_mean[ch] = mean; save_invstd[ch] = invstd; }
   }
-  if (!on) return;
+  const int c_pad = (c + 7) & ~7;
+  if (!on) {  // zero padding columns of the bf16 copy
+    if (y16 && ch < c_pad)
+      for (int64_t r = ty; r < n; r += kRowLanes) y16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
+    return;
+  }
   const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
   for (int64_t r = ty; r < n; r += kRowLanes) {
-    const float v = (x[r * c + ch] - mean) * invstd * g + b;
-    y[r * c + ch] = (relu && v < 0.f) ? 0.f : v;
+    float v = (x[r * c + ch] - mean) * invstd * g + b;
+    v = (relu && v < 0.f) ? 0.f : v;
+    if (y) y[r * c + ch] = v;
+    if (y16) y16[r * c_pad + ch] = __float2bfloat16_rn(v);
   }
 }
 
 __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
     const float* __restrict__ x, const float* __restrict__ dy, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_,
-    const float* __restrict__ invstd_, int relu, float* __restrict__ dx, float* __restrict__ d_gamma,
-    float* __restrict__ d_beta) {
+    const float* __restrict__ invstd_, int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+    float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   __shared__ float red[kRowLanes][kCh];
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -280,14 +338,21 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
     }
   s0 = block_col_sum(s0, red, tx, ty);
   s1 = block_col_sum(s1, red, tx, ty);
-  if (!on) return;
+  const int c_pad = (c + 7) & ~7;
+  if (!on) {
+    if (dx16 && ch < c_pad)
+      for (int64_t r = ty; r < n; r += kRowLanes) dx16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
+    return;
+  }
   if (ty == 0) { d_beta[ch] = s0; d_gamma[ch] = s1; }
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
   for (int64_t r = ty; r < n; r += kRowLanes) {
     const float xh = (x[r * c + ch] - m) * is;
     float d = dy[r * c + ch];
     if (relu && xh * g + b <= 0.f) d = 0.f;
-    dx[r * c + ch] = g * is * (d - s0 * inv_n - xh * s1 * inv_n);
+    const float t = g * is * (d - s0 * inv_n - xh * s1 * inv_n);
+    if (dx) dx[r * c + ch] = t;
+    if (dx16) dx16[r * c_pad + ch] = __float2bfloat16_rn(t);
   }
 }
 
@@ -306,18 +371,20 @@ extern "C" size_t wfsp_bn_workspace_bytes(int64_t n_rows, int c) {
   return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRows)) * 2 * c * sizeof(float), 256);
 }
 
-extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
-                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                                int training, int relu, float* y, float* save_mean, float* save_invstd,
-                                void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
+                                  const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                  int training, int relu, float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                                  void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
+  WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "batch norm needs at least one output");
   if (n_rows == 0) return WFSP_OK;
   cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
   if (!training) WFSP_REQUIRE(running_mean && running_var, "eval-mode batch norm needs running statistics");
   if (n_rows <= kSmallRows) {
-    bn_fwd_small<<<ceil_div(c, kCh), dim3(kCh, kRowLanes), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, running_mean,
-                                                                    running_var, momentum, eps, training, relu, y,
-                                                                    save_mean, save_invstd);
+    bn_fwd_small<<<ceil_div((c + 7) & ~7, kCh), dim3(kCh, kRowLanes), 0, st>>>(
+        x, n_rows, n_rows_dev, c, gamma, beta, running_mean, running_var, momentum, eps, training, relu, y, y16,
+        save_mean, save_invstd);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -332,30 +399,40 @@ extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n
                                                         running_var, save_mean, save_invstd);
     count_launches(2);
   } else {
-    WFSP_REQUIRE(running_mean && running_var, "eval-mode batch norm needs running statistics");
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(c, eps, running_mean, running_var, save_mean, save_invstd);
     count_launches(1);
   }
-  bn_apply<<<stream_blocks(n_rows * c), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y);
+  bn_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+                                                                   save_invstd, relu, y, y16);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
 
-extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
-                                const float* gamma, const float* beta, const float* save_mean,
-                                const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
+extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                int training, int relu, float* y, float* save_mean, float* save_invstd,
                                 void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return wfsp_bn_relu_fwd_x(x, n_rows, n_rows_dev, c, gamma, beta, running_mean, running_var, momentum, eps, training,
+                            relu, y, nullptr, save_mean, save_invstd, workspace, workspace_bytes, stream);
+}
+
+extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                                  const float* gamma, const float* beta, const float* save_mean,
+                                  const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
+                                  float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
+  WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "batch norm backward needs at least one output");
   cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
   if (n_rows == 0) {
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_gamma, 0, size_t(c) * 4, st));
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_beta, 0, size_t(c) * 4, st));
     return WFSP_OK;
   }
   if (n_rows <= kSmallRows) {
-    bn_bwd_small<<<ceil_div(c, kCh), dim3(kCh, kRowLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
-                                                                    save_invstd, relu, dx, d_gamma, d_beta);
+    bn_bwd_small<<<ceil_div((c + 7) & ~7, kCh), dim3(kCh, kRowLanes), 0, st>>>(
+        x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -366,9 +443,44 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
   bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
-  bn_bwd_apply<<<stream_blocks(n_rows * c), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
-                                                          save_invstd, d_gamma, d_beta, relu, dx);
+  bn_bwd_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+                                                                       save_invstd, d_gamma, d_beta, relu, dx, dx16);
   count_launches(3);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                                const float* gamma, const float* beta, const float* save_mean,
+                                const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
+                                void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return wfsp_bn_relu_bwd_x(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, dx, nullptr, d_gamma,
+                            d_beta, workspace, workspace_bytes, stream);
+}
+
+// Activation-only blocks (a convolution followed by ReLU / nothing, no BatchNorm): the same streaming
+// kernels with the normalisation switched off.
+extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, int relu, float* y,
+                            void* y_bf16, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
+  WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "needs at least one output");
+  if (n_rows == 0) return WFSP_OK;
+  bn_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, as_stream(stream)>>>(
+      x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c, int relu,
+                            float* dx, void* dx_bf16, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
+  WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "needs at least one output");
+  if (n_rows == 0) return WFSP_OK;
+  bn_bwd_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, as_stream(stream)>>>(
+      x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
+      static_cast<__nv_bfloat16*>(dx_bf16));
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }

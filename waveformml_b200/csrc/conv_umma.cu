@@ -125,6 +125,22 @@ __global__ void __launch_bounds__(256) prep_and_cast_kernel(const float* __restr
   }
 }
 
+// weight preparation of several layers / directions in one launch (the weights of a training step are
+// fixed until the optimiser runs, so every layout the step needs can be made up front)
+constexpr int kMaxPrepJobs = 16;
+struct PrepJob { const float* w; __nv_bfloat16* out; int kvol, c_red, c_dst, transpose_w; int block0, blocks; };
+struct PrepBatch { PrepJob job[kMaxPrepJobs]; int n; };
+
+__global__ void __launch_bounds__(256) prep_weights_batch_kernel(const PrepBatch b) {
+  int j = 0;
+  while (j + 1 < b.n && int(blockIdx.x) >= b.job[j + 1].block0) ++j;
+  const PrepJob& q = b.job[j];
+  const int n_pad = (q.c_dst + 15) / 16 * 16, kc_pad = (q.c_red + 63) / 64 * 64, num_kb = kc_pad / 64;
+  const int64_t total = int64_t(q.kvol) * n_pad * kc_pad;
+  for (int64_t i = (int64_t(blockIdx.x) - q.block0) * blockDim.x + threadIdx.x; i < total; i += int64_t(q.blocks) * blockDim.x)
+    q.out[i] = __float2bfloat16_rn(prep_weight_value(q.w, i, q.c_red, q.c_dst, q.transpose_w, n_pad, num_kb));
+}
+
 int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
   CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8, nullptr};
   const int64_t c0 = a.n * (a.c_pad >> 3), c1 = j1.n * (j1.c_pad >> 3);
@@ -414,11 +430,16 @@ struct WgradParams {
   const int32_t* pair_a; const int32_t* pair_b; const int32_t* pair_num;
   int kvol; int64_t pitch;
   float* dw;
-  int n_tile, m_tiles, nsplit, stages, use_atomic;
+  int n_tile, m_groups, nsplit, stages, use_atomic, acc_stride;
   int64_t chunk;
   const int32_t* n_a_dev;
 };
 
+constexpr int kIdxGroup = 4;  // pair-index loads are issued this many pipeline slices ahead, as one batch
+
+// MT = 128-channel blocks of `a` per CTA: they share every gathered slice of `b` rows and its pair
+// indices (the a-side of d_weight is at most a few hundred channels, so MT = 2 usually covers it).
+template <int MT>
 __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PipeBarriers bars;
@@ -426,20 +447,22 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = blockIdx.y / p.nsplit, split = blockIdx.y % p.nsplit;
-  const int mt = blockIdx.x % p.m_tiles, nt = blockIdx.x / p.m_tiles;
-  const int a_c0 = mt * kTileM, b_c0 = nt * p.n_tile;
+  const int mg = blockIdx.x % p.m_groups, nt = blockIdx.x / p.m_groups;
+  const int a_c0 = mg * (kTileM * MT), b_c0 = nt * p.n_tile;
   const int64_t n_pairs = p.pair_num ? int64_t(p.pair_num[k]) : (p.n_a_dev ? int64_t(*p.n_a_dev) : p.n_a);
   const int64_t begin = int64_t(split) * p.chunk;
   int64_t end = begin + p.chunk;
   if (end > n_pairs || split == p.nsplit - 1) end = n_pairs;  // the last split takes whatever the launch-shape hint missed
   if (begin >= n_pairs && (split > 0 || p.use_atomic)) return;  // nothing to add (uniform per CTA)
   const int iters = begin < end ? int((end - begin + kSliceK - 1) / kSliceK) : 0;
+  int mt_live = (p.c_a - a_c0 + kTileM - 1) / kTileM;  // 128-channel blocks of this CTA that hold real channels
+  if (mt_live > MT) mt_live = MT;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_panels = (p.n_tile + 63) / 64;
-  const uint32_t a_bytes = 2u * 8192u;
+  constexpr uint32_t a_bytes = 2u * MT * 8192u;
   const uint32_t stage_bytes = a_bytes + uint32_t(b_panels) * 8192u;
-  const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(p.n_tile));
+  const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(MT * p.acc_stride));
 
   if (tid == 0) init_pipe(bars, kProducerThreads);
   if (warp == 4) {
@@ -450,6 +473,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  const uint32_t smem0 = smem_u32(smem);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
@@ -457,57 +481,71 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
     const int psub = tid >> 3;  // this thread covers pairs psub + 16*i of the 64-pair slice
     const int32_t* pa = p.pair_a ? p.pair_a + int64_t(k) * p.pitch : nullptr;
     const int32_t* pb = p.pair_b ? p.pair_b + int64_t(k) * p.pitch : nullptr;
-    auto load_idx = [&](int it, int (&ia)[4], int (&ib)[4]) {
+    // Pair indices of kIdxGroup slices are fetched as one batch of independent loads while the previous
+    // group's slices are being issued: one memory round trip per group, off the critical path.
+    auto load_group = [&](int it0, int (&ia)[kIdxGroup][4], int (&ib)[kIdxGroup][4]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t q = begin + int64_t(it) * kSliceK + psub + 16 * i;
-        int va = -1, vb = -1;
-        if (q < end) {
-          va = pa ? __ldg(pa + q) : int(q);
-          vb = pb ? __ldg(pb + q) : int(q);
+      for (int u = 0; u < kIdxGroup; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t q = begin + int64_t(it0 + u) * kSliceK + psub + 16 * i;
+          int va = -1, vb = -1;
+          if (q < end) {
+            va = pa ? __ldg(pa + q) : int(q);
+            vb = pb ? __ldg(pb + q) : int(q);
+          }
+          ia[u][i] = va; ib[u][i] = vb;
         }
-        if (va < 0 || vb < 0 || va >= p.n_a || vb >= p.n_b) { va = -1; vb = -1; }
-        ia[i] = va; ib[i] = vb;
       }
     };
     // loop invariants: swizzled smem offset of this thread's chunk (pairs psub + 16 i are 2048 B
     // apart, panels 8192 B apart), which panels' chunks lie inside the padded rows
     const uint32_t off0 = sw128_offset(uint32_t(psub), uint32_t(c16));
-    const uint32_t smem0 = smem_u32(smem);
     const size_t a_row_bytes = size_t(p.ca_pad) * 2, b_row_bytes = size_t(p.cb_pad) * 2;
     const char* a_c = reinterpret_cast<const char*>(p.a) + size_t(a_c0 + c16 * 8) * 2;
     const char* b_c = reinterpret_cast<const char*>(p.b) + size_t(b_c0 + c16 * 8) * 2;
-    uint32_t a_ok[2], b_ok[4];
+    uint32_t a_ok[2 * MT], b_ok[4];
 #pragma unroll
-    for (int pn = 0; pn < 2; ++pn) a_ok[pn] = (a_c0 + pn * 64 + c16 * 8 < p.ca_pad) ? 16u : 0u;
+    for (int pn = 0; pn < 2 * MT; ++pn) a_ok[pn] = (a_c0 + pn * 64 + c16 * 8 < p.ca_pad) ? 16u : 0u;
 #pragma unroll
     for (int pn = 0; pn < 4; ++pn) b_ok[pn] = (pn < b_panels && b_c0 + pn * 64 + c16 * 8 < p.cb_pad) ? 16u : 0u;
-    int ia[4], ib[4], na[4], nb[4];
-    if (iters > 0) load_idx(0, ia, ib);
+    int ia[kIdxGroup][4], ib[kIdxGroup][4], na[kIdxGroup][4], nb[kIdxGroup][4];
+    if (iters > 0) load_group(0, ia, ib);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < iters; ++it) {
-      if (it + 1 < iters) load_idx(it + 1, na, nb);  // prefetch the next slice's pair indices
-      if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
-      const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
-      const uint32_t sb = sa + a_bytes;
+    for (int it0 = 0; it0 < iters; it0 += kIdxGroup) {
+      if (it0 + kIdxGroup < iters) load_group(it0 + kIdxGroup, na, nb);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t live = ia[i] >= 0 ? 16u : 0u;
-        const char* ga = a_c + (ia[i] >= 0 ? size_t(ia[i]) * a_row_bytes : size_t(0));
-        const char* gb = b_c + (ib[i] >= 0 ? size_t(ib[i]) * b_row_bytes : size_t(0));
-        // A: [64 pairs][128 channels of a] as two 64-channel swizzled panels
+      for (int u = 0; u < kIdxGroup; ++u) {
+        const int it = it0 + u;
+        if (it < iters) {
+          if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
+          const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
-        for (int pn = 0; pn < 2; ++pn) cp_async16(sa + pn * 8192 + i * 2048, ga + pn * 128, live & a_ok[pn]);
-        // B: [64 pairs][n_tile channels of b]
+          for (int i = 0; i < 4; ++i) {
+            int va = ia[u][i], vb = ib[u][i];
+            const bool ok = va >= 0 && vb >= 0 && va < p.n_a && vb < p.n_b;
+            const uint32_t live = ok ? 16u : 0u;
+            const char* ga = a_c + (ok ? size_t(va) * a_row_bytes : size_t(0));
+            const char* gb = b_c + (ok ? size_t(vb) * b_row_bytes : size_t(0));
+            // A: [64 pairs][MT x 128 channels of a] as 64-channel swizzled panels
 #pragma unroll
-        for (int pn = 0; pn < 4; ++pn)
-          if (pn < b_panels) cp_async16(sb + pn * 8192 + i * 2048, gb + pn * 128, live & b_ok[pn]);
+            for (int pn = 0; pn < 2 * MT; ++pn)
+              if (pn < 2 * mt_live) cp_async16(sa + pn * 8192 + i * 2048, ga + pn * 128, live & a_ok[pn]);
+            // B: [64 pairs][n_tile channels of b]
+#pragma unroll
+            for (int pn = 0; pn < 4; ++pn)
+              if (pn < b_panels) cp_async16(sb + pn * 8192 + i * 2048, gb + pn * 128, live & b_ok[pn]);
+          }
+          cp_async_arrive_noinc(&bars.full[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
       }
-      cp_async_arrive_noinc(&bars.full[s]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { ia[i] = na[i]; ib[i] = nb[i]; }
-      if (++s == p.stages) { s = 0; ph ^= 1u; }
+      for (int u = 0; u < kIdxGroup; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ia[u][i] = na[u][i]; ib[u][i] = nb[u][i]; }
     }
     // ------------------------------------------------------------------ epilogue
     // TMEM -> registers (thread = a-channel) -> this warp's smem tile -> global, a warp adding / storing
@@ -517,42 +555,43 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
       tc_fence_after();
     }
     float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
-    const int ca0 = a_c0 + warp * 32;
-    float* out = p.dw + (int64_t(k) * p.c_a + ca0) * p.c_b;
-    int rmax = p.c_a - ca0;
-    if (rmax > 32) rmax = 32;
-    for (int col = 0; col < p.n_tile; col += 32) {
-      const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
-      uint32_t acc[32];
-      if (iters > 0) {
-        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col), *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        if (ncols > 16)
-          tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + uint32_t(col + 16), *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0u;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (4 * q < ncols)
-          *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-      __syncwarp();
-      const int cb = b_c0 + col + lane;
-      if (lane < ncols && cb < p.c_b) {
-        float* o = out + cb;
-        if (p.use_atomic) {
-          for (int r = 0; r < rmax; ++r) atomicAdd(o + int64_t(r) * p.c_b, tile[r * kEpiPitch + lane]);
+    for (int mt = 0; mt < mt_live; ++mt) {
+      const int ca0 = a_c0 + mt * kTileM + warp * 32;
+      float* out = p.dw + (int64_t(k) * p.c_a + ca0) * p.c_b;
+      int rmax = p.c_a - ca0;
+      if (rmax > 32) rmax = 32;
+      for (int col = 0; col < p.n_tile; col += 32) {
+        const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
+        uint32_t acc[32];
+        if (iters > 0) {
+          const uint32_t taddr = tmem + (uint32_t(warp * 32) << 16) + uint32_t(mt * p.acc_stride + col);
+          tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          if (ncols > 16) tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+          tmem_ld_wait();
         } else {
-          for (int r = 0; r < rmax; ++r) o[int64_t(r) * p.c_b] = tile[r * kEpiPitch + lane];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[e] = 0u;
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (4 * q < ncols)
+            *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        __syncwarp();
+        const int cb = b_c0 + col + lane;
+        if (lane < ncols && cb < p.c_b) {
+          float* o = out + cb;
+          if (p.use_atomic) {
+            for (int r = 0; r < rmax; ++r) atomicAdd(o + int64_t(r) * p.c_b, tile[r * kEpiPitch + lane]);
+          } else {
+            for (int r = 0; r < rmax; ++r) o[int64_t(r) * p.c_b] = tile[r * kEpiPitch + lane];
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 1, 1);
-    const uint32_t smem0 = smem_u32(smem);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
@@ -560,12 +599,14 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
       fence_proxy_async_smem();
       tc_fence_after();
       const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
+      for (int mt = 0; mt < mt_live; ++mt) {
 #pragma unroll
-      for (int kk = 0; kk < kSliceK / 16; ++kk) {
-        // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
-        const uint64_t adesc = make_desc_sw128(a_addr + kk * 2048, 8192, 1024);
-        const uint64_t bdesc = make_desc_sw128(b_addr + kk * 2048, 8192, 1024);
-        mma_bf16(tmem, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kSliceK / 16; ++kk) {
+          // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
+          const uint64_t adesc = make_desc_sw128(a_addr + mt * 16384 + kk * 2048, 8192, 1024);
+          const uint64_t bdesc = make_desc_sw128(b_addr + kk * 2048, 8192, 1024);
+          mma_bf16(tmem + uint32_t(mt * p.acc_stride), adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
       }
       mma_commit(&bars.free_[s]);
       if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -621,15 +662,16 @@ size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) 
   return apply_plan(kvol, n_src, c_red, c_dst).total;
 }
 
+int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
+                           const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, cudaStream_t st);
+
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
                     size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
                     cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
-  const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
-  int n_tile, n_tiles;
-  choose_column_tiles(a.n_pad, ceil_div<int64_t>(live, kTileM), n_tile, n_tiles);
   if (ws == nullptr || ws_bytes < a.total) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, a.total);
   __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + a.off_act);
@@ -645,7 +687,19 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
+  return conv_apply_umma_launch(act, n_src, c_red, wt, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev, n_dst_dev,
+                                n_dst_hint, st);
+}
 
+// bf16 activations [n_src, round_up(c_red, 8)] and prepared weights in, fp32 [n_dst, c_dst] out
+int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
+                           const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, cudaStream_t st) {
+  if (n_dst == 0) return WFSP_OK;
+  ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
+  const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
+  int n_tile, n_tiles;
+  choose_column_tiles(a.n_pad, ceil_div<int64_t>(live, kTileM), n_tile, n_tiles);
   ApplyParams p{};
   p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
   p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst; p.n_tile = n_tile;
@@ -698,6 +752,11 @@ size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b
   return align_up(size_t(n_a) * round_up(c_a, 8) * 2, 256) + align_up(size_t(n_b) * round_up(c_b, 8) * 2, 256);
 }
 
+int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const __nv_bfloat16* b16, int64_t n_b, int c_b,
+                           const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
+                           int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
+                           cudaStream_t st);
+
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
@@ -705,41 +764,54 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch);
   if (need > 0 && (ws == nullptr || ws_bytes < need))
     return set_error(WFSP_EWORKSPACE, "conv_wgrad workspace %zu < %zu", ws_bytes, need);
+  const int ca_pad = round_up(c_a, 8), cb_pad = round_up(c_b, 8);
+  __nv_bfloat16* a16 = static_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + align_up(size_t(n_a) * ca_pad * 2, 256));
+  CastJob ja{a, a16, n_a, c_a, ca_pad, n_a_dev}, jb{b, b16, n_b, c_b, cb_pad, n_b_dev};
+  if (int rc = launch_cast(ja, &jb, st)) return rc;
+  return conv_wgrad_umma_launch(a16, n_a, c_a, b16, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, accumulate,
+                                n_a_dev, pairs_hint, st);
+}
+
+// bf16 rows in (pitches round_up(c, 8)), fp32 d_weight out
+int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const __nv_bfloat16* b16, int64_t n_b, int c_b,
+                           const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
+                           int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
+                           cudaStream_t st) {
   WgradParams p{};
   p.ca_pad = round_up(c_a, 8);
   p.cb_pad = round_up(c_b, 8);
-  __nv_bfloat16* a16 = static_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + align_up(size_t(n_a) * p.ca_pad * 2, 256));
-  CastJob ja{a, a16, n_a, c_a, p.ca_pad, n_a_dev}, jb{b, b16, n_b, c_b, p.cb_pad, n_b_dev};
   p.n_a_dev = n_a_dev;
-  if (int rc = launch_cast(ja, &jb, st)) return rc;
   p.a = a16; p.n_a = n_a; p.c_a = c_a; p.b = b16; p.n_b = n_b; p.c_b = c_b;
   p.pair_a = pair_a; p.pair_b = pair_b; p.pair_num = pair_num; p.kvol = kvol; p.pitch = pitch; p.dw = d_weight;
   const int n_tiles = (c_b + 255) / 256;
   p.n_tile = round_up((c_b + n_tiles - 1) / n_tiles, 16);
-  p.m_tiles = (c_a + kTileM - 1) / kTileM;
-  const int tiles = p.m_tiles * n_tiles;
+  p.acc_stride = round_up(p.n_tile, 32);
+  // two 128-channel blocks of `a` per CTA when `a` has more than 128 channels and both accumulators fit
+  const int mt = (c_a > kTileM && 2 * p.acc_stride <= 512) ? 2 : 1;
+  p.m_groups = ceil_div(c_a, kTileM * mt);
+  const int tiles = p.m_groups * n_tiles;
   const int b_panels = (p.n_tile + 63) / 64;
-  const int stage_bytes = 2 * 8192 + b_panels * 8192;
+  const int stage_bytes = 2 * mt * 8192 + b_panels * 8192;
   p.stages = pick_stages(stage_bytes, 1024);
   const size_t smem = size_t(p.stages) * stage_bytes + 1024;
   // pairs per offset that bound the split of the reduction: the caller's hint (graph path, where only
   // capacities are known on the host) or the capacity itself
   int64_t rows = pair_a ? pitch : n_a;
   if (pairs_hint > 0 && pairs_hint < rows) rows = pairs_hint;
-  // Split the pair list so that the CTAs fill whole waves of the machine: cost(ns) ~ waves(ns) / ns with
-  // waves = ceil(tiles * kvol * ns / resident CTA slots); the smallest ns among the best is taken (fewer
-  // partial tiles to reduce with atomics).  At least 256 pairs per split.
+  // Split the pair list so that the CTAs fill whole rounds of the machine.  Modelled cost of a launch =
+  // rounds x (pipeline slices of one CTA + a fixed term for its prologue and the atomic epilogue).
   int nsplit = 1;
   if (rows > 0) {
-    const int64_t slots = int64_t(sm_count()) * ((2 * (smem + 2048) <= size_t(227) * 1024) ? 2 : 1);
+    const int64_t slots = int64_t(sm_count()) * ((2 * (smem + 2048) <= size_t(227) * 1024 && 2 * mt * p.acc_stride <= 512) ? 2 : 1);
     const int64_t units = int64_t(tiles) * kvol;
     int64_t maxs = ceil_div<int64_t>(rows, 256);
     if (maxs > 64) maxs = 64;
     if (maxs * kvol > 65535) maxs = 65535 / kvol;
-    double best = 1e30;
+    double best = 1e300;
     for (int64_t ns = 1; ns <= maxs; ++ns) {
-      const double cost = double(ceil_div<int64_t>(units * ns, slots)) / double(ns);
+      const double rounds = double(ceil_div<int64_t>(units * ns, slots));
+      const double cost = rounds * (double(ceil_div<int64_t>(rows, ns * kSliceK)) + 24.0);
       if (cost < best * 0.98) { best = cost; nsplit = int(ns); }
     }
   }
@@ -749,11 +821,47 @@ int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_
   if (p.use_atomic && !accumulate)
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
   dim3 grid(unsigned(tiles), unsigned(kvol * nsplit));
-  WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  conv_wgrad_umma_kernel<<<grid, kThreads, smem, st>>>(p);
+  if (mt == 2) {
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    conv_wgrad_umma_kernel<2><<<grid, kThreads, smem, st>>>(p);
+  } else {
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    conv_wgrad_umma_kernel<1><<<grid, kThreads, smem, st>>>(p);
+  }
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
+}
+
+size_t prepared_weight_bytes(int kvol, int c_red, int c_dst) {
+  return align_up(size_t(kvol) * round_up(c_dst, 16) * round_up(c_red, kSliceK) * sizeof(__nv_bfloat16), 256);
+}
+
+int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st) {
+  for (int j0 = 0; j0 < n_jobs; j0 += kMaxPrepJobs) {
+    PrepBatch b{};
+    b.n = n_jobs - j0 < kMaxPrepJobs ? n_jobs - j0 : kMaxPrepJobs;
+    int blocks = 0;
+    for (int j = 0; j < b.n; ++j) {
+      const wfsp_prep_job& q = jobs[j0 + j];
+      if (q.weight == nullptr || q.out == nullptr || q.kvol < 1 || q.c_red < 1 || q.c_dst < 1)
+        return set_error(WFSP_EINVAL, "bad weight-preparation job %d", j0 + j);
+      const int64_t total = int64_t(q.kvol) * round_up(q.c_dst, 16) * round_up(q.c_red, kSliceK);
+      int64_t nb = ceil_div<int64_t>(total, 256 * 4);
+      if (nb > 4 * sm_count()) nb = 4 * sm_count();
+      b.job[j] = PrepJob{q.weight, static_cast<__nv_bfloat16*>(q.out), q.kvol, q.c_red, q.c_dst, q.transpose_w, blocks, int(nb)};
+      blocks += int(nb);
+    }
+    prep_weights_batch_kernel<<<unsigned(blocks), 256, 0, st>>>(b);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+  }
+  return WFSP_OK;
+}
+
+int cast_rows_bf16(const float* src, int64_t n, const int32_t* n_dev, int c, void* dst16, cudaStream_t st) {
+  CastJob j{src, static_cast<__nv_bfloat16*>(dst16), n, c, round_up(c, 8), n_dev};
+  return launch_cast(j, nullptr, st);
 }
 
 }  // namespace wfsp

@@ -21,11 +21,11 @@ import torch
 from torch import nn
 
 from . import functional as Fsp
-from . import ops
+from . import fused, ops
 from .ops import Rulebook, get_conv_output_size, get_indice_pairs  # noqa: F401
 
 __all__ = ["SparseConvTensor", "SparseModule", "SparseConvolution", "SparseConv2d", "SubMConv2d",
-           "SparseInverseConv2d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode"]
+           "SparseInverseConv2d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode", "set_fused"]
 
 _math_mode = os.environ.get("WFSP_MATH", "bf16")
 assert _math_mode in ("bf16", "fp32")
@@ -40,6 +40,9 @@ def set_math_mode(mode):
 
 def get_math_mode():
     return _math_mode
+
+
+set_fused = fused.set_fused
 
 
 class SparseConvTensor:
@@ -129,35 +132,37 @@ class SparseConvolution(SparseModule):
             self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.dilation,
             self.subm, self.inverse, self.indice_key)
 
-    def forward(self, input):
-        assert isinstance(input, SparseConvTensor)
-        features, indices = input.features, input.indices
-        mode = self.math or _math_mode
+    def geometry(self, input):
+        """Rulebook lookup / construction for this layer on `input` (upstream conv.py forward: reuse the
+        entry cached under indice_key, else build and cache it -- also under key None).  Returns
+        (rulebook or None for the 1x1 shortcut, output indices, output spatial shape, device row count
+        of the output or None)."""
         if self.conv1x1:
-            out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, None, False, mode,
-                                                        input.n_rows)
-            out = SparseConvTensor(out_features, indices, input.spatial_shape, input.batch_size, n_rows=input.n_rows)
-            out.indice_dict, out.grid = input.indice_dict, input.grid
-            return out
+            return None, input.indices, input.spatial_shape, input.n_rows
         datas = input.find_indice_pair(self.indice_key)
         if self.inverse:
             assert datas is not None and self.indice_key is not None
             rb = datas
             assert rb.kvol == int(np.prod(self.kernel_size)), \
                 "inverse conv must have same kernel size as its couple conv"
-            outids, out_spatial_shape, out_rows = rb.indices, rb.spatial_shape, rb.n_in_dev
+            return rb, rb.indices, rb.spatial_shape, rb.n_in_dev
+        if self.indice_key is not None and datas is not None:
+            rb = datas
         else:
-            if self.indice_key is not None and datas is not None:
-                rb = datas
-            else:
-                pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
-                stride = [1] * self.ndim if self.subm else self.stride
-                rb = ops.build_rulebook(indices, input.batch_size, input.spatial_shape, self.kernel_size, stride,
-                                        pad, self.dilation, self.subm, n_rows=input.n_rows)
-                input.indice_dict[self.indice_key] = rb
-            outids, out_rows = rb.outids, rb.n_out_dev
-            out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
-        out_features = Fsp.SparseConvFunction.apply(features, self.weight, self.bias, rb, self.inverse, mode, None)
+            pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
+            stride = [1] * self.ndim if self.subm else self.stride
+            rb = ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape, self.kernel_size, stride,
+                                    pad, self.dilation, self.subm, n_rows=input.n_rows)
+            input.indice_dict[self.indice_key] = rb
+        out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
+        return rb, rb.outids, out_spatial_shape, rb.n_out_dev
+
+    def forward(self, input):
+        assert isinstance(input, SparseConvTensor)
+        mode = self.math or _math_mode
+        rb, outids, out_spatial_shape, out_rows = self.geometry(input)
+        out_features = Fsp.SparseConvFunction.apply(input.features, self.weight, self.bias, rb, self.inverse, mode,
+                                                    input.n_rows if rb is None else None)
         out = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size, n_rows=out_rows)
         out.indice_dict, out.grid = input.indice_dict, input.grid
         return out
@@ -255,6 +260,16 @@ class SparseSequential(SparseModule):
 
     def forward(self, input):
         mods = list(self._modules.items())
+        if (fused.is_enabled() and isinstance(input, SparseConvTensor) and input.features is not None
+                and input.features.is_cuda and input.indices.shape[0] > 0
+                and all((m.math or _math_mode) == "bf16" for _, m in mods if isinstance(m, SparseConvolution))):
+            # whole stack as one autograd node with bf16-resident operands (fused.py); None = not covered
+            plan = fused.compile_stack([m for _, m in mods], SparseConvolution, ToDense)
+            if plan is not None:
+                for k, module in mods:
+                    if is_spconv_module(module):
+                        self._sparity_dict[k] = input.sparity
+                return fused.run(plan, input)
         i = 0
         while i < len(mods):
             k, module = mods[i]

@@ -1,0 +1,320 @@
+"""bf16-resident execution of a whole SparseSequential stack (include/wfsp.h section 6).
+
+The reference builds its sparse networks as spconv.SparseSequential(SparseConv2d, BatchNorm1d, ReLU,
+..., ToDense) (src/models/SPConvBlocks.py:498-516, :261-313, :756-822).  Run module by module, every
+layer boundary costs a cast of the activations to the tensor-core operand type (once in forward, again
+in wgrad, and the gradient twice: dgrad + wgrad) and a weight re-layout per call.  Here the stack is
+one autograd node:
+
+  forward   one launch prepares the bf16 weights of every layer (forward + dgrad layouts);
+            conv (bf16 in, fp32 out) -> BatchNorm statistics -> normalise + ReLU written directly as the
+            next layer's bf16 operand; only the last block writes fp32 (what ToDense / the caller reads);
+  backward  BatchNorm/ReLU backward writes the bf16 gradient that wgrad and dgrad both read;
+            dgrad's fp32 output is the previous block's dy.
+
+Arithmetic is unchanged: the same values are rounded to bf16 at the same points as on the per-layer
+path (conv operands only), accumulation and BatchNorm stay fp32.  Anything the plan does not cover
+(fp32 math mode, eval-mode BatchNorm under autograd, Dropout in training, forward hooks on inner
+modules, unknown modules) falls back to the per-layer path in SparseSequential.forward.
+"""
+import ctypes
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from .. import _lib
+from . import functional as Fsp
+
+_enabled = True
+
+
+def set_fused(flag):
+    """Globally enable / disable the fused stack path (per-layer execution is always available)."""
+    global _enabled
+    _enabled = bool(flag)
+
+
+def is_enabled():
+    return _enabled
+
+
+def pitch8(c):
+    return (c + 7) // 8 * 8
+
+
+class Block:
+    __slots__ = ("conv", "bn", "relu")
+
+    def __init__(self, conv):
+        self.conv, self.bn, self.relu = conv, None, False
+
+
+class Plan:
+    def __init__(self, blocks, to_dense):
+        self.blocks, self.to_dense = blocks, to_dense
+
+    def params(self):
+        out = []
+        for b in self.blocks:
+            out.append(b.conv.weight)
+            out.append(b.conv.bias)
+            out.append(b.bn.weight if b.bn is not None else None)
+            out.append(b.bn.bias if b.bn is not None else None)
+        return out
+
+
+def compile_stack(modules, sparse_conv_cls, to_dense_cls):
+    """modules: list of the SparseSequential's children.  Returns a Plan or None if the stack contains
+    something the fused path does not cover."""
+    blocks, to_dense, cur = [], False, None
+    n = len(modules)
+    for i, m in enumerate(modules):
+        if getattr(m, "_forward_hooks", None) or getattr(m, "_forward_pre_hooks", None):
+            return None  # someone is observing per-layer activations (e.g. scripts/PlotModelWeights.py:44-53)
+        if isinstance(m, sparse_conv_cls):
+            cur = Block(m)
+            blocks.append(cur)
+        elif isinstance(m, nn.BatchNorm1d):
+            if cur is None or cur.bn is not None or cur.relu or m.momentum is None or not m.track_running_stats:
+                return None
+            if not m.training and torch.is_grad_enabled():
+                return None  # eval-mode BN backward is affine, not the batch-statistics formula
+            cur.bn = m
+        elif isinstance(m, nn.ReLU):
+            if cur is None or cur.relu:
+                return None
+            cur.relu = True
+        elif isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and (not m.training or m.p == 0)):
+            continue
+        elif isinstance(m, to_dense_cls):
+            if i != n - 1 or cur is None:
+                return None
+            to_dense = True
+        else:
+            return None
+    if not blocks:
+        return None
+    return Plan(blocks, to_dense)
+
+
+def _bn_ws(lib, n, c, dev):
+    return torch.empty((lib.wfsp_bn_workspace_bytes(n, c),), dtype=torch.uint8, device=dev)
+
+
+class FusedStackFunction(Function):
+    @staticmethod
+    def forward(ctx, plan, x, holder, features, *params):
+        lib = _lib.load()
+        _lib.require_cuda(features, x.indices)
+        dev = features.device
+        feats = features if features.dtype == torch.float32 else features.float()
+        feats = feats.contiguous()
+        st = _lib.stream
+        blocks = plan.blocks
+        need_in_grad = features.requires_grad
+        with torch.cuda.device(dev):
+            # ---- every layer's weights -> bf16 tensor-core layouts, one launch
+            jobs, offs, total = [], [], 0
+            for bi, b in enumerate(blocks):
+                kvol = 1 if b.conv.conv1x1 else int(b.conv.kernel_size[0] * b.conv.kernel_size[1])
+                cin, cout = b.conv.in_channels, b.conv.out_channels
+                f_off = total
+                total += lib.wfsp_prepared_weight_bytes(kvol, cin, cout)
+                d_off = None
+                if bi > 0 or need_in_grad:
+                    d_off = total
+                    total += lib.wfsp_prepared_weight_bytes(kvol, cout, cin)
+                offs.append((f_off, d_off))
+            wbuf = torch.empty((total,), dtype=torch.uint8, device=dev)
+            for bi, b in enumerate(blocks):
+                kvol = 1 if b.conv.conv1x1 else int(b.conv.kernel_size[0] * b.conv.kernel_size[1])
+                cin, cout = b.conv.in_channels, b.conv.out_channels
+                w = params[4 * bi]
+                assert w.dtype == torch.float32 and w.is_contiguous()
+                f_off, d_off = offs[bi]
+                jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + f_off, kvol, cin, cout, 0))
+                if d_off is not None:
+                    jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + d_off, kvol, cout, cin, 1))
+            arr = (_lib.PrepJob * len(jobs))(*jobs)
+            _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
+
+            # ---- input activations -> bf16 once
+            n0, c0 = feats.shape
+            a16 = torch.empty((max(n0, 1), pitch8(c0)), dtype=torch.bfloat16, device=dev)
+            if n0:
+                _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(feats), n0, _lib.ptr(x.n_rows), c0, _lib.ptr(a16), st()))
+
+            saved, cur, out32 = [], x, None
+            for bi, b in enumerate(blocks):
+                conv = b.conv
+                rb, outids, out_shape, out_rows = conv.geometry(cur)
+                last = bi == len(blocks) - 1
+                kvol = 1 if rb is None else rb.kvol
+                cin, cout = conv.in_channels, conv.out_channels
+                if rb is None:
+                    nbr, n_dst, n_src_dev, n_dst_dev = None, cur.indices.shape[0], cur.n_rows, cur.n_rows
+                elif conv.inverse:
+                    nbr, n_dst = rb.nbr_in, rb.nbr_in.shape[0]
+                    n_src_dev, n_dst_dev = rb.n_out_dev, rb.n_in_dev
+                else:
+                    nbr, n_dst = rb.nbr_out, rb.nbr_out.shape[0]
+                    n_src_dev, n_dst_dev = rb.n_in_dev, rb.n_out_dev
+                n_src = a16.shape[0] if cur.indices.shape[0] else 0
+                xf = torch.empty((n_dst, cout), dtype=torch.float32, device=dev)
+                bias = params[4 * bi + 1]
+                if n_dst:
+                    hint = Fsp.hints.get(n_dst_dev)
+                    _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
+                                                        ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
+                                                        _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
+                                                        hint, cout, st()))
+                # ---- BatchNorm / ReLU -> next operand (bf16) or the stack's output (fp32)
+                y32 = y16 = mean = invstd = None
+                if b.bn is not None or b.relu:
+                    if last:
+                        y32 = torch.empty_like(xf)
+                    else:
+                        y16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
+                    if b.bn is not None:
+                        bn = b.bn
+                        mean = torch.empty((cout,), dtype=torch.float32, device=dev)
+                        invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
+                        if bn.training and bn.num_batches_tracked is not None:
+                            bn.num_batches_tracked.add_(1)
+                        if n_dst:
+                            ws = _bn_ws(lib, n_dst, cout, dev)
+                            _lib.check(lib.wfsp_bn_relu_fwd_x(
+                                _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
+                                _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), float(bn.momentum), float(bn.eps),
+                                int(bn.training), int(b.relu), _lib.ptr(y32), _lib.ptr(y16), _lib.ptr(mean),
+                                _lib.ptr(invstd), _lib.ptr(ws), ws.numel(), st()))
+                    elif n_dst:
+                        _lib.check(lib.wfsp_act_fwd(_lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, 1, _lib.ptr(y32),
+                                                    _lib.ptr(y16), st()))
+                elif last:
+                    y32 = xf
+                else:
+                    y16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
+                    if n_dst:
+                        _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout,
+                                                           _lib.ptr(y16), st()))
+                keep_x = xf if (b.bn is not None or b.relu) else None
+                saved.append((a16, keep_x, mean, invstd, rb, cur.indices.shape[0], n_dst, n_src_dev, n_dst_dev))
+                nxt = x.__class__(None, outids, out_shape, cur.batch_size, n_rows=out_rows)
+                nxt.indice_dict, nxt.grid = cur.indice_dict, cur.grid
+                cur, a16, out32 = nxt, y16, y32
+
+            holder["tensor"] = cur  # geometry of the stack's output
+            ctx.plan, ctx.saved, ctx.offs, ctx.wbuf = plan, saved, offs, wbuf
+            ctx.params = params
+            ctx.need_in_grad, ctx.in_dtype = need_in_grad, features.dtype
+            ctx.final = cur
+            if plan.to_dense:
+                h, w = cur.spatial_shape
+                n, c = out32.shape
+                dense = torch.empty((cur.batch_size, c, h, w), dtype=torch.float32, device=dev)
+                table = torch.empty((max(cur.batch_size * h * w, 1),), dtype=torch.int32, device=dev)
+                _lib.check(lib.wfsp_to_dense(_lib.ptr(out32), _lib.ptr(cur.indices.contiguous()), n, _lib.ptr(cur.n_rows),
+                                             c, cur.batch_size, h, w, _lib.ptr(dense), _lib.ptr(table), st()))
+                return dense
+            return out32
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        plan, saved, offs, wbuf, params = ctx.plan, ctx.saved, ctx.offs, ctx.wbuf, ctx.params
+        blocks = plan.blocks
+        dev = grad_out.device
+        st = _lib.stream
+        grads = [None] * len(params)
+        with torch.cuda.device(dev):
+            g = grad_out if grad_out.dtype == torch.float32 else grad_out.float()
+            g = g.contiguous()
+            final = ctx.final
+            if plan.to_dense:
+                n, c = saved[-1][6], blocks[-1].conv.out_channels
+                h, w = final.spatial_shape
+                dy = torch.empty((n, c), dtype=torch.float32, device=dev)
+                _lib.check(lib.wfsp_to_dense_bwd(_lib.ptr(g), _lib.ptr(final.indices.contiguous()), n,
+                                                 _lib.ptr(final.n_rows), c, final.batch_size, h, w, _lib.ptr(dy), st()))
+            else:
+                dy = g
+            for bi in range(len(blocks) - 1, -1, -1):
+                b = blocks[bi]
+                conv = b.conv
+                a16, xf, mean, invstd, rb, n_in, n_dst, n_src_dev, n_dst_dev = saved[bi]
+                cin, cout = conv.in_channels, conv.out_channels
+                kvol = 1 if rb is None else rb.kvol
+                w_p, bias_p, gamma_p, beta_p = params[4 * bi: 4 * bi + 4]
+                want_bias = bias_p is not None and ctx.needs_input_grad[4 + 4 * bi + 1]
+                g16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
+                dx32 = torch.empty((n_dst, cout), dtype=torch.float32, device=dev) if want_bias else None
+                if b.bn is not None:
+                    dgam = torch.empty((cout,), dtype=torch.float32, device=dev)
+                    dbet = torch.empty((cout,), dtype=torch.float32, device=dev)
+                    ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
+                    _lib.check(lib.wfsp_bn_relu_bwd_x(
+                        _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
+                        _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
+                        _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
+                    if gamma_p is not None:
+                        grads[4 * bi + 2] = dgam
+                    if beta_p is not None:
+                        grads[4 * bi + 3] = dbet
+                elif n_dst:
+                    if b.relu:
+                        _lib.check(lib.wfsp_act_bwd(_lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), cout, 1,
+                                                    _lib.ptr(dx32), _lib.ptr(g16), st()))
+                    else:
+                        _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(g16),
+                                                           st()))
+                        dx32 = dy if want_bias else None
+                if want_bias:
+                    if n_dst_dev is None:
+                        grads[4 * bi + 1] = dx32.sum(0)
+                    else:  # graph path: only the live rows of the capacity-sized gradient count
+                        live = (torch.arange(n_dst, device=dev) < n_dst_dev).unsqueeze(1)
+                        grads[4 * bi + 1] = torch.where(live, dx32, torch.zeros((), device=dev)).sum(0)
+                # ---- wgrad
+                if ctx.needs_input_grad[4 + 4 * bi]:
+                    dw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=dev)
+                    if rb is None:
+                        pa = pb = pn = None
+                        pitch = n_in
+                    else:
+                        pa, pb = (rb.pairs[1], rb.pairs[0]) if conv.inverse else (rb.pairs[0], rb.pairs[1])
+                        pn, pitch = rb.pair_num, rb.pairs.shape[-1]
+                    hint = 0
+                    if n_src_dev is not None:
+                        hint = Fsp.hints.get(pn if pn is not None else n_src_dev)
+                    _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, _lib.ptr(n_src_dev), cin, _lib.ptr(g16), n_dst,
+                                                        _lib.ptr(n_dst_dev), cout, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(pn),
+                                                        kvol, pitch, hint, _lib.ptr(dw), 0, st()))
+                    grads[4 * bi] = dw.view(w_p.shape)
+                # ---- dgrad -> dy of the previous block (or of the stack's input)
+                if bi > 0 or ctx.need_in_grad:
+                    nbr_t = None if rb is None else (rb.nbr_out if conv.inverse else rb.nbr_in)
+                    dy = torch.empty((n_in, cin), dtype=torch.float32, device=dev)
+                    if n_in:
+                        hint = Fsp.hints.get(n_src_dev)
+                        _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(g16), n_dst, _lib.ptr(n_dst_dev), cout,
+                                                            ctypes.c_void_p(wbuf.data_ptr() + offs[bi][1]), None,
+                                                            _lib.ptr(nbr_t), kvol, _lib.ptr(dy), n_in, _lib.ptr(n_src_dev),
+                                                            hint, cin, st()))
+            d_feats = None
+            if ctx.need_in_grad:
+                d_feats = dy if ctx.in_dtype == torch.float32 else dy.to(ctx.in_dtype)
+        return (None, None, None, d_feats) + tuple(grads)
+
+
+def run(plan, x):
+    """Runs the planned stack on SparseConvTensor x; returns a dense tensor (ToDense tail) or the
+    output SparseConvTensor."""
+    holder = {}
+    out = FusedStackFunction.apply(plan, x, holder, x.features, *plan.params())
+    if plan.to_dense:
+        return out
+    res = holder["tensor"]
+    res.features = out
+    return res
