@@ -9,7 +9,11 @@ rows = [r for r in rows if r.get("Metric Name") == "gpu__time_duration.sum"]
 if len(sys.argv) > 2:
     rows = rows[-int(sys.argv[2]):]
 def dur_us(r):
-    v = float(r["Metric Value"].replace(",", "")); u = r["Metric Unit"]
+    try:
+        v = float(r["Metric Value"].replace(",", ""))
+    except ValueError:
+        return 0.0
+    u = r["Metric Unit"]
     return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
 agg = collections.OrderedDict()
 for r in rows:

@@ -116,37 +116,45 @@ __device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// One thread = 8 consecutive channels of one row.  Outputs (each optional): y fp32 [rows, c] and
-// y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as zero) -- the operand format of
-// the tcgen05 convolution kernels, so the next layer needs no cast pass.
+// Streaming normalise(+ReLU) pass.  A block owns kApplyRows consecutive rows (one contiguous span of x);
+// a thread handles two adjacent channels of a row at a time, so a warp reads 256 contiguous bytes and
+// writes 256 (fp32) / 128 (bf16) contiguous bytes per instruction.  Outputs (each optional): y fp32
+// [rows, c] and y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as zero) -- the operand
+// format of the tcgen05 convolution kernels, so the next layer needs no cast pass.
+// mean == nullptr switches the normalisation off (plain ReLU / cast).
+constexpr int kApplyRows = 32;
+
 __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                 int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
-  const int cpr = (c + 7) >> 3;
-  const int64_t total = live_rows(n_cap, n_dev) * cpr;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t row = i / cpr;
-    const int col = int(i - row * cpr) << 3;
-    float v[8];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
+  const float inv_ppr = 1.f / float(ppr);
+  for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
+    const int rows = int(n - r0 < kApplyRows ? n - r0 : kApplyRows);
+    const float* xb = x + r0 * c;
+    float* yb = y ? y + r0 * c : nullptr;
+    uint32_t* y16b = y16 ? reinterpret_cast<uint32_t*>(y16 + r0 * c_pad) : nullptr;
+    const int total = rows * ppr;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      int row = int((float(t) + 0.5f) * inv_ppr);
+      int pr = t - row * ppr;
+      if (pr < 0) { --row; pr += ppr; } else if (pr >= ppr) { ++row; pr -= ppr; }
+      const int ch = pr << 1;
+      float v[2] = {0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = col + e;
-      float t = 0.f;
-      if (ch < c) {
-        t = x[row * c + ch];
-        if (mean) t = (t - mean[ch]) * invstd[ch] * (gamma ? gamma[ch] : 1.f) + (beta ? beta[ch] : 0.f);
-        if (relu && t < 0.f) t = 0.f;
-        if (y) y[row * c + ch] = t;
+      for (int e = 0; e < 2; ++e) {
+        if (ch + e < c) {
+          float tv = xb[row * c + ch + e];
+          if (mean) tv = (tv - mean[ch + e]) * invstd[ch + e] * (gamma ? gamma[ch + e] : 1.f) + (beta ? beta[ch + e] : 0.f);
+          if (relu && tv < 0.f) tv = 0.f;
+          if (yb) yb[row * c + ch + e] = tv;
+          v[e] = tv;
+        }
       }
-      v[e] = t;
-    }
-    if (y16) {
-      uint4 u;
-      u.x = bn_pack_bf16x2(v[0], v[1]); u.y = bn_pack_bf16x2(v[2], v[3]);
-      u.z = bn_pack_bf16x2(v[4], v[5]); u.w = bn_pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(y16 + row * (int64_t(cpr) << 3) + col) = u;
+      if (y16b) y16b[row * ppr + pr] = bn_pack_bf16x2(v[0], v[1]);
     }
   }
 }
@@ -219,36 +227,41 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
                                                     const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                                                     int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16) {
   const int64_t n = live_rows(n_cap, n_dev);
-  const int cpr = (c + 7) >> 3;
-  const int64_t total = n * cpr;
+  const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
+  const float inv_ppr = 1.f / float(ppr);
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t row = i / cpr;
-    const int col = int(i - row * cpr) << 3;
-    float v[8];
+  for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
+    const int rows = int(n - r0 < kApplyRows ? n - r0 : kApplyRows);
+    const float* xb = x + r0 * c;
+    const float* dyb = dy + r0 * c;
+    float* dxb = dx ? dx + r0 * c : nullptr;
+    uint32_t* dx16b = dx16 ? reinterpret_cast<uint32_t*>(dx16 + r0 * c_pad) : nullptr;
+    const int total = rows * ppr;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      int row = int((float(t) + 0.5f) * inv_ppr);
+      int pr = t - row * ppr;
+      if (pr < 0) { --row; pr += ppr; } else if (pr >= ppr) { ++row; pr -= ppr; }
+      const int ch0 = pr << 1;
+      float v[2] = {0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = col + e;
-      float t = 0.f;
-      if (ch < c) {
-        float d = dy[row * c + ch];
-        if (mean) {
-          const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-          const float xh = (x[row * c + ch] - mean[ch]) * is;
-          if (relu && xh * g + b <= 0.f) d = 0.f;
-          t = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
-        } else {
-          t = (relu && x[row * c + ch] <= 0.f) ? 0.f : d;
+      for (int e = 0; e < 2; ++e) {
+        const int ch = ch0 + e;
+        if (ch < c) {
+          float d = dyb[row * c + ch];
+          float tv;
+          if (mean) {
+            const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+            const float xh = (xb[row * c + ch] - mean[ch]) * is;
+            if (relu && xh * g + b <= 0.f) d = 0.f;
+            tv = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
+          } else {
+            tv = (relu && xb[row * c + ch] <= 0.f) ? 0.f : d;
+          }
+          if (dxb) dxb[row * c + ch] = tv;
+          v[e] = tv;
         }
-        if (dx) dx[row * c + ch] = t;
       }
-      v[e] = t;
-    }
-    if (dx16) {
-      uint4 u;
-      u.x = bn_pack_bf16x2(v[0], v[1]); u.y = bn_pack_bf16x2(v[2], v[3]);
-      u.z = bn_pack_bf16x2(v[4], v[5]); u.w = bn_pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(dx16 + row * (int64_t(cpr) << 3) + col) = u;
+      if (dx16b) dx16b[row * ppr + pr] = bn_pack_bf16x2(v[0], v[1]);
     }
   }
 }
@@ -356,8 +369,8 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
   }
 }
 
-inline unsigned stream_blocks(int64_t elems) {
-  int64_t b = ceil_div<int64_t>(elems > 0 ? elems : 1, 256);
+inline unsigned apply_blocks(int64_t rows) {
+  int64_t b = ceil_div<int64_t>(rows > 0 ? rows : 1, kApplyRows);
   const int64_t cap = int64_t(sm_count()) * 16;
   return unsigned(b > cap ? cap : b);
 }
@@ -402,7 +415,7 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(c, eps, running_mean, running_var, save_mean, save_invstd);
     count_launches(1);
   }
-  bn_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+  bn_apply<<<apply_blocks(n_rows), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                                    save_invstd, relu, y, y16);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -443,7 +456,7 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
   bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
-  bn_bwd_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+  bn_bwd_apply<<<apply_blocks(n_rows), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                                        save_invstd, d_gamma, d_beta, relu, dx, dx16);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
@@ -465,7 +478,7 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, as_stream(stream)>>>(
+  bn_apply<<<apply_blocks(n_rows), 256, 0, as_stream(stream)>>>(
       x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -477,7 +490,7 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_bwd_apply<<<stream_blocks(n_rows * ((c + 7) >> 3)), 256, 0, as_stream(stream)>>>(
+  bn_bwd_apply<<<apply_blocks(n_rows), 256, 0, as_stream(stream)>>>(
       x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
       static_cast<__nv_bfloat16*>(dx_bf16));
   count_launches(1);

@@ -41,6 +41,10 @@ constexpr int kABytes = kTileM * 128;
 constexpr int kMaxStages = 8;
 constexpr int kNbrStageK = 32;  // kernel volumes up to this keep the CTA's neighbour tile in smem
 constexpr int kSmemMax = 222 * 1024;
+// The opt-in limit is set to the same (maximum) value at every launch: a CUDA graph replays kernel nodes
+// with whatever the function attribute is at replay time, so per-launch values would let a later, smaller
+// launch of the same function starve an earlier node.
+constexpr int kSmemOptIn = 226 * 1024;  // 227 KB per CTA minus room for the kernels' static shared memory
 constexpr int kMaxRowBlocks = 4;  // 128-row blocks per CTA of the apply kernel
 constexpr int kEpiPitch = 36;  // words per row of a warp's 32 x 32 epilogue tile (16-byte aligned, conflict-free)
 
@@ -736,7 +740,7 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
 #define WFSP_LAUNCH_APPLY(RB)                                                                                        \
     case RB:                                                                                                         \
       WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                           int(smem)));                                                              \
+                                           kSmemOptIn));                                                             \
       conv_apply_umma_kernel<RB><<<grid, kThreads, smem, st>>>(p);                                                   \
       break;
     WFSP_LAUNCH_APPLY(1) WFSP_LAUNCH_APPLY(2) WFSP_LAUNCH_APPLY(3) WFSP_LAUNCH_APPLY(4)
@@ -822,10 +826,10 @@ int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
   dim3 grid(unsigned(tiles), unsigned(kvol * nsplit));
   if (mt == 2) {
-    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     conv_wgrad_umma_kernel<2><<<grid, kThreads, smem, st>>>(p);
   } else {
-    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     conv_wgrad_umma_kernel<1><<<grid, kThreads, smem, st>>>(p);
   }
   count_launches(1);
