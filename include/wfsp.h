@@ -126,6 +126,18 @@ int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol
                          int64_t pair_pitch, int64_t n_in, int64_t n_out, int32_t* nbr_out,
                          int32_t* nbr_in, int32_t* dup_flag, wfsp_stream_t stream);
 
+/* Rulebook and neighbour tables in one call: wfsp_rulebook_conv (subm == 0) or wfsp_rulebook_subm
+ * (subm != 0; stride / pad / out_indices / n_out ignored, may be NULL) followed by
+ * wfsp_rulebook_tables, with nbr_out sized [out_cap, kvol] (subm: [n_in, kvol]).  *dup_flag is
+ * written (0 / 1), no need to clear it.  Inputs of up to 1024 rows are built by a single kernel
+ * launch (no memsets): at the reference's batch size of 64 events the step is launch-latency bound. */
+int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                        const int* in_shape_host, const int* ksize_host, const int* stride_host,
+                        const int* pad_host, const int* dil_host, int subm, int32_t* out_indices,
+                        int64_t out_cap, int32_t* pairs, int32_t* pair_num, int32_t* n_out,
+                        int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag, void* workspace,
+                        size_t workspace_bytes, wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (3) Gather-GEMM forward / dgrad / wgrad.  Replaces upstream indice_conv /
  * indice_conv_backward reached from spconv.SparseConv2d / SubMConv2d / SparseInverseConv2d

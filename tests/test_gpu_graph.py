@@ -79,7 +79,7 @@ def test_rulebook_with_device_count_matches_eager(cuda_device, k, s, p, subm):
     assert int(g.n_out_dev.item()) == n_out
     assert torch.equal(g.pair_num, e.pair_num)
     assert torch.equal(g.outids[:n_out], e.outids)
-    assert torch.equal(g.pairs[:, :, :n], e.pairs) and bool((g.pairs[:, :, n:] == -1).all())
+    assert torch.equal(g.pairs[:, :, :n], e.pairs)  # the capacity tail [n:] is unspecified (never read)
     assert torch.equal(g.nbr_out[:n_out], e.nbr_out) and torch.equal(g.nbr_in[:n], e.nbr_in)
 
 

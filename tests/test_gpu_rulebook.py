@@ -99,6 +99,18 @@ def test_c1_and_chained_layers(cuda_device):
     assert rb2.outids.shape[0] > rb1.outids.shape[0] > idx.shape[0]
 
 
+def test_mid_sizes_both_builders(cuda_device):
+    """~2,700 rows: the single-launch builder walks them in three rounds of 1024; its output (~9,900 rows)
+    is past that builder's limit and goes through the multi-kernel phases with the direct table."""
+    idx = _indices(900, 77)
+    assert 2048 < idx.shape[0] <= 8192
+    rb1 = _check(idx, 900, 3, 1, 0, 1, False, cuda_device)
+    _check(idx, 900, 5, 1, 0, 1, True, cuda_device)
+    assert rb1.outids.shape[0] > 8192
+    _check(rb1.outids.cpu().contiguous(), 900, 3, 1, 0, 1, False, cuda_device)
+    _check(rb1.outids.cpu().contiguous(), 900, 3, 1, 0, 1, True, cuda_device)
+
+
 def test_full_grid_1024_matches_oracle(cuda_device):
     """C5 at full size: 1024 events x 154 cells = 157,696 rows, ~1 M pairs."""
     idx = _indices(1024, 1, full=True)

@@ -9,49 +9,63 @@
 // fixed order, so the result does not depend on scheduling.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace wfsp {
 namespace {
 
-constexpr int kRows = 128;  // rows per partial
-constexpr int kCh = 32;     // channels per block (one 128-byte row segment)
+constexpr int kRows = 1024;  // rows per partial
+constexpr int kCh = 32;      // channels per block (one 128-byte row segment)
 
 __device__ __forceinline__ int64_t live_rows(int64_t n, const int32_t* n_dev) { return n_dev ? int64_t(*n_dev) : n; }
 
-// grid (ceil(cap/kRows), ceil(c/kCh)), block (32, 8)
+// grid (ceil(cap/kRows), ceil(c/kCh)), block (32, 8).  One pass over x: every thread accumulates sum and
+// sum of squares of (x - K), K = its first value (a shift that removes the cancellation of the textbook
+// formula), turns them into (count, mean, M2) and the eight row lanes are merged with Chan's formula in a
+// fixed order.
 __global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict__ x, int64_t n_cap,
                                                         const int32_t* __restrict__ n_dev, int c,
                                                         float* __restrict__ part /* [nblk][2][c] mean, M2 */) {
-  __shared__ float red[8][kCh];
+  __shared__ float s_cnt[8][kCh], s_mean[8][kCh], s_m2[8][kCh];
   const int64_t n = live_rows(n_cap, n_dev);
   const int64_t r0 = int64_t(blockIdx.x) * kRows;
   if (r0 >= n) return;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.y * kCh + tx;
   const int rows = int(n - r0 < kRows ? n - r0 : kRows);
-  float s = 0.f;
-  if (ch < c)
-    for (int r = ty; r < rows; r += 8) s += x[(r0 + r) * c + ch];
-  red[ty][tx] = s;
-  __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i][tx];
-  const float mean = tot / float(rows);
-  __syncthreads();
-  float m2 = 0.f;
-  if (ch < c)
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  if (ch < c && ty < rows) {
+    const float* xp = x + r0 * c + ch;
+    const float K = xp[int64_t(ty) * c];
+    float sd = 0.f, sq = 0.f;
+#pragma unroll 4
     for (int r = ty; r < rows; r += 8) {
-      const float d = x[(r0 + r) * c + ch] - mean;
-      m2 += d * d;
+      const float d = xp[int64_t(r) * c] - K;
+      sd += d;
+      sq += d * d;
     }
-  red[ty][tx] = m2;
+    cnt = float((rows - ty + 7) / 8);
+    mean = K + sd / cnt;
+    m2 = sq - sd * sd / cnt;
+    if (m2 < 0.f) m2 = 0.f;
+  }
+  s_cnt[ty][tx] = cnt; s_mean[ty][tx] = mean; s_m2[ty][tx] = m2;
   __syncthreads();
   if (ty == 0 && ch < c) {
-    float t2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t2 += red[i][tx];
+    for (int l = 1; l < 8; ++l) {
+      const float nb = s_cnt[l][tx];
+      if (nb > 0.f) {
+        const float delta = s_mean[l][tx] - mean, tot = cnt + nb;
+        mean += delta * nb / tot;
+        m2 += s_m2[l][tx] + delta * delta * cnt * nb / tot;
+        cnt = tot;
+      }
+    }
     part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = mean;
-    part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = t2;
+    part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = m2;
   }
 }
 
@@ -116,13 +130,13 @@ __device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// Streaming normalise(+ReLU) pass.  A block owns kApplyRows consecutive rows (one contiguous span of x);
-// a thread handles two adjacent channels of a row at a time, so a warp reads 256 contiguous bytes and
-// writes 256 (fp32) / 128 (bf16) contiguous bytes per instruction.  Outputs (each optional): y fp32
-// [rows, c] and y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as zero) -- the operand
-// format of the tcgen05 convolution kernels, so the next layer needs no cast pass.
+// Streaming normalise(+ReLU) pass.  Block (bdx, bdy): thread x owns one pair of adjacent channels and keeps
+// its statistics / affine parameters in registers, thread y strides over the kApplyRows rows of the block's
+// chunk; a warp reads 256 contiguous bytes of a row and writes 256 (fp32) / 128 (bf16).  Outputs (each
+// optional): y fp32 [rows, c] and y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as
+// zero) -- the operand format of the tcgen05 convolution kernels, so the next layer needs no cast pass.
 // mean == nullptr switches the normalisation off (plain ReLU / cast).
-constexpr int kApplyRows = 32;
+constexpr int kApplyRows = 64;
 
 __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
@@ -131,30 +145,33 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
                                                 int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
-  const float inv_ppr = 1.f / float(ppr);
-  for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
-    const int rows = int(n - r0 < kApplyRows ? n - r0 : kApplyRows);
-    const float* xb = x + r0 * c;
-    float* yb = y ? y + r0 * c : nullptr;
-    uint32_t* y16b = y16 ? reinterpret_cast<uint32_t*>(y16 + r0 * c_pad) : nullptr;
-    const int total = rows * ppr;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      int row = int((float(t) + 0.5f) * inv_ppr);
-      int pr = t - row * ppr;
-      if (pr < 0) { --row; pr += ppr; } else if (pr >= ppr) { ++row; pr -= ppr; }
-      const int ch = pr << 1;
-      float v[2] = {0.f, 0.f};
+  uint32_t* y16w = reinterpret_cast<uint32_t*>(y16);
+  for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
+    const int ch = pc << 1;
+    float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (ch + e < c) {
-          float tv = xb[row * c + ch + e];
-          if (mean) tv = (tv - mean[ch + e]) * invstd[ch + e] * (gamma ? gamma[ch + e] : 1.f) + (beta ? beta[ch + e] : 0.f);
-          if (relu && tv < 0.f) tv = 0.f;
-          if (yb) yb[row * c + ch + e] = tv;
-          v[e] = tv;
-        }
+    for (int e = 0; e < 2; ++e)
+      if (mean && ch + e < c) {
+        m[e] = mean[ch + e]; is[e] = invstd[ch + e];
+        if (gamma) g[e] = gamma[ch + e];
+        if (beta) b[e] = beta[ch + e];
       }
-      if (y16b) y16b[row * ppr + pr] = bn_pack_bf16x2(v[0], v[1]);
+    for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
+      const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
+      for (int64_t r = r0 + threadIdx.y; r < r_end; r += blockDim.y) {
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (ch + e < c) {
+            float tv = x[r * c + ch + e];
+            if (mean) tv = (tv - m[e]) * is[e] * g[e] + b[e];
+            if (relu && tv < 0.f) tv = 0.f;
+            if (y) y[r * c + ch + e] = tv;
+            v[e] = tv;
+          }
+        }
+        if (y16w) y16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+      }
     }
   }
 }
@@ -228,40 +245,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
                                                     int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
-  const float inv_ppr = 1.f / float(ppr);
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
-  for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
-    const int rows = int(n - r0 < kApplyRows ? n - r0 : kApplyRows);
-    const float* xb = x + r0 * c;
-    const float* dyb = dy + r0 * c;
-    float* dxb = dx ? dx + r0 * c : nullptr;
-    uint32_t* dx16b = dx16 ? reinterpret_cast<uint32_t*>(dx16 + r0 * c_pad) : nullptr;
-    const int total = rows * ppr;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      int row = int((float(t) + 0.5f) * inv_ppr);
-      int pr = t - row * ppr;
-      if (pr < 0) { --row; pr += ppr; } else if (pr >= ppr) { ++row; pr -= ppr; }
-      const int ch0 = pr << 1;
-      float v[2] = {0.f, 0.f};
+  uint32_t* dx16w = reinterpret_cast<uint32_t*>(dx16);
+  for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
+    const int ch = pc << 1;
+    float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f}, db[2] = {0.f, 0.f}, dg[2] = {0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int ch = ch0 + e;
-        if (ch < c) {
-          float d = dyb[row * c + ch];
-          float tv;
-          if (mean) {
-            const float is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-            const float xh = (xb[row * c + ch] - mean[ch]) * is;
-            if (relu && xh * g + b <= 0.f) d = 0.f;
-            tv = g * is * (d - d_beta[ch] * inv_n - xh * d_gamma[ch] * inv_n);
-          } else {
-            tv = (relu && xb[row * c + ch] <= 0.f) ? 0.f : d;
-          }
-          if (dxb) dxb[row * c + ch] = tv;
-          v[e] = tv;
-        }
+    for (int e = 0; e < 2; ++e)
+      if (mean && ch + e < c) {
+        m[e] = mean[ch + e]; is[e] = invstd[ch + e];
+        if (gamma) g[e] = gamma[ch + e];
+        if (beta) b[e] = beta[ch + e];
+        db[e] = d_beta[ch + e] * inv_n; dg[e] = d_gamma[ch + e] * inv_n;
       }
-      if (dx16b) dx16b[row * ppr + pr] = bn_pack_bf16x2(v[0], v[1]);
+    for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
+      const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
+      for (int64_t r = r0 + threadIdx.y; r < r_end; r += blockDim.y) {
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (ch + e < c) {
+            float d = dy[r * c + ch + e];
+            const float xv = x[r * c + ch + e];
+            float tv;
+            if (mean) {
+              const float xh = (xv - m[e]) * is[e];
+              if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
+              tv = g[e] * is[e] * (d - db[e] - xh * dg[e]);
+            } else {
+              tv = (relu && xv <= 0.f) ? 0.f : d;
+            }
+            if (dx) dx[r * c + ch + e] = tv;
+            v[e] = tv;
+          }
+        }
+        if (dx16w) dx16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+      }
     }
   }
 }
@@ -272,55 +291,80 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
 // when the row capacity is small (a whole C2 step is launch-latency bound).
 constexpr int kSmallRows = 16384;
 constexpr int kRowLanes = 16;
+constexpr int kClusterY = 8;  // CTAs of one thread-block cluster: they split the rows of a channel group
 
-__device__ __forceinline__ float block_col_sum(float v, float (*red)[kCh], int tx, int ty) {
-  red[ty][tx] = v;
-  __syncthreads();
-  float t = 0.f;
+// Column sums over ALL rows of the cluster: per-CTA partial in shared memory, cluster barrier, then every CTA
+// adds the kClusterY partials in rank order through distributed shared memory (same order everywhere, so
+// all CTAs hold bit-identical statistics).  NV values per channel are reduced at once.
+template <int NV>
+__device__ __forceinline__ void cluster_col_sum(float (&v)[NV], float (*red)[kCh], float (*part)[kCh], int tx, int ty,
+                                                cg::cluster_group& cluster) {
 #pragma unroll
-  for (int i = 0; i < kRowLanes; ++i) t += red[i][tx];
-  __syncthreads();
-  return t;
+  for (int q = 0; q < NV; ++q) {
+    red[ty][tx] = v[q];
+    __syncthreads();
+    if (ty == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRowLanes; ++i) t += red[i][tx];
+      part[q][tx] = t;
+    }
+    __syncthreads();
+  }
+  cluster.sync();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    float t = 0.f;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) t += cluster.map_shared_rank(&part[q][0], r)[tx];
+    v[q] = t;
+  }
+  cluster.sync();  // the partials may be overwritten (or the CTA may exit) only after every peer has read them
 }
 
+// grid (channel groups, kClusterY), cluster (1, kClusterY, 1), block (32, 16)
 __global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
     const float* __restrict__ x, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
     float* __restrict__ running_var, float momentum, float eps, int training, int relu, float* __restrict__ y,
     __nv_bfloat16* __restrict__ y16, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   __shared__ float red[kRowLanes][kCh];
+  __shared__ float part[1][kCh];
+  cg::cluster_group cluster = cg::this_cluster();
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
   const bool on = ch < c;
+  const int64_t row0 = int64_t(cluster.block_rank()) * kRowLanes + ty, rstep = int64_t(cluster.num_blocks()) * kRowLanes;
+  const bool lead = cluster.block_rank() == 0 && ty == 0;
   float mean, invstd;
   if (training) {
-    float s = 0.f;
-    if (on) for (int64_t r = ty; r < n; r += kRowLanes) s += x[r * c + ch];
-    mean = n > 0 ? block_col_sum(s, red, tx, ty) / float(n) : 0.f;
-    float m2 = 0.f;
-    if (on) for (int64_t r = ty; r < n; r += kRowLanes) { const float d = x[r * c + ch] - mean; m2 += d * d; }
-    m2 = block_col_sum(m2, red, tx, ty);
-    invstd = n > 0 ? rsqrtf(m2 / float(n) + eps) : 0.f;
-    if (on && ty == 0) {
+    float s[1] = {0.f};
+    if (on) for (int64_t r = row0; r < n; r += rstep) s[0] += x[r * c + ch];
+    cluster_col_sum<1>(s, red, part, tx, ty, cluster);
+    mean = n > 0 ? s[0] / float(n) : 0.f;
+    float m2[1] = {0.f};
+    if (on) for (int64_t r = row0; r < n; r += rstep) { const float d = x[r * c + ch] - mean; m2[0] += d * d; }
+    cluster_col_sum<1>(m2, red, part, tx, ty, cluster);
+    invstd = n > 0 ? rsqrtf(m2[0] / float(n) + eps) : 0.f;
+    if (on && lead) {
       save_mean[ch] = mean;
       save_invstd[ch] = invstd;
       if (n > 0 && running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
-      if (n > 1 && running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (m2 / float(n - 1));
+      if (n > 1 && running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (m2[0] / float(n - 1));
     }
   } else {
     mean = on ? running_mean[ch] : 0.f;
     invstd = on ? rsqrtf(running_var[ch] + eps) : 0.f;
-    if (on && ty == 0) { save_mean[ch] = mean; save_invstd[ch] = invstd; }
+    if (on && lead) { save_mean[ch] = mean; save_invstd[ch] = invstd; }
   }
   const int c_pad = (c + 7) & ~7;
   if (!on) {  // zero padding columns of the bf16 copy
     if (y16 && ch < c_pad)
-      for (int64_t r = ty; r < n; r += kRowLanes) y16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
+      for (int64_t r = row0; r < n; r += rstep) y16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
     return;
   }
   const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-  for (int64_t r = ty; r < n; r += kRowLanes) {
+  for (int64_t r = row0; r < n; r += rstep) {
     float v = (x[r * c + ch] - mean) * invstd * g + b;
     v = (relu && v < 0.f) ? 0.f : v;
     if (y) y[r * c + ch] = v;
@@ -334,32 +378,35 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
     const float* __restrict__ invstd_, int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   __shared__ float red[kRowLanes][kCh];
+  __shared__ float part[2][kCh];
+  cg::cluster_group cluster = cg::this_cluster();
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
   const bool on = ch < c;
+  const int64_t row0 = int64_t(cluster.block_rank()) * kRowLanes + ty, rstep = int64_t(cluster.num_blocks()) * kRowLanes;
   const float m = on ? mean_[ch] : 0.f, is = on ? invstd_[ch] : 0.f;
   const float g = (on && gamma) ? gamma[ch] : 1.f, b = (on && beta) ? beta[ch] : 0.f;
-  float s0 = 0.f, s1 = 0.f;
+  float s[2] = {0.f, 0.f};
   if (on)
-    for (int64_t r = ty; r < n; r += kRowLanes) {
+    for (int64_t r = row0; r < n; r += rstep) {
       const float xh = (x[r * c + ch] - m) * is;
       float d = dy[r * c + ch];
       if (relu && xh * g + b <= 0.f) d = 0.f;
-      s0 += d;
-      s1 += d * xh;
+      s[0] += d;
+      s[1] += d * xh;
     }
-  s0 = block_col_sum(s0, red, tx, ty);
-  s1 = block_col_sum(s1, red, tx, ty);
+  cluster_col_sum<2>(s, red, part, tx, ty, cluster);
+  const float s0 = s[0], s1 = s[1];
   const int c_pad = (c + 7) & ~7;
   if (!on) {
     if (dx16 && ch < c_pad)
-      for (int64_t r = ty; r < n; r += kRowLanes) dx16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
+      for (int64_t r = row0; r < n; r += rstep) dx16[r * c_pad + ch] = __float2bfloat16_rn(0.f);
     return;
   }
-  if (ty == 0) { d_beta[ch] = s0; d_gamma[ch] = s1; }
+  if (cluster.block_rank() == 0 && ty == 0) { d_beta[ch] = s0; d_gamma[ch] = s1; }
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
-  for (int64_t r = ty; r < n; r += kRowLanes) {
+  for (int64_t r = row0; r < n; r += rstep) {
     const float xh = (x[r * c + ch] - m) * is;
     float d = dy[r * c + ch];
     if (relu && xh * g + b <= 0.f) d = 0.f;
@@ -369,10 +416,37 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
   }
 }
 
+// launch of the small kernels as thread-block clusters of kClusterY CTAs along y
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cluster(void (*kernel)(KArgs...), int groups, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(groups), kClusterY, 1);
+  cfg.blockDim = dim3(kCh, kRowLanes, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = kClusterY;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline unsigned apply_blocks(int64_t rows) {
   int64_t b = ceil_div<int64_t>(rows > 0 ? rows : 1, kApplyRows);
   const int64_t cap = int64_t(sm_count()) * 16;
   return unsigned(b > cap ? cap : b);
+}
+
+// block shape of the apply kernels: x = channel pairs (a multiple of 32, at most 256), y = row lanes
+inline dim3 apply_block(int c) {
+  const int ppr = ((c + 7) & ~7) >> 1;
+  int bx = (ppr + 31) / 32 * 32;
+  if (bx > 256) bx = 256;
+  int by = 256 / bx;
+  return dim3(unsigned(bx), unsigned(by < 1 ? 1 : by), 1);
 }
 
 }  // namespace
@@ -395,11 +469,10 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
   if (!training) WFSP_REQUIRE(running_mean && running_var, "eval-mode batch norm needs running statistics");
   if (n_rows <= kSmallRows) {
-    bn_fwd_small<<<ceil_div((c + 7) & ~7, kCh), dim3(kCh, kRowLanes), 0, st>>>(
-        x, n_rows, n_rows_dev, c, gamma, beta, running_mean, running_var, momentum, eps, training, relu, y, y16,
-        save_mean, save_invstd);
+    WFSP_CHECK_CUDA(launch_cluster(bn_fwd_small, ceil_div((c + 7) & ~7, kCh), st, x, n_rows, n_rows_dev, c, gamma, beta,
+                                   running_mean, running_var, momentum, eps, training, relu, y, y16, save_mean,
+                                   save_invstd));
     count_launches(1);
-    WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   }
   if (training) {
@@ -415,7 +488,7 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(c, eps, running_mean, running_var, save_mean, save_invstd);
     count_launches(1);
   }
-  bn_apply<<<apply_blocks(n_rows), 256, 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+  bn_apply<<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                                    save_invstd, relu, y, y16);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -444,10 +517,9 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
     return WFSP_OK;
   }
   if (n_rows <= kSmallRows) {
-    bn_bwd_small<<<ceil_div((c + 7) & ~7, kCh), dim3(kCh, kRowLanes), 0, st>>>(
-        x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta);
+    WFSP_CHECK_CUDA(launch_cluster(bn_bwd_small, ceil_div((c + 7) & ~7, kCh), st, x, dy, n_rows, n_rows_dev, c, gamma, beta,
+                                   save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta));
     count_launches(1);
-    WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   }
   if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
@@ -456,7 +528,7 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
   bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
-  bn_bwd_apply<<<apply_blocks(n_rows), 256, 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
+  bn_bwd_apply<<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                                        save_invstd, d_gamma, d_beta, relu, dx, dx16);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
@@ -478,7 +550,7 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_apply<<<apply_blocks(n_rows), 256, 0, as_stream(stream)>>>(
+  bn_apply<<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
       x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -490,7 +562,7 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_bwd_apply<<<apply_blocks(n_rows), 256, 0, as_stream(stream)>>>(
+  bn_bwd_apply<<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
       x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
       static_cast<__nv_bfloat16*>(dx_bf16));
   count_launches(1);

@@ -314,6 +314,158 @@ __global__ void __launch_bounds__(kBlock) rb_tables(const int32_t* __restrict__ 
   if (prev != -1) *dup_flag = 1;
 }
 
+// ---- small inputs: the whole rulebook (table, output rows, pairs, neighbour tables) in ONE launch ----
+// A single CTA of 1024 threads walks the input rows in rounds of 1024 (thread t = row round*1024 + t).
+// Same phases as above with __syncthreads in place of kernel boundaries and running bases carried from
+// round to round; the CTA also initialises the coordinate table, the -1 padding of the pair arrays and the
+// neighbour tables, so no memset nodes are needed.  The number of rounds follows the LIVE row count, so a
+// capacity-sized graph buffer costs nothing.  A 64-event batch of the reference's detector (a few hundred
+// hits) is launch-latency bound: this replaces ~11 graph nodes per rulebook by one.
+constexpr int kSmallBlock = 1024;
+constexpr int kSmallWarps = kSmallBlock / 32;
+constexpr int64_t kSmallMaxRows = 8192;
+
+template <bool SUBM>
+__global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restrict__ indices, int64_t n_cap, Geom g,
+                                                        int32_t* __restrict__ table, int64_t cells,
+                                                        int32_t* __restrict__ out_indices, int64_t out_cap,
+                                                        int32_t* __restrict__ pairs, int32_t* __restrict__ pair_num,
+                                                        int32_t* __restrict__ n_out, int32_t* __restrict__ nbr_out,
+                                                        int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag) {
+  extern __shared__ int s_dyn[];  // [K][kSmallWarps] per-warp pair counts / prefixes, then [K] running bases
+  __shared__ int s_warp[kSmallWarps];
+  __shared__ int s_base;
+  const int K = g.kvol;
+  int* s_kbase = s_dyn + K * kSmallWarps;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Table t{table, nullptr, 0};
+  const int n = int(n_cap);
+  const int live = g.n_dev ? min(int(*g.n_dev), n) : n;
+  const int rounds = (live + kSmallBlock - 1) / kSmallBlock;
+  // phase 0: initialise.  The -1 padding of the pair arrays is part of the upstream-visible result; with
+  // device-side counts it is written for the live rows only (nothing reads the capacity tail).
+  for (int64_t i = tid; i < cells; i += kSmallBlock) table[i] = SUBM ? -1 : kRankInf;
+  if (!g.n_dev) {
+    for (int64_t i = tid; i < int64_t(2) * K * n; i += kSmallBlock) pairs[i] = -1;
+  } else {  // rows [0, live) of every (side, offset) list; the capacity tail stays unspecified
+    for (int64_t i = tid; i < int64_t(2) * K * live; i += kSmallBlock) pairs[(i / live) * n + (i % live)] = -1;
+  }
+  for (int64_t i = tid; i < int64_t(live) * K; i += kSmallBlock) nbr_in[i] = -1;
+  for (int k = tid; k < K; k += kSmallBlock) s_kbase[k] = 0;
+  if (tid == 0) { *dup_flag = 0; s_base = 0; }
+  __syncthreads();
+  // phase 1: claim cells
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int j = rd * kSmallBlock + tid;
+    Row r = load_row(indices, n, j, g);
+    if (!r.ok) continue;
+    if (SUBM) {
+      atomicMax(&table[(r.b * g.in_h + r.x) * g.in_w + r.y], j);
+    } else {
+      for (int kx = 0; kx < g.kh; ++kx) {
+        if (!((r.mx >> kx) & 1)) continue;
+        for (int ky = 0; ky < g.kw; ++ky) {
+          if (!((r.my >> ky) & 1)) continue;
+          int ox, oy;
+          atomicMin(&table[out_key(r, g, kx, ky, ox, oy)], j * K + kx * g.kw + ky);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  int64_t rows_out = live;
+  if (!SUBM) {
+    // phase 2: first touchers -> output rows in rank order, round after round
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int j = rd * kSmallBlock + tid;
+      Row r = load_row(indices, n, j, g);
+      int first = 0;
+      for (int kx = 0; kx < g.kh; ++kx)
+        for (int ky = 0; ky < g.kw; ++ky) {
+          int slot = 0, val, ox, oy;
+          if (candidate<false, false>(r, g, t, kx, ky, slot, val, ox, oy) && table[slot] == j * K + kx * g.kw + ky) ++first;
+        }
+      int incl = first;
+      for (int o = 1; o < 32; o <<= 1) {
+        int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      int off = s_base + incl - first;
+      for (int w = 0; w < warp; ++w) off += s_warp[w];
+      // a first toucher only rewrites its own cells, and nobody else's test `== own rank` can succeed on them
+      if (first) {
+        for (int kx = 0; kx < g.kh; ++kx)
+          for (int ky = 0; ky < g.kw; ++ky) {
+            int slot = 0, val, ox, oy;
+            if (candidate<false, false>(r, g, t, kx, ky, slot, val, ox, oy) && table[slot] == j * K + kx * g.kw + ky) {
+              if (off < out_cap) {
+                out_indices[3 * int64_t(off) + 0] = r.b;
+                out_indices[3 * int64_t(off) + 1] = ox;
+                out_indices[3 * int64_t(off) + 2] = oy;
+              }
+              table[slot] = -off - 1;
+              ++off;
+            }
+          }
+      }
+      __syncthreads();
+      if (tid == kSmallBlock - 1) s_base = off;  // inclusive end of the last thread = total so far
+      __syncthreads();
+    }
+    rows_out = s_base;
+    if (tid == 0) *n_out = s_base;
+  }
+  if (rows_out > out_cap) rows_out = out_cap;
+  for (int64_t i = tid; i < rows_out * K; i += kSmallBlock) nbr_out[i] = -1;
+  __syncthreads();
+  // phase 3: per-offset compaction in ascending input order
+  const unsigned lt = (1u << lane) - 1u;
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int j = rd * kSmallBlock + tid;
+    Row r = load_row(indices, n, j, g);
+    for (int kx = 0; kx < g.kh; ++kx)
+      for (int ky = 0; ky < g.kw; ++ky) {
+        int slot = 0, val = 0, ox, oy;
+        bool v = candidate<false, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+        unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) s_dyn[(kx * g.kw + ky) * kSmallWarps + warp] = __popc(bal);
+      }
+    __syncthreads();
+    for (int k = tid; k < K; k += kSmallBlock) {
+      int run = s_kbase[k];
+      for (int w = 0; w < kSmallWarps; ++w) {
+        const int c = s_dyn[k * kSmallWarps + w];
+        s_dyn[k * kSmallWarps + w] = run;
+        run += c;
+      }
+      s_kbase[k] = run;
+    }
+    __syncthreads();
+    for (int kx = 0; kx < g.kh; ++kx)
+      for (int ky = 0; ky < g.kw; ++ky) {
+        const int k = kx * g.kw + ky;
+        int slot = 0, val = 0, ox, oy;
+        bool v = candidate<false, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+        unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (v) {
+          const int pos = s_dyn[k * kSmallWarps + warp] + __popc(bal & lt);
+          const int o = SUBM ? val : -table[slot] - 1;
+          pairs[(int64_t(0) * K + k) * n + pos] = j;
+          pairs[(int64_t(1) * K + k) * n + pos] = o;
+          nbr_in[int64_t(j) * K + k] = o;
+          if (o < out_cap) {
+            const int prev = atomicExch(&nbr_out[int64_t(o) * K + k], j);
+            if (prev != -1) *dup_flag = 1;
+          }
+        }
+      }
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += kSmallBlock) pair_num[k] = s_kbase[k];
+}
+
 struct Plan {
   bool hash;
   int64_t table_slots;
@@ -480,4 +632,55 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
+}
+
+
+// Rulebook + neighbour tables in one call (what a layer needs before its first convolution).  Small
+// inputs (<= 1024 rows, direct table, kernel volume <= 256) take the single-launch path; everything else
+// runs the phase kernels above followed by rb_tables.
+extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                                   const int* in_shape, const int* ksize, const int* stride, const int* pad,
+                                   const int* dil, int subm, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
+                                   int32_t* pair_num, int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in,
+                                   int32_t* dup_flag, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(pair_num && dup_flag, "null output");
+  WFSP_REQUIRE(n_in == 0 || (pairs && nbr_out && nbr_in), "null output");
+  WFSP_REQUIRE(subm || n_out, "regular convolution needs n_out");
+  const int one[2] = {1, 1};
+  const int spad[2] = {ksize[0] / 2, ksize[1] / 2};
+  const int* st_ = subm ? one : stride;
+  const int* pd_ = subm ? spad : pad;
+  if (int rc = check_geom(ksize, st_, pd_, dil)) return rc;
+  int out_shape[2] = {in_shape[0], in_shape[1]};
+  if (!subm) wfsp_conv_out_shape(in_shape, ksize, stride, pad, dil, out_shape);
+  const int oh = out_shape[0] > 0 ? out_shape[0] : 0, ow = out_shape[1] > 0 ? out_shape[1] : 0;
+  const int kvol = ksize[0] * ksize[1];
+  const int64_t cells = int64_t(batch) * oh * ow;
+  cudaStream_t st = as_stream(stream);
+  if (n_in > 0 && n_in <= kSmallMaxRows && kvol <= 256 && !g_force_hash && cells > 0 && cells <= (int64_t(1) << 20) &&
+      n_in * int64_t(kvol) < int64_t(kRankInf)) {
+    WFSP_REQUIRE(workspace_bytes >= size_t(cells > 0 ? cells : 1) * 4, "rulebook workspace too small");
+    Geom g{in_shape[0], in_shape[1], oh, ow, ksize[0], ksize[1], st_[0], st_[1], pd_[0], pd_[1], dil[0], dil[1], kvol,
+           batch, n_in_dev};
+    const size_t smem = size_t(kvol) * (kSmallWarps + 1) * sizeof(int);
+    if (subm)
+      rb_small<true><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, static_cast<int32_t*>(workspace), cells, nullptr, n_in,
+                                                   pairs, pair_num, nullptr, nbr_out, nbr_in, dup_flag);
+    else
+      rb_small<false><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, static_cast<int32_t*>(workspace), cells, out_indices,
+                                                    out_cap, pairs, pair_num, n_out, nbr_out, nbr_in, dup_flag);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return WFSP_OK;
+  }
+  int rc;
+  if (subm)
+    rc = wfsp_rulebook_subm(indices, n_in, n_in_dev, batch, in_shape, ksize, dil, pairs, pair_num, workspace, workspace_bytes,
+                            stream);
+  else
+    rc = wfsp_rulebook_conv(indices, n_in, n_in_dev, batch, in_shape, ksize, stride, pad, dil, out_indices, out_cap, pairs,
+                            pair_num, n_out, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  WFSP_CHECK_CUDA(cudaMemsetAsync(dup_flag, 0, 4, st));
+  return wfsp_rulebook_tables(pairs, pair_num, kvol, n_in, n_in, subm ? n_in : out_cap, nbr_out, nbr_in, dup_flag, stream);
 }

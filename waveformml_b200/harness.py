@@ -43,6 +43,8 @@ class FlatGrads:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # one backward per step: the fused sparse stack writes these gradients in place (spconv/fused.py)
+            p._wfsp_grad_out = p.grad
             off += p.numel()
 
     def zero(self):

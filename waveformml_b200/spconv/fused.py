@@ -98,6 +98,18 @@ def compile_stack(modules, sparse_conv_cls, to_dense_cls):
     return Plan(blocks, to_dense)
 
 
+def _grad_target(param, shape, dev):
+    """Where a parameter gradient is written.  A training harness that owns a flat gradient buffer and
+    runs ONE backward per step can attach `param._wfsp_grad_out` (a contiguous fp32 view of the parameter's
+    shape, e.g. harness.FlatGrads): the kernel then writes the gradient there and autograd gets None -- no
+    accumulation kernel per parameter.  Otherwise a fresh tensor is returned to autograd as usual."""
+    tgt = getattr(param, "_wfsp_grad_out", None) if param is not None else None
+    if tgt is not None and tgt.dtype == torch.float32 and tgt.is_contiguous() and tgt.numel() == param.numel() \
+            and tgt.device == dev:
+        return tgt.view(shape), True
+    return torch.empty(shape, dtype=torch.float32, device=dev), False
+
+
 def _bn_ws(lib, n, c, dev):
     return torch.empty((lib.wfsp_bn_workspace_bytes(n, c),), dtype=torch.uint8, device=dev)
 
@@ -251,16 +263,16 @@ class FusedStackFunction(Function):
                 g16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
                 dx32 = torch.empty((n_dst, cout), dtype=torch.float32, device=dev) if want_bias else None
                 if b.bn is not None:
-                    dgam = torch.empty((cout,), dtype=torch.float32, device=dev)
-                    dbet = torch.empty((cout,), dtype=torch.float32, device=dev)
+                    dgam, gam_through = _grad_target(gamma_p, (cout,), dev)
+                    dbet, bet_through = _grad_target(beta_p, (cout,), dev)
                     ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
                     _lib.check(lib.wfsp_bn_relu_bwd_x(
                         _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
                         _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
                         _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
-                    if gamma_p is not None:
+                    if gamma_p is not None and not gam_through:
                         grads[4 * bi + 2] = dgam
-                    if beta_p is not None:
+                    if beta_p is not None and not bet_through:
                         grads[4 * bi + 3] = dbet
                 elif n_dst:
                     if b.relu:
@@ -278,7 +290,7 @@ class FusedStackFunction(Function):
                         grads[4 * bi + 1] = torch.where(live, dx32, torch.zeros((), device=dev)).sum(0)
                 # ---- wgrad
                 if ctx.needs_input_grad[4 + 4 * bi]:
-                    dw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=dev)
+                    dw, w_through = _grad_target(w_p, (kvol, cin, cout), dev)
                     if rb is None:
                         pa = pb = pn = None
                         pitch = n_in
@@ -291,7 +303,8 @@ class FusedStackFunction(Function):
                     _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, _lib.ptr(n_src_dev), cin, _lib.ptr(g16), n_dst,
                                                         _lib.ptr(n_dst_dev), cout, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(pn),
                                                         kvol, pitch, hint, _lib.ptr(dw), 0, st()))
-                    grads[4 * bi] = dw.view(w_p.shape)
+                    if not w_through:
+                        grads[4 * bi] = dw.view(w_p.shape)
                 # ---- dgrad -> dy of the previous block (or of the stack's input)
                 if bi > 0 or ctx.need_in_grad:
                     nbr_t = None if rb is None else (rb.nbr_out if conv.inverse else rb.nbr_in)

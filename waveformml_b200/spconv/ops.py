@@ -89,12 +89,16 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     n_in_dev = n_rows if static else None
     n_out_dev = None
+    dup = torch.empty((1,), dtype=torch.int32, device=dev)
+    nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         if subm:
-            _lib.check(lib.wfsp_rulebook_subm(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
-                                              _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(dilation),
-                                              _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(ws), ws.numel(),
-                                              _lib.stream()))
+            nbr_out = torch.empty((N, K), dtype=torch.int32, device=dev)
+            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+                                               _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
+                                               _lib.ints(padding), _lib.ints(dilation), 1, None, N, _lib.ptr(pairs),
+                                               _lib.ptr(pair_num), None, _lib.ptr(nbr_out), _lib.ptr(nbr_in),
+                                               _lib.ptr(dup), _lib.ptr(ws), ws.numel(), _lib.stream()))
             outids, n_out = indices, N
             n_out_dev = n_in_dev
         else:
@@ -102,21 +106,19 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
             cap = max(1, min(N * K, cells))
             outbuf = torch.empty((cap, 3), dtype=torch.int32, device=dev)
             n_out_t = torch.empty((1,), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_conv(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
-                                              _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
-                                              _lib.ints(padding), _lib.ints(dilation), _lib.ptr(outbuf), cap,
-                                              _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t), _lib.ptr(ws),
-                                              ws.numel(), _lib.stream()))
+            # nbr_out is sized at the bound: its live rows are known only on the device
+            nbr_cap = torch.empty((cap, K), dtype=torch.int32, device=dev)
+            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+                                               _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
+                                               _lib.ints(padding), _lib.ints(dilation), 0, _lib.ptr(outbuf), cap,
+                                               _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t),
+                                               _lib.ptr(nbr_cap), _lib.ptr(nbr_in), _lib.ptr(dup), _lib.ptr(ws),
+                                               ws.numel(), _lib.stream()))
             if static:
-                n_out, outids, n_out_dev = cap, outbuf, n_out_t
+                n_out, outids, n_out_dev, nbr_out = cap, outbuf, n_out_t, nbr_cap
             else:
                 n_out = int(n_out_t.item())  # the one readback per rulebook (output tensor shapes need it)
-                outids = outbuf[:n_out]
-        nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
-        nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
-        dup = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(lib.wfsp_rulebook_tables(_lib.ptr(pairs), _lib.ptr(pair_num), K, N, N, n_out, _lib.ptr(nbr_out),
-                                            _lib.ptr(nbr_in), _lib.ptr(dup), _lib.stream()))
+                outids, nbr_out = outbuf[:n_out], nbr_cap[:n_out]
     if check_duplicates and not static and int(dup.item()) != 0:
         raise RuntimeError("duplicate (batch, x, y) coordinates in the input: not supported by the "
                            "output-stationary kernels")
