@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
     float* __restrict__ running_var, float momentum, float eps, int training, int relu, float* __restrict__ y,
     __nv_bfloat16* __restrict__ y16, float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  __shared__ float red[kRowLanes][kCh];
-  __shared__ float part[1][kCh];
+  __shared__ float red[kRowLanes][kCh], red2[kRowLanes][kCh], red3[kRowLanes][kCh];
+  __shared__ float part[3][kCh];
   cg::cluster_group cluster = cg::this_cluster();
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -338,19 +338,54 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_fwd_small(
   const bool lead = cluster.block_rank() == 0 && ty == 0;
   float mean, invstd;
   if (training) {
-    float s[1] = {0.f};
-    if (on) for (int64_t r = row0; r < n; r += rstep) s[0] += x[r * c + ch];
-    cluster_col_sum<1>(s, red, part, tx, ty, cluster);
-    mean = n > 0 ? s[0] / float(n) : 0.f;
-    float m2[1] = {0.f};
-    if (on) for (int64_t r = row0; r < n; r += rstep) { const float d = x[r * c + ch] - mean; m2[0] += d * d; }
-    cluster_col_sum<1>(m2, red, part, tx, ty, cluster);
-    invstd = n > 0 ? rsqrtf(m2[0] / float(n) + eps) : 0.f;
+    // one pass: per-thread (count, mean, M2) from sums shifted by the thread's first value, merged with Chan's
+    // formula over the 16 row lanes (by lane 0, in lane order) and then over the cluster's CTAs in rank order
+    float cnt = 0.f, mu = 0.f, m2 = 0.f;
+    if (on && row0 < n) {
+      const float K = x[row0 * c + ch];
+      float sd = 0.f, sq = 0.f;
+      for (int64_t r = row0; r < n; r += rstep) {
+        const float d = x[r * c + ch] - K;
+        sd += d;
+        sq += d * d;
+        cnt += 1.f;
+      }
+      mu = K + sd / cnt;
+      m2 = fmaxf(sq - sd * sd / cnt, 0.f);
+    }
+    red[ty][tx] = cnt; red2[ty][tx] = mu; red3[ty][tx] = m2;
+    __syncthreads();
+    if (ty == 0) {
+      for (int l = 1; l < kRowLanes; ++l) {
+        const float nb = red[l][tx];
+        if (nb > 0.f) {
+          const float delta = red2[l][tx] - mu, tot = cnt + nb;
+          mu += delta * nb / tot;
+          m2 += red3[l][tx] + delta * delta * cnt * nb / tot;
+          cnt = tot;
+        }
+      }
+      part[0][tx] = cnt; part[1][tx] = mu; part[2][tx] = m2;
+    }
+    cluster.sync();
+    cnt = 0.f; mu = 0.f; m2 = 0.f;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+      const float nb = cluster.map_shared_rank(&part[0][0], r)[tx];
+      if (nb > 0.f) {
+        const float delta = cluster.map_shared_rank(&part[1][0], r)[tx] - mu, tot = cnt + nb;
+        mu += delta * nb / tot;
+        m2 += cluster.map_shared_rank(&part[2][0], r)[tx] + delta * delta * cnt * nb / tot;
+        cnt = tot;
+      }
+    }
+    cluster.sync();  // peers have read this CTA's partials
+    mean = mu;
+    invstd = n > 0 ? rsqrtf(m2 / float(n) + eps) : 0.f;
     if (on && lead) {
       save_mean[ch] = mean;
       save_invstd[ch] = invstd;
       if (n > 0 && running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
-      if (n > 1 && running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (m2[0] / float(n - 1));
+      if (n > 1 && running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (m2 / float(n - 1));
     }
   } else {
     mean = on ? running_mean[ch] : 0.f;

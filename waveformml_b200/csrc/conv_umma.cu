@@ -652,10 +652,13 @@ ApplyPlan apply_plan(int kvol, int64_t n_src, int c_red, int c_dst) {
 }
 
 // stages that fit: prefer two resident CTAs per SM when a 4-deep ring fits in ~110 KB
-int pick_stages(int stage_bytes, int extra_bytes) {
-  if (4 * stage_bytes + extra_bytes <= 110 * 1024) return 4;
+// `alone`: the launch has at most one CTA per SM anyway (a small, latency-bound problem): take the deepest
+// ring that fits, every extra slice in flight shortens the serial walk over (offset, channel slice).
+int pick_stages(int stage_bytes, int extra_bytes, bool alone = false) {
+  if (!alone && 4 * stage_bytes + extra_bytes <= 110 * 1024) return 4;
   int s = (kSmemMax - extra_bytes) / stage_bytes;
-  return s < 2 ? 2 : (s > 6 ? 6 : s);
+  const int cap = alone ? kMaxStages : 6;
+  return s < 2 ? 2 : (s > cap ? cap : s);
 }
 
 }  // namespace
@@ -732,7 +735,8 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
   const int stage_bytes = p.rblk * kABytes + n_tile * 128;
   p.staged = (nbr != nullptr && kvol <= kNbrStageK) ? 1 : 0;
   const int nbr_bytes = p.staged ? p.rblk * kTileM * kvol * 4 : 0;
-  p.stages = pick_stages(stage_bytes, nbr_bytes + 1024);
+  const bool alone = ceil_div<int64_t>(row_blocks, p.rblk) * n_tiles <= sm_count();
+  p.stages = pick_stages(stage_bytes, nbr_bytes + 1024, alone);
   const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + 1024;
   if (smem > size_t(227) * 1024) return set_error(WFSP_EUNSUPPORTED, "conv_apply tile needs %zu B of shared memory", smem);
   dim3 grid(unsigned(ceil_div<int64_t>(n_dst, int64_t(kTileM) * p.rblk)), unsigned(n_tiles));
@@ -788,21 +792,26 @@ int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const
   p.n_a_dev = n_a_dev;
   p.a = a16; p.n_a = n_a; p.c_a = c_a; p.b = b16; p.n_b = n_b; p.c_b = c_b;
   p.pair_a = pair_a; p.pair_b = pair_b; p.pair_num = pair_num; p.kvol = kvol; p.pitch = pitch; p.dw = d_weight;
-  const int n_tiles = (c_b + 255) / 256;
+  // pairs per offset that bound the split of the reduction: the caller's hint (graph path, where only
+  // capacities are known on the host) or the capacity itself
+  int64_t rows = pair_a ? pitch : n_a;
+  if (pairs_hint > 0 && pairs_hint < rows) rows = pairs_hint;
+  // A short pair list (a few pipeline slices) makes the launch latency bound: its cost is the epilogue of
+  // the few CTAs, so the d_weight tile is cut small (128 x 64) and spread over many CTAs.  Long lists take
+  // wide tiles (up to 256 x 256) that reuse every gathered row as much as TMEM allows.
+  const bool few_pairs = rows <= 32 * kSliceK;
+  int n_tiles = (c_b + 255) / 256;
+  if (few_pairs) n_tiles = (c_b + 63) / 64;
   p.n_tile = round_up((c_b + n_tiles - 1) / n_tiles, 16);
   p.acc_stride = round_up(p.n_tile, 32);
   // two 128-channel blocks of `a` per CTA when `a` has more than 128 channels and both accumulators fit
-  const int mt = (c_a > kTileM && 2 * p.acc_stride <= 512) ? 2 : 1;
+  const int mt = (!few_pairs && c_a > kTileM && 2 * p.acc_stride <= 512) ? 2 : 1;
   p.m_groups = ceil_div(c_a, kTileM * mt);
   const int tiles = p.m_groups * n_tiles;
   const int b_panels = (p.n_tile + 63) / 64;
   const int stage_bytes = 2 * mt * 8192 + b_panels * 8192;
   p.stages = pick_stages(stage_bytes, 1024);
   const size_t smem = size_t(p.stages) * stage_bytes + 1024;
-  // pairs per offset that bound the split of the reduction: the caller's hint (graph path, where only
-  // capacities are known on the host) or the capacity itself
-  int64_t rows = pair_a ? pitch : n_a;
-  if (pairs_hint > 0 && pairs_hint < rows) rows = pairs_hint;
   // Split the pair list so that the CTAs fill whole rounds of the machine.  Modelled cost of a launch =
   // rounds x (pipeline slices of one CTA + a fixed term for its prologue and the atomic epilogue).
   int nsplit = 1;

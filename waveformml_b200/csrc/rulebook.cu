@@ -325,18 +325,21 @@ constexpr int kSmallBlock = 1024;
 constexpr int kSmallWarps = kSmallBlock / 32;
 constexpr int64_t kSmallMaxRows = 8192;
 
-template <bool SUBM>
+template <bool SUBM, bool SMEM_TABLE>
 __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restrict__ indices, int64_t n_cap, Geom g,
-                                                        int32_t* __restrict__ table, int64_t cells,
+                                                        int32_t* __restrict__ table_gmem, int64_t cells,
                                                         int32_t* __restrict__ out_indices, int64_t out_cap,
                                                         int32_t* __restrict__ pairs, int32_t* __restrict__ pair_num,
                                                         int32_t* __restrict__ n_out, int32_t* __restrict__ nbr_out,
                                                         int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag) {
-  extern __shared__ int s_dyn[];  // [K][kSmallWarps] per-warp pair counts / prefixes, then [K] running bases
+  extern __shared__ int s_dyn[];  // [K][kSmallWarps] per-warp pair counts / prefixes, [K] running bases, [cells] table
   __shared__ int s_warp[kSmallWarps];
   __shared__ int s_base;
   const int K = g.kvol;
   int* s_kbase = s_dyn + K * kSmallWarps;
+  // the coordinate table lives in shared memory when it fits: every probe is then an on-chip access instead
+  // of a dependent L2 round trip (nine per row and phase)
+  int32_t* table = SMEM_TABLE ? s_kbase + K : table_gmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Table t{table, nullptr, 0};
   const int n = int(n_cap);
@@ -662,13 +665,25 @@ extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const i
     WFSP_REQUIRE(workspace_bytes >= size_t(cells > 0 ? cells : 1) * 4, "rulebook workspace too small");
     Geom g{in_shape[0], in_shape[1], oh, ow, ksize[0], ksize[1], st_[0], st_[1], pd_[0], pd_[1], dil[0], dil[1], kvol,
            batch, n_in_dev};
-    const size_t smem = size_t(kvol) * (kSmallWarps + 1) * sizeof(int);
-    if (subm)
-      rb_small<true><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, static_cast<int32_t*>(workspace), cells, nullptr, n_in,
-                                                   pairs, pair_num, nullptr, nbr_out, nbr_in, dup_flag);
-    else
-      rb_small<false><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, static_cast<int32_t*>(workspace), cells, out_indices,
-                                                    out_cap, pairs, pair_num, n_out, nbr_out, nbr_in, dup_flag);
+    size_t smem = size_t(kvol) * (kSmallWarps + 1) * sizeof(int);
+    const bool in_smem = smem + size_t(cells) * 4 <= size_t(200) * 1024;
+    if (in_smem) smem += size_t(cells) * 4;
+    int32_t* tab = static_cast<int32_t*>(workspace);
+#define WFSP_RB_SMALL(SUBM, SM, OUT, CAP, NOUT)                                                                  \
+    do {                                                                                                        \
+      WFSP_CHECK_CUDA(cudaFuncSetAttribute(rb_small<SUBM, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           208 * 1024));                                                        \
+      rb_small<SUBM, SM><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, tab, cells, OUT, CAP, pairs, pair_num,  \
+                                                       NOUT, nbr_out, nbr_in, dup_flag);                         \
+    } while (0)
+    if (subm) {
+      if (in_smem) WFSP_RB_SMALL(true, true, nullptr, n_in, nullptr);
+      else WFSP_RB_SMALL(true, false, nullptr, n_in, nullptr);
+    } else {
+      if (in_smem) WFSP_RB_SMALL(false, true, out_indices, out_cap, n_out);
+      else WFSP_RB_SMALL(false, false, out_indices, out_cap, n_out);
+    }
+#undef WFSP_RB_SMALL
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
