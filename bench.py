@@ -37,6 +37,15 @@ WORKLOADS = {
 }
 
 
+_RESULT = None  # the process's real stdout (see _quiet_stdout)
+
+
+def emit(line):
+    out = _RESULT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +156,26 @@ def cpu_step_fn(model_cpu_state, batch, n_linear):
     return step
 
 
+def pick_cpu_threads(step):
+    """The CPU path is many small GEMMs and gathers: more threads is not faster (on a 100+-core host all cores
+    is several times SLOWER than a handful).  To time the reference at its best, try a few thread counts on
+    one step each and keep the fastest; the count used is reported as `cores`."""
+    ncpu = os.cpu_count() or 1
+    best_t, best_s = 1, None
+    for t in sorted({1, 4, 16, min(64, ncpu), ncpu}):
+        if t > ncpu:
+            continue
+        torch.set_num_threads(t)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if best_s is None or dt < best_s:
+            best_t, best_s = t, dt
+    torch.set_num_threads(best_t)
+    return best_t
+
+
 def time_cpu(step, budget_s, warmup=2, min_steps=3, max_steps=200):
     for _ in range(warmup):
         step()
@@ -164,11 +193,11 @@ def run_reference(args):
     if rank != 0:
         return 0
     from waveformml_b200 import stacks
-    torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     model = stacks.PSDClassifier()
     batch = make_batch(args, 0)
     step = cpu_step_fn(cpu_reference_model(model), batch, model.n_linear)
+    pick_cpu_threads(step)
     for _ in range(max(args.warmup, 1)):
         step()
     times = []
@@ -188,11 +217,12 @@ def run_reference(args):
                    "rows": int(batch["coords"].shape[0])},
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d full training steps of %d events (restated spconv-1.2.1 CPU algorithm: C hash "
-                                   "rulebook + per-offset gather/torch.mm/scatter-add, torch-CPU BN/ReLU/Linear/SGD)"
-                                   % (len(times), args.batch)},
+                                   "rulebook + per-offset gather/torch.mm/scatter-add, torch-CPU BN/ReLU/Linear/SGD); "
+                                   "thread count = fastest of {1,4,16,64,all} on this host (%d cores)"
+                                   % (len(times), args.batch, os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -231,31 +261,68 @@ def conv_breakdown(model, idx, feats, batch_size, flush, reps=10):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts)) * 1e-3
 
+    import ctypes
+    from waveformml_b200 import _lib
+    from waveformml_b200.spconv.fused import pitch8
+    lib = _lib.load()
+    st = _lib.stream
+
+    def cast16(t):
+        out = torch.empty((t.shape[0], pitch8(t.shape[1])), dtype=torch.bfloat16, device=t.device)
+        _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(t), t.shape[0], None, t.shape[1], _lib.ptr(out), st()))
+        return out
+
+    def prep(w3, kvol, c_red, c_dst, transpose):
+        buf = torch.empty((lib.wfsp_prepared_weight_bytes(kvol, c_red, c_dst),), dtype=torch.uint8, device=w3.device)
+        job = (_lib.PrepJob * 1)(_lib.PrepJob(w3.data_ptr(), buf.data_ptr(), kvol, c_red, c_dst, transpose))
+        _lib.check(lib.wfsp_prep_weights(ctypes.cast(job, ctypes.c_void_p), 1, st()))
+        return buf
+
     rows = []
     for li, (mod, fin, rb, fout) in enumerate(captured):
         kvol = 1 if rb is None else rb.kvol
         cin, cout = mod.in_channels, mod.out_channels
-        w3 = mod.weight.detach().view(kvol, cin, cout)
+        w3 = mod.weight.detach().view(kvol, cin, cout).contiguous()
         n_in, n_out = fin.shape[0], fout.shape[0]
         pairs = n_in if rb is None else int(rb.pair_num.sum().item())
         g = torch.randn_like(fout)
+        a16, g16 = cast16(fin.contiguous()), cast16(g)
+        w_f, w_d = prep(w3, kvol, cin, cout, 0), prep(w3, kvol, cout, cin, 1)
+        out_f = torch.empty((n_out, cout), device=fin.device)
+        out_d = torch.empty((n_in, cin), device=fin.device)
+        dw = torch.empty((kvol, cin, cout), device=fin.device)
         flops = 2.0 * pairs * cin * cout
-        # minimum traffic with fp32 activations in HBM and the weights read once (bytes, SURVEY 8d with the
-        # activation element size that is actually stored: 4)
-        w_bytes = kvol * cin * cout * 4
-        fwd_b = 4 * (n_in * cin + n_out * cout) + w_bytes + 4 * pairs
-        dg_b = 4 * (n_out * cout + n_in * cin) + w_bytes + 4 * pairs
-        wg_b = 4 * (n_in * cin + n_out * cout) + w_bytes + 8 * pairs
+        # algorithmic traffic of ONE kernel launch: bf16 operand rows read once, fp32
+        # result rows written once, bf16 weights read once (wgrad: fp32 d_weight written once), 4 B of
+        # neighbour index per pair (wgrad: 8 B, both sides of the pair)
+        fwd_b = 2 * n_in * pitch8(cin) + 4 * n_out * cout + 2 * kvol * cin * cout + 4 * pairs
+        dg_b = 2 * n_out * pitch8(cout) + 4 * n_in * cin + 2 * kvol * cin * cout + 4 * pairs
+        wg_b = 2 * n_in * pitch8(cin) + 2 * n_out * pitch8(cout) + 4 * kvol * cin * cout + 8 * pairs
         nbr_o = None if rb is None else rb.nbr_out
         nbr_i = None if rb is None else rb.nbr_in
         pa = None if rb is None else rb.pairs[0]
         pb = None if rb is None else rb.pairs[1]
         pn = None if rb is None else rb.pair_num
+        pitch = n_in if rb is None else rb.pairs.shape[-1]
         name = "L%d %d->%d k%d" % (li, cin, cout, mod.kernel_size[0])
-        rows.append({"name": name + " fwd", "kernel": "conv_apply", "s": timed(lambda: Fsp.conv_apply(fin, w3, 0, None, nbr_o, n_out, cout, mode)), "flops": flops, "bytes": fwd_b})
+
+        def fwd():
+            _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), n_in, None, cin, _lib.ptr(w_f), None, _lib.ptr(nbr_o), kvol,
+                                                _lib.ptr(out_f), n_out, None, 0, cout, st()))
+
+        def dgrad():
+            _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(g16), n_out, None, cout, _lib.ptr(w_d), None, _lib.ptr(nbr_i), kvol,
+                                                _lib.ptr(out_d), n_in, None, 0, cin, st()))
+
+        def wgrad():
+            _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, None, cin, _lib.ptr(g16), n_out, None, cout,
+                                                _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(pn), kvol, pitch, 0, _lib.ptr(dw), 0,
+                                                st()))
+
+        rows.append({"name": name + " fwd", "kernel": "conv_apply_umma_kernel", "s": timed(fwd), "flops": flops, "bytes": fwd_b})
         if li > 0:
-            rows.append({"name": name + " dgrad", "kernel": "conv_apply", "s": timed(lambda: Fsp.conv_apply(g, w3, 1, None, nbr_i, n_in, cin, mode)), "flops": flops, "bytes": dg_b})
-        rows.append({"name": name + " wgrad", "kernel": "conv_wgrad", "s": timed(lambda: Fsp.conv_wgrad(fin, g, pa, pb, pn, kvol, mode)), "flops": flops, "bytes": wg_b})
+            rows.append({"name": name + " dgrad", "kernel": "conv_apply_umma_kernel", "s": timed(dgrad), "flops": flops, "bytes": dg_b})
+        rows.append({"name": name + " wgrad", "kernel": "conv_wgrad_umma_kernel", "s": timed(wgrad), "flops": flops, "bytes": wg_b})
     return rows, e
 
 
@@ -402,7 +469,18 @@ def run_ours(args):
         else:
             roof = {"bound": "hbm", "achieved": top["bytes"] / top["s"] / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        # DRAM bytes of the same launch from the committed `ncu --set full` capture of this command line
+        # (profiles/r1_traffic.json, made by scripts/ncu_traffic.py); null if that capture does not exist
         roof["traffic"] = None
+        roof["algorithmic_bytes"] = top["bytes"]
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            parts = top["name"].split()
+            ent = tr["%s_%d" % (args.workload, B)][parts[0] + " " + parts[-1]]
+            roof["traffic"] = ent["dram_bytes"]
+            roof["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, %s)" % ent["kernel"]
+        except Exception:
+            pass
         roof["kernel"] = top["name"] + " (" + top["kernel"] + ")"
         roof["kernel_ms"] = top["s"] * 1e3
         roof["share_of_step"] = top["s"] * 1e3 / ms_per_step
@@ -415,15 +493,15 @@ def run_ours(args):
         line["conv_kernels_share_of_step"] = tot * 1e3 / ms_per_step
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count())
         cstep = cpu_step_fn(cpu_reference_model(model), batch, model.n_linear)
+        pick_cpu_threads(cstep)
         times = time_cpu(cstep, args.cpu_seconds)
         cms = float(np.mean(times))
         line["cpu_baseline"] = {"value": B / cms, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "%d full training steps of the same %d-event batch (restated spconv-1.2.1 "
                                           "CPU algorithm, oracle/)" % (len(times), B)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
@@ -437,6 +515,16 @@ def run_ours(args):
     return 0
 
 
+def _quiet_stdout():
+    """Libraries print to fd 1 behind our back (NCCL's version banner, cuBLAS notices).  The contract is ONE
+    JSON line on stdout: send fd 1 to stderr for the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
     a = parse()
+    _RESULT = _quiet_stdout()
     sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
