@@ -18,6 +18,7 @@ namespace {
 
 constexpr int kRows = 1024;  // rows per partial
 constexpr int kCh = 32;      // channels per block (one 128-byte row segment)
+constexpr int kPartLanes = 32;  // row lanes of the partial-statistics kernels: 1024 threads per block keep enough loads in flight
 
 __device__ __forceinline__ int64_t live_rows(int64_t n, const int32_t* n_dev) { return n_dev ? int64_t(*n_dev) : n; }
 
@@ -25,10 +26,10 @@ __device__ __forceinline__ int64_t live_rows(int64_t n, const int32_t* n_dev) { 
 // sum of squares of (x - K), K = its first value (a shift that removes the cancellation of the textbook
 // formula), turns them into (count, mean, M2) and the eight row lanes are merged with Chan's formula in a
 // fixed order.
-__global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict__ x, int64_t n_cap,
+__global__ void __launch_bounds__(kCh * kPartLanes) bn_partial_stats(const float* __restrict__ x, int64_t n_cap,
                                                         const int32_t* __restrict__ n_dev, int c,
                                                         float* __restrict__ part /* [nblk][2][c] mean, M2 */) {
-  __shared__ float s_cnt[8][kCh], s_mean[8][kCh], s_m2[8][kCh];
+  __shared__ float s_cnt[kPartLanes][kCh], s_mean[kPartLanes][kCh], s_m2[kPartLanes][kCh];
   const int64_t n = live_rows(n_cap, n_dev);
   const int64_t r0 = int64_t(blockIdx.x) * kRows;
   if (r0 >= n) return;
@@ -40,13 +41,13 @@ __global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict_
     const float* xp = x + r0 * c + ch;
     const float K = xp[int64_t(ty) * c];
     float sd = 0.f, sq = 0.f;
-#pragma unroll 4
-    for (int r = ty; r < rows; r += 8) {
+#pragma unroll 8
+    for (int r = ty; r < rows; r += kPartLanes) {
       const float d = xp[int64_t(r) * c] - K;
       sd += d;
       sq += d * d;
     }
-    cnt = float((rows - ty + 7) / 8);
+    cnt = float((rows - ty + kPartLanes - 1) / kPartLanes);
     mean = K + sd / cnt;
     m2 = sq - sd * sd / cnt;
     if (m2 < 0.f) m2 = 0.f;
@@ -54,8 +55,7 @@ __global__ void __launch_bounds__(256) bn_partial_stats(const float* __restrict_
   s_cnt[ty][tx] = cnt; s_mean[ty][tx] = mean; s_m2[ty][tx] = m2;
   __syncthreads();
   if (ty == 0 && ch < c) {
-#pragma unroll
-    for (int l = 1; l < 8; ++l) {
+    for (int l = 1; l < kPartLanes; ++l) {
       const float nb = s_cnt[l][tx];
       if (nb > 0.f) {
         const float delta = s_mean[l][tx] - mean, tot = cnt + nb;
@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
 }
 
 // backward partials: sum(dy') and sum(dy' * xhat) per (row chunk, channel); dy' = dy masked by relu
-__global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(kCh * kPartLanes) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
                                                       int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       int relu, float* __restrict__ part /* [nblk][2][c] */) {
-  __shared__ float red0[8][kCh], red1[8][kCh];
+  __shared__ float red0[kPartLanes][kCh], red1[kPartLanes][kCh];
   const int64_t n = live_rows(n_cap, n_dev);
   const int64_t r0 = int64_t(blockIdx.x) * kRows;
   if (r0 >= n) return;
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ 
   float s0 = 0.f, s1 = 0.f;
   if (ch < c) {
     const float m = mean[ch], is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-    for (int r = ty; r < rows; r += 8) {
+#pragma unroll 4
+    for (int r = ty; r < rows; r += kPartLanes) {
       const float xh = (x[(r0 + r) * c + ch] - m) * is;
       float d = dy[(r0 + r) * c + ch];
       if (relu && xh * g + b <= 0.f) d = 0.f;
@@ -205,8 +206,7 @@ __global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ 
   __syncthreads();
   if (ty == 0 && ch < c) {
     float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
+    for (int i = 0; i < kPartLanes; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
     part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = t0;
     part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = t1;
   }
@@ -515,7 +515,7 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
       return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
     float* part = static_cast<float*>(workspace);
     dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
-    bn_partial_stats<<<grid, dim3(32, 8), 0, st>>>(x, n_rows, n_rows_dev, c, part);
+    bn_partial_stats<<<grid, dim3(32, kPartLanes), 0, st>>>(x, n_rows, n_rows_dev, c, part);
     bn_finalize_stats<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, eps, momentum, running_mean,
                                                         running_var, save_mean, save_invstd);
     count_launches(2);
@@ -561,7 +561,7 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
     return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
   float* part = static_cast<float*>(workspace);
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
-  bn_bwd_partial<<<grid, dim3(32, 8), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+  bn_bwd_partial<<<grid, dim3(32, kPartLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
   bn_bwd_apply<<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
                                                                        save_invstd, d_gamma, d_beta, relu, dx, dx16);

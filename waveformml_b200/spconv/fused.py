@@ -110,6 +110,19 @@ def _grad_target(param, shape, dev):
     return torch.empty(shape, dtype=torch.float32, device=dev), False
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One extra stream per device.  The geometry of a stack (rulebooks: indices only) does not depend on
+    the features, and wgrad does not feed the dgrad chain, so both run beside the main stream and join it
+    through events -- inside a CUDA graph capture these become parallel branches of the graph."""
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
 def _bn_ws(lib, n, c, dev):
     return torch.empty((lib.wfsp_bn_workspace_bytes(n, c),), dtype=torch.uint8, device=dev)
 
@@ -157,10 +170,27 @@ class FusedStackFunction(Function):
             if n0:
                 _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(feats), n0, _lib.ptr(x.n_rows), c0, _lib.ptr(a16), st()))
 
+            # ---- geometry of every block on the side stream (overlaps weight preparation and the first layers)
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            geoms, gcur = [], x
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                for b in blocks:
+                    rb, outids, out_shape, out_rows = b.conv.geometry(gcur)
+                    ready = torch.cuda.Event()
+                    ready.record(side)
+                    nxt = x.__class__(None, outids, out_shape, gcur.batch_size, n_rows=out_rows)
+                    nxt.indice_dict, nxt.grid = gcur.indice_dict, gcur.grid
+                    geoms.append((rb, outids, out_shape, out_rows, gcur, nxt, ready))
+                    gcur = nxt
+
             saved, cur, out32 = [], x, None
             for bi, b in enumerate(blocks):
                 conv = b.conv
-                rb, outids, out_shape, out_rows = conv.geometry(cur)
+                rb, outids, out_shape, out_rows, cur, nxt, ready = geoms[bi]
+                main.wait_event(ready)
                 last = bi == len(blocks) - 1
                 kvol = 1 if rb is None else rb.kvol
                 cin, cout = conv.in_channels, conv.out_channels
@@ -213,8 +243,6 @@ class FusedStackFunction(Function):
                                                            _lib.ptr(y16), st()))
                 keep_x = xf if (b.bn is not None or b.relu) else None
                 saved.append((a16, keep_x, mean, invstd, rb, cur.indices.shape[0], n_dst, n_src_dev, n_dst_dev))
-                nxt = x.__class__(None, outids, out_shape, cur.batch_size, n_rows=out_rows)
-                nxt.indice_dict, nxt.grid = cur.indice_dict, cur.grid
                 cur, a16, out32 = nxt, y16, y32
 
             holder["tensor"] = cur  # geometry of the stack's output
@@ -252,6 +280,8 @@ class FusedStackFunction(Function):
                                                  _lib.ptr(final.n_rows), c, final.batch_size, h, w, _lib.ptr(dy), st()))
             else:
                 dy = g
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            side_used = False
             for bi in range(len(blocks) - 1, -1, -1):
                 b = blocks[bi]
                 conv = b.conv
@@ -300,9 +330,16 @@ class FusedStackFunction(Function):
                     hint = 0
                     if n_src_dev is not None:
                         hint = Fsp.hints.get(pn if pn is not None else n_src_dev)
-                    _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, _lib.ptr(n_src_dev), cin, _lib.ptr(g16), n_dst,
-                                                        _lib.ptr(n_dst_dev), cout, _lib.ptr(pa), _lib.ptr(pb), _lib.ptr(pn),
-                                                        kvol, pitch, hint, _lib.ptr(dw), 0, st()))
+                    # wgrad only feeds the optimiser: it runs on the side stream while dgrad / the previous
+                    # block's BatchNorm backward continue on the main one
+                    g_ready = torch.cuda.Event()
+                    g_ready.record(main)
+                    with torch.cuda.stream(side):
+                        side.wait_event(g_ready)
+                        _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, _lib.ptr(n_src_dev), cin, _lib.ptr(g16),
+                                                            n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(pa), _lib.ptr(pb),
+                                                            _lib.ptr(pn), kvol, pitch, hint, _lib.ptr(dw), 0, st()))
+                    side_used = True
                     if not w_through:
                         grads[4 * bi] = dw.view(w_p.shape)
                 # ---- dgrad -> dy of the previous block (or of the stack's input)
@@ -315,6 +352,10 @@ class FusedStackFunction(Function):
                                                             ctypes.c_void_p(wbuf.data_ptr() + offs[bi][1]), None,
                                                             _lib.ptr(nbr_t), kvol, _lib.ptr(dy), n_in, _lib.ptr(n_src_dev),
                                                             hint, cin, st()))
+            if side_used:
+                joined = torch.cuda.Event()
+                joined.record(side)
+                main.wait_event(joined)
             d_feats = None
             if ctx.need_in_grad:
                 d_feats = dy if ctx.in_dtype == torch.float32 else dy.to(ctx.in_dtype)
