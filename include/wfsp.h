@@ -63,6 +63,10 @@ int wfsp_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host)
 int wfsp_set_option(const char* name, int value);
 /* number of CUDA kernels this library has launched in the calling process (monotonic) */
 unsigned long long wfsp_kernel_launches(void);
+/* test hook for the TMA gather path: rows idx128[0..127] (any value; rows outside [0, rows) read as
+ * zero) x channels [c0, c0+64) of the bf16 matrix [rows][pitch] -> out_bf16 [128][64] */
+int wfsp_selftest_gather4(const void* src_bf16, int64_t rows, int channels, int64_t pitch,
+                          const int32_t* idx128, int c0, void* out_bf16, wfsp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (1) Sparse-tensor batcher.

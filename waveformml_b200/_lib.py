@@ -22,6 +22,7 @@ SIGNATURES = {
     "wfsp_device_info": (_int, [_intp, _intp, _intp]),
     "wfsp_set_option": (_int, [_c.c_char_p, _int]),
     "wfsp_kernel_launches": (_c.c_ulonglong, []),
+    "wfsp_selftest_gather4": (_int, [_vp, _i64, _int, _i64, _vp, _int, _vp, _vp]),
     "wfsp_batch_pack": (_int, [_vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _i64, _f32, _vp, _vp, _int, _i64, _vp]),
     "wfsp_conv_out_shape": (_int, [_intp] * 6),
     "wfsp_rulebook_workspace_bytes": (_sz, [_i64, _int, _intp, _intp]),

@@ -33,8 +33,12 @@ namespace {
 
 using namespace umma;
 
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+constexpr int kProducerWarps = 8;  // two per scheduler: a lone producer warp per scheduler was instruction-issue bound
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = kProducerThreads + 32;  // + the MMA issuer warp
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kRowStep = kProducerThreads / 8;   // tile rows covered by one pass of the producers (8 threads per row)
+constexpr int kRowsPerThread = 128 / kRowStep;   // rows of a 128-row tile per producer thread
 constexpr int kTileM = 128;   // destination rows (apply) / a-channels (wgrad) per CTA
 constexpr int kSliceK = 64;   // reduction elements per stage (one 128 B swizzle row of bf16)
 constexpr int kABytes = kTileM * 128;
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
 
   for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kThreads) s_active[i] = 0;
   if (tid == 0) init_pipe(bars, kProducerThreads + 1);
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
   }
@@ -292,12 +296,12 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   const int total_iters = n_active * num_kb;
   const uint32_t smem0 = smem_u32(smem);
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ------------------------------------------------------------------ producers
     // A: 16-byte cp.async of this thread's chunk of 8 rows per row block (rows rsub + 16 i are 2048 B
     // apart in the swizzled tile); B: thread 0 issues one bulk copy of the pre-swizzled weight slice.
     const int c16 = tid & 7;    // 16-byte chunk inside the 128-byte slice row
-    const int rsub = tid >> 3;  // this thread covers tile rows rsub + 16*i
+    const int rsub = tid >> 3;  // this thread covers tile rows rsub + kRowStep*i
     const uint32_t off0 = sw128_offset(uint32_t(rsub), uint32_t(c16));
     const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;  // slices in which the chunk is inside the row
     int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
@@ -312,12 +316,12 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
       while (mask) {
         const int k = kw * 32 + __ffs(mask) - 1;
         mask &= mask - 1;
-        int rows[RB * 8];
+        int rows[RB * kRowsPerThread];
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rb * kTileM + rsub + 16 * i;
+          for (int i = 0; i < kRowsPerThread; ++i) {
+            const int r = rb * kTileM + rsub + kRowStep * i;
             int v = -1;
             if (rb < rb_live) {
               if (!p.nbr) {
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
                 if (v >= p.n_src) v = -1;
               }
             }
-            rows[rb * 8 + i] = v;
+            rows[rb * kRowsPerThread + i] = v;
           }
         }
         const char* wk = reinterpret_cast<const char*>(p.wt) + ((size_t(k) * num_kb) * p.n_pad + n0) * 128;
@@ -345,10 +349,10 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
           for (int rb = 0; rb < RB; ++rb) {
             if (rb < rb_live) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int v = rows[rb * 8 + i];
+              for (int i = 0; i < kRowsPerThread; ++i) {
+                const int v = rows[rb * kRowsPerThread + i];
                 const bool ok = col_ok && v >= 0;
-                cp_async16(sa + off0 + rb * kABytes + i * 2048, src_c + (ok ? size_t(v) * a_row_bytes + kb * 128 : size_t(0)),
+                cp_async16(sa + off0 + rb * kABytes + i * (kRowStep * 128), src_c + (ok ? size_t(v) * a_row_bytes + kb * 128 : size_t(0)),
                            ok ? 16u : 0u);
               }
             }
@@ -368,14 +372,16 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
     const bool al16 = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(p.dst) & 7) == 0;
     const int vec = ((p.c_dst & 3) == 0 && al16) ? 4 : (((p.c_dst & 1) == 0 && al8) ? 2 : 1);
     for (int rb = 0; rb < rb_live; ++rb) {
-      const int wr0 = rb * kTileM + warp * 32;  // first row of this warp's block inside the CTA tile
+      // warps w and w+4 share TMEM lane quarter w (a warp may only read lanes 32*(warp%4)..+31): they take
+      // alternate 32-column chunks of it
+      const int wr0 = rb * kTileM + (warp & 3) * 32;  // first row of this warp's block inside the CTA tile
       int rmax = rows_left - wr0;
       if (rmax > 32) rmax = 32;
-      for (int col = 0; col < p.n_tile; col += 32) {
+      for (int col = (warp >> 2) * 32; col < p.n_tile; col += 64) {
         const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
         uint32_t acc[32];
         if (total_iters > 0) {
-          const uint32_t taddr = tmem + (uint32_t(warp * 32) << 16) + uint32_t(rb * p.acc_stride + col);
+          const uint32_t taddr = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(rb * p.acc_stride + col);
           tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
           if (ncols > 16) tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
           tmem_ld_wait();
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, tmem_cols);
 }
 
 struct WgradParams {
@@ -439,6 +445,7 @@ struct WgradParams {
   const int32_t* n_a_dev;
 };
 
+constexpr int kPairsPerThread = kSliceK / kRowStep;  // pairs of a 64-pair slice per producer thread
 constexpr int kIdxGroup = 4;  // pair-index loads are issued this many pipeline slices ahead, as one batch
 
 // MT = 128-channel blocks of `a` per CTA: they share every gathered slice of `b` rows and its pair
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(MT * p.acc_stride));
 
   if (tid == 0) init_pipe(bars, kProducerThreads);
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&s_tmem, tmem_cols);
     tmem_relinquish();
   }
@@ -479,20 +486,20 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   const uint32_t tmem = s_tmem;
   const uint32_t smem0 = smem_u32(smem);
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ------------------------------------------------------------------ producers
     const int c16 = tid & 7;    // 16-byte chunk inside a 64-channel panel row
-    const int psub = tid >> 3;  // this thread covers pairs psub + 16*i of the 64-pair slice
+    const int psub = tid >> 3;  // this thread covers pairs psub + kRowStep*i of the 64-pair slice
     const int32_t* pa = p.pair_a ? p.pair_a + int64_t(k) * p.pitch : nullptr;
     const int32_t* pb = p.pair_b ? p.pair_b + int64_t(k) * p.pitch : nullptr;
     // Pair indices of kIdxGroup slices are fetched as one batch of independent loads while the previous
     // group's slices are being issued: one memory round trip per group, off the critical path.
-    auto load_group = [&](int it0, int (&ia)[kIdxGroup][4], int (&ib)[kIdxGroup][4]) {
+    auto load_group = [&](int it0, int (&ia)[kIdxGroup][kPairsPerThread], int (&ib)[kIdxGroup][kPairsPerThread]) {
 #pragma unroll
       for (int u = 0; u < kIdxGroup; ++u) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int64_t q = begin + int64_t(it0 + u) * kSliceK + psub + 16 * i;
+        for (int i = 0; i < kPairsPerThread; ++i) {
+          const int64_t q = begin + int64_t(it0 + u) * kSliceK + psub + kRowStep * i;
           int va = -1, vb = -1;
           if (q < end) {
             va = pa ? __ldg(pa + q) : int(q);
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
     for (int pn = 0; pn < 2 * MT; ++pn) a_ok[pn] = (a_c0 + pn * 64 + c16 * 8 < p.ca_pad) ? 16u : 0u;
 #pragma unroll
     for (int pn = 0; pn < 4; ++pn) b_ok[pn] = (pn < b_panels && b_c0 + pn * 64 + c16 * 8 < p.cb_pad) ? 16u : 0u;
-    int ia[kIdxGroup][4], ib[kIdxGroup][4], na[kIdxGroup][4], nb[kIdxGroup][4];
+    int ia[kIdxGroup][kPairsPerThread], ib[kIdxGroup][kPairsPerThread], na[kIdxGroup][kPairsPerThread], nb[kIdxGroup][kPairsPerThread];
     if (iters > 0) load_group(0, ia, ib);
     int s = 0;
     uint32_t ph = 0;
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
           const uint32_t sa = smem0 + uint32_t(s) * stage_bytes + off0;
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kPairsPerThread; ++i) {
             int va = ia[u][i], vb = ib[u][i];
             const bool ok = va >= 0 && vb >= 0 && va < p.n_a && vb < p.n_b;
             const uint32_t live = ok ? 16u : 0u;
@@ -536,11 +543,11 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
             // A: [64 pairs][MT x 128 channels of a] as 64-channel swizzled panels
 #pragma unroll
             for (int pn = 0; pn < 2 * MT; ++pn)
-              if (pn < 2 * mt_live) cp_async16(sa + pn * 8192 + i * 2048, ga + pn * 128, live & a_ok[pn]);
+              if (pn < 2 * mt_live) cp_async16(sa + pn * 8192 + i * (kRowStep * 128), ga + pn * 128, live & a_ok[pn]);
             // B: [64 pairs][n_tile channels of b]
 #pragma unroll
             for (int pn = 0; pn < 4; ++pn)
-              if (pn < b_panels) cp_async16(sb + pn * 8192 + i * 2048, gb + pn * 128, live & b_ok[pn]);
+              if (pn < b_panels) cp_async16(sb + pn * 8192 + i * (kRowStep * 128), gb + pn * 128, live & b_ok[pn]);
           }
           cp_async_arrive_noinc(&bars.full[s]);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
 #pragma unroll
       for (int u = 0; u < kIdxGroup; ++u)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ia[u][i] = na[u][i]; ib[u][i] = nb[u][i]; }
+        for (int i = 0; i < kPairsPerThread; ++i) { ia[u][i] = na[u][i]; ib[u][i] = nb[u][i]; }
     }
     // ------------------------------------------------------------------ epilogue
     // TMEM -> registers (thread = a-channel) -> this warp's smem tile -> global, a warp adding / storing
@@ -560,15 +567,15 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
     }
     float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
     for (int mt = 0; mt < mt_live; ++mt) {
-      const int ca0 = a_c0 + mt * kTileM + warp * 32;
+      const int ca0 = a_c0 + mt * kTileM + (warp & 3) * 32;
       float* out = p.dw + (int64_t(k) * p.c_a + ca0) * p.c_b;
       int rmax = p.c_a - ca0;
       if (rmax > 32) rmax = 32;
-      for (int col = 0; col < p.n_tile; col += 32) {
+      for (int col = (warp >> 2) * 32; col < p.n_tile; col += 64) {  // warps w, w+4: alternate chunks of lane quarter w
         const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
         uint32_t acc[32];
         if (iters > 0) {
-          const uint32_t taddr = tmem + (uint32_t(warp * 32) << 16) + uint32_t(mt * p.acc_stride + col);
+          const uint32_t taddr = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(mt * p.acc_stride + col);
           tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
           if (ncols > 16) tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
           tmem_ld_wait();
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, tmem_cols);
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -786,6 +793,10 @@ int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const
                            const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
                            int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
                            cudaStream_t st) {
+  if (n_a == 0 || n_b == 0 || (pair_a != nullptr && pitch == 0)) {  // no pairs: the gradient is zero
+    if (!accumulate) WFSP_CHECK_CUDA(cudaMemsetAsync(d_weight, 0, size_t(kvol) * c_a * c_b * sizeof(float), st));
+    return WFSP_OK;
+  }
   WgradParams p{};
   p.ca_pad = round_up(c_a, 8);
   p.cb_pad = round_up(c_b, 8);
