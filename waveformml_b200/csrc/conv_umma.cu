@@ -33,10 +33,11 @@ namespace {
 
 using namespace umma;
 
-constexpr int kProducerWarps = 8;  // two per scheduler: a lone producer warp per scheduler was instruction-issue bound
+constexpr int kProducerWarps = 16;  // two per scheduler: a lone producer warp per scheduler was instruction-issue bound
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 32;  // + the MMA issuer warp
 constexpr int kMmaWarp = kProducerWarps;
+constexpr int kEpiWarps = 8;  // producer warps 0..7 drain TMEM (pairs w, w+4 share lane quarter w)
 constexpr int kRowStep = kProducerThreads / 8;   // tile rows covered by one pass of the producers (8 threads per row)
 constexpr int kRowsPerThread = 128 / kRowStep;   // rows of a 128-row tile per producer thread
 constexpr int kTileM = 128;   // destination rows (apply) / a-channels (wgrad) per CTA
@@ -368,10 +369,10 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
       mbar_wait(&bars.done, 0);
       tc_fence_after();
     }
-    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
+    float* tile = reinterpret_cast<float*>(smem) + (warp % kEpiWarps) * (32 * kEpiPitch);
     const bool al16 = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(p.dst) & 7) == 0;
     const int vec = ((p.c_dst & 3) == 0 && al16) ? 4 : (((p.c_dst & 1) == 0 && al8) ? 2 : 1);
-    for (int rb = 0; rb < rb_live; ++rb) {
+    for (int rb = 0; rb < (warp < kEpiWarps ? rb_live : 0); ++rb) {
       // warps w and w+4 share TMEM lane quarter w (a warp may only read lanes 32*(warp%4)..+31): they take
       // alternate 32-column chunks of it
       const int wr0 = rb * kTileM + (warp & 3) * 32;  // first row of this warp's block inside the CTA tile
@@ -565,8 +566,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
       mbar_wait(&bars.done, 0);
       tc_fence_after();
     }
-    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * kEpiPitch);
-    for (int mt = 0; mt < mt_live; ++mt) {
+    float* tile = reinterpret_cast<float*>(smem) + (warp % kEpiWarps) * (32 * kEpiPitch);
+    for (int mt = 0; mt < (warp < kEpiWarps ? mt_live : 0); ++mt) {
       const int ca0 = a_c0 + mt * kTileM + (warp & 3) * 32;
       float* out = p.dw + (int64_t(k) * p.c_a + ca0) * p.c_b;
       int rmax = p.c_a - ca0;
