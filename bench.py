@@ -308,11 +308,11 @@ def conv_breakdown(model, idx, feats, batch_size, flush, reps=10):
 
         def fwd():
             _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), n_in, None, cin, _lib.ptr(w_f), None, _lib.ptr(nbr_o), kvol,
-                                                _lib.ptr(out_f), n_out, None, 0, cout, st()))
+                                                _lib.ptr(out_f), n_out, None, 0, cout, None, st()))
 
         def dgrad():
             _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(g16), n_out, None, cout, _lib.ptr(w_d), None, _lib.ptr(nbr_i), kvol,
-                                                _lib.ptr(out_d), n_in, None, 0, cin, st()))
+                                                _lib.ptr(out_d), n_in, None, 0, cin, None, st()))
 
         def wgrad():
             _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, None, cin, _lib.ptr(g16), n_out, None, cout,

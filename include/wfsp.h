@@ -257,11 +257,16 @@ int wfsp_prep_weights(const wfsp_prep_job* jobs_host, int n_jobs, wfsp_stream_t 
 int wfsp_cast_rows_bf16(const float* src, int64_t n_rows, const int32_t* n_rows_dev, int c,
                         void* dst_bf16, wfsp_stream_t stream);
 
-/* wfsp_conv_apply on bf16 activations and prepared weights (no workspace, no cast pass) */
+/* wfsp_conv_apply on bf16 activations and prepared weights (no workspace, no cast pass).
+ * bn_partials (may be NULL): wfsp_bn_partials_bytes(n_dst, c_dst) bytes, starting with fp32
+ * [ceil(n_dst / 32)][2][c_dst]; the epilogue writes (mean, M2) of every
+ * output column over each chunk of 32 destination rows, which wfsp_bn_relu_fwd_stats turns into the
+ * BatchNorm statistics without re-reading dst (WFSP_BN_CHUNK_ROWS). */
+#define WFSP_BN_CHUNK_ROWS 32
 int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
                          const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,
                          float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint,
-                         int c_dst, wfsp_stream_t stream);
+                         int c_dst, float* bn_partials, wfsp_stream_t stream);
 
 /* wfsp_conv_wgrad on bf16 rows (a = layer input, b = gradient of the layer output) */
 int wfsp_conv_wgrad_bf16(const void* a_bf16, int64_t n_a, const int32_t* n_a_dev, int c_a,
@@ -277,6 +282,18 @@ int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t* n_rows_dev
                        float* running_var, float momentum, float eps, int training, int relu,
                        float* y, void* y_bf16, float* save_mean, float* save_invstd,
                        void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+
+/* size of the bn_partials buffer of wfsp_conv_apply_bf16 / wfsp_bn_relu_fwd_stats for n_rows output
+ * rows (the partial list followed by the scratch of the merge kernel) */
+size_t wfsp_bn_partials_bytes(int64_t n_rows, int c);
+
+/* training-mode forward whose per-chunk statistics were already written by wfsp_conv_apply_bf16
+ * (bn_partials, chunks of WFSP_BN_CHUNK_ROWS rows): merge + normalise, no statistics pass over x */
+int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                           const float* bn_partials, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float momentum, float eps,
+                           int relu, float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                           wfsp_stream_t stream);
 
 int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
                        int c, const float* gamma, const float* beta, const float* save_mean,

@@ -148,11 +148,13 @@ def test_layer_parity(cuda_device, name, factory, cin, mode):
     check_all(g, refs, mode, name)
 
 
-def test_fused_equals_per_layer(cuda_device):
+@pytest.mark.parametrize("B,full", [(40, False), (160, True)], ids=["small", "24640_rows"])
+def test_fused_equals_per_layer(cuda_device, B, full):
     """The fused stack rounds the same values to bf16 at the same points as the per-layer path, so
-    a conv-BN-ReLU stack must agree with it closely (outputs, input and parameter gradients, BN buffers)."""
-    B = 40
-    idx, feats = events(B, 23, 30)
+    a conv-BN-ReLU stack must agree with it closely (outputs, input and parameter gradients, BN buffers).
+    The large case crosses the row count above which BatchNorm statistics come from the convolution
+    epilogue (per-32-row partials) and the multi-kernel BatchNorm / rulebook paths are taken."""
+    idx, feats = events(B, 23, 30, full=full)
 
     def make():
         torch.manual_seed(11)

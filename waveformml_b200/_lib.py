@@ -48,7 +48,10 @@ SIGNATURES = {
     "wfsp_prepared_weight_bytes": (_sz, [_int, _int, _int]),
     "wfsp_prep_weights": (_int, [_vp, _int, _vp]),
     "wfsp_cast_rows_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp]),
-    "wfsp_conv_apply_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp]),
+    "wfsp_conv_apply_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "wfsp_bn_partials_bytes": (_sz, [_i64, _int]),
+    "wfsp_bn_relu_fwd_stats": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp,
+                                      _vp, _vp]),
     "wfsp_conv_wgrad_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _i64, _vp,
                                     _int, _vp]),
     "wfsp_bn_relu_fwd_x": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,

@@ -69,45 +69,72 @@ __global__ void __launch_bounds__(kCh * kPartLanes) bn_partial_stats(const float
   }
 }
 
-// One block per 32 channels; 32 row lanes each merge every 32nd partial (Chan's parallel-variance merge, in
-// double), then lane 0 merges the 32 lane results in lane order: a fixed order, so the statistics do
-// not depend on scheduling, and nblk/32 dependent steps instead of nblk.
+// One block per 32 channels; 32 row lanes each fold every 32nd partial, then lane 0 adds the 32 lane results
+// in lane order (a fixed order, so the statistics do not depend on scheduling).  Partials (n_b, mean_b, M2_b)
+// are folded as plain double-precision sums N = sum n_b, A = sum n_b mean_b, Q = sum (M2_b + n_b mean_b^2),
+// and mean = A / N, M2 = Q - N mean^2: no division per partial (FP64 division is slow on this part), and in
+// double the subtraction costs ~1e-16 * mean^2 / var of relative accuracy.
 constexpr int kFinLanes = 32;
+constexpr int kFinSegMax = 32;  // the partial list is cut into up to this many segments, one block each per channel group
 
-__global__ void __launch_bounds__(kCh * kFinLanes) bn_finalize_stats(const float* __restrict__ part, int64_t n_cap,
+// grid (channel groups, S).  Block (g, seg) folds segment seg of the partial list; the last of the S blocks of
+// a channel group to finish (ticket counter) adds the S segment results in segment order and writes the
+// statistics.  `inter` = [S][2][c] doubles, `tickets` = [channel groups] zeroed ints (left zero again).
+__global__ void __launch_bounds__(kCh * kFinLanes) bn_finalize_stats(const float* __restrict__ part, int chunk_rows, int64_t n_cap,
                                                          const int32_t* __restrict__ n_dev, int c, float eps,
                                                          float momentum, float* __restrict__ running_mean,
                                                          float* __restrict__ running_var,
-                                                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  __shared__ double s_cnt[kFinLanes][kCh], s_mean[kFinLanes][kCh], s_m2[kFinLanes][kCh];
+                                                         float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                         double* __restrict__ inter, unsigned* __restrict__ tickets) {
+  __shared__ double s_a[kFinLanes][kCh], s_q[kFinLanes][kCh];
+  __shared__ unsigned s_ticket;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
+  const int S = gridDim.y, seg = blockIdx.y;
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t nblk = n > 0 ? (n + kRows - 1) / kRows : 0;
-  double cnt = 0.0, mean = 0.0, m2 = 0.0;
+  const int64_t nblk = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0;
+  const int64_t per = (nblk + S - 1) / S;
+  const int64_t lo = seg * per, hi = lo + per < nblk ? lo + per : nblk;
+  double a = 0.0, q = 0.0;
   if (ch < c) {
 #pragma unroll 4
-    for (int64_t b = ty; b < nblk; b += kFinLanes) {
-      const double nb = double(b + 1 < nblk ? kRows : n - b * kRows);
+    for (int64_t b = lo + ty; b < hi; b += kFinLanes) {
+      const double nb = double(b + 1 < nblk ? chunk_rows : n - b * chunk_rows);
       const double mb = part[(b * 2 + 0) * c + ch], m2b = part[(b * 2 + 1) * c + ch];
-      const double delta = mb - mean, tot = cnt + nb;
-      mean += delta * nb / tot;
-      m2 += m2b + delta * delta * cnt * nb / tot;
-      cnt = tot;
+      a += nb * mb;
+      q += m2b + nb * mb * mb;
     }
   }
-  s_cnt[ty][tx] = cnt; s_mean[ty][tx] = mean; s_m2[ty][tx] = m2;
+  s_a[ty][tx] = a; s_q[ty][tx] = q;
   __syncthreads();
+  if (ty == 0) {
+    for (int l = 1; l < kFinLanes; ++l) { a += s_a[l][tx]; q += s_q[l][tx]; }
+  }
+  if (S > 1) {
+    if (ty == 0 && ch < c) {
+      inter[(int64_t(seg) * 2 + 0) * c + ch] = a;
+      inter[(int64_t(seg) * 2 + 1) * c + ch] = q;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+    __syncthreads();
+    if (s_ticket != unsigned(S - 1)) return;  // not the last block of this channel group
+    __threadfence();
+    if (tx == 0 && ty == 0) tickets[blockIdx.x] = 0u;
+    if (ty == 0 && ch < c) {
+      a = 0.0; q = 0.0;
+      for (int sg = 0; sg < S; ++sg) {
+        a += __ldcg(&inter[(int64_t(sg) * 2 + 0) * c + ch]);
+        q += __ldcg(&inter[(int64_t(sg) * 2 + 1) * c + ch]);
+      }
+    }
+  }
   if (ty != 0 || ch >= c) return;
   if (n <= 0) { save_mean[ch] = 0.f; save_invstd[ch] = 0.f; return; }
-  for (int l = 1; l < kFinLanes; ++l) {
-    const double nb = s_cnt[l][tx];
-    if (nb <= 0.0) continue;
-    const double delta = s_mean[l][tx] - mean, tot = cnt + nb;
-    mean += delta * nb / tot;
-    m2 += s_m2[l][tx] + delta * delta * cnt * nb / tot;
-    cnt = tot;
-  }
+  const double cnt = double(n), mean = a / cnt;
+  double m2 = q - cnt * mean * mean;
+  if (m2 < 0.0) m2 = 0.0;
   const double var = m2 / cnt;
   save_mean[ch] = float(mean);
   save_invstd[ch] = float(1.0 / sqrt(var + double(eps)));
@@ -138,6 +165,11 @@ __device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
 // mean == nullptr switches the normalisation off (plain ReLU / cast).
 constexpr int kApplyRows = 64;
 
+// VEC2: c is even and the buffers are 8-byte aligned, so a channel pair is one float2.  Four rows are
+// loaded before any is used (independent loads in flight: these kernels are pure HBM streams).
+constexpr int kApplyUnroll = 4;
+
+template <bool VEC2>
 __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -149,28 +181,51 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
   for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
     const int ch = pc << 1;
     float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f};
+    const bool on[2] = {ch < c, ch + 1 < c};
 #pragma unroll
     for (int e = 0; e < 2; ++e)
-      if (mean && ch + e < c) {
+      if (mean && on[e]) {
         m[e] = mean[ch + e]; is[e] = invstd[ch + e];
         if (gamma) g[e] = gamma[ch + e];
         if (beta) b[e] = beta[ch + e];
       }
     for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
       const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
-      for (int64_t r = r0 + threadIdx.y; r < r_end; r += blockDim.y) {
-        float v[2] = {0.f, 0.f};
+      for (int64_t rb = r0 + threadIdx.y; rb < r_end; rb += int64_t(kApplyUnroll) * blockDim.y) {
+        float xv[kApplyUnroll][2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (ch + e < c) {
-            float tv = x[r * c + ch + e];
-            if (mean) tv = (tv - m[e]) * is[e] * g[e] + b[e];
-            if (relu && tv < 0.f) tv = 0.f;
-            if (y) y[r * c + ch + e] = tv;
-            v[e] = tv;
+        for (int u = 0; u < kApplyUnroll; ++u) {
+          const int64_t r = rb + int64_t(u) * blockDim.y;
+          xv[u][0] = xv[u][1] = 0.f;
+          if (r < r_end) {
+            if (VEC2) {
+              if (on[0]) { const float2 t = *reinterpret_cast<const float2*>(x + r * c + ch); xv[u][0] = t.x; xv[u][1] = t.y; }
+            } else {
+              if (on[0]) xv[u][0] = x[r * c + ch];
+              if (on[1]) xv[u][1] = x[r * c + ch + 1];
+            }
           }
         }
-        if (y16w) y16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+#pragma unroll
+        for (int u = 0; u < kApplyUnroll; ++u) {
+          const int64_t r = rb + int64_t(u) * blockDim.y;
+          if (r >= r_end) continue;
+          float v[2] = {0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (on[e]) {
+              float tv = xv[u][e];
+              if (mean) tv = (tv - m[e]) * is[e] * g[e] + b[e];
+              if (relu && tv < 0.f) tv = 0.f;
+              v[e] = tv;
+            }
+          }
+          if (y) {
+            if (VEC2) { if (on[0]) *reinterpret_cast<float2*>(y + r * c + ch) = make_float2(v[0], v[1]); }
+            else { if (on[0]) y[r * c + ch] = v[0]; if (on[1]) y[r * c + ch + 1] = v[1]; }
+          }
+          if (y16w) y16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+        }
       }
     }
   }
@@ -237,6 +292,7 @@ __global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* 
 }
 
 // same thread mapping as bn_apply; mean == nullptr means "no normalisation" (plain ReLU backward)
+template <bool VEC2>
 __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
                                                     int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -250,9 +306,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
   for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
     const int ch = pc << 1;
     float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f}, db[2] = {0.f, 0.f}, dg[2] = {0.f, 0.f};
+    const bool on[2] = {ch < c, ch + 1 < c};
 #pragma unroll
     for (int e = 0; e < 2; ++e)
-      if (mean && ch + e < c) {
+      if (mean && on[e]) {
         m[e] = mean[ch + e]; is[e] = invstd[ch + e];
         if (gamma) g[e] = gamma[ch + e];
         if (beta) b[e] = beta[ch + e];
@@ -260,26 +317,49 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
       }
     for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
       const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
-      for (int64_t r = r0 + threadIdx.y; r < r_end; r += blockDim.y) {
-        float v[2] = {0.f, 0.f};
+      for (int64_t rb = r0 + threadIdx.y; rb < r_end; rb += int64_t(kApplyUnroll) * blockDim.y) {
+        float xv[kApplyUnroll][2], dv[kApplyUnroll][2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (ch + e < c) {
-            float d = dy[r * c + ch + e];
-            const float xv = x[r * c + ch + e];
-            float tv;
-            if (mean) {
-              const float xh = (xv - m[e]) * is[e];
-              if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
-              tv = g[e] * is[e] * (d - db[e] - xh * dg[e]);
+        for (int u = 0; u < kApplyUnroll; ++u) {
+          const int64_t r = rb + int64_t(u) * blockDim.y;
+          xv[u][0] = xv[u][1] = dv[u][0] = dv[u][1] = 0.f;
+          if (r < r_end) {
+            if (VEC2) {
+              if (on[0]) {
+                const float2 t = *reinterpret_cast<const float2*>(x + r * c + ch);
+                const float2 d = *reinterpret_cast<const float2*>(dy + r * c + ch);
+                xv[u][0] = t.x; xv[u][1] = t.y; dv[u][0] = d.x; dv[u][1] = d.y;
+              }
             } else {
-              tv = (relu && xv <= 0.f) ? 0.f : d;
+              if (on[0]) { xv[u][0] = x[r * c + ch]; dv[u][0] = dy[r * c + ch]; }
+              if (on[1]) { xv[u][1] = x[r * c + ch + 1]; dv[u][1] = dy[r * c + ch + 1]; }
             }
-            if (dx) dx[r * c + ch + e] = tv;
-            v[e] = tv;
           }
         }
-        if (dx16w) dx16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+#pragma unroll
+        for (int u = 0; u < kApplyUnroll; ++u) {
+          const int64_t r = rb + int64_t(u) * blockDim.y;
+          if (r >= r_end) continue;
+          float v[2] = {0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (on[e]) {
+              float d = dv[u][e];
+              if (mean) {
+                const float xh = (xv[u][e] - m[e]) * is[e];
+                if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
+                v[e] = g[e] * is[e] * (d - db[e] - xh * dg[e]);
+              } else {
+                v[e] = (relu && xv[u][e] <= 0.f) ? 0.f : d;
+              }
+            }
+          }
+          if (dx) {
+            if (VEC2) { if (on[0]) *reinterpret_cast<float2*>(dx + r * c + ch) = make_float2(v[0], v[1]); }
+            else { if (on[0]) dx[r * c + ch] = v[0]; if (on[1]) dx[r * c + ch + 1] = v[1]; }
+          }
+          if (dx16w) dx16w[r * ppr + pc] = bn_pack_bf16x2(v[0], v[1]);
+        }
       }
     }
   }
@@ -469,10 +549,35 @@ cudaError_t launch_cluster(void (*kernel)(KArgs...), int groups, cudaStream_t st
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// scratch of bn_finalize_stats behind a partial list of `chunks` entries: [S][2][c] doubles + tickets
+inline int fin_segments(int64_t chunks) {
+  int64_t s = chunks / 128;
+  return int(s < 1 ? 1 : (s > kFinSegMax ? kFinSegMax : s));
+}
+inline size_t fin_scratch_bytes(int c) { return size_t(kFinSegMax) * 2 * c * sizeof(double) + 1024; }
+
+int launch_finalize(const float* part, int chunk_rows, int64_t n_rows, const int32_t* n_rows_dev, int c, float eps,
+                    float momentum, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                    void* scratch, cudaStream_t st) {
+  const int S = fin_segments(ceil_div<int64_t>(n_rows, chunk_rows));
+  double* inter = static_cast<double*>(scratch);
+  unsigned* tickets = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + size_t(kFinSegMax) * 2 * c * sizeof(double));
+  if (S > 1) WFSP_CHECK_CUDA(cudaMemsetAsync(tickets, 0, 1024, st));
+  bn_finalize_stats<<<dim3(unsigned(ceil_div(c, kCh)), unsigned(S)), dim3(kCh, kFinLanes), 0, st>>>(
+      part, chunk_rows, n_rows, n_rows_dev, c, eps, momentum, running_mean, running_var, save_mean, save_invstd, inter,
+      tickets);
+  return WFSP_OK;
+}
+
 inline unsigned apply_blocks(int64_t rows) {
   int64_t b = ceil_div<int64_t>(rows > 0 ? rows : 1, kApplyRows);
   const int64_t cap = int64_t(sm_count()) * 16;
   return unsigned(b > cap ? cap : b);
+}
+
+// float2 path of the apply kernels: even channel count and 8-byte aligned fp32 buffers (NULL = not used)
+inline bool vec2_ok(int c, const void* a, const void* b) {
+  return (c & 1) == 0 && (reinterpret_cast<uintptr_t>(a) & 7) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0;
 }
 
 // block shape of the apply kernels: x = channel pairs (a multiple of 32, at most 256), y = row lanes
@@ -490,7 +595,13 @@ inline dim3 apply_block(int c) {
 using namespace wfsp;
 
 extern "C" size_t wfsp_bn_workspace_bytes(int64_t n_rows, int c) {
-  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRows)) * 2 * c * sizeof(float), 256);
+  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRows)) * 2 * c * sizeof(float), 256) +
+         fin_scratch_bytes(c);
+}
+
+extern "C" size_t wfsp_bn_partials_bytes(int64_t n_rows, int c) {
+  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, WFSP_BN_CHUNK_ROWS)) * 2 * c * sizeof(float), 256) +
+         fin_scratch_bytes(c);
 }
 
 extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
@@ -516,16 +627,45 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     float* part = static_cast<float*>(workspace);
     dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
     bn_partial_stats<<<grid, dim3(32, kPartLanes), 0, st>>>(x, n_rows, n_rows_dev, c, part);
-    bn_finalize_stats<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, eps, momentum, running_mean,
-                                                        running_var, save_mean, save_invstd);
+    char* scratch = static_cast<char*>(workspace) +
+                    align_up(size_t(ceil_div<int64_t>(n_rows, kRows)) * 2 * c * sizeof(float), 256);
+    if (int rc = launch_finalize(part, kRows, n_rows, n_rows_dev, c, eps, momentum, running_mean, running_var, save_mean,
+                                 save_invstd, scratch, st))
+      return rc;
     count_launches(2);
   } else {
     bn_eval_stats<<<ceil_div(c, 128), 128, 0, st>>>(c, eps, running_mean, running_var, save_mean, save_invstd);
     count_launches(1);
   }
-  bn_apply<<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean,
-                                                                   save_invstd, relu, y, y16);
+  if (vec2_ok(c, x, y))
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+  else
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
   count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+                                      const float* bn_partials, const float* gamma, const float* beta,
+                                      float* running_mean, float* running_var, float momentum, float eps, int relu,
+                                      float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                                      wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1 && bn_partials != nullptr, "bad batch-norm arguments");
+  WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "batch norm needs at least one output");
+  if (n_rows == 0) return WFSP_OK;
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
+  char* scratch = reinterpret_cast<char*>(const_cast<float*>(bn_partials)) +
+                  align_up(size_t(ceil_div<int64_t>(n_rows, WFSP_BN_CHUNK_ROWS)) * 2 * c * sizeof(float), 256);
+  if (int rc = launch_finalize(bn_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, eps, momentum, running_mean,
+                               running_var, save_mean, save_invstd, scratch, st))
+    return rc;
+  if (vec2_ok(c, x, y))
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+  else
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+  count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -563,8 +703,10 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
   bn_bwd_partial<<<grid, dim3(32, kPartLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
-  bn_bwd_apply<<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean,
-                                                                       save_invstd, d_gamma, d_beta, relu, dx, dx16);
+  if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
+    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16);
+  else
+    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -585,8 +727,12 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_apply<<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-      x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
+  if (vec2_ok(c, x, y))
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
+  else
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -597,9 +743,14 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad sizes");
   WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
-  bn_bwd_apply<<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-      x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-      static_cast<__nv_bfloat16*>(dx_bf16));
+  if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
+    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+        x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
+        static_cast<__nv_bfloat16*>(dx_bf16));
+  else
+    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+        x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
+        static_cast<__nv_bfloat16*>(dx_bf16));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

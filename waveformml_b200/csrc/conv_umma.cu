@@ -220,6 +220,7 @@ struct ApplyParams {
   float* dst; int64_t n_dst; int c_dst;
   int n_tile, stages, rblk, acc_stride, staged;
   const int32_t* n_src_dev; const int32_t* n_dst_dev;
+  float* stats;  // optional [ceil(n_dst/32)][2][c_dst]: per 32-row chunk (mean, M2) of every output column
 };
 
 // A CTA owns rblk (1..4) consecutive 128-row blocks of destination rows and one column tile.  Every
@@ -395,6 +396,23 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
           if (4 * q < ncols)
             *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         __syncwarp();
+        if (rmax > 0 && p.stats != nullptr && lane < ncols && n0 + col + lane < p.c_dst) {
+          // BatchNorm statistics of this 32-row chunk, straight from the tile (saves the pass that would
+          // re-read the output from HBM): shifted sums -> (mean, M2), merged later by bn_finalize_stats
+          const int ccol = n0 + col + lane;
+          const float bv = p.bias ? __ldg(p.bias + ccol) : 0.f;
+          const float K = tile[lane];
+          float sd = 0.f, sq = 0.f;
+          for (int r = 0; r < rmax; ++r) {
+            const float d = tile[r * kEpiPitch + lane] - K;
+            sd += d;
+            sq += d * d;
+          }
+          const float cnt = float(rmax);
+          float* sp = p.stats + ((row0 + wr0) >> 5) * 2 * p.c_dst + ccol;
+          sp[0] = K + bv + sd / cnt;
+          sp[p.c_dst] = fmaxf(sq - sd * sd / cnt, 0.f);
+        }
         if (rmax > 0) {
           const int cc = n0 + col;
           float* o = p.dst + (row0 + wr0) * p.c_dst + cc;
@@ -679,7 +697,8 @@ size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) 
 
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
                            const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, cudaStream_t st);
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, float* stats,
+                           cudaStream_t st);
 
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
@@ -703,13 +722,14 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     WFSP_CHECK_LAUNCH();
   }
   return conv_apply_umma_launch(act, n_src, c_red, wt, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev, n_dst_dev,
-                                n_dst_hint, st);
+                                n_dst_hint, nullptr, st);
 }
 
 // bf16 activations [n_src, round_up(c_red, 8)] and prepared weights in, fp32 [n_dst, c_dst] out
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
                            const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, cudaStream_t st) {
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, float* stats,
+                           cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
   const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
@@ -719,6 +739,7 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
   p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
   p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst; p.n_tile = n_tile;
   p.n_src_dev = n_src_dev; p.n_dst_dev = n_dst_dev;
+  p.stats = stats;
   p.acc_stride = round_up(n_tile, 32);
   // Row blocking: rblk 128-row blocks per CTA share every weight slice.  Modelled cost of a launch =
   // rounds of CTAs over the SMs x (operand KB a CTA moves + a per-CTA prologue / epilogue term); the weight

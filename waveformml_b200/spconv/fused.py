@@ -27,6 +27,8 @@ from .. import _lib
 from . import functional as Fsp
 
 _enabled = True
+# BatchNorm over at most this many rows is ONE cluster launch (bn_fwd_small): nothing to fuse there
+_STATS_FUSE_MIN_ROWS = 16384
 
 
 def set_fused(flag):
@@ -205,12 +207,17 @@ class FusedStackFunction(Function):
                 n_src = a16.shape[0] if cur.indices.shape[0] else 0
                 xf = torch.empty((n_dst, cout), dtype=torch.float32, device=dev)
                 bias = params[4 * bi + 1]
+                # large outputs followed by a training-mode BatchNorm: the conv epilogue also emits the
+                # per-32-row-chunk statistics, so BatchNorm does not re-read the output to get them
+                partials = None
+                if b.bn is not None and b.bn.training and n_dst > _STATS_FUSE_MIN_ROWS:
+                    partials = torch.empty((lib.wfsp_bn_partials_bytes(n_dst, cout),), dtype=torch.uint8, device=dev)
                 if n_dst:
                     hint = Fsp.hints.get(n_dst_dev)
                     _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
                                                         ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
                                                         _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
-                                                        hint, cout, st()))
+                                                        hint, cout, _lib.ptr(partials), st()))
                 # ---- BatchNorm / ReLU -> next operand (bf16) or the stack's output (fp32)
                 y32 = y16 = mean = invstd = None
                 if b.bn is not None or b.relu:
@@ -224,7 +231,13 @@ class FusedStackFunction(Function):
                         invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
                         if bn.training and bn.num_batches_tracked is not None:
                             bn.num_batches_tracked.add_(1)
-                        if n_dst:
+                        if n_dst and partials is not None:
+                            _lib.check(lib.wfsp_bn_relu_fwd_stats(
+                                _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(partials), _lib.ptr(bn.weight),
+                                _lib.ptr(bn.bias), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var),
+                                float(bn.momentum), float(bn.eps), int(b.relu), _lib.ptr(y32), _lib.ptr(y16),
+                                _lib.ptr(mean), _lib.ptr(invstd), st()))
+                        elif n_dst:
                             ws = _bn_ws(lib, n_dst, cout, dev)
                             _lib.check(lib.wfsp_bn_relu_fwd_x(
                                 _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
@@ -351,7 +364,7 @@ class FusedStackFunction(Function):
                         _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(g16), n_dst, _lib.ptr(n_dst_dev), cout,
                                                             ctypes.c_void_p(wbuf.data_ptr() + offs[bi][1]), None,
                                                             _lib.ptr(nbr_t), kvol, _lib.ptr(dy), n_in, _lib.ptr(n_src_dev),
-                                                            hint, cin, st()))
+                                                            hint, cin, None, st()))
             if side_used:
                 joined = torch.cuda.Event()
                 joined.record(side)
