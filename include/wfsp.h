@@ -307,6 +307,18 @@ int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int 
 int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
                  int relu, float* dx, void* dx_bf16, wfsp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (7) Optimiser step over flat buffers.  The reference trains with torch.optim.SGD (lr 0.02, momentum
+ * 0.98, nesterov: config/examples/GEP.json:56-68) after Lightning's DDP gradient mean
+ * (src/utils/util.py:233-236).  With all parameters / gradients in one flat fp32 buffer each
+ * (harness.FlatGrads) the update is one streaming launch:
+ *   g = grads * grad_scale + weight_decay * p;  buf = momentum * buf + g;
+ *   p -= lr * (nesterov ? g + momentum * buf : buf)         (buf starts at zero; no dampening)
+ * grad_scale = 1 / world_size folds the data-parallel mean into the update. */
+int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr,
+                  float momentum, int nesterov, float weight_decay, float grad_scale,
+                  wfsp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,3 +56,19 @@ def test_no_cpu_fallback():
             layer(x)
     with pytest.raises(RuntimeError, match="no CPU path"):
         x.dense()
+
+
+def test_sparseconvnet_facade_builds_reference_config():
+    """config/examples/OPs3ns_SCNet.json:27-66 names classes by string (`sparseconvnet.Convolution`, args as a list);
+    build that algorithm list the way src/utils/util.py ModuleUtility does -- no GPU needed to construct."""
+    import importlib
+    algorithm = ["sparseconvnet.Convolution", [2, 300, 37, 1, 1, False], "sparseconvnet.Convolution", [2, 37, 37, 3, 1, False],
+                 "sparseconvnet.Convolution", [2, 37, 18, 3, 2, False], "sparseconvnet.SparseToDense", [2, 18]]
+    mods = []
+    for name, args in zip(algorithm[0::2], algorithm[1::2]):
+        mod, cls = name.rsplit(".", 1)
+        mods.append(getattr(importlib.import_module(mod), cls)(*args))
+    scn = importlib.import_module("sparseconvnet")
+    net = scn.Sequential(*mods)
+    assert len(net) == 4 and tuple(net[1].weight.shape) == (9, 37, 37) and net[2].stride == [2, 2]
+    assert scn.InputLayer(2, [14, 11], mode=0).spatial_size == [14, 11]

@@ -134,3 +134,26 @@ def test_training_reduces_loss(cuda_device):
     step = harness.TrainStep(model, "psd", lr=0.01, momentum=0.9)
     losses = [float(step.step(idx, feats, labels, 64)) for _ in range(8)]
     assert losses[-1] < losses[0], losses
+
+
+def test_flat_sgd_matches_torch_nesterov(cuda_device):
+    """wfsp_sgd_step over the flat buffers == torch.optim.SGD(momentum, nesterov) step for step
+    (config/examples/GEP.json:56-68), including the 1 / world_size gradient scale."""
+    from waveformml_b200 import harness
+    torch.manual_seed(0)
+    shapes = [(7, 5), (13,), (3, 3, 4, 6), (1,)]
+    ours = [torch.nn.Parameter(torch.randn(s, device=cuda_device)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    fg = harness.FlatGrads(ours)
+    opt = harness.FlatSGD(fg, lr=0.02, momentum=0.98, nesterov=True)
+    ropt = torch.optim.SGD(ref, lr=0.02, momentum=0.98, nesterov=True)
+    for step in range(4):
+        gs = [torch.randn(s, device=cuda_device) for s in shapes]
+        for p, r, g in zip(ours, ref, gs):
+            p.grad.copy_(g)
+            r.grad = (g * 0.5).clone()
+        opt.step(grad_scale=0.5)
+        ropt.step()
+        for p, r in zip(ours, ref):
+            torch.testing.assert_close(p.detach(), r.detach(), rtol=1e-5, atol=1e-6)
+    assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in ours)  # parameters live in the flat buffer

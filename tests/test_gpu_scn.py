@@ -1,0 +1,90 @@
+"""SparseConvNet-signature facade (src/models/SCNet.py:62-77,
+config/examples/OPs3ns_SCNet.json:22-66): the stack the reference builds with `sparseconvnet`, checked
+against dense convolutions of the densified input (SURVEY.md A.5 identities)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sparseconvnet as scn
+from waveformml_b200 import spconv
+from waveformml_b200.synth import make_events
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(B, C, seed, dev):
+    ev = make_events(B, n_samples=1, seed=seed)
+    coords = torch.from_numpy(ev["coords"]).long()  # (x, y, batch): the order SCNet.forward hands to InputLayer
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.rand(coords.shape[0], C, generator=g)
+    dense = torch.zeros(B, C, 14, 11)
+    dense[coords[:, 2], :, coords[:, 0], coords[:, 1]] = feats
+    return coords.to(dev), feats.to(dev), dense
+
+
+def _w(conv):  # [volume, nIn, nOut] -> conv2d weight [nOut, nIn, kH, kW]
+    k = conv.filter_size
+    return conv.weight.detach().cpu().view(k[0], k[1], conv.nIn, conv.nOut).permute(3, 2, 0, 1).contiguous()
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_ops3ns_stack_matches_dense_convolutions(cuda_device, mode, tol):
+    """Convolution(2,300,37,1,1) . Convolution(2,37,37,3,1) . Convolution(2,37,18,3,2) . SparseToDense(2,18)"""
+    torch.manual_seed(1)
+    B = 21
+    coords, feats, dense = _batch(B, 300, 5, cuda_device)
+    convs = [scn.Convolution(2, 300, 37, 1, 1, False), scn.Convolution(2, 37, 37, 3, 1, False),
+             scn.Convolution(2, 37, 18, 3, 2, False)]
+    net = scn.Sequential(*convs, scn.SparseToDense(2, 18)).to(cuda_device)
+    spconv.set_math_mode(mode)
+    try:
+        x = scn.InputLayer(2, torch.LongTensor([14, 11]), mode=0)([coords, feats])
+        y = net(x)
+    finally:
+        spconv.set_math_mode("bf16")
+    ref = dense
+    for c, s in zip(convs, (1, 1, 2)):
+        ref = F.conv2d(ref, _w(c), None, stride=s)
+    assert tuple(y.shape) == tuple(ref.shape) == (B, 18, 5, 4)
+    err = (y.detach().cpu() - ref).abs().max() / ref.abs().max()
+    assert float(err) < tol, float(err)
+
+
+def test_submanifold_and_batchnormrelu(cuda_device):
+    torch.manual_seed(2)
+    B = 17
+    coords, feats, dense = _batch(B, 12, 9, cuda_device)
+    conv = scn.SubmanifoldConvolution(2, 12, 10, 3, True)
+    bn = scn.BatchNormReLU(10)
+    net = scn.Sequential(conv, bn, scn.OutputLayer(2)).to(cuda_device)
+    spconv.set_math_mode("fp32")
+    try:
+        out = net(scn.InputLayer(2, [14, 11], mode=0)([coords, feats]))
+    finally:
+        spconv.set_math_mode("bf16")
+    c = coords.cpu()
+    full = F.conv2d(dense, _w(conv), conv.bias.detach().cpu(), padding=1)
+    rows = full[c[:, 2], :, c[:, 0], c[:, 1]]                      # submanifold: outputs at the input sites, same order
+    ref_bn = torch.nn.BatchNorm1d(10, eps=1e-4, momentum=0.1)      # SparseConvNet momentum 0.9 == torch momentum 0.1
+    ref = torch.relu(ref_bn(rows))
+    torch.testing.assert_close(out.detach().cpu(), ref, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(bn.running_mean.cpu(), ref_bn.running_mean, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_and_per_layer_agree_with_facade_bn(cuda_device):
+    """BatchNormReLU carries its own ReLU: both execution paths must apply it exactly once."""
+    B = 30
+    coords, feats, _ = _batch(B, 20, 3, cuda_device)
+    outs = []
+    for fused_on in (True, False):
+        torch.manual_seed(4)
+        net = scn.Sequential(scn.Convolution(2, 20, 16, 3, 1, False), scn.BatchNormReLU(16),
+                             scn.SubmanifoldConvolution(2, 16, 8, 3, False), scn.SparseToDense(2, 8)).to(cuda_device)
+        spconv.set_fused(fused_on)
+        try:
+            y = net(scn.InputLayer(2, [14, 11], mode=0)([coords, feats]))
+        finally:
+            spconv.set_fused(True)
+        assert float(y.min()) < 0  # the last layer has no activation
+        outs.append(y.detach())
+    torch.testing.assert_close(outs[0], outs[1], rtol=5e-3, atol=5e-3 * float(outs[1].abs().max()))

@@ -243,3 +243,46 @@ extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, i
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
+
+
+// ---- optimiser step over the flat parameter / gradient buffers ----------------------------------------
+// torch.optim.SGD semantics (config/examples/GEP.json:56-68: lr 0.02, momentum 0.98, nesterov):
+//   g = grad * grad_scale + weight_decay * p;  buf = momentum * buf + g;
+//   p -= lr * (nesterov ? g + momentum * buf : buf)
+// with the momentum buffer starting at zero (== torch's "first step copies the gradient", no dampening).
+// One streaming launch over all parameters instead of a multi-tensor kernel with a few blocks;
+// grad_scale folds the 1 / world_size of the data-parallel mean into the update.
+namespace wfsp {
+namespace {
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                                       int64_t n, float lr, float momentum, int nesterov, float weight_decay,
+                                                       float grad_scale) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float pv = p[i];
+    float gv = g[i] * grad_scale + weight_decay * pv;
+    float step = gv;
+    if (momentum != 0.f) {
+      const float b = momentum * buf[i] + gv;
+      buf[i] = b;
+      step = nesterov ? gv + momentum * b : b;
+    }
+    p[i] = pv - lr * step;
+  }
+}
+}  // namespace
+}  // namespace wfsp
+
+extern "C" int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                             int nesterov, float weight_decay, float grad_scale, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n >= 0 && params != nullptr && grads != nullptr, "bad optimiser arguments");
+  WFSP_REQUIRE(momentum == 0.f || momentum_buf != nullptr, "momentum needs a buffer");
+  if (n == 0) return WFSP_OK;
+  int64_t blocks = wfsp::ceil_div<int64_t>(n, 256 * 4);
+  const int64_t cap = int64_t(wfsp::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  wfsp::sgd_flat_kernel<<<unsigned(blocks), 256, 0, wfsp::as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum,
+                                                                               nesterov, weight_decay, grad_scale);
+  wfsp::count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}

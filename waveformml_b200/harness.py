@@ -55,6 +55,46 @@ class FlatGrads:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))
 
+    def all_reduce_sum(self, group=None):
+        """SUM only; returns the factor (1 / world size) that turns it into the mean -- FlatSGD folds it into
+        the update instead of spending a kernel on the division."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return 1.0 / dist.get_world_size(group)
+        return 1.0
+
+
+class FlatSGD:
+    """torch.optim.SGD(momentum, nesterov) semantics (config/examples/GEP.json:56-68) as ONE streaming kernel
+    over flat buffers (wfsp_sgd_step).  The parameters are re-homed into one flat fp32 buffer (each
+    `param.data` becomes a view of it, values preserved), laid out like the FlatGrads buffer."""
+
+    def __init__(self, grads, lr, momentum=0.0, nesterov=False, weight_decay=0.0):
+        self.grads, self.lr, self.momentum, self.nesterov, self.weight_decay = grads, lr, momentum, nesterov, weight_decay
+        self.flat_p = torch.empty_like(grads.flat)
+        off = 0
+        with torch.no_grad():
+            for p in grads.params:
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+        self.buf = torch.zeros_like(grads.flat)
+
+    def step(self, grad_scale=1.0):
+        from . import _lib
+        lib = _lib.load()
+        with torch.cuda.device(self.flat_p.device):
+            _lib.check(lib.wfsp_sgd_step(_lib.ptr(self.flat_p), _lib.ptr(self.grads.flat), _lib.ptr(self.buf),
+                                         self.flat_p.numel(), float(self.lr), float(self.momentum), int(self.nesterov),
+                                         float(self.weight_decay), float(grad_scale), _lib.stream()))
+
+    def state_dict(self):
+        return {"momentum_buffer": self.buf.clone()}
+
+    def load_state_dict(self, sd):
+        self.buf.copy_(sd["momentum_buffer"])
+
 
 def segment_l1_loss(indices, predictions, target, spatial_size, batch_size, n_rows=None):
     """LitBase._calc_segment_loss with use_float=True, SE_only=False (LitBase.py:124-174): both the
@@ -74,11 +114,19 @@ class TrainStep:
         assert task in ("psd", "z")
         self.model, self.task, self.group = model, task, group
         self.grads = FlatGrads(model.parameters())
-        # fused=True: one multi-tensor kernel for the whole update instead of four foreach passes
-        on_gpu = self.grads.flat.is_cuda
-        self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov,
-                                   fused=True if on_gpu else None, foreach=None if on_gpu else True)
+        if self.grads.flat.is_cuda:
+            self.opt = FlatSGD(self.grads, lr, momentum, nesterov)
+        else:  # host-side tests of the plumbing (gloo): stock optimiser
+            self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov, foreach=True)
         self.criterion = nn.CrossEntropyLoss()
+
+    def _update(self):
+        """gradient exchange + optimiser step"""
+        if isinstance(self.opt, FlatSGD):
+            self.opt.step(self.grads.all_reduce_sum(self.group))
+        else:
+            self.grads.all_reduce_mean(self.group)
+            self.opt.step()
 
     def loss(self, indices, feats, target, batch_size, n_rows=None):
         x = [indices, feats, batch_size] if n_rows is None else [indices, feats, batch_size, n_rows]
@@ -95,8 +143,7 @@ class TrainStep:
 
     def step(self, indices, feats, target, batch_size, n_rows=None):
         loss = self.forward_backward(indices, feats, target, batch_size, n_rows)
-        self.grads.all_reduce_mean(self.group)
-        self.opt.step()
+        self._update()
         return loss.detach()
 
 
@@ -138,8 +185,7 @@ class GraphTrainStep(TrainStep):
                                         tables=self.tables)
         loss = self.forward_backward(idx, feats, self.target, self.batch_size, self.n_rows)
         if self.capture_update:
-            self.grads.all_reduce_mean(self.group)
-            self.opt.step()
+            self._update()
         return loss.detach()
 
     def _snapshot(self):
@@ -148,8 +194,11 @@ class GraphTrainStep(TrainStep):
 
     def _restore(self, snap):
         # strictly in place: the captured graph holds the addresses of the parameters, BatchNorm buffers
-        # and momentum buffers
+        # and the momentum buffer
         self.model.load_state_dict(snap[0])
+        if isinstance(self.opt, FlatSGD):
+            self.opt.load_state_dict(snap[1])
+            return
         old = snap[1]["state"]
         for i, p in enumerate(self.grads.params):
             st = self.opt.state.get(p, {})
@@ -194,6 +243,5 @@ class GraphTrainStep(TrainStep):
             self.capture()
         self.graph.replay()
         if not self.capture_update:
-            self.grads.all_reduce_mean(self.group)
-            self.opt.step()
+            self._update()
         return self.loss_out

@@ -284,8 +284,9 @@ class SparseSequential(SparseModule):
                     # over the live rows by our own kernel (fused with a directly following ReLU);
                     # element-wise modules may run over the whole capacity-sized buffer
                     if isinstance(module, nn.BatchNorm1d):
-                        fuse = i < len(mods) and isinstance(mods[i][1], nn.ReLU)
-                        input.features = Fsp.batch_norm_relu(input.features, input.n_rows, module, fuse)
+                        own = getattr(module, "fused_relu", False)  # sparseconvnet.BatchNormReLU facade
+                        fuse = (not own) and i < len(mods) and isinstance(mods[i][1], nn.ReLU)
+                        input.features = Fsp.batch_norm_relu(input.features, input.n_rows, module, fuse or own)
                         i += 1 if fuse else 0
                     elif isinstance(module, (nn.ReLU, nn.Dropout, nn.Identity, nn.LeakyReLU, nn.Sigmoid, nn.Tanh)):
                         input.features = module(input.features)

@@ -83,6 +83,8 @@ def compile_stack(modules, sparse_conv_cls, to_dense_cls):
             if not m.training and torch.is_grad_enabled():
                 return None  # eval-mode BN backward is affine, not the batch-statistics formula
             cur.bn = m
+            if getattr(m, "fused_relu", False):  # sparseconvnet.BatchNormReLU facade
+                cur.relu = True
         elif isinstance(m, nn.ReLU):
             if cur is None or cur.relu:
                 return None
