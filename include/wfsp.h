@@ -319,6 +319,29 @@ int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_
                   float momentum, int nesterov, float weight_decay, float grad_scale,
                   wfsp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8) Dense classification head + loss.  SPConvNet flattens the ToDense output and applies
+ * LinearBlock = Linear(k0, h1) . Linear(h1, n_class), no activation in between
+ * (src/models/SPConvNet.py:67-68, src/models/ConvBlocks.py:82-102); LitPSD.training_step takes
+ * CrossEntropyLoss (mean) of it (src/engineering/LitPSD.py:94-104).  At 64 events those ~25 library
+ * kernels are >40 % of a training step; here they are three launches, same fp32 arithmetic.
+ *   wfsp_head_ce_fwd: h1 = x w1^T + b1; logits = h1 w2^T + b2; *loss = mean CE(logits, labels); and the
+ *     small half of the backward pass for d loss = 1: dlogits [B,C], dh1 [B,h1], dw2 [C,h1], db2 [C].
+ *   wfsp_head_bwd: dx = dh1 w1 [B,k0] (dx may be NULL), dw1 = dh1^T x [h1,k0], db1 (may be NULL), and
+ *     dw2 / db2 copied from the forward's values -- all multiplied by *grad_out (device scalar, NULL = 1).
+ * Limits: h1 <= 128, n_class <= 64; one CTA reduces the batch, so intended for batch <= ~256.
+ * x [B,k0], w1 [h1,k0], w2 [n_class,h1] row-major fp32 (torch.nn.Linear layout); labels int64. */
+size_t wfsp_head_workspace_bytes(int batch, int k0, int h1);
+int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const int64_t* labels, int batch, int k0, int h1_dim,
+                     int n_class, float* h1, float* logits, float* loss, float* dlogits, float* dh1,
+                     float* dw2, float* db2, void* workspace, size_t workspace_bytes,
+                     wfsp_stream_t stream);
+int wfsp_head_bwd(const float* x, const float* w1, const float* dh1, const float* dw2_in,
+                  const float* db2_in, const float* grad_out, int batch, int k0, int h1_dim,
+                  int n_class, float* dx, float* dw1, float* db1, float* dw2, float* db2,
+                  wfsp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,26 @@ def test_flat_sgd_matches_torch_nesterov(cuda_device):
         for p, r in zip(ours, ref):
             torch.testing.assert_close(p.detach(), r.detach(), rtol=1e-5, atol=1e-6)
     assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in ours)  # parameters live in the flat buffer
+
+
+@pytest.mark.parametrize("B,k0,h1,C", [(64, 4480, 116, 3), (5, 70, 128, 2), (200, 333, 17, 64)])
+def test_fused_head_matches_torch(cuda_device, B, k0, h1, C):
+    """wfsp_head_ce_fwd / wfsp_head_bwd == Linear . Linear . CrossEntropyLoss(mean) of torch: loss, input gradient
+    and all four parameter gradients, also under a non-unit incoming gradient."""
+    from waveformml_b200 import head
+    torch.manual_seed(B)
+    lin = torch.nn.Sequential(torch.nn.Linear(k0, h1), torch.nn.Linear(h1, C)).to(cuda_device)
+    x = torch.randn(B, k0, device=cuda_device, requires_grad=True)
+    y = torch.randint(0, C, (B,), device=cuda_device)
+    crit = torch.nn.CrossEntropyLoss()
+    assert head.supported(lin, x, crit)
+    loss = head.head_cross_entropy(lin, x, y)
+    (loss * 0.7).backward()
+    got = [loss.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in lin.parameters()]
+    x.grad = None
+    lin.zero_grad()
+    ref = crit(lin(x), y)
+    (ref * 0.7).backward()
+    want = [ref.detach(), x.grad] + [p.grad for p in lin.parameters()]
+    for a, b in zip(got, want):
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5 * max(float(b.abs().max()), 1e-3))

@@ -169,23 +169,66 @@ constexpr int kApplyRows = 64;
 // loaded before any is used (independent loads in flight: these kernels are pure HBM streams).
 constexpr int kApplyUnroll = 4;
 
+// Statistics of the fused small path: every CTA folds the (few) per-chunk partials of its own channels itself
+// -- the same sums, in the same order, as bn_finalize_stats, so all CTAs get bit-identical values -- and CTA 0
+// also records them (save_mean / save_invstd / running estimates).  One launch, no cluster barrier.
+struct PartStats {
+  const float* part;  // [chunks][2][c] (mean, M2) per chunk of chunk_rows rows, or nullptr
+  int chunk_rows;
+  float eps, momentum;
+  float* running_mean; float* running_var; float* save_mean; float* save_invstd;
+};
+
+__device__ __forceinline__ void stats_from_partials(const PartStats& ps, int64_t n, int c, int ch, float& mean, float& invstd,
+                                                    bool record) {
+  const int64_t nblk = (n + ps.chunk_rows - 1) / ps.chunk_rows;
+  double a = 0.0, q = 0.0;
+  for (int64_t b = 0; b < nblk; ++b) {
+    const double nb = double(b + 1 < nblk ? ps.chunk_rows : n - b * ps.chunk_rows);
+    const double mb = ps.part[(b * 2 + 0) * c + ch], m2b = ps.part[(b * 2 + 1) * c + ch];
+    a += nb * mb;
+    q += m2b + nb * mb * mb;
+  }
+  const double cnt = double(n), mu = a / cnt;
+  double m2 = q - cnt * mu * mu;
+  if (m2 < 0.0) m2 = 0.0;
+  mean = float(mu);
+  invstd = float(1.0 / sqrt(m2 / cnt + double(ps.eps)));
+  if (record) {
+    ps.save_mean[ch] = mean;
+    ps.save_invstd[ch] = invstd;
+    if (ps.running_mean) ps.running_mean[ch] = (1.f - ps.momentum) * ps.running_mean[ch] + ps.momentum * mean;
+    if (ps.running_var && cnt > 1.0)
+      ps.running_var[ch] = (1.f - ps.momentum) * ps.running_var[ch] + ps.momentum * float(m2 / (cnt - 1.0));
+  }
+}
+
 template <bool VEC2>
 __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
+                                                int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
+                                                const PartStats ps) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
   uint32_t* y16w = reinterpret_cast<uint32_t*>(y16);
+  if (int64_t(blockIdx.x) * kApplyRows >= n && !(ps.part && blockIdx.x == 0)) return;
+  __shared__ float s_m[512], s_is[512];  // fused small path: statistics of this CTA's channels (c <= 512)
+  if (ps.part && n > 0) {
+    for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y)
+      stats_from_partials(ps, n, c, ch, s_m[ch], s_is[ch], blockIdx.x == 0);
+    __syncthreads();
+  }
   for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
     const int ch = pc << 1;
     float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f};
     const bool on[2] = {ch < c, ch + 1 < c};
 #pragma unroll
     for (int e = 0; e < 2; ++e)
-      if (mean && on[e]) {
-        m[e] = mean[ch + e]; is[e] = invstd[ch + e];
+      if ((mean || ps.part) && on[e]) {
+        if (ps.part) { m[e] = s_m[ch + e]; is[e] = s_is[ch + e]; }
+        else { m[e] = mean[ch + e]; is[e] = invstd[ch + e]; }
         if (gamma) g[e] = gamma[ch + e];
         if (beta) b[e] = beta[ch + e];
       }
@@ -215,7 +258,7 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
           for (int e = 0; e < 2; ++e) {
             if (on[e]) {
               float tv = xv[u][e];
-              if (mean) tv = (tv - m[e]) * is[e] * g[e] + b[e];
+              if (mean || ps.part) tv = (tv - m[e]) * is[e] * g[e] + b[e];
               if (relu && tv < 0.f) tv = 0.f;
               v[e] = tv;
             }
@@ -638,9 +681,9 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     count_launches(1);
   }
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -656,15 +699,26 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
   if (n_rows == 0) return WFSP_OK;
   cudaStream_t st = as_stream(stream);
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
+  if (n_rows <= kSmallRows && c <= 512) {
+    // few chunks: every CTA of the apply kernel folds the partials of its channels itself -- ONE launch
+    const PartStats ps{bn_partials, WFSP_BN_CHUNK_ROWS, eps, momentum, running_mean, running_var, save_mean, save_invstd};
+    if (vec2_ok(c, x, y))
+      bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps);
+    else
+      bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return WFSP_OK;
+  }
   char* scratch = reinterpret_cast<char*>(const_cast<float*>(bn_partials)) +
                   align_up(size_t(ceil_div<int64_t>(n_rows, WFSP_BN_CHUNK_ROWS)) * 2 * c * sizeof(float), 256);
   if (int rc = launch_finalize(bn_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, eps, momentum, running_mean,
                                running_var, save_mean, save_invstd, scratch, st))
     return rc;
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16);
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -729,10 +783,10 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   if (n_rows == 0) return WFSP_OK;
   if (vec2_ok(c, x, y))
     bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{});
   else
     bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16));
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{});
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

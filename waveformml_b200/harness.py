@@ -110,9 +110,9 @@ def segment_l1_loss(indices, predictions, target, spatial_size, batch_size, n_ro
 
 
 class TrainStep:
-    def __init__(self, model, task="psd", lr=0.02, momentum=0.98, nesterov=True, group=None):
+    def __init__(self, model, task="psd", lr=0.02, momentum=0.98, nesterov=True, group=None, fused_head=True):
         assert task in ("psd", "z")
-        self.model, self.task, self.group = model, task, group
+        self.model, self.task, self.group, self.fused_head = model, task, group, fused_head
         self.grads = FlatGrads(model.parameters())
         if self.grads.flat.is_cuda:
             self.opt = FlatSGD(self.grads, lr, momentum, nesterov)
@@ -130,6 +130,8 @@ class TrainStep:
 
     def loss(self, indices, feats, target, batch_size, n_rows=None):
         x = [indices, feats, batch_size] if n_rows is None else [indices, feats, batch_size, n_rows]
+        if self.task == "psd" and self.fused_head and hasattr(self.model, "forward_loss"):
+            return self.model.forward_loss(x, target, self.criterion)
         out = self.model(x)
         if self.task == "psd":
             return self.criterion(out, target)

@@ -1,0 +1,91 @@
+"""Fused dense head + cross-entropy for the PSD classifier (include/wfsp.h section 8).
+
+    flatten(ToDense) -> Linear(k0, h1) -> Linear(h1, n_class) -> CrossEntropyLoss(mean)
+    src/models/SPConvNet.py:67-68, src/models/ConvBlocks.py:82-102, src/engineering/LitPSD.py:94-104
+
+as one autograd node of three launches (wfsp_head_ce_fwd = 2, wfsp_head_bwd = 1) instead of ~25 library
+kernels.  Used by the training harness when the head is exactly two nn.Linear layers, the batch is small
+(<= MAX_BATCH) and the loss is mean cross-entropy; anything else runs the stock torch modules.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib
+from .spconv.fused import _grad_target
+
+MAX_BATCH = 256   # one CTA reduces over the batch: beyond this the library GEMMs win
+MAX_HIDDEN = 128
+MAX_CLASSES = 64
+
+
+def supported(linear, x, criterion=None):
+    """linear: nn.Sequential of the head; x: [B, k0] input of the head."""
+    if not (isinstance(linear, nn.Sequential) and len(linear) == 2 and all(isinstance(m, nn.Linear) for m in linear)):
+        return False
+    if criterion is not None and not (isinstance(criterion, nn.CrossEntropyLoss) and criterion.reduction == "mean"
+                                      and criterion.weight is None and criterion.label_smoothing == 0.0
+                                      and criterion.ignore_index < 0):
+        return False
+    l1, l2 = linear[0], linear[1]
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] <= MAX_BATCH
+            and l1.out_features <= MAX_HIDDEN and l2.out_features <= MAX_CLASSES and l1.in_features == x.shape[1]
+            and l2.in_features == l1.out_features)
+
+
+class HeadCEFunction(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, labels):
+        lib = _lib.load()
+        x = x.contiguous()
+        B, k0 = x.shape
+        h1d, C = w1.shape[0], w2.shape[0]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        h1 = torch.empty((B, h1d), **f32)
+        logits = torch.empty((B, C), **f32)
+        loss = torch.empty((), **f32)
+        dlogits = torch.empty((B, C), **f32)
+        dh1 = torch.empty((B, h1d), **f32)
+        dw2 = torch.empty((C, h1d), **f32)
+        db2 = torch.empty((C,), **f32)
+        ws_bytes = lib.wfsp_head_workspace_bytes(B, k0, h1d)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        labels = labels.contiguous()
+        assert labels.dtype == torch.int64
+        with torch.cuda.device(dev):
+            _lib.check(lib.wfsp_head_ce_fwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                            _lib.ptr(labels), B, k0, h1d, C, _lib.ptr(h1), _lib.ptr(logits), _lib.ptr(loss),
+                                            _lib.ptr(dlogits), _lib.ptr(dh1), _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws),
+                                            ws_bytes, _lib.stream()))
+        ctx.save_for_backward(x, w1, dh1, dw2, db2)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.logits = logits
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        x, w1, dh1, dw2_in, db2_in = ctx.saved_tensors
+        w1_p, b1_p, w2_p, b2_p = ctx.params
+        B, k0 = x.shape
+        h1d, C = w1.shape[0], dw2_in.shape[0]
+        dev = x.device
+        go = grad_out.contiguous().float()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw1, w1_thr = _grad_target(w1_p, (h1d, k0), dev)
+        db1, b1_thr = _grad_target(b1_p, (h1d,), dev) if b1_p is not None else (None, True)
+        dw2, w2_thr = _grad_target(w2_p, (C, h1d), dev)
+        db2, b2_thr = _grad_target(b2_p, (C,), dev) if b2_p is not None else (torch.empty((C,), device=dev), True)
+        with torch.cuda.device(dev):
+            _lib.check(lib.wfsp_head_bwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(dh1), _lib.ptr(dw2_in), _lib.ptr(db2_in),
+                                         _lib.ptr(go), B, k0, h1d, C, _lib.ptr(dx), _lib.ptr(dw1), _lib.ptr(db1),
+                                         _lib.ptr(dw2), _lib.ptr(db2), _lib.stream()))
+        return (dx, None if w1_thr else dw1, None if b1_thr else db1, None if w2_thr else dw2, None if b2_thr else db2,
+                None)
+
+
+def head_cross_entropy(linear, x, labels):
+    """mean cross-entropy of linear(x) against labels through the fused head."""
+    l1, l2 = linear[0], linear[1]
+    return HeadCEFunction.apply(x, l1.weight, l1.bias, l2.weight, l2.bias, labels)

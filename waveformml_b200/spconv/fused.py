@@ -27,8 +27,9 @@ from .. import _lib
 from . import functional as Fsp
 
 _enabled = True
-# BatchNorm over at most this many rows is ONE cluster launch (bn_fwd_small): nothing to fuse there
-_STATS_FUSE_MIN_ROWS = 16384
+# BatchNorm statistics come from the convolution epilogue (per-32-row partials) whenever the output has more
+# rows than this; small outputs then normalise in ONE launch that folds the few partials itself
+_STATS_FUSE_MIN_ROWS = 0
 
 
 def set_fused(flag):
@@ -117,11 +118,11 @@ def _grad_target(param, shape, dev):
 _side_streams = {}
 
 
-def _side_stream(dev):
+def _side_stream(dev, which=0):
     """One extra stream per device.  The geometry of a stack (rulebooks: indices only) does not depend on
     the features, and wgrad does not feed the dgrad chain, so both run beside the main stream and join it
     through events -- inside a CUDA graph capture these become parallel branches of the graph."""
-    key = (dev.type, dev.index)
+    key = (dev.type, dev.index, which)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=dev)
     return _side_streams[key]
@@ -166,7 +167,15 @@ class FusedStackFunction(Function):
                 if d_off is not None:
                     jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + d_off, kvol, cout, cin, 1))
             arr = (_lib.PrepJob * len(jobs))(*jobs)
-            _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
+            # the weights do not depend on this step's data: prepared on the side stream, beside the input cast
+            main, side, side2 = torch.cuda.current_stream(), _side_stream(dev), _side_stream(dev, 1)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side2):
+                side2.wait_event(fork)
+                _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
+                w_ready = torch.cuda.Event()
+                w_ready.record(side2)
 
             # ---- input activations -> bf16 once
             n0, c0 = feats.shape
@@ -175,10 +184,7 @@ class FusedStackFunction(Function):
                 _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(feats), n0, _lib.ptr(x.n_rows), c0, _lib.ptr(a16), st()))
 
             # ---- geometry of every block on the side stream (overlaps weight preparation and the first layers)
-            main, side = torch.cuda.current_stream(), _side_stream(dev)
             geoms, gcur = [], x
-            fork = torch.cuda.Event()
-            fork.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(fork)
                 for b in blocks:
@@ -190,6 +196,7 @@ class FusedStackFunction(Function):
                     geoms.append((rb, outids, out_shape, out_rows, gcur, nxt, ready))
                     gcur = nxt
 
+            main.wait_event(w_ready)
             saved, cur, out32 = [], x, None
             for bi, b in enumerate(blocks):
                 conv = b.conv
@@ -212,7 +219,7 @@ class FusedStackFunction(Function):
                 # large outputs followed by a training-mode BatchNorm: the conv epilogue also emits the
                 # per-32-row-chunk statistics, so BatchNorm does not re-read the output to get them
                 partials = None
-                if b.bn is not None and b.bn.training and n_dst > _STATS_FUSE_MIN_ROWS:
+                if b.bn is not None and b.bn.training and n_dst > _STATS_FUSE_MIN_ROWS and cout <= 512:
                     partials = torch.empty((lib.wfsp_bn_partials_bytes(n_dst, cout),), dtype=torch.uint8, device=dev)
                 if n_dst:
                     hint = Fsp.hints.get(n_dst_dev)

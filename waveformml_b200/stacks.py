@@ -69,6 +69,15 @@ class PSDClassifier(nn.Module):
         d = self.sparseModel(_wrap(x, self.spatial_size))
         return self.linear(d.view(-1, self.n_linear))
 
+    def forward_loss(self, x, target, criterion):
+        """criterion(self(x), target) -- LitPSD.training_step (src/engineering/LitPSD.py:94-104) -- with the dense
+        head and the loss fused into three launches when the head / loss / batch are the supported case."""
+        from . import head
+        d = self.sparseModel(_wrap(x, self.spatial_size)).view(-1, self.n_linear)
+        if head.supported(self.linear, d, criterion):
+            return head.head_cross_entropy(self.linear, d, target)
+        return criterion(self.linear(d), target)
+
 
 class ZRegressor(nn.Module):
     """config/examples/SingleEndedZCNN.json -> SingleEndedZConv + SparseConv2DForZ (SPConvBlocks.py:261-313):
