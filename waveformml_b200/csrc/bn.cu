@@ -163,7 +163,7 @@ __device__ __forceinline__ uint32_t bn_pack_bf16x2(float lo, float hi) {
 // optional): y fp32 [rows, c] and y16 bf16 [rows, c_pad] (c_pad = c rounded up to 8, padding written as
 // zero) -- the operand format of the tcgen05 convolution kernels, so the next layer needs no cast pass.
 // mean == nullptr switches the normalisation off (plain ReLU / cast).
-constexpr int kApplyRows = 64;
+constexpr int kApplyRows = 64;  // rows per CTA pass at most (large inputs); small inputs take fewer, see apply_rows()
 
 // VEC2: c is even and the buffers are 8-byte aligned, so a channel pair is one float2.  Four rows are
 // loaded before any is used (independent loads in flight: these kernels are pure HBM streams).
@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                 int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
-                                                const PartStats ps) {
+                                                const PartStats ps, int rows_per_cta) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
   uint32_t* y16w = reinterpret_cast<uint32_t*>(y16);
-  if (int64_t(blockIdx.x) * kApplyRows >= n && !(ps.part && blockIdx.x == 0)) return;
+  if (int64_t(blockIdx.x) * rows_per_cta >= n && !(ps.part && blockIdx.x == 0)) return;
   __shared__ float s_m[512], s_is[512];  // fused small path: statistics of this CTA's channels (c <= 512)
   if (ps.part && n > 0) {
     for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y)
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
         if (gamma) g[e] = gamma[ch + e];
         if (beta) b[e] = beta[ch + e];
       }
-    for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
-      const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
+    for (int64_t r0 = int64_t(blockIdx.x) * rows_per_cta; r0 < n; r0 += int64_t(gridDim.x) * rows_per_cta) {
+      const int64_t r_end = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
       for (int64_t rb = r0 + threadIdx.y; rb < r_end; rb += int64_t(kApplyUnroll) * blockDim.y) {
         float xv[kApplyUnroll][2];
 #pragma unroll
@@ -341,7 +341,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                                     const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
-                                                    int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16) {
+                                                    int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+                                                    int rows_per_cta) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
@@ -358,8 +359,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
         if (beta) b[e] = beta[ch + e];
         db[e] = d_beta[ch + e] * inv_n; dg[e] = d_gamma[ch + e] * inv_n;
       }
-    for (int64_t r0 = int64_t(blockIdx.x) * kApplyRows; r0 < n; r0 += int64_t(gridDim.x) * kApplyRows) {
-      const int64_t r_end = r0 + kApplyRows < n ? r0 + kApplyRows : n;
+    for (int64_t r0 = int64_t(blockIdx.x) * rows_per_cta; r0 < n; r0 += int64_t(gridDim.x) * rows_per_cta) {
+      const int64_t r_end = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
       for (int64_t rb = r0 + threadIdx.y; rb < r_end; rb += int64_t(kApplyUnroll) * blockDim.y) {
         float xv[kApplyUnroll][2], dv[kApplyUnroll][2];
 #pragma unroll
@@ -612,8 +613,15 @@ int launch_finalize(const float* part, int chunk_rows, int64_t n_rows, const int
   return WFSP_OK;
 }
 
+// rows per CTA pass of the apply kernels: 64 for large inputs; small (latency-bound) inputs are spread over
+// ~4 CTAs per SM so that no thread walks more than a couple of dependent load batches
+inline int apply_rows(int64_t rows) {
+  int64_t r = ceil_div<int64_t>(rows > 0 ? rows : 1, int64_t(sm_count()) * 4);
+  r = (r + 7) / 8 * 8;
+  return int(r < 8 ? 8 : (r > kApplyRows ? kApplyRows : r));
+}
 inline unsigned apply_blocks(int64_t rows) {
-  int64_t b = ceil_div<int64_t>(rows > 0 ? rows : 1, kApplyRows);
+  int64_t b = ceil_div<int64_t>(rows > 0 ? rows : 1, apply_rows(rows));
   const int64_t cap = int64_t(sm_count()) * 16;
   return unsigned(b > cap ? cap : b);
 }
@@ -681,9 +689,9 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     count_launches(1);
   }
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -703,9 +711,9 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
     // few chunks: every CTA of the apply kernel folds the partials of its channels itself -- ONE launch
     const PartStats ps{bn_partials, WFSP_BN_CHUNK_ROWS, eps, momentum, running_mean, running_var, save_mean, save_invstd};
     if (vec2_ok(c, x, y))
-      bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps);
+      bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
     else
-      bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps);
+      bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -716,9 +724,9 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
                                running_var, save_mean, save_invstd, scratch, st))
     return rc;
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
+    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{});
+    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -758,9 +766,9 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   bn_bwd_partial<<<grid, dim3(32, kPartLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
-    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16);
+    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows));
   else
-    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16);
+    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows));
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -783,10 +791,10 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   if (n_rows == 0) return WFSP_OK;
   if (vec2_ok(c, x, y))
     bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{});
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
   else
     bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{});
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -800,11 +808,11 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
     bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16));
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows));
   else
     bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16));
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

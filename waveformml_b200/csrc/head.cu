@@ -84,28 +84,40 @@ __global__ void __launch_bounds__(256) head_l1_reduce(const float* __restrict__ 
   if (q == 0 && i < B * H1) h1[i] = s + (b1 ? b1[i % H1] : 0.f);
 }
 
-// one CTA of 1024 threads: everything that is O(batch x hidden) or smaller
+// one CTA of 1024 threads: everything that is O(batch x hidden) or smaller.  h1, w2 and dlogits are staged in
+// shared memory once (coalesced), so the serial inner loops run on chip instead of on L2 latency.
+// dynamic smem: h1 [B][H1+1] | w2 [C][H1+1] | dlogits [B][C] | logits [B][C]
 __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, const float* __restrict__ b2,
                                                   const int64_t* __restrict__ labels, int B, int H1, int C,
                                                   const float* __restrict__ h1, float* __restrict__ logits, float* __restrict__ loss,
                                                   float* __restrict__ dlogits, float* __restrict__ dh1, float* __restrict__ dw2,
                                                   float* __restrict__ db2) {
+  extern __shared__ float sm[];
   __shared__ float s_red[32];
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, hp = H1 + 1;
+  float* s_h1 = sm;
+  float* s_w2 = s_h1 + B * hp;
+  float* s_dl = s_w2 + C * hp;
+  float* s_lg = s_dl + B * C;
+  for (int i = tid; i < B * H1; i += nt) s_h1[(i / H1) * hp + i % H1] = h1[i];
+  for (int i = tid; i < C * H1; i += nt) s_w2[(i / H1) * hp + i % H1] = w2[i];
+  __syncthreads();
   // logits = h1 w2^T + b2
   for (int i = tid; i < B * C; i += nt) {
     const int b = i / C, c = i % C;
     float s = b2 ? b2[c] : 0.f;
-    const float* hr = h1 + int64_t(b) * H1;
-    const float* wr = w2 + int64_t(c) * H1;
+    const float* hr = s_h1 + b * hp;
+    const float* wr = s_w2 + c * hp;
+#pragma unroll 4
     for (int h = 0; h < H1; ++h) s += hr[h] * wr[h];
+    s_lg[i] = s;
     logits[i] = s;
   }
   __syncthreads();
   // cross entropy (mean over the batch) and dlogits = (softmax - onehot) / B
   float lsum = 0.f;
   for (int b = tid; b < B; b += nt) {
-    const float* lr = logits + int64_t(b) * C;
+    const float* lr = s_lg + b * C;
     float m = lr[0];
     for (int c = 1; c < C; ++c) m = fmaxf(m, lr[c]);
     float z = 0.f;
@@ -113,7 +125,11 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
     const float lse = m + logf(z);
     const int y = int(labels[b]);
     lsum += lse - lr[y];
-    for (int c = 0; c < C; ++c) dlogits[int64_t(b) * C + c] = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) / float(B);
+    for (int c = 0; c < C; ++c) {
+      const float d = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) / float(B);
+      s_dl[b * C + c] = d;
+      dlogits[int64_t(b) * C + c] = d;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
@@ -127,19 +143,20 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   for (int i = tid; i < C * H1; i += nt) {
     const int c = i / H1, h = i % H1;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dlogits[int64_t(b) * C + c] * h1[int64_t(b) * H1 + h];
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) s += s_dl[b * C + c] * s_h1[b * hp + h];
     dw2[i] = s;
   }
   for (int c = tid; c < C; c += nt) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dlogits[int64_t(b) * C + c];
+    for (int b = 0; b < B; ++b) s += s_dl[b * C + c];
     db2[c] = s;
   }
   // dh1[b][h] = sum_c dlogits[b][c] w2[c][h]
   for (int i = tid; i < B * H1; i += nt) {
     const int b = i / H1, h = i % H1;
     float s = 0.f;
-    for (int c = 0; c < C; ++c) s += dlogits[int64_t(b) * C + c] * w2[int64_t(c) * H1 + h];
+    for (int c = 0; c < C; ++c) s += s_dl[b * C + c] * s_w2[c * hp + h];
     dh1[i] = s;
   }
 }
@@ -172,8 +189,8 @@ __global__ void __launch_bounds__(256) head_bwd(const float* __restrict__ x, con
   __shared__ float xs[kBB][kKB + 1];      // x tile   [32 rows][32 k]
   __shared__ float w1s[kMaxH1][kKB + 1];  // W1 chunk [H1][32 k]
   const int k0 = blockIdx.x * kKB;
-  for (int i = tid; i < H1 * kKB; i += 256) {
-    const int h = i / kKB, k = i % kKB;
+  for (int h = tid >> 5; h < H1; h += 8) {  // a warp reads one 128-byte row segment of W1
+    const int k = tid & 31;
     w1s[h][k] = (k0 + k < K0) ? w1[int64_t(h) * K0 + k0 + k] : 0.f;
   }
   // dW1 accumulators: thread (tk = tid % 32, th = tid / 32) owns column k0 + tk, rows h = th + 8 j
@@ -183,12 +200,10 @@ __global__ void __launch_bounds__(256) head_bwd(const float* __restrict__ x, con
   for (int j = 0; j < kMaxH1 / 8; ++j) accw[j] = 0.f;
   for (int b0 = 0; b0 < B; b0 += kBB) {
     __syncthreads();
-    for (int i = tid; i < kBB * H1; i += 256) {
-      const int r = i / H1, h = i % H1;
-      dhs[r][h] = (b0 + r < B) ? dh1[int64_t(b0 + r) * H1 + h] : 0.f;
-    }
-    for (int i = tid; i < kBB * kKB; i += 256) {
-      const int r = i / kKB, k = i % kKB;
+    for (int r = tid >> 5; r < kBB; r += 8) {
+      for (int h = tid & 31; h < kMaxH1; h += 32)
+        dhs[r][h] = (b0 + r < B && h < H1) ? dh1[int64_t(b0 + r) * H1 + h] : 0.f;
+      const int k = tid & 31;
       xs[r][k] = (b0 + r < B && k0 + k < K0) ? x[int64_t(b0 + r) * K0 + k0 + k] : 0.f;
     }
     __syncthreads();
@@ -243,7 +258,10 @@ extern "C" int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1
   dim3 grid(unsigned(splits), unsigned((h1_dim + kHT - 1) / kHT), unsigned((batch + kBT - 1) / kBT));
   head_l1_partial<<<grid, 256, 0, st>>>(x, w1, batch, k0, h1_dim, partial);
   head_l1_reduce<<<unsigned((batch * h1_dim * 4 + 255) / 256), 256, 0, st>>>(partial, splits, b1, batch, h1_dim, h1);
-  head_tail<<<1, 1024, 0, st>>>(w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2);
+  const size_t tail_smem = (size_t(batch) * (h1_dim + 1) + size_t(n_class) * (h1_dim + 1) + size_t(2) * batch * n_class) * sizeof(float);
+  if (tail_smem > size_t(200) * 1024) return set_error(WFSP_EUNSUPPORTED, "head batch %d too large for the fused tail", batch);
+  WFSP_CHECK_CUDA(cudaFuncSetAttribute(head_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  head_tail<<<1, 1024, tail_smem, st>>>(w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from .spconv.fused import _grad_target
 
-MAX_BATCH = 256   # one CTA reduces over the batch: beyond this the library GEMMs win
+MAX_BATCH = 256   # one CTA reduces over the batch (staged in shared memory): beyond this the library GEMMs win
 MAX_HIDDEN = 128
 MAX_CLASSES = 64
 
