@@ -337,6 +337,13 @@ int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1, const flo
                      int n_class, float* h1, float* logits, float* loss, float* dlogits, float* dh1,
                      float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                      wfsp_stream_t stream);
+/* backward split for callers with a GEMM library at hand: this entry does the small part (dh1_scaled = dh1 *
+ * *grad_out, db1, dw2, db2); the caller then computes dw1 = dh1_scaled^T x and dx = dh1_scaled w1 as two
+ * plain GEMMs (what waveformml_b200/head.py does with cuBLAS -- the all-in-one wfsp_head_bwd below is an
+ * fp32 SIMT kernel that the library GEMMs beat). */
+int wfsp_head_bwd_small(const float* dh1, const float* dw2_in, const float* db2_in,
+                        const float* grad_out, int batch, int h1_dim, int n_class, float* dh1_scaled,
+                        float* db1, float* dw2, float* db2, wfsp_stream_t stream);
 int wfsp_head_bwd(const float* x, const float* w1, const float* dh1, const float* dw2_in,
                   const float* db2_in, const float* grad_out, int batch, int k0, int h1_dim,
                   int n_class, float* dx, float* dw1, float* db1, float* dw2, float* db2,

@@ -180,3 +180,29 @@ def test_fused_head_matches_torch(cuda_device, B, k0, h1, C):
     want = [ref.detach(), x.grad] + [p.grad for p in lin.parameters()]
     for a, b in zip(got, want):
         torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5 * max(float(b.abs().max()), 1e-3))
+
+
+def test_head_bwd_all_in_one_entry(cuda_device):
+    """wfsp_head_bwd (the C-ABI entry for callers without a GEMM library) against torch autograd."""
+    from waveformml_b200 import _lib
+    lib = _lib.load()
+    B, k0, h1, C = 70, 150, 40, 5
+    torch.manual_seed(3)
+    x = torch.randn(B, k0, device=cuda_device)
+    w1 = torch.randn(h1, k0, device=cuda_device, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    dh1 = torch.randn(B, h1, device=cuda_device)
+    dw2_in, db2_in = torch.randn(C, h1, device=cuda_device), torch.randn(C, device=cuda_device)
+    go = torch.tensor(1.3, device=cuda_device)
+    dx, dw1, db1 = torch.empty_like(x), torch.empty_like(w1), torch.empty(h1, device=cuda_device)
+    dw2, db2 = torch.empty_like(dw2_in), torch.empty_like(db2_in)
+    with torch.cuda.device(cuda_device):
+        _lib.check(lib.wfsp_head_bwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(dh1), _lib.ptr(dw2_in), _lib.ptr(db2_in), _lib.ptr(go),
+                                     B, k0, h1, C, _lib.ptr(dx), _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2),
+                                     _lib.stream()))
+    ((xr @ w1.t()) * dh1).sum().mul(1.3).backward()
+    torch.testing.assert_close(dx, xr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dw1, w1.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db1, dh1.sum(0) * 1.3, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dw2, dw2_in * 1.3)
+    torch.testing.assert_close(db2, db2_in * 1.3)

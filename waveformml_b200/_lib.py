@@ -64,6 +64,7 @@ SIGNATURES = {
     "wfsp_head_ce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _vp]),
     "wfsp_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wfsp_head_bwd_small": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "wfsp_sgd_step": (_int, [_vp, _vp, _vp, _i64, _f32, _f32, _int, _f32, _f32, _vp]),
 }
 

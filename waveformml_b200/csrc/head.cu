@@ -233,6 +233,28 @@ __global__ void __launch_bounds__(256) head_bwd(const float* __restrict__ x, con
   }
 }
 
+// the small half of the backward pass: dh1_scaled = dh1 * g (operand of the two library GEMMs dW1 = dh1^T x,
+// dx = dh1 W1), db1 = column sums * g, dW2 / db2 = forward's values * g.  grid = ceil(H1 / 8) CTAs of 256.
+__global__ void __launch_bounds__(256) head_bwd_small(const float* __restrict__ dh1, const float* __restrict__ dw2_in,
+                                                      const float* __restrict__ db2_in, const float* __restrict__ go, int B,
+                                                      int H1, int C, float* __restrict__ dh1_scaled, float* __restrict__ db1,
+                                                      float* __restrict__ dw2, float* __restrict__ db2) {
+  const float g = go ? *go : 1.f;
+  const int tid = threadIdx.x, gtid = blockIdx.x * 256 + tid, gn = gridDim.x * 256;
+  for (int i = gtid; i < B * H1; i += gn) dh1_scaled[i] = dh1[i] * g;
+  for (int i = gtid; i < C * H1; i += gn) dw2[i] = dw2_in[i] * g;
+  for (int i = gtid; i < C; i += gn) db2[i] = db2_in[i] * g;
+  if (db1) {  // warp w of this CTA sums column blockIdx.x * 8 + w over the batch
+    const int h = blockIdx.x * 8 + (tid >> 5);
+    if (h < H1) {
+      float s = 0.f;
+      for (int b = tid & 31; b < B; b += 32) s += dh1[int64_t(b) * H1 + h];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((tid & 31) == 0) db1[h] = s * g;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace wfsp
 
@@ -275,6 +297,18 @@ extern "C" int wfsp_head_bwd(const float* x, const float* w1, const float* dh1, 
   const int chunks = (k0 + kKB - 1) / kKB;
   head_bwd<<<unsigned(chunks + 1), 256, 0, as_stream(stream)>>>(x, w1, dh1, dw2_in, db2_in, grad_out, batch, k0, h1_dim, n_class,
                                                                dx, dw1, db1, dw2, db2);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_head_bwd_small(const float* dh1, const float* dw2_in, const float* db2_in, const float* grad_out, int batch,
+                                   int h1_dim, int n_class, float* dh1_scaled, float* db1, float* dw2, float* db2,
+                                   wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 1 && h1_dim >= 1 && n_class >= 1, "bad head sizes");
+  WFSP_REQUIRE(dh1 && dw2_in && db2_in && dh1_scaled && dw2 && db2, "null argument");
+  head_bwd_small<<<unsigned((h1_dim + 7) / 8), 256, 0, as_stream(stream)>>>(dh1, dw2_in, db2_in, grad_out, batch, h1_dim, n_class,
+                                                                            dh1_scaled, db1, dw2, db2);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

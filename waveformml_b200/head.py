@@ -77,10 +77,14 @@ class HeadCEFunction(Function):
         db1, b1_thr = _grad_target(b1_p, (h1d,), dev) if b1_p is not None else (None, True)
         dw2, w2_thr = _grad_target(w2_p, (C, h1d), dev)
         db2, b2_thr = _grad_target(b2_p, (C,), dev) if b2_p is not None else (torch.empty((C,), device=dev), True)
+        dh1s = torch.empty_like(dh1)
         with torch.cuda.device(dev):
-            _lib.check(lib.wfsp_head_bwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(dh1), _lib.ptr(dw2_in), _lib.ptr(db2_in),
-                                         _lib.ptr(go), B, k0, h1d, C, _lib.ptr(dx), _lib.ptr(dw1), _lib.ptr(db1),
-                                         _lib.ptr(dw2), _lib.ptr(db2), _lib.stream()))
+            # small half in one launch; the two large products are plain GEMMs -> cuBLAS
+            _lib.check(lib.wfsp_head_bwd_small(_lib.ptr(dh1), _lib.ptr(dw2_in), _lib.ptr(db2_in), _lib.ptr(go), B, h1d, C,
+                                               _lib.ptr(dh1s), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2), _lib.stream()))
+            torch.mm(dh1s.t(), x, out=dw1)
+            if dx is not None:
+                torch.mm(dh1s, w1, out=dx)
         return (dx, None if w1_thr else dw1, None if b1_thr else db1, None if w2_thr else dw2, None if b2_thr else db2,
                 None)
 
