@@ -349,6 +349,20 @@ int wfsp_head_bwd(const float* x, const float* w1, const float* dh1, const float
                   int n_class, float* dx, float* dw1, float* db1, float* dw2, float* db2,
                   wfsp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (9) Window edges.  Replaces the reference's only native function, cffi_window_edges
+ * (src/custom_functions/cffi.c:5-37, bound in src/custom_functions/__init__.py:5-35 and called from
+ * src/utils/GraphUtils.py:7-40): for every hit i an optional self loop, then for every later hit j of the
+ * same contiguous run of equal batch ids with |x_i - x_j| < n and |y_i - y_j| < n the edges (i,j), (j,i)
+ * (n = max_dist + 1), in exactly the CPU loop's order.  x, y, b: int64 [num_elem]; edges1 / edges2: int64
+ * [edge_cap]; *edge_count (device int64) = number of edges.  With edges1 == NULL only the count is
+ * produced (first pass to size the output). */
+size_t wfsp_window_edges_workspace_bytes(int64_t num_elem);
+int wfsp_window_edges(int64_t n, int64_t num_elem, const int64_t* x, const int64_t* y, const int64_t* b,
+                      int self_loop, int64_t* edges1, int64_t* edges2, int64_t edge_cap,
+                      int64_t* edge_count, void* workspace, size_t workspace_bytes,
+                      wfsp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

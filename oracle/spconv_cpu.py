@@ -54,8 +54,28 @@ def lib():
         L.wfo_batch_pack.argtypes = [i32p, ctypes.POINTER(ctypes.c_int16), ctypes.c_int64,
                                      ctypes.c_int64, i64p, i64p, ctypes.c_int64, ctypes.c_float,
                                      i32p, f32p]
+        L.wfo_window_edges.restype = ctypes.c_int64
+        L.wfo_window_edges.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, i64p, ctypes.c_int, i64p, i64p]
         _LIB = L
     return _LIB
+
+
+def window_edges(coo, batch, max_dist=1, self_loops=True):
+    """Oracle of src/utils/GraphUtils.py:7-40 (window_edges): coo int64 [N, 2], batch int64 [N] -> int64 [2, E]."""
+    coo = np.ascontiguousarray(np.asarray(coo, dtype=np.int64))
+    batch = np.ascontiguousarray(np.asarray(batch, dtype=np.int64))
+    n = coo.shape[0]
+    x, y = np.ascontiguousarray(coo[:, 0]), np.ascontiguousarray(coo[:, 1])
+    # bound: every hit pairs with at most (longest run of equal batch ids - 1) later hits
+    run = 1
+    if n:
+        brk = np.flatnonzero(np.diff(batch) != 0)
+        run = int(np.max(np.diff(np.concatenate([[-1], brk, [n - 1]]))))
+    cap = max(1, n * (1 + 2 * run))
+    e1, e2 = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64)
+    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+    cnt = lib().wfo_window_edges(max_dist + 1, n, p(x), p(y), p(batch), int(bool(self_loops)), p(e1), p(e2))
+    return np.stack([e1[:cnt], e2[:cnt]], 0)
 
 
 def _p(t, ct):

@@ -261,3 +261,28 @@ int32_t wfo_batch_pack(const int32_t* coords, const int16_t* wave, int64_t N, in
   for (int64_t i = 0; i < N * C; ++i) feats[i] = (float)wave[i] * scale;
   return N > 0 ? indices[(N - 1) * 3] + 1 : 0;
 }
+
+/* ---- window edges -----------------------------------------------------------
+ * Restatement of /root/reference/src/custom_functions/cffi.c:5-37 (cffi_window_edges), the reference's only
+ * native code (called from src/utils/GraphUtils.py:7-40): for every element i, an optional self loop,
+ * then for every later element j of the same contiguous run of equal batch ids with |dx| < n and
+ * |dy| < n the two directed edges (i,j), (j,i).  n = max_dist + 1.  Returns the number of edges.
+ * (The reference takes abs() of the long long difference through C's int abs; coordinates here are tiny,
+ * so the truncation never matters -- noted, not reproduced.)                                          */
+int64_t wfo_window_edges(int64_t n, int64_t num_elem, const int64_t* x, const int64_t* y, const int64_t* b,
+                         int self_loop, int64_t* edges1, int64_t* edges2) {
+  int64_t e = 0;
+  for (int64_t i = 0; i < num_elem; ++i) {
+    if (self_loop) { edges1[e] = i; edges2[e] = i; ++e; }
+    for (int64_t j = i + 1; j < num_elem && b[i] == b[j]; ++j) {
+      int64_t dx = x[i] - x[j], dy = y[i] - y[j];
+      if (dx < 0) dx = -dx;
+      if (dy < 0) dy = -dy;
+      if (dx < n && dy < n) {
+        edges1[e] = i; edges2[e] = j; ++e;
+        edges2[e] = i; edges1[e] = j; ++e;
+      }
+    }
+  }
+  return e;
+}

@@ -65,6 +65,8 @@ SIGNATURES = {
                                 _vp, _sz, _vp]),
     "wfsp_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wfsp_head_bwd_small": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "wfsp_window_edges_workspace_bytes": (_sz, [_i64]),
+    "wfsp_window_edges": (_int, [_i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "wfsp_sgd_step": (_int, [_vp, _vp, _vp, _i64, _f32, _f32, _int, _f32, _f32, _vp]),
 }
 

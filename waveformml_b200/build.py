@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "rulebook.cu", "conv_simt.cu", "conv_umma.cu", "dense_pack.cu", "bn.cu", "tma.cu", "head.cu"]
+SOURCES = ["api.cu", "rulebook.cu", "conv_simt.cu", "conv_umma.cu", "dense_pack.cu", "bn.cu", "tma.cu", "head.cu", "edges.cu"]
 LIB = os.path.join(HERE, "libwfsp.so")
 
 
