@@ -2,17 +2,20 @@
 // accumulation in tensor memory.  They replace upstream indiceConv / indiceConvBackward
 // (reference call sites src/models/SPConvBlocks.py:498-502 etc.).
 //
-// Both kernels are warp-specialised (160 threads):
-//   warps 0-3  producers: issue 16-byte cp.async copies of gathered bf16 rows and of the weight /
-//              gradient slice straight into 128-byte-swizzled shared-memory tiles, then
-//              cp.async.mbarrier.arrive.noinc on the stage's "full" barrier and move on -- they
-//              never wait for data, so up to `stages` slices are in flight per CTA;
-//   warp 4     one elected lane waits on "full", issues 4 tcgen05.mma (K=16 each) accumulating in
-//              TMEM and tcgen05.commit's to the stage's "free" barrier;
-//   warps 0-3  epilogue after the last commit: tcgen05.ld -> registers -> global.
+// Both kernels are warp-specialised (544 threads):
+//   warps 0-15 producers: issue 16-byte cp.async copies of gathered bf16 rows straight into
+//              128-byte-swizzled shared-memory tiles, then cp.async.mbarrier.arrive.noinc on the stage's
+//              "full" barrier and move on -- they never wait for data, so up to `stages` slices are in
+//              flight per CTA.  Sixteen warps (four per scheduler) because a lone producer warp per
+//              scheduler was instruction-issue bound (ncu: ~0.27 IPC).  The weight slice of the apply
+//              kernel arrives by ONE cp.async.bulk of a pre-swizzled block (thread 0, expect_tx);
+//   warp 16    one elected lane waits on "full", issues tcgen05.mma (K=16 each) accumulating in TMEM and
+//              tcgen05.commit's to the stage's "free" barrier;
+//   warps 0-7  epilogue after the last commit: tcgen05.ld -> registers -> shared-memory tile -> coalesced
+//              global rows (warps w and w+4 share TMEM lane quarter w and take alternate column chunks).
 //
 // apply kernel (forward, dgrad, inverse forward, inverse dgrad) -- output-stationary implicit GEMM:
-//   a CTA owns 128 destination rows and walks (active kernel offset k) x (64-channel slice):
+//   a CTA owns RB x 128 destination rows and walks (active kernel offset k) x (64-channel slice):
 //   A tile = rows nbr[r][k] of the bf16 activation copy (zero-filled for -1 through cp.async
 //   src-size 0), B tile = slice of the pre-transposed bf16 weights.  No scatter-add, no atomics,
 //   fixed summation order.
