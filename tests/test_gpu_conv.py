@@ -307,3 +307,30 @@ def test_row_blocked_tiles(cuda_device, rblk):
     finally:
         _lib.load().wfsp_set_option(b"apply_row_blocks", 0)
     check_all(g, refs, "bf16", "row blocks %d" % rblk)
+
+
+def test_fused_stack_takes_bf16_operand_input(cuda_device):
+    """Features already in the bf16 operand format (pitch rounded up to 8, e.g. from batcher.pack_batch) are used
+    without a cast pass and give the same result as the fp32 features they were rounded from -- on the fused
+    path and, through the fallback conversion, on the per-layer path."""
+    B = 30
+    idx, feats = events(B, 29, 20)  # 20 channels -> pitch 24
+    torch.manual_seed(12)
+    net = spconv.SparseSequential(spconv.SparseConv2d(20, 16, 3, 1, 1, 1, 1, False), torch.nn.BatchNorm1d(16), torch.nn.ReLU(),
+                                  spconv.SubMConv2d(16, 8, 3, bias=False, indice_key="subm0"), spconv.ToDense()).to(cuda_device)
+    f32 = feats.to(cuda_device).bfloat16().float()  # values exactly representable in bf16
+    f16 = torch.zeros((f32.shape[0], 24), dtype=torch.bfloat16, device=cuda_device)
+    f16[:, :20] = f32.bfloat16()
+    outs = {}
+    for name, fused_on, f in (("fused16", True, f16), ("fused32", True, f32), ("layer16", False, f16)):
+        spconv.set_fused(fused_on)
+        try:
+            net.zero_grad()
+            y = net(spconv.SparseConvTensor(f, idx.to(cuda_device), [14, 11], B))
+            y.square().sum().backward()
+            outs[name] = (y.detach().clone(), net[0].weight.grad.clone())
+        finally:
+            spconv.set_fused(True)
+    torch.testing.assert_close(outs["fused16"][0], outs["fused32"][0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(outs["fused16"][1], outs["fused32"][1], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(outs["layer16"][0], outs["fused32"][0], rtol=5e-3, atol=5e-3 * float(outs["fused32"][0].abs().max()))

@@ -80,3 +80,19 @@ def test_to_dense_empty(cuda_device):
     d = spconv.SparseConvTensor(torch.zeros(0, 3, device=cuda_device), torch.zeros(0, 3, dtype=torch.int32, device=cuda_device),
                                 [14, 11], 2).dense()
     assert d.shape == (2, 3, 14, 11) and float(d.abs().sum()) == 0.0
+
+
+def test_pack_bf16_operand_format_padding(cuda_device):
+    """bf16 output = tensor-core operand format: pitch rounded up to 8 channels, padding zero (both kernels:
+    the 4-wide vector path c % 4 == 0 and the scalar path)."""
+    for c in (12, 300, 7):
+        g = torch.Generator().manual_seed(c)
+        n = 37
+        wave = torch.randint(0, 2 ** 14, (n, c), generator=g, dtype=torch.int16).to(cuda_device)
+        coords = torch.zeros((n, 3), dtype=torch.int32, device=cuda_device)
+        _, f32 = batcher.pack_batch(coords, wave, [0, n], [1])
+        _, f16 = batcher.pack_batch(coords, wave, [0, n], [1], out_dtype=torch.bfloat16)
+        pitch = (c + 7) // 8 * 8
+        assert tuple(f16.shape) == (n, pitch)
+        assert torch.equal(f16[:, :c], f32.bfloat16())
+        assert bool((f16[:, c:] == 0).all())

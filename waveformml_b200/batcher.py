@@ -44,11 +44,15 @@ def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RAN
     wdt = {torch.int16: _lib.I16, torch.float32: _lib.F32}[wave.dtype]
     odt = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[out_dtype]
     indices = torch.empty((n, 3), dtype=torch.int32, device=dev)
-    feats = torch.empty((n, c), dtype=out_dtype, device=dev)
+    # bf16 output = the tensor-core operand format (include/wfsp.h section 6): row pitch rounded up to 8 channels,
+    # padding zero -- the fused sparse stack then reads the batcher's output directly, no fp32 copy and no cast pass
+    pitch = (c + 7) // 8 * 8 if out_dtype == torch.bfloat16 else c
+    alloc = torch.empty if (pitch == c or c % 4 == 0) else torch.zeros  # the vector kernel zeroes the padding itself
+    feats = alloc((n, pitch), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), _lib.ptr(wave), wdt, n, _lib.ptr(n_rows), c,
                                        _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), _lib.ptr(indices),
-                                       _lib.ptr(feats), odt, c, _lib.stream()))
+                                       _lib.ptr(feats), odt, pitch, _lib.stream()))
     return indices, feats
 
 

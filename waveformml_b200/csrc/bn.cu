@@ -16,7 +16,8 @@ namespace cg = cooperative_groups;
 namespace wfsp {
 namespace {
 
-constexpr int kRows = 1024;  // rows per partial
+constexpr int kRows = 1024;  // rows per partial (forward statistics of the per-layer path)
+constexpr int kRowsBwd = 256;  // rows per partial of the backward sums: more, smaller CTAs keep enough loads in flight
 constexpr int kCh = 32;      // channels per block (one 128-byte row segment)
 constexpr int kPartLanes = 32;  // row lanes of the partial-statistics kernels: 1024 threads per block keep enough loads in flight
 
@@ -274,39 +275,84 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
   }
 }
 
-// backward partials: sum(dy') and sum(dy' * xhat) per (row chunk, channel); dy' = dy masked by relu
-__global__ void __launch_bounds__(kCh * kPartLanes) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
+// backward partials: sum(dy') and sum(dy' * xhat) per (row chunk, channel); dy' = dy masked by relu.
+// Same thread mapping as the apply kernels: thread x owns one pair of adjacent channels (statistics and affine
+// parameters in registers, float2 accesses when VEC2), thread y strides over the chunk's rows with four rows in
+// flight; a warp reads 256 contiguous bytes per row.  grid = row chunks of kRowsBwd, block = apply_block(c).
+template <bool VEC2>
+__global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
                                                       int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       int relu, float* __restrict__ part /* [nblk][2][c] */) {
-  __shared__ float red0[kPartLanes][kCh], red1[kPartLanes][kCh];
+  __shared__ float red[2][2][256];  // [sum kind][channel of the pair][thread]
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t r0 = int64_t(blockIdx.x) * kRows;
+  const int64_t r0 = int64_t(blockIdx.x) * kRowsBwd;
   if (r0 >= n) return;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int ch = blockIdx.y * kCh + tx;
-  const int rows = int(n - r0 < kRows ? n - r0 : kRows);
-  float s0 = 0.f, s1 = 0.f;
-  if (ch < c) {
-    const float m = mean[ch], is = invstd[ch], g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
-#pragma unroll 4
-    for (int r = ty; r < rows; r += kPartLanes) {
-      const float xh = (x[(r0 + r) * c + ch] - m) * is;
-      float d = dy[(r0 + r) * c + ch];
-      if (relu && xh * g + b <= 0.f) d = 0.f;
-      s0 += d;
-      s1 += d * xh;
+  const int64_t r_end = r0 + kRowsBwd < n ? r0 + kRowsBwd : n;
+  const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
+  const int tflat = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int pc0 = 0; pc0 < ppr; pc0 += blockDim.x) {
+    const int pc = pc0 + threadIdx.x, ch = pc << 1;
+    const bool on[2] = {pc < ppr && ch < c, pc < ppr && ch + 1 < c};
+    float m[2] = {0.f, 0.f}, is[2] = {0.f, 0.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (on[e]) {
+        m[e] = mean[ch + e]; is[e] = invstd[ch + e];
+        if (gamma) g[e] = gamma[ch + e];
+        if (beta) b[e] = beta[ch + e];
+      }
+    float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+    for (int64_t rb = r0 + threadIdx.y; rb < r_end; rb += int64_t(kApplyUnroll) * blockDim.y) {
+      float xv[kApplyUnroll][2], dv[kApplyUnroll][2];
+#pragma unroll
+      for (int u = 0; u < kApplyUnroll; ++u) {
+        const int64_t r = rb + int64_t(u) * blockDim.y;
+        xv[u][0] = xv[u][1] = dv[u][0] = dv[u][1] = 0.f;
+        if (r < r_end) {
+          if (VEC2) {
+            if (on[0]) {
+              const float2 t = *reinterpret_cast<const float2*>(x + r * c + ch);
+              const float2 d = *reinterpret_cast<const float2*>(dy + r * c + ch);
+              xv[u][0] = t.x; xv[u][1] = t.y; dv[u][0] = d.x; dv[u][1] = d.y;
+            }
+          } else {
+            if (on[0]) { xv[u][0] = x[r * c + ch]; dv[u][0] = dy[r * c + ch]; }
+            if (on[1]) { xv[u][1] = x[r * c + ch + 1]; dv[u][1] = dy[r * c + ch + 1]; }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kApplyUnroll; ++u) {
+        if (rb + int64_t(u) * blockDim.y >= r_end) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float xh = (xv[u][e] - m[e]) * is[e];
+          float d = dv[u][e];
+          if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
+          s0[e] += d;
+          s1[e] += d * xh;
+        }
+      }
     }
-  }
-  red0[ty][tx] = s0;
-  red1[ty][tx] = s1;
-  __syncthreads();
-  if (ty == 0 && ch < c) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int i = 0; i < kPartLanes; ++i) { t0 += red0[i][tx]; t1 += red1[i][tx]; }
-    part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = t0;
-    part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = t1;
+    // combine the row lanes (threadIdx.y) of every channel pair in a fixed order
+    red[0][0][tflat] = s0[0]; red[0][1][tflat] = s0[1]; red[1][0][tflat] = s1[0]; red[1][1][tflat] = s1[1];
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (!on[e]) continue;
+        float t0 = 0.f, t1 = 0.f;
+        for (int l = 0; l < int(blockDim.y); ++l) {
+          t0 += red[0][e][l * blockDim.x + threadIdx.x];
+          t1 += red[1][e][l * blockDim.x + threadIdx.x];
+        }
+        part[(int64_t(blockIdx.x) * 2 + 0) * c + ch + e] = t0;
+        part[(int64_t(blockIdx.x) * 2 + 1) * c + ch + e] = t1;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -317,7 +363,7 @@ __global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* 
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t nblk = n > 0 ? (n + kRows - 1) / kRows : 0;
+  const int64_t nblk = n > 0 ? (n + kRowsBwd - 1) / kRowsBwd : 0;
   double s0 = 0.0, s1 = 0.0;
   if (ch < c) {
 #pragma unroll 4
@@ -646,7 +692,8 @@ inline dim3 apply_block(int c) {
 using namespace wfsp;
 
 extern "C" size_t wfsp_bn_workspace_bytes(int64_t n_rows, int c) {
-  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRows)) * 2 * c * sizeof(float), 256) +
+  // sized for the finer of the two partial lists (backward: kRowsBwd rows per partial)
+  return align_up(size_t(ceil_div<int64_t>(n_rows > 0 ? n_rows : 1, kRowsBwd)) * 2 * c * sizeof(float), 256) +
          fin_scratch_bytes(c);
 }
 
@@ -762,8 +809,11 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
     return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
   float* part = static_cast<float*>(workspace);
-  dim3 grid(unsigned(ceil_div<int64_t>(n_rows, kRows)), unsigned(ceil_div(c, kCh)));
-  bn_bwd_partial<<<grid, dim3(32, kPartLanes), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+  const unsigned pgrid = unsigned(ceil_div<int64_t>(n_rows, kRowsBwd));
+  if (vec2_ok(c, x, dy))
+    bn_bwd_partial<true><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+  else
+    bn_bwd_partial<false><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
     bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows));

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(256) pack_feats_kernel(const In* __restrict__ 
       u.x = *reinterpret_cast<uint32_t*>(&lo);
       u.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(d) = u;
+      if (col + 4 == c)  // the row's last chunk also zeroes the pitch padding (bf16 operand format: pitch = c rounded up to 8)
+        for (int64_t pc = c; pc < pitch; ++pc) feats[row * pitch + pc] = Out(0.f);
     }
   }
 }

@@ -183,8 +183,10 @@ class GraphTrainStep(TrainStep):
         self.n_rows.fill_(n)  # the value travels as a kernel argument: no host buffer to race with
 
     def _body(self):
+        # bf16 math + fused stack: the batcher writes the tensor-core operand format directly
+        direct = spconv.get_math_mode() == "bf16" and spconv.fused.is_enabled()
         idx, feats = batcher.pack_batch(self.coords, self.wave, scale=self.scale, n_rows=self.n_rows,
-                                        tables=self.tables)
+                                        tables=self.tables, out_dtype=torch.bfloat16 if direct else torch.float32)
         loss = self.forward_backward(idx, feats, self.target, self.batch_size, self.n_rows)
         if self.capture_update:
             self._update()

@@ -270,6 +270,12 @@ class SparseSequential(SparseModule):
                     if is_spconv_module(module):
                         self._sparity_dict[k] = input.sparity
                 return fused.run(plan, input)
+        first = next((m for _, m in mods if isinstance(m, SparseConvolution)), None)
+        if (first is not None and isinstance(input, SparseConvTensor) and input.features is not None
+                and fused.is_operand_format(input.features, first.in_channels)
+                and input.features.shape[1] != first.in_channels):
+            # per-layer path fed with the padded bf16 operand format: back to [N, C] fp32
+            input.features = input.features[:, :first.in_channels].float()
         i = 0
         while i < len(mods):
             k, module = mods[i]

@@ -46,6 +46,12 @@ def pitch8(c):
     return (c + 7) // 8 * 8
 
 
+def is_operand_format(features, channels):
+    """bf16 [N, channels rounded up to 8], contiguous: the layout the tensor-core kernels gather from."""
+    return (features.dtype == torch.bfloat16 and features.dim() == 2 and features.shape[1] == pitch8(channels)
+            and features.is_contiguous())
+
+
 class Block:
     __slots__ = ("conv", "bn", "relu")
 
@@ -138,11 +144,14 @@ class FusedStackFunction(Function):
         lib = _lib.load()
         _lib.require_cuda(features, x.indices)
         dev = features.device
-        feats = features if features.dtype == torch.float32 else features.float()
+        blocks = plan.blocks
+        # bf16 features in the operand format ([N, C rounded up to 8], e.g. straight from batcher.pack_batch) are
+        # used as they are; anything else is brought to fp32 and cast once
+        ready16 = is_operand_format(features, blocks[0].conv.in_channels)
+        feats = features if (ready16 or features.dtype == torch.float32) else features.float()
         feats = feats.contiguous()
         st = _lib.stream
-        blocks = plan.blocks
-        need_in_grad = features.requires_grad
+        need_in_grad = features.requires_grad and not ready16
         with torch.cuda.device(dev):
             # ---- every layer's weights -> bf16 tensor-core layouts, one launch
             jobs, offs, total = [], [], 0
@@ -179,9 +188,12 @@ class FusedStackFunction(Function):
 
             # ---- input activations -> bf16 once
             n0, c0 = feats.shape
-            a16 = torch.empty((max(n0, 1), pitch8(c0)), dtype=torch.bfloat16, device=dev)
-            if n0:
-                _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(feats), n0, _lib.ptr(x.n_rows), c0, _lib.ptr(a16), st()))
+            if ready16:
+                a16 = feats
+            else:
+                a16 = torch.empty((max(n0, 1), pitch8(c0)), dtype=torch.bfloat16, device=dev)
+                if n0:
+                    _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(feats), n0, _lib.ptr(x.n_rows), c0, _lib.ptr(a16), st()))
 
             # ---- geometry of every block on the side stream (overlaps weight preparation and the first layers)
             geoms, gcur = [], x
