@@ -334,3 +334,35 @@ def test_fused_stack_takes_bf16_operand_input(cuda_device):
     torch.testing.assert_close(outs["fused16"][0], outs["fused32"][0], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(outs["fused16"][1], outs["fused32"][1], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(outs["layer16"][0], outs["fused32"][0], rtol=5e-3, atol=5e-3 * float(outs["fused32"][0].abs().max()))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-4), ("bf16", 2e-2)])
+def test_adjoint_identities_full_size(cuda_device, mode, tol):
+    """Size-independent check of dgrad and wgrad at BASELINE's full size (C5: 1024 full-grid events, 157,696
+    rows, ~1 M pairs): y = conv(x; W) is linear in x and in W, so for any g
+        <y, g> == <x, dL/dx> == <W, dL/dW>      with L = <y, g>.
+    Also covers the strided rulebook + inverse convolution pair at that size."""
+    B = 1024
+    ev = make_events(B, n_samples=1, seed=3, full_grid=True)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous().to(cuda_device)
+    torch.manual_seed(1)
+    for layers in ([spconv.SparseConv2d(48, 40, 3, 1, 0, 1, 1, False)],
+                   [spconv.SparseConv2d(24, 24, 3, 2, 1, 1, 1, False, indice_key="p"),
+                    spconv.SparseInverseConv2d(24, 16, 3, "p", bias=False)]):
+        net = spconv.SparseSequential(*layers).to(cuda_device)
+        for m in net.modules():
+            if isinstance(m, spconv.SparseConvolution):
+                m.math = mode
+        cin = layers[0].in_channels
+        x = torch.rand(idx.shape[0], cin, device=cuda_device).requires_grad_(True)
+        y = net(spconv.SparseConvTensor(x, idx, [14, 11], B)).features
+        g = torch.randn_like(y)
+        lhs = (y.detach().double() * g.double()).sum()
+        (y * g).sum().backward()
+        via_x = (x.detach().double() * x.grad.double()).sum()
+        scale = float((y.detach().double().abs() * g.double().abs()).sum())
+        assert abs(float(lhs - via_x)) < tol * scale * 1e-2 + tol * abs(float(lhs)), (mode, float(lhs), float(via_x))
+        if len(layers) == 1:  # a single layer is also linear in its weight
+            w = layers[0].weight
+            via_w = (w.detach().double() * w.grad.double()).sum()
+            assert abs(float(lhs - via_w)) < tol * scale * 1e-2 + tol * abs(float(lhs)), (mode, float(lhs), float(via_w))
