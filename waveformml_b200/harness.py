@@ -139,8 +139,17 @@ class TrainStep:
 
     def forward_backward(self, indices, feats, target, batch_size, n_rows=None):
         self.grads.zero()
-        loss = self.loss(indices, feats, target, batch_size, n_rows)
-        loss.backward()
+        # bf16 math mode = tensor-core operands with fp32 accumulation everywhere: the dense head's library
+        # GEMMs (batches too large for the fused head) then run as TF32 tensor-core GEMMs instead of fp32 SIMT
+        # ones (85 -> ~10 us for Linear(4480,116) at 1024 events).  fp32 mode keeps exact fp32 products.
+        tf32 = self.grads.flat.is_cuda and spconv.get_math_mode() == "bf16"
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32 or prev
+        try:
+            loss = self.loss(indices, feats, target, batch_size, n_rows)
+            loss.backward()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
         return loss
 
     def step(self, indices, feats, target, batch_size, n_rows=None):
