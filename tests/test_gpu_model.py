@@ -206,3 +206,41 @@ def test_head_bwd_all_in_one_entry(cuda_device):
     torch.testing.assert_close(db1, dh1.sum(0) * 1.3, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(dw2, dw2_in * 1.3)
     torch.testing.assert_close(db2, db2_in * 1.3)
+
+
+@pytest.mark.parametrize("name", ["z", "ez_subm", "ioni_preserve"])
+def test_c3_models_batch_1024_bf16(cuda_device, name):
+    """BASELINE configs[2]: the regression / preserve stacks at batch 1024, training mode, tcgen05 bf16 kernels
+    through the fused stack vs the oracle with bf16-rounded GEMM operands: output, and every parameter gradient
+    of a sum-of-squares loss (norm-wise)."""
+    torch.manual_seed(4)
+    spconv.set_math_mode("bf16")
+    osp.set_operand_rounding("bf16")
+    try:
+        B = 1024
+        if name == "z":
+            model, ns, net = stacks.ZRegressor().to(cuda_device).train(), 150, None
+            net = model.model.network
+        elif name == "ez_subm":
+            model, ns = stacks.EZSubM().to(cuda_device).train(), 150
+            net = model.network
+        else:
+            model, ns = stacks.IoniPreserve().to(cuda_device).train(), 65
+            net = model.model.func
+        ev, idx, feats = _batch(B, ns, 9, cuda_device)
+        got = model([idx, feats, B])
+        (got.square().sum() / got.numel()).backward()
+        onet = mirror.to_oracle(net).train()
+        ref = mirror.run_stack(onet, idx.cpu(), feats.cpu(), [14, 11], B)
+        ref = ref.features if isinstance(ref, osp.SparseConvTensor) else ref
+        (ref.square().sum() / ref.numel()).backward()
+        assert got.shape == ref.shape and _rel(got, ref) < 1e-2, _rel(got, ref)
+        # the preserve stack is 12 convolutions deep with 6 BatchNorm+ReLU gates between the loss and its first
+        # layer: gates that flip on either side (each side thresholds its own bf16-rounded activations) compound,
+        # so its early-layer gradients get a wider norm-wise bound than the 2-5 layer stacks
+        gtol = 0.1 if name == "ioni_preserve" else 3e-2
+        for (k, a), (_, b) in zip(net.named_parameters(), onet.named_parameters()):
+            assert a.shape == b.shape
+            assert _rel(a.grad, b.grad) < gtol, (k, _rel(a.grad, b.grad))
+    finally:
+        osp.set_operand_rounding(None)
