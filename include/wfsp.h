@@ -133,9 +133,11 @@ int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol
 /* Rulebook and neighbour tables in one call: wfsp_rulebook_conv (subm == 0) or wfsp_rulebook_subm
  * (subm != 0; stride / pad / out_indices / n_out ignored, may be NULL) followed by
  * wfsp_rulebook_tables, with nbr_out sized [out_cap, kvol] (subm: [n_in, kvol]).  *dup_flag is
- * written (0 / 1), no need to clear it.  Inputs of up to 1024 rows are built by a single kernel
- * launch (no memsets): at the reference's batch size of 64 events the step is launch-latency bound. */
-int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+ * written (0 / 1), no need to clear it.  Inputs of up to 2048 (expected live) rows are built by a
+ * single kernel launch (no memsets): at the reference's batch size of 64 events the step is
+ * launch-latency bound.  n_in_hint (graph path; 0 = none): expected live rows, launch shaping only. */
+int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                        int64_t n_in_hint, int batch,
                         const int* in_shape_host, const int* ksize_host, const int* stride_host,
                         const int* pad_host, const int* dil_host, int subm, int32_t* out_indices,
                         int64_t out_cap, int32_t* pairs, int32_t* pair_num, int32_t* n_out,
@@ -288,15 +290,18 @@ int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t* n_rows_dev
 size_t wfsp_bn_partials_bytes(int64_t n_rows, int c);
 
 /* training-mode forward whose per-chunk statistics were already written by wfsp_conv_apply_bf16
- * (bn_partials, chunks of WFSP_BN_CHUNK_ROWS rows): merge + normalise, no statistics pass over x */
-int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+ * (bn_partials, chunks of WFSP_BN_CHUNK_ROWS rows): merge + normalise, no statistics pass over x.
+ * n_rows_hint (here and in wfsp_bn_relu_bwd_x; graph path, 0 = none): expected live rows -- only
+ * selects between the single-launch variants for few rows and the streaming kernels. */
+int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev,
+                           int64_t n_rows_hint, int c,
                            const float* bn_partials, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps,
                            int relu, float* y, void* y_bf16, float* save_mean, float* save_invstd,
                            wfsp_stream_t stream);
 
 int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
-                       int c, const float* gamma, const float* beta, const float* save_mean,
+                       int64_t n_rows_hint, int c, const float* gamma, const float* beta, const float* save_mean,
                        const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
                        float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
 

@@ -83,6 +83,37 @@ def test_rulebook_with_device_count_matches_eager(cuda_device, k, s, p, subm):
     assert torch.equal(g.nbr_out[:n_out], e.nbr_out) and torch.equal(g.nbr_in[:n], e.nbr_in)
 
 
+@pytest.mark.parametrize("full_grid,B", [(False, 64), (True, 20), (True, 64)])
+@pytest.mark.parametrize("subm", [False, True])
+def test_rulebook_builder_choice_by_live_hint(cuda_device, full_grid, B, subm):
+    """The expected-live-rows hint only picks the builder (one-CTA kernel up to 2,048 live rows, the phase
+    kernels above); the rulebook is the same either way, also when the hint is wrong in both directions."""
+    ev = make_events(B, n_samples=1, seed=9, full_grid=full_grid)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous().to(cuda_device)
+    n = idx.shape[0]
+    cap = B * 154
+    padded = torch.zeros((cap, 3), dtype=torch.int32, device=cuda_device)
+    padded[:n] = idx
+    n_dev = torch.tensor([n], dtype=torch.int32, device=cuda_device)
+    k, s, p = (3, 1, 1) if subm else (3, 2, 0)
+    e = ops.build_rulebook(idx, B, [14, 11], [k, k], [s, s], [p, p], [1, 1], subm)
+    n_out = e.outids.shape[0]
+    for hint in (None, n, 1, cap):
+        if hint is None:
+            Fsp.hints.stop()
+        else:
+            Fsp.hints.start("replay")
+            Fsp.hints.values = [hint]
+        try:
+            g = ops.build_rulebook(padded, B, [14, 11], [k, k], [s, s], [p, p], [1, 1], subm, n_rows=n_dev)
+        finally:
+            Fsp.hints.stop()
+        assert int(g.n_out_dev.item()) == n_out
+        assert torch.equal(g.pair_num, e.pair_num) and torch.equal(g.outids[:n_out], e.outids)
+        assert torch.equal(g.pairs[:, :, :n], e.pairs)
+        assert torch.equal(g.nbr_out[:n_out], e.nbr_out) and torch.equal(g.nbr_in[:n], e.nbr_in)
+
+
 def _psd_inputs(B, seed, dev):
     ev = make_events(B, n_samples=150, seed=seed)
     return (torch.from_numpy(ev["coords"]).to(dev), torch.from_numpy(ev["wave"]).to(dev),

@@ -30,8 +30,8 @@ SIGNATURES = {
                                   _vp, _sz, _vp]),
     "wfsp_rulebook_subm": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_rulebook_tables": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "wfsp_rulebook_build": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _intp, _intp, _int, _vp, _i64, _vp, _vp,
-                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "wfsp_rulebook_build": (_int, [_vp, _i64, _vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _int, _vp, _i64, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_conv_apply_workspace_bytes": (_sz, [_int, _i64, _int, _int, _int]),
     "wfsp_conv_apply": (_int, [_vp, _i64, _vp, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _int, _vp,
                                _sz, _vp]),
@@ -50,14 +50,14 @@ SIGNATURES = {
     "wfsp_cast_rows_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp]),
     "wfsp_conv_apply_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "wfsp_bn_partials_bytes": (_sz, [_i64, _int]),
-    "wfsp_bn_relu_fwd_stats": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp,
-                                      _vp, _vp]),
+    "wfsp_bn_relu_fwd_stats": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp,
+                                      _vp, _vp, _vp]),
     "wfsp_conv_wgrad_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _i64, _vp,
                                     _int, _vp]),
     "wfsp_bn_relu_fwd_x": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,
                                   _vp, _sz, _vp]),
-    "wfsp_bn_relu_bwd_x": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _sz,
-                                  _vp]),
+    "wfsp_bn_relu_bwd_x": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                                  _sz, _vp]),
     "wfsp_act_fwd": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_act_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_head_workspace_bytes": (_sz, [_int, _int, _int]),

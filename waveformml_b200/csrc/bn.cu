@@ -460,6 +460,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
 // estimates and the normalise(+ReLU) pass in one kernel; the slab it re-reads stays in L1/L2.  Used
 // when the row capacity is small (a whole C2 step is launch-latency bound).
 constexpr int kSmallRows = 16384;
+constexpr int kFoldRows = 2048;     // (expected live) rows up to which the apply kernel folds the conv partials itself
+constexpr int kClusterRows = 4096;  // (expected live) rows up to which the backward runs as one cluster launch
 constexpr int kRowLanes = 16;
 constexpr int kClusterY = 8;  // CTAs of one thread-block cluster: they split the rows of a channel group
 
@@ -744,7 +746,7 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
   return WFSP_OK;
 }
 
-extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c,
+extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint, int c,
                                       const float* bn_partials, const float* gamma, const float* beta,
                                       float* running_mean, float* running_var, float momentum, float eps, int relu,
                                       float* y, void* y_bf16, float* save_mean, float* save_invstd,
@@ -754,7 +756,8 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
   if (n_rows == 0) return WFSP_OK;
   cudaStream_t st = as_stream(stream);
   __nv_bfloat16* y16 = static_cast<__nv_bfloat16*>(y_bf16);
-  if (n_rows <= kSmallRows && c <= 512) {
+  const int64_t live = (n_rows_dev != nullptr && n_rows_hint > 0 && n_rows_hint < n_rows) ? n_rows_hint : n_rows;
+  if (live <= kFoldRows && c <= 512) {
     // few chunks: every CTA of the apply kernel folds the partials of its channels itself -- ONE launch
     const PartStats ps{bn_partials, WFSP_BN_CHUNK_ROWS, eps, momentum, running_mean, running_var, save_mean, save_invstd};
     if (vec2_ok(c, x, y))
@@ -787,7 +790,8 @@ extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n
                             relu, y, nullptr, save_mean, save_invstd, workspace, workspace_bytes, stream);
 }
 
-extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int c,
+extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint,
+                                  int c,
                                   const float* gamma, const float* beta, const float* save_mean,
                                   const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
                                   float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
@@ -800,7 +804,8 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
     WFSP_CHECK_CUDA(cudaMemsetAsync(d_beta, 0, size_t(c) * 4, st));
     return WFSP_OK;
   }
-  if (n_rows <= kSmallRows) {
+  const int64_t live = (n_rows_dev != nullptr && n_rows_hint > 0 && n_rows_hint < n_rows) ? n_rows_hint : n_rows;
+  if (live <= kClusterRows && n_rows <= kSmallRows * 4) {
     WFSP_CHECK_CUDA(launch_cluster(bn_bwd_small, ceil_div((c + 7) & ~7, kCh), st, x, dy, n_rows, n_rows_dev, c, gamma, beta,
                                    save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta));
     count_launches(1);
@@ -828,7 +833,7 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
                                 const float* gamma, const float* beta, const float* save_mean,
                                 const float* save_invstd, int relu, float* dx, float* d_gamma, float* d_beta,
                                 void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
-  return wfsp_bn_relu_bwd_x(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, dx, nullptr, d_gamma,
+  return wfsp_bn_relu_bwd_x(x, dy, n_rows, n_rows_dev, 0, c, gamma, beta, save_mean, save_invstd, relu, dx, nullptr, d_gamma,
                             d_beta, workspace, workspace_bytes, stream);
 }
 

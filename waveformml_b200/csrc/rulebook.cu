@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kBlock) rb_tables(const int32_t* __restrict__ 
 // hits) is launch-latency bound: this replaces ~11 graph nodes per rulebook by one.
 constexpr int kSmallBlock = 1024;
 constexpr int kSmallWarps = kSmallBlock / 32;
-constexpr int64_t kSmallMaxRows = 8192;
+constexpr int64_t kSmallMaxRows = 2048;   // live rows (two rounds): beyond this the multi-kernel phases win
+constexpr int64_t kSmallMaxCap = 65536;    // capacity bound of the single-launch builder (its cost follows the LIVE count)
 
 template <bool SUBM, bool SMEM_TABLE>
 __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restrict__ indices, int64_t n_cap, Geom g,
@@ -641,7 +642,7 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
 // Rulebook + neighbour tables in one call (what a layer needs before its first convolution).  Small
 // inputs (<= 1024 rows, direct table, kernel volume <= 256) take the single-launch path; everything else
 // runs the phase kernels above followed by rb_tables.
-extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int64_t n_in_hint, int batch,
                                    const int* in_shape, const int* ksize, const int* stride, const int* pad,
                                    const int* dil, int subm, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
                                    int32_t* pair_num, int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in,
@@ -660,7 +661,10 @@ extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const i
   const int kvol = ksize[0] * ksize[1];
   const int64_t cells = int64_t(batch) * oh * ow;
   cudaStream_t st = as_stream(stream);
-  if (n_in > 0 && n_in <= kSmallMaxRows && kvol <= 256 && !g_force_hash && cells > 0 && cells <= (int64_t(1) << 20) &&
+  // expected live rows: the capacity, or the caller's hint where only the device knows the count (graph path);
+  // a wrong hint only costs time (the single-launch builder walks the live rows in rounds of 1024)
+  const int64_t live = (n_in_dev != nullptr && n_in_hint > 0 && n_in_hint < n_in) ? n_in_hint : n_in;
+  if (n_in > 0 && live <= kSmallMaxRows && n_in <= kSmallMaxCap && kvol <= 256 && !g_force_hash && cells > 0 && cells <= (int64_t(1) << 20) &&
       n_in * int64_t(kvol) < int64_t(kRankInf)) {
     WFSP_REQUIRE(workspace_bytes >= size_t(cells > 0 ? cells : 1) * 4, "rulebook workspace too small");
     Geom g{in_shape[0], in_shape[1], oh, ow, ksize[0], ksize[1], st_[0], st_[1], pd_[0], pd_[1], dil[0], dil[1], kvol,

@@ -233,6 +233,7 @@ class FusedStackFunction(Function):
                 partials = None
                 if b.bn is not None and b.bn.training and n_dst > _STATS_FUSE_MIN_ROWS and cout <= 512:
                     partials = torch.empty((lib.wfsp_bn_partials_bytes(n_dst, cout),), dtype=torch.uint8, device=dev)
+                hint = 0
                 if n_dst:
                     hint = Fsp.hints.get(n_dst_dev)
                     _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
@@ -254,7 +255,7 @@ class FusedStackFunction(Function):
                             bn.num_batches_tracked.add_(1)
                         if n_dst and partials is not None:
                             _lib.check(lib.wfsp_bn_relu_fwd_stats(
-                                _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(partials), _lib.ptr(bn.weight),
+                                _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), hint, cout, _lib.ptr(partials), _lib.ptr(bn.weight),
                                 _lib.ptr(bn.bias), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var),
                                 float(bn.momentum), float(bn.eps), int(b.relu), _lib.ptr(y32), _lib.ptr(y16),
                                 _lib.ptr(mean), _lib.ptr(invstd), st()))
@@ -276,7 +277,7 @@ class FusedStackFunction(Function):
                         _lib.check(lib.wfsp_cast_rows_bf16(_lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout,
                                                            _lib.ptr(y16), st()))
                 keep_x = xf if (b.bn is not None or b.relu) else None
-                saved.append((a16, keep_x, mean, invstd, rb, cur.indices.shape[0], n_dst, n_src_dev, n_dst_dev))
+                saved.append((a16, keep_x, mean, invstd, rb, cur.indices.shape[0], n_dst, n_src_dev, n_dst_dev, hint))
                 cur, a16, out32 = nxt, y16, y32
 
             holder["tensor"] = cur  # geometry of the stack's output
@@ -319,7 +320,7 @@ class FusedStackFunction(Function):
             for bi in range(len(blocks) - 1, -1, -1):
                 b = blocks[bi]
                 conv = b.conv
-                a16, xf, mean, invstd, rb, n_in, n_dst, n_src_dev, n_dst_dev = saved[bi]
+                a16, xf, mean, invstd, rb, n_in, n_dst, n_src_dev, n_dst_dev, dst_hint = saved[bi]
                 cin, cout = conv.in_channels, conv.out_channels
                 kvol = 1 if rb is None else rb.kvol
                 w_p, bias_p, gamma_p, beta_p = params[4 * bi: 4 * bi + 4]
@@ -331,7 +332,7 @@ class FusedStackFunction(Function):
                     dbet, bet_through = _grad_target(beta_p, (cout,), dev)
                     ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
                     _lib.check(lib.wfsp_bn_relu_bwd_x(
-                        _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
+                        _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), dst_hint, cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
                         _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
                         _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
                     if gamma_p is not None and not gam_through:

@@ -89,12 +89,14 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     n_in_dev = n_rows if static else None
     n_out_dev = None
+    from .functional import hints
+    n_hint = hints.get(n_rows) if static else 0  # expected live rows: picks the builder, never the result
     dup = torch.empty((1,), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         if subm:
             nbr_out = torch.empty((N, K), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size,
                                                _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
                                                _lib.ints(padding), _lib.ints(dilation), 1, None, N, _lib.ptr(pairs),
                                                _lib.ptr(pair_num), None, _lib.ptr(nbr_out), _lib.ptr(nbr_in),
@@ -108,7 +110,7 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
             n_out_t = torch.empty((1,), dtype=torch.int32, device=dev)
             # nbr_out is sized at the bound: its live rows are known only on the device
             nbr_cap = torch.empty((cap, K), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), batch_size,
+            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size,
                                                _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
                                                _lib.ints(padding), _lib.ints(dilation), 0, _lib.ptr(outbuf), cap,
                                                _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t),
