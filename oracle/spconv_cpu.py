@@ -43,6 +43,10 @@ def lib():
                                         intp, intp, i32p, i32p, i32p]
         L.wfo_rulebook_subm.restype = ctypes.c_int64
         L.wfo_rulebook_subm.argtypes = [i32p, ctypes.c_int64, ctypes.c_int, intp, intp, intp, i32p, i32p]
+        L.wfo_rulebook_conv_nd.restype = ctypes.c_int64
+        L.wfo_rulebook_conv_nd.argtypes = [ctypes.c_int] + L.wfo_rulebook_conv.argtypes
+        L.wfo_rulebook_subm_nd.restype = ctypes.c_int64
+        L.wfo_rulebook_subm_nd.argtypes = [ctypes.c_int] + L.wfo_rulebook_subm.argtypes
         L.wfo_gather_rows.restype = None
         L.wfo_gather_rows.argtypes = [f32p, ctypes.c_int64, i32p, ctypes.c_int64, f32p]
         L.wfo_scatter_add_rows.restype = None
@@ -96,8 +100,10 @@ def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=False):
-    """Upstream ops.get_indice_pairs, CPU path.  Returns (outids, pairs[2,K,N], pair_num[K])."""
-    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 3
+    """Upstream ops.get_indice_pairs, CPU path.  Returns (outids, pairs[2,K,N], pair_num[K]).
+    2-d (indices [N,3]) for the 14x11 grid; 3-d (indices [N,4]) for net_type "3DConvolution"."""
+    nd = len(spatial_shape)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == nd + 1 and nd in (2, 3)
     indices = indices.contiguous()
     N = indices.shape[0]
     K = int(np.prod(ksize))
@@ -106,19 +112,19 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize, stride, padding,
     pairs = torch.empty((2, K, N), dtype=torch.int32)
     pair_num = torch.empty((K,), dtype=torch.int32)
     if subm:
-        n_out = lib().wfo_rulebook_subm(_p(indices, ctypes.c_int32), N, int(batch_size),
-                                        _ints(spatial_shape), _ints(ksize), _ints(dilation),
-                                        _p(pairs, ctypes.c_int32), _p(pair_num, ctypes.c_int32))
+        n_out = lib().wfo_rulebook_subm_nd(nd, _p(indices, ctypes.c_int32), N, int(batch_size),
+                                           _ints(spatial_shape, nd), _ints(ksize, nd), _ints(dilation, nd),
+                                           _p(pairs, ctypes.c_int32), _p(pair_num, ctypes.c_int32))
         assert n_out == N
         return indices, pairs, pair_num
     out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
     cap = max(1, min(N * K, int(batch_size) * int(np.prod(out_shape)) if min(out_shape) > 0 else 0))
-    outids = torch.empty((cap, 3), dtype=torch.int32)
-    n_out = lib().wfo_rulebook_conv(_p(indices, ctypes.c_int32), N, int(batch_size),
-                                    _ints(spatial_shape), _ints(out_shape), _ints(ksize),
-                                    _ints(stride), _ints(padding), _ints(dilation),
-                                    _p(outids, ctypes.c_int32), _p(pairs, ctypes.c_int32),
-                                    _p(pair_num, ctypes.c_int32))
+    outids = torch.empty((cap, nd + 1), dtype=torch.int32)
+    n_out = lib().wfo_rulebook_conv_nd(nd, _p(indices, ctypes.c_int32), N, int(batch_size),
+                                       _ints(spatial_shape, nd), _ints(out_shape, nd), _ints(ksize, nd),
+                                       _ints(stride, nd), _ints(padding, nd), _ints(dilation, nd),
+                                       _p(outids, ctypes.c_int32), _p(pairs, ctypes.c_int32),
+                                       _p(pair_num, ctypes.c_int32))
     assert n_out >= 0
     return outids[:n_out].clone(), pairs, pair_num
 
@@ -229,13 +235,13 @@ class SparseConvTensor:
         return self.indice_dict.get(key)
 
     def dense(self, channels_first=True):
-        B, (H, W), C = self.batch_size, self.spatial_shape, self.features.shape[1]
+        B, C, nd = self.batch_size, self.features.shape[1], len(self.spatial_shape)
         idx = self.indices.long()
-        ret = torch.zeros((B, H, W, C), dtype=self.features.dtype)
-        ret[idx[:, 0], idx[:, 1], idx[:, 2]] = self.features
+        ret = torch.zeros((B, *self.spatial_shape, C), dtype=self.features.dtype)
+        ret[tuple(idx[:, i] for i in range(nd + 1))] = self.features
         if not channels_first:
             return ret
-        return ret.permute(0, 3, 1, 2).contiguous()
+        return ret.permute(0, nd + 1, *range(1, nd + 1)).contiguous()
 
 
 def to_dense_c(features, indices, batch_size, spatial_shape):
@@ -250,13 +256,14 @@ def to_dense_c(features, indices, batch_size, spatial_shape):
 
 
 class SparseConvolution(nn.Module):
-    """Upstream spconv/conv.py SparseConvolution, ndim=2."""
+    """Upstream spconv/conv.py SparseConvolution, ndim 2 or 3."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
-                 groups=1, bias=True, subm=False, inverse=False, indice_key=None):
+                 groups=1, bias=True, subm=False, inverse=False, indice_key=None, ndim=2):
         super().__init__()
         assert groups == 1
-        t = lambda v: [int(v)] * 2 if isinstance(v, (int, np.integer)) else [int(x) for x in v]
+        self.ndim = ndim
+        t = lambda v: [int(v)] * ndim if isinstance(v, (int, np.integer)) else [int(x) for x in v]
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding, self.dilation = t(kernel_size), t(stride), t(padding), t(dilation)
         self.conv1x1 = int(np.prod(self.kernel_size)) == 1
@@ -296,7 +303,7 @@ class SparseConvolution(nn.Module):
             outids, _, pairs, pair_num, _ = datas
         else:
             pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
-            stride = [1, 1] if self.subm else self.stride
+            stride = [1] * self.ndim if self.subm else self.stride
             outids, pairs, pair_num = get_indice_pairs(x.indices, x.batch_size, x.spatial_shape,
                                                        self.kernel_size, stride, pad, self.dilation, self.subm)
             x.indice_dict[self.indice_key] = (outids, x.indices, pairs, pair_num, x.spatial_shape)
@@ -326,6 +333,26 @@ class SparseInverseConv2d(SparseConvolution):
     def __init__(self, in_channels, out_channels, kernel_size, indice_key, bias=True):
         super().__init__(in_channels, out_channels, kernel_size, bias=bias, inverse=True,
                          indice_key=indice_key)
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, indice_key=None, use_hash=False):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
+                         bias, indice_key=indice_key, ndim=3)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
+                 groups=1, bias=True, indice_key=None, use_hash=False):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
+                         bias, subm=True, indice_key=indice_key, ndim=3)
+
+
+class SparseInverseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, bias=bias, inverse=True,
+                         indice_key=indice_key, ndim=3)
 
 
 class ToDense(nn.Module):

@@ -26,7 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define WFO_NDIM 2
+#define WFO_MAX_NDIM 3 /* 2: the 14x11 segment grid; 3: net_type "3DConvolution" (src/models/SPConvNet.py:42-49) */
 #define WFO_MAX_KVOL 1024
 
 /* ----------------------------------------------------------------------------------------- */
@@ -81,11 +81,11 @@ static inline uint64_t wfo_map_slot(const wfo_map* m, int64_t key) {
 /* Enumeration: last dim fastest, each dim from its upper bound downwards in steps of the      */
 /* dilation => ascending kernel offset.  Integer divisions are C divisions (truncate to zero), */
 /* exactly as upstream; see SURVEY.md A.2 for why that never changes the emitted pairs.        */
-static int wfo_valid_out_pos(const int32_t* in_pos, const int* ksize, const int* stride,
+static int wfo_valid_out_pos(int nd, const int32_t* in_pos, const int* ksize, const int* stride,
                              const int* pad, const int* dil, const int* out_shape, int32_t* out) {
-  int lowers[WFO_NDIM], uppers[WFO_NDIM], counter[WFO_NDIM], csize[WFO_NDIM];
+  int lowers[WFO_MAX_NDIM], uppers[WFO_MAX_NDIM], counter[WFO_MAX_NDIM], csize[WFO_MAX_NDIM];
   int npoints = 1;
-  for (int i = 0; i < WFO_NDIM; ++i) {
+  for (int i = 0; i < nd; ++i) {
     lowers[i] = (in_pos[i] - (ksize[i] - 1) * dil[i] - 1 + stride[i] + pad[i]) / stride[i];
     uppers[i] = (in_pos[i] + pad[i]) / stride[i];
     csize[i] = (uppers[i] - lowers[i]) / dil[i] + 1;
@@ -95,17 +95,17 @@ static int wfo_valid_out_pos(const int32_t* in_pos, const int* ksize, const int*
   int nvalid = 0;
   for (int i = 0; i < npoints; ++i) {
     int valid = 1, m = 1, offset = 0;
-    for (int j = WFO_NDIM - 1; j >= 0; --j) {
+    for (int j = nd - 1; j >= 0; --j) {
       int val = uppers[j] - counter[j] * dil[j];
-      out[nvalid * (WFO_NDIM + 1) + j] = val;
+      out[nvalid * (nd + 1) + j] = val;
       if (val < 0 || val > out_shape[j] - 1) valid = 0;
       offset += m * (in_pos[j] - val * stride[j] + pad[j]) / dil[j];
       m *= ksize[j];
     }
-    out[nvalid * (WFO_NDIM + 1) + WFO_NDIM] = offset;
+    out[nvalid * (nd + 1) + nd] = offset;
     if (valid) ++nvalid;
-    counter[WFO_NDIM - 1] += 1;
-    for (int c = WFO_NDIM - 1; c >= 0; --c) {
+    counter[nd - 1] += 1;
+    for (int c = nd - 1; c >= 0; --c) {
       if (counter[c] == csize[c] && c > 0) {
         counter[c - 1] += 1;
         counter[c] = 0;
@@ -115,45 +115,46 @@ static int wfo_valid_out_pos(const int32_t* in_pos, const int* ksize, const int*
   return nvalid;
 }
 
-static inline int64_t wfo_flat(const int32_t* pos, const int* shape) {
+static inline int64_t wfo_flat(int nd, const int32_t* pos, const int* shape) {
   int64_t f = 0;
-  for (int i = 0; i < WFO_NDIM; ++i) f = f * shape[i] + pos[i];
+  for (int i = 0; i < nd; ++i) f = f * shape[i] + pos[i];
   return f;
 }
 
 /* ----------------------------------------------------------------------------------------- */
 /* Regular (strided / dilated / padded) conv rulebook, upstream getIndicePairsConv CPU path.   */
-/* indices: int32 [N, 1+D] rows (b, x, y).  pairs: int32 [2, K, N] pre-filled with -1 here.    */
+/* indices: int32 [N, 1+D] rows (b, x, y[, z]).  pairs: int32 [2, K, N] pre-filled with -1 here. */
 /* out_indices must have room for min(N*K, B*vol_out) rows.  Returns N_out, or <0 on error.    */
-int64_t wfo_rulebook_conv(const int32_t* indices, int64_t N, int batch, const int* in_shape,
-                          const int* out_shape, const int* ksize, const int* stride,
-                          const int* pad, const int* dil, int32_t* out_indices, int32_t* pairs,
-                          int32_t* pair_num) {
+int64_t wfo_rulebook_conv_nd(int nd, const int32_t* indices, int64_t N, int batch, const int* in_shape,
+                             const int* out_shape, const int* ksize, const int* stride,
+                             const int* pad, const int* dil, int32_t* out_indices, int32_t* pairs,
+                             int32_t* pair_num) {
   (void)batch; (void)in_shape;
+  if (nd < 1 || nd > WFO_MAX_NDIM) return -3;
   int K = 1;
   int64_t vol = 1;
-  for (int i = 0; i < WFO_NDIM; ++i) { K *= ksize[i]; vol *= out_shape[i]; }
+  for (int i = 0; i < nd; ++i) { K *= ksize[i]; vol *= out_shape[i]; }
   if (K > WFO_MAX_KVOL) return -2;
   for (int64_t i = 0; i < 2 * (int64_t)K * N; ++i) pairs[i] = -1;
   for (int k = 0; k < K; ++k) pair_num[k] = 0;
   wfo_map map;
   if (wfo_map_init(&map, N * (int64_t)K < (int64_t)batch * vol ? N * (int64_t)K : (int64_t)batch * vol)) return -1;
-  int32_t* cand = (int32_t*)malloc((size_t)K * (WFO_NDIM + 1) * sizeof(int32_t));
+  int32_t* cand = (int32_t*)malloc((size_t)K * (nd + 1) * sizeof(int32_t));
   int64_t num_act = 0;
   for (int64_t j = 0; j < N; ++j) {
-    const int32_t* row = indices + j * (WFO_NDIM + 1);
+    const int32_t* row = indices + j * (nd + 1);
     int b = row[0];
-    int nv = wfo_valid_out_pos(row + 1, ksize, stride, pad, dil, out_shape, cand);
+    int nv = wfo_valid_out_pos(nd, row + 1, ksize, stride, pad, dil, out_shape, cand);
     for (int v = 0; v < nv; ++v) {
-      const int32_t* c = cand + v * (WFO_NDIM + 1);
-      int off = c[WFO_NDIM];
-      int64_t key = wfo_flat(c, out_shape) + vol * (int64_t)b;
+      const int32_t* c = cand + v * (nd + 1);
+      int off = c[nd];
+      int64_t key = wfo_flat(nd, c, out_shape) + vol * (int64_t)b;
       uint64_t s = wfo_map_slot(&map, key);
       if (map.keys[s] == -1) { /* first touch creates the output row */
         map.keys[s] = key;
         map.vals[s] = (int32_t)num_act;
-        out_indices[num_act * (WFO_NDIM + 1)] = b;
-        for (int i = 0; i < WFO_NDIM; ++i) out_indices[num_act * (WFO_NDIM + 1) + 1 + i] = c[i];
+        out_indices[num_act * (nd + 1)] = b;
+        for (int i = 0; i < nd; ++i) out_indices[num_act * (nd + 1) + 1 + i] = c[i];
         ++num_act;
       }
       int32_t o = map.vals[s];
@@ -169,13 +170,14 @@ int64_t wfo_rulebook_conv(const int32_t* indices, int64_t N, int batch, const in
 
 /* Submanifold rulebook, upstream getIndicePairsSubM CPU path.  pad := k/2, stride := 1 are    */
 /* forced by the caller (upstream spconv_ops.cc).  Output rows == input rows.                  */
-int64_t wfo_rulebook_subm(const int32_t* indices, int64_t N, int batch, const int* shape,
-                          const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num) {
+int64_t wfo_rulebook_subm_nd(int nd, const int32_t* indices, int64_t N, int batch, const int* shape,
+                             const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num) {
   (void)batch;
+  if (nd < 1 || nd > WFO_MAX_NDIM) return -3;
   int K = 1;
   int64_t vol = 1;
-  int stride[WFO_NDIM], pad[WFO_NDIM];
-  for (int i = 0; i < WFO_NDIM; ++i) {
+  int stride[WFO_MAX_NDIM], pad[WFO_MAX_NDIM];
+  for (int i = 0; i < nd; ++i) {
     K *= ksize[i]; vol *= shape[i];
     stride[i] = 1; pad[i] = ksize[i] / 2;
   }
@@ -185,20 +187,20 @@ int64_t wfo_rulebook_subm(const int32_t* indices, int64_t N, int batch, const in
   wfo_map map;
   if (wfo_map_init(&map, N)) return -1;
   for (int64_t j = 0; j < N; ++j) { /* later duplicates overwrite */
-    const int32_t* row = indices + j * (WFO_NDIM + 1);
-    int64_t key = wfo_flat(row + 1, shape) + vol * (int64_t)row[0];
+    const int32_t* row = indices + j * (nd + 1);
+    int64_t key = wfo_flat(nd, row + 1, shape) + vol * (int64_t)row[0];
     uint64_t s = wfo_map_slot(&map, key);
     map.keys[s] = key;
     map.vals[s] = (int32_t)j;
   }
-  int32_t* cand = (int32_t*)malloc((size_t)K * (WFO_NDIM + 1) * sizeof(int32_t));
+  int32_t* cand = (int32_t*)malloc((size_t)K * (nd + 1) * sizeof(int32_t));
   for (int64_t j = 0; j < N; ++j) {
-    const int32_t* row = indices + j * (WFO_NDIM + 1);
-    int nv = wfo_valid_out_pos(row + 1, ksize, stride, pad, dil, shape, cand);
+    const int32_t* row = indices + j * (nd + 1);
+    int nv = wfo_valid_out_pos(nd, row + 1, ksize, stride, pad, dil, shape, cand);
     for (int v = 0; v < nv; ++v) {
-      const int32_t* c = cand + v * (WFO_NDIM + 1);
-      int off = c[WFO_NDIM];
-      int64_t key = wfo_flat(c, shape) + vol * (int64_t)row[0];
+      const int32_t* c = cand + v * (nd + 1);
+      int off = c[nd];
+      int64_t key = wfo_flat(nd, c, shape) + vol * (int64_t)row[0];
       uint64_t s = wfo_map_slot(&map, key);
       if (map.keys[s] != -1) {
         int32_t slot = pair_num[off]++;
@@ -210,6 +212,19 @@ int64_t wfo_rulebook_subm(const int32_t* indices, int64_t N, int batch, const in
   free(cand);
   wfo_map_free(&map);
   return N;
+}
+
+/* the 2-d entry points (the 14x11 grid) */
+int64_t wfo_rulebook_conv(const int32_t* indices, int64_t N, int batch, const int* in_shape,
+                          const int* out_shape, const int* ksize, const int* stride,
+                          const int* pad, const int* dil, int32_t* out_indices, int32_t* pairs,
+                          int32_t* pair_num) {
+  return wfo_rulebook_conv_nd(2, indices, N, batch, in_shape, out_shape, ksize, stride, pad, dil, out_indices, pairs,
+                              pair_num);
+}
+int64_t wfo_rulebook_subm(const int32_t* indices, int64_t N, int batch, const int* shape,
+                          const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num) {
+  return wfo_rulebook_subm_nd(2, indices, N, batch, shape, ksize, dil, pairs, pair_num);
 }
 
 /* ----------------------------------------------------------------------------------------- */

@@ -54,3 +54,25 @@ def make_events(n_events, n_samples=150, seed=1234, full_grid=False, n_classes=3
     labels = rng.integers(0, n_classes, size=n_events).astype(np.int64)
     z = rng.random(n, dtype=np.float32)
     return {"coords": coords, "wave": wave, "labels": labels, "z": z}
+
+
+def make_events_3d(n_events, n_samples=16, seed=1234, n_classes=3, occupancy=0.3):
+    """Voxel form of the same events for net_type "3DConvolution" (src/models/SPConvNet.py:42-49: spatial size
+    [14, 11, n_samples], coordinate columns permuted [3, 0, 1, 2]): every hit of make_events() contributes the
+    time samples where its waveform is "above threshold" (a contiguous pulse of random start and length plus
+    random isolated samples at rate `occupancy`/4), one row per (x, y, t) with the two PMT values as features.
+    Returns dict(coords int32 [N,4] = (x, y, t, evt) sorted by (evt, x, y, t), wave int16 [N,2], labels int64 [B])."""
+    base = make_events(n_events, n_samples=1, seed=seed, n_classes=n_classes)
+    rng = np.random.default_rng(seed + 7)
+    rows = []
+    for x, y, e in base["coords"]:
+        start = int(rng.integers(0, n_samples))
+        length = 1 + int(rng.integers(0, max(1, int(occupancy * n_samples))))
+        on = np.zeros(n_samples, dtype=bool)
+        on[start:start + length] = True
+        on |= rng.random(n_samples) < occupancy / 4
+        for t in np.nonzero(on)[0]:
+            rows.append((x, y, t, e))
+    coords = np.array(rows, dtype=np.int32).reshape(-1, 4)
+    wave = rng.integers(0, 2 ** N_ADC_BITS, size=(coords.shape[0], 2), dtype=np.int16)
+    return {"coords": coords, "wave": wave, "labels": base["labels"]}
