@@ -144,6 +144,25 @@ int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_i
                         int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag, void* workspace,
                         size_t workspace_bytes, wfsp_stream_t stream);
 
+/* The same three calls for ndim = 2 or 3 spatial dimensions.  ndim 3 is the reference's net_type
+ * "3DConvolution" (src/models/SPConvNet.py:42-49, src/models/SCNet.py:53-55: spatial size
+ * [14, 11, n_samples], index rows (b, x, y, t) = int32 [n, 4]); all *_host arrays hold ndim ints, kernel
+ * offsets are numbered row-major over (kx, ky, kt) as upstream does, out_indices has ndim + 1 columns.
+ * The rulebook is what spconv.SparseConv3d / SubMConv3d (src/utils/ModelValidation.py:24-31) would build;
+ * wfsp_conv_apply* / wfsp_conv_wgrad* consume it unchanged (they only see kvol and the tables). */
+int wfsp_conv_out_shape_nd(int ndim, const int* in_shape_host, const int* ksize_host,
+                           const int* stride_host, const int* pad_host, const int* dil_host,
+                           int* out_shape_host);
+size_t wfsp_rulebook_workspace_bytes_nd(int ndim, int64_t n_in, int batch, const int* out_shape_host,
+                                        const int* ksize_host);
+int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                           int64_t n_in_hint, int batch, const int* in_shape_host,
+                           const int* ksize_host, const int* stride_host, const int* pad_host,
+                           const int* dil_host, int subm, int32_t* out_indices, int64_t out_cap,
+                           int32_t* pairs, int32_t* pair_num, int32_t* n_out, int32_t* nbr_out,
+                           int32_t* nbr_in, int32_t* dup_flag, void* workspace, size_t workspace_bytes,
+                           wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (3) Gather-GEMM forward / dgrad / wgrad.  Replaces upstream indice_conv /
  * indice_conv_backward reached from spconv.SparseConv2d / SubMConv2d / SparseInverseConv2d

@@ -42,9 +42,19 @@ def test_output_shape_contract():
 
 
 def test_unused_layer_types_raise():
-    for name in ("SparseConv3d", "SubMConv3d", "SparseConvTranspose2d", "SparseConv1d"):
+    for name in ("SparseConv4d", "SparseConvTranspose2d", "SparseConvTranspose3d", "SparseConv1d"):
         with pytest.raises(NotImplementedError):
             getattr(spconv, name)(4, 4, 3)
+
+
+def test_3d_layer_types_construct():
+    """src/utils/ModelValidation.py:24-31 lists SparseConv3d / SubMConv3d; net_type "3DConvolution"
+    (src/models/SPConvNet.py:42-49) would build them on the [14, 11, n_samples] grid."""
+    c = spconv.SparseConv3d(4, 6, 3, 2, 1, 1, 1, False)
+    assert tuple(c.weight.shape) == (3, 3, 3, 4, 6) and c.stride == [2, 2, 2] and c.bias is None and c.ndim == 3
+    s = spconv.SubMConv3d(4, 6, [3, 3, 5], indice_key="subm0")
+    assert tuple(s.weight.shape) == (3, 3, 5, 4, 6) and s.subm and s.indice_key == "subm0"
+    assert spconv.SparseConv3d(4, 4, 1).conv1x1
 
 
 def test_import_as_spconv():

@@ -32,12 +32,21 @@ constexpr uint32_t kEmptyKey = 0xffffffffu;
 constexpr int kRankInf = 0x7f7f7f7f;  // memset(0x7f) pattern
 constexpr int64_t kDirectMaxCells = int64_t(1) << 24;
 
+// Three spatial dimensions (h, w, t).  The 2-d layers of the 14x11 grid are the case in_t = out_t = kt = 1
+// with three-column index rows (cols = 3); the 3-d variant (src/models/SPConvNet.py:42-49) has cols = 4.
 struct Geom {
-  int in_h, in_w, out_h, out_w;
-  int kh, kw, sh, sw, ph, pw, dh, dw;
-  int kvol, batch;
+  int in_h, in_w, in_t, out_h, out_w, out_t;
+  int kh, kw, kt, sh, sw, st, ph, pw, pt, dh, dw, dt;
+  int kvol, batch, cols;
   const int32_t* n_dev;  // live row count (graph path); NULL = the host count is exact
 };
+
+// every kernel tap in ascending offset order k = (kx * kw + ky) * kt + kz
+#define WFSP_FOR_TAPS(g, kx, ky, kz)        \
+  for (int kx = 0; kx < (g).kh; ++kx)       \
+    for (int ky = 0; ky < (g).kw; ++ky)     \
+      for (int kz = 0; kz < (g).kt; ++kz)
+#define WFSP_TAP(g, kx, ky, kz) (((kx) * (g).kw + (ky)) * (g).kt + (kz))
 
 struct Table {
   int32_t* vals;
@@ -86,8 +95,8 @@ __device__ __forceinline__ uint32_t tap_mask(int c, int k, int s, int p, int d, 
 }
 
 struct Row {
-  int b, x, y;
-  uint32_t mx, my;
+  int b, x, y, z;
+  uint32_t mx, my, mz;
   bool ok;
 };
 
@@ -95,25 +104,44 @@ __device__ __forceinline__ Row load_row(const int32_t* __restrict__ indices, int
                                         const Geom& g) {
   Row r;
   r.ok = j < (g.n_dev ? int64_t(*g.n_dev) : n);
-  r.b = r.x = r.y = 0;
-  r.mx = r.my = 0;
+  r.b = r.x = r.y = r.z = 0;
+  r.mx = r.my = r.mz = 0;
   if (r.ok) {
-    r.b = indices[3 * j + 0];
-    r.x = indices[3 * j + 1];
-    r.y = indices[3 * j + 2];
-    r.ok = r.b >= 0 && r.b < g.batch && r.x >= 0 && r.x < g.in_h && r.y >= 0 && r.y < g.in_w;
+    r.b = indices[g.cols * j + 0];
+    r.x = indices[g.cols * j + 1];
+    r.y = indices[g.cols * j + 2];
+    if (g.cols > 3) r.z = indices[g.cols * j + 3];
+    r.ok = r.b >= 0 && r.b < g.batch && r.x >= 0 && r.x < g.in_h && r.y >= 0 && r.y < g.in_w && r.z >= 0 &&
+           r.z < g.in_t;
     if (r.ok) {
       r.mx = tap_mask(r.x, g.kh, g.sh, g.ph, g.dh, g.out_h);
       r.my = tap_mask(r.y, g.kw, g.sw, g.pw, g.dw, g.out_w);
+      r.mz = tap_mask(r.z, g.kt, g.st, g.pt, g.dt, g.out_t);
     }
   }
   return r;
 }
 
-__device__ __forceinline__ uint32_t out_key(const Row& r, const Geom& g, int kx, int ky, int& ox, int& oy) {
-  ox = (r.x + g.ph - kx * g.dh) / g.sh;
-  oy = (r.y + g.pw - ky * g.dw) / g.sw;
-  return uint32_t((r.b * g.out_h + ox) * g.out_w + oy);
+struct Pos {
+  int x, y, z;
+};
+
+__device__ __forceinline__ void store_pos(int32_t* __restrict__ out_indices, int64_t row, const Geom& g, int b,
+                                          const Pos& o) {
+  int32_t* p = out_indices + g.cols * row;
+  p[0] = b; p[1] = o.x; p[2] = o.y;
+  if (g.cols > 3) p[3] = o.z;
+}
+
+__device__ __forceinline__ uint32_t in_key(const Geom& g, int b, int x, int y, int z) {
+  return uint32_t(((b * g.in_h + x) * g.in_w + y) * g.in_t + z);
+}
+
+__device__ __forceinline__ uint32_t out_key(const Row& r, const Geom& g, int kx, int ky, int kz, Pos& o) {
+  o.x = (r.x + g.ph - kx * g.dh) / g.sh;
+  o.y = (r.y + g.pw - ky * g.dw) / g.sw;
+  o.z = (r.z + g.pt - kz * g.dt) / g.st;
+  return uint32_t(((r.b * g.out_h + o.x) * g.out_w + o.y) * g.out_t + o.z);
 }
 
 // ---- regular conv, phase 1: atomicMin(rank) per touched output cell ---------------------------
@@ -123,15 +151,12 @@ __global__ void __launch_bounds__(kBlock) rb_conv_mark(const int32_t* __restrict
   int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   Row r = load_row(indices, n, j, g);
   if (!r.ok) return;
-  for (int kx = 0; kx < g.kh; ++kx) {
-    if (!((r.mx >> kx) & 1)) continue;
-    for (int ky = 0; ky < g.kw; ++ky) {
-      if (!((r.my >> ky) & 1)) continue;
-      int ox, oy;
-      uint32_t key = out_key(r, g, kx, ky, ox, oy);
-      int slot = table_insert<HASH>(t, key);
-      atomicMin(&t.vals[slot], int(j) * g.kvol + kx * g.kw + ky);
-    }
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+    if (!(((r.mx >> kx) & 1) && ((r.my >> ky) & 1) && ((r.mz >> kz) & 1))) continue;
+    Pos o;
+    uint32_t key = out_key(r, g, kx, ky, kz, o);
+    int slot = table_insert<HASH>(t, key);
+    atomicMin(&t.vals[slot], int(j) * g.kvol + WFSP_TAP(g, kx, ky, kz));
   }
 }
 
@@ -141,20 +166,20 @@ __global__ void __launch_bounds__(kBlock) rb_subm_insert(const int32_t* __restri
                                                          Geom g, Table t) {
   int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   if (j >= (g.n_dev ? int64_t(*g.n_dev) : n)) return;
-  int b = indices[3 * j], x = indices[3 * j + 1], y = indices[3 * j + 2];
-  if (b < 0 || b >= g.batch || x < 0 || x >= g.in_h || y < 0 || y >= g.in_w) return;
-  uint32_t key = uint32_t((b * g.in_h + x) * g.in_w + y);
+  Row r = load_row(indices, n, j, g);
+  if (!r.ok) return;
+  uint32_t key = in_key(g, r.b, r.x, r.y, r.z);
   int slot = table_insert<HASH>(t, key);
   atomicMax(&t.vals[slot], int(j));
 }
 
-// validity of candidate (row, kx, ky); for SUBM also returns the output row in `val`,
+// validity of candidate (row, kx, ky, kz); for SUBM also returns the output row in `val`,
 // for CONV the table slot in `slot`.
 template <bool HASH, bool SUBM>
-__device__ __forceinline__ bool candidate(const Row& r, const Geom& g, const Table& t, int kx, int ky,
-                                          int& slot, int& val, int& ox, int& oy) {
-  if (!(r.ok && ((r.mx >> kx) & 1) && ((r.my >> ky) & 1))) return false;
-  uint32_t key = out_key(r, g, kx, ky, ox, oy);
+__device__ __forceinline__ bool candidate(const Row& r, const Geom& g, const Table& t, int kx, int ky, int kz,
+                                          int& slot, int& val, Pos& o) {
+  if (!(r.ok && ((r.mx >> kx) & 1) && ((r.my >> ky) & 1) && ((r.mz >> kz) & 1))) return false;
+  uint32_t key = out_key(r, g, kx, ky, kz, o);
   slot = table_find<HASH>(t, key);
   if (SUBM) {
     if (slot < 0) return false;
@@ -176,15 +201,14 @@ __global__ void __launch_bounds__(kBlock) rb_count(const int32_t* __restrict__ i
   Row r = load_row(indices, n, j, g);
   const int lane = threadIdx.x & 31;
   int first = 0;
-  for (int kx = 0; kx < g.kh; ++kx) {
-    for (int ky = 0; ky < g.kw; ++ky) {
-      int slot = 0, val = 0, ox, oy;
-      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
-      const int k = kx * g.kw + ky;
-      if (!SUBM && v && t.vals[slot] == int(j) * K + k) ++first;
-      unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (lane == 0 && bal) atomicAdd(&s_cnt[k], __popc(bal));
-    }
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+    int slot = 0, val = 0;
+    Pos o;
+    bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
+    const int k = WFSP_TAP(g, kx, ky, kz);
+    if (!SUBM && v && t.vals[slot] == int(j) * K + k) ++first;
+    unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (lane == 0 && bal) atomicAdd(&s_cnt[k], __popc(bal));
   }
   if (!SUBM) {
     for (int o = 16; o > 0; o >>= 1) first += __shfl_xor_sync(0xffffffffu, first, o);
@@ -229,11 +253,11 @@ __global__ void __launch_bounds__(kBlock) rb_conv_assign(const int32_t* __restri
   Row r = load_row(indices, n, j, g);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int first = 0;
-  for (int kx = 0; kx < g.kh; ++kx)
-    for (int ky = 0; ky < g.kw; ++ky) {
-      int slot = 0, val, ox, oy;
-      if (candidate<HASH, false>(r, g, t, kx, ky, slot, val, ox, oy) &&
-          t.vals[slot] == int(j) * K + kx * g.kw + ky)
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+      int slot = 0, val;
+      Pos o;
+      if (candidate<HASH, false>(r, g, t, kx, ky, kz, slot, val, o) &&
+          t.vals[slot] == int(j) * K + WFSP_TAP(g, kx, ky, kz))
         ++first;
     }
   // block-wide exclusive scan of `first`
@@ -247,15 +271,13 @@ __global__ void __launch_bounds__(kBlock) rb_conv_assign(const int32_t* __restri
   int off = blk_base[int64_t(blockIdx.x) * (K + 1) + K] + incl - first;
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   if (first == 0) return;
-  for (int kx = 0; kx < g.kh; ++kx)
-    for (int ky = 0; ky < g.kw; ++ky) {
-      int slot = 0, val, ox, oy;
-      if (candidate<HASH, false>(r, g, t, kx, ky, slot, val, ox, oy) &&
-          t.vals[slot] == int(j) * K + kx * g.kw + ky) {
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+      int slot = 0, val;
+      Pos o;
+      if (candidate<HASH, false>(r, g, t, kx, ky, kz, slot, val, o) &&
+          t.vals[slot] == int(j) * K + WFSP_TAP(g, kx, ky, kz)) {
         if (off < out_cap) {
-          out_indices[3 * int64_t(off) + 0] = r.b;
-          out_indices[3 * int64_t(off) + 1] = ox;
-          out_indices[3 * int64_t(off) + 2] = oy;
+          store_pos(out_indices, off, g, r.b, o);
         }
         t.vals[slot] = -off - 1;  // only the first toucher ever rewrites its cell
         ++off;
@@ -273,20 +295,20 @@ __global__ void __launch_bounds__(kBlock) rb_pairs(const int32_t* __restrict__ i
   int64_t j = int64_t(blockIdx.x) * kBlock + threadIdx.x;
   Row r = load_row(indices, n, j, g);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int kx = 0; kx < g.kh; ++kx)
-    for (int ky = 0; ky < g.kw; ++ky) {
-      int slot = 0, val = 0, ox, oy;
-      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+      int slot = 0, val = 0;
+      Pos o;
+      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
       unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (lane == 0) s_wcnt[(kx * g.kw + ky) * kWarps + warp] = __popc(bal);
+      if (lane == 0) s_wcnt[(WFSP_TAP(g, kx, ky, kz)) * kWarps + warp] = __popc(bal);
     }
   __syncthreads();
   const unsigned lt = (1u << lane) - 1u;
-  for (int kx = 0; kx < g.kh; ++kx)
-    for (int ky = 0; ky < g.kw; ++ky) {
-      const int k = kx * g.kw + ky;
-      int slot = 0, val = 0, ox, oy;
-      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+  WFSP_FOR_TAPS(g, kx, ky, kz) {
+      const int k = WFSP_TAP(g, kx, ky, kz);
+      int slot = 0, val = 0;
+      Pos o;
+      bool v = candidate<HASH, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
       unsigned bal = __ballot_sync(0xffffffffu, v);
       if (v) {
         int pos = blk_base[int64_t(blockIdx.x) * (K + 1) + k] + __popc(bal & lt);
@@ -364,15 +386,12 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
     Row r = load_row(indices, n, j, g);
     if (!r.ok) continue;
     if (SUBM) {
-      atomicMax(&table[(r.b * g.in_h + r.x) * g.in_w + r.y], j);
+      atomicMax(&table[in_key(g, r.b, r.x, r.y, r.z)], j);
     } else {
-      for (int kx = 0; kx < g.kh; ++kx) {
-        if (!((r.mx >> kx) & 1)) continue;
-        for (int ky = 0; ky < g.kw; ++ky) {
-          if (!((r.my >> ky) & 1)) continue;
-          int ox, oy;
-          atomicMin(&table[out_key(r, g, kx, ky, ox, oy)], j * K + kx * g.kw + ky);
-        }
+      WFSP_FOR_TAPS(g, kx, ky, kz) {
+        if (!(((r.mx >> kx) & 1) && ((r.my >> ky) & 1) && ((r.mz >> kz) & 1))) continue;
+        Pos o;
+        atomicMin(&table[out_key(r, g, kx, ky, kz, o)], j * K + WFSP_TAP(g, kx, ky, kz));
       }
     }
   }
@@ -384,10 +403,10 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
       const int j = rd * kSmallBlock + tid;
       Row r = load_row(indices, n, j, g);
       int first = 0;
-      for (int kx = 0; kx < g.kh; ++kx)
-        for (int ky = 0; ky < g.kw; ++ky) {
-          int slot = 0, val, ox, oy;
-          if (candidate<false, false>(r, g, t, kx, ky, slot, val, ox, oy) && table[slot] == j * K + kx * g.kw + ky) ++first;
+      WFSP_FOR_TAPS(g, kx, ky, kz) {
+          int slot = 0, val;
+      Pos o;
+          if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz)) ++first;
         }
       int incl = first;
       for (int o = 1; o < 32; o <<= 1) {
@@ -400,14 +419,12 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
       for (int w = 0; w < warp; ++w) off += s_warp[w];
       // a first toucher only rewrites its own cells, and nobody else's test `== own rank` can succeed on them
       if (first) {
-        for (int kx = 0; kx < g.kh; ++kx)
-          for (int ky = 0; ky < g.kw; ++ky) {
-            int slot = 0, val, ox, oy;
-            if (candidate<false, false>(r, g, t, kx, ky, slot, val, ox, oy) && table[slot] == j * K + kx * g.kw + ky) {
+        WFSP_FOR_TAPS(g, kx, ky, kz) {
+            int slot = 0, val;
+      Pos o;
+            if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz)) {
               if (off < out_cap) {
-                out_indices[3 * int64_t(off) + 0] = r.b;
-                out_indices[3 * int64_t(off) + 1] = ox;
-                out_indices[3 * int64_t(off) + 2] = oy;
+                store_pos(out_indices, off, g, r.b, o);
               }
               table[slot] = -off - 1;
               ++off;
@@ -429,12 +446,12 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   for (int rd = 0; rd < rounds; ++rd) {
     const int j = rd * kSmallBlock + tid;
     Row r = load_row(indices, n, j, g);
-    for (int kx = 0; kx < g.kh; ++kx)
-      for (int ky = 0; ky < g.kw; ++ky) {
-        int slot = 0, val = 0, ox, oy;
-        bool v = candidate<false, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+    WFSP_FOR_TAPS(g, kx, ky, kz) {
+        int slot = 0, val = 0;
+      Pos o;
+        bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
         unsigned bal = __ballot_sync(0xffffffffu, v);
-        if (lane == 0) s_dyn[(kx * g.kw + ky) * kSmallWarps + warp] = __popc(bal);
+        if (lane == 0) s_dyn[(WFSP_TAP(g, kx, ky, kz)) * kSmallWarps + warp] = __popc(bal);
       }
     __syncthreads();
     for (int k = tid; k < K; k += kSmallBlock) {
@@ -447,11 +464,11 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
       s_kbase[k] = run;
     }
     __syncthreads();
-    for (int kx = 0; kx < g.kh; ++kx)
-      for (int ky = 0; ky < g.kw; ++ky) {
-        const int k = kx * g.kw + ky;
-        int slot = 0, val = 0, ox, oy;
-        bool v = candidate<false, SUBM>(r, g, t, kx, ky, slot, val, ox, oy);
+    WFSP_FOR_TAPS(g, kx, ky, kz) {
+        const int k = WFSP_TAP(g, kx, ky, kz);
+        int slot = 0, val = 0;
+      Pos o;
+        bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
         unsigned bal = __ballot_sync(0xffffffffu, v);
         if (v) {
           const int pos = s_dyn[k * kSmallWarps + warp] + __popc(bal & lt);
@@ -477,9 +494,9 @@ struct Plan {
   size_t off_vals, off_keys, off_cnt, off_base, total;
 };
 
-Plan make_plan(int64_t n_in, int batch, int out_h, int out_w, int kvol) {
+Plan make_plan(int64_t n_in, int batch, int64_t out_vol, int kvol) {
   Plan p;
-  int64_t cells = int64_t(batch) * out_h * out_w;
+  int64_t cells = int64_t(batch) * out_vol;
   if (cells < 1) cells = 1;
   p.hash = g_force_hash || cells > kDirectMaxCells;
   if (p.hash) {
@@ -501,13 +518,56 @@ Plan make_plan(int64_t n_in, int batch, int out_h, int out_w, int kvol) {
   return p;
 }
 
-int check_geom(const int* ksize, const int* stride, const int* pad, const int* dil) {
-  for (int i = 0; i < 2; ++i) {
+int check_geom(int ndim, const int* ksize, const int* stride, const int* pad, const int* dil) {
+  WFSP_REQUIRE(ndim == 2 || ndim == 3, "ndim %d: only 2-d and 3-d rulebooks", ndim);
+  for (int i = 0; i < ndim; ++i) {
     WFSP_REQUIRE(ksize[i] >= 1 && ksize[i] <= 32, "kernel size %d outside [1,32]", ksize[i]);
     WFSP_REQUIRE(stride[i] >= 1 && dil[i] >= 1 && pad[i] >= 0, "bad stride/dilation/padding");
     WFSP_REQUIRE(stride[i] == 1 || dil[i] == 1, "don't support this: stride>1 with dilation>1");
   }
   return WFSP_OK;
+}
+
+int out_shape_nd(int ndim, const int* in_shape, const int* ksize, const int* stride, const int* pad, const int* dil,
+                 int* out_shape) {
+  for (int i = 0; i < ndim; ++i) {
+    WFSP_REQUIRE(stride[i] >= 1, "stride must be >= 1");
+    int num = in_shape[i] + 2 * pad[i] - dil[i] * (ksize[i] - 1) - 1;
+    int q = num >= 0 ? num / stride[i] : -((-num + stride[i] - 1) / stride[i]);  // floor
+    out_shape[i] = q + 1;
+  }
+  return WFSP_OK;
+}
+
+// the geometry of one layer, padded to three dimensions (a 2-d layer has a third dimension of extent 1)
+struct Geom3 {
+  int in[3], out[3], k[3], s[3], p[3], d[3];
+  int kvol;
+  int64_t out_vol;
+};
+
+Geom3 pad3(int ndim, const int* in_shape, const int* out_shape, const int* ksize, const int* stride, const int* pad,
+           const int* dil) {
+  Geom3 q;
+  q.kvol = 1;
+  q.out_vol = 1;
+  for (int i = 0; i < 3; ++i) {
+    const bool on = i < ndim;
+    q.in[i] = on ? in_shape[i] : 1;
+    q.out[i] = on ? (out_shape[i] > 0 ? out_shape[i] : 0) : 1;
+    q.k[i] = on ? ksize[i] : 1;
+    q.s[i] = on ? stride[i] : 1;
+    q.p[i] = on ? pad[i] : 0;
+    q.d[i] = on ? dil[i] : 1;
+    q.kvol *= q.k[i];
+    q.out_vol *= q.out[i];
+  }
+  return q;
+}
+
+Geom make_geom(const Geom3& q, int ndim, int batch, const int32_t* n_dev) {
+  return Geom{q.in[0], q.in[1], q.in[2], q.out[0], q.out[1], q.out[2], q.k[0], q.k[1], q.k[2], q.s[0], q.s[1], q.s[2],
+              q.p[0], q.p[1], q.p[2], q.d[0], q.d[1], q.d[2], q.kvol, batch, ndim + 1, n_dev};
 }
 
 template <bool HASH>
@@ -542,43 +602,21 @@ int run_subm(const int32_t* indices, int64_t n, const Geom& g, const Table& t, c
   return WFSP_OK;
 }
 
-}  // namespace
-}  // namespace wfsp
-
-using namespace wfsp;
-
-extern "C" int wfsp_conv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* pad,
-                                   const int* dil, int* out_shape) {
-  for (int i = 0; i < 2; ++i) {
-    WFSP_REQUIRE(stride[i] >= 1, "stride must be >= 1");
-    int num = in_shape[i] + 2 * pad[i] - dil[i] * (ksize[i] - 1) - 1;
-    int q = num >= 0 ? num / stride[i] : -((-num + stride[i] - 1) / stride[i]);  // floor
-    out_shape[i] = q + 1;
-  }
-  return WFSP_OK;
-}
-
-extern "C" size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const int* out_shape, const int* ksize) {
-  return make_plan(n_in, batch, out_shape[0], out_shape[1], ksize[0] * ksize[1]).total;
-}
-
-extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
-                                  const int* in_shape,
-                                  const int* ksize, const int* stride, const int* pad, const int* dil,
-                                  int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
-                                  int32_t* n_out, void* workspace, size_t workspace_bytes,
-                                  wfsp_stream_t stream) {
-  if (int rc = check_geom(ksize, stride, pad, dil)) return rc;
-  int out_shape[2];
-  wfsp_conv_out_shape(in_shape, ksize, stride, pad, dil, out_shape);
+int rulebook_conv_impl(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                       const int* in_shape, const int* ksize, const int* stride, const int* pad, const int* dil,
+                       int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num, int32_t* n_out,
+                       void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  if (int rc = check_geom(ndim, ksize, stride, pad, dil)) return rc;
+  int out_shape[3];
+  out_shape_nd(ndim, in_shape, ksize, stride, pad, dil, out_shape);
   WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
-  Geom g{in_shape[0], in_shape[1], out_shape[0] > 0 ? out_shape[0] : 0, out_shape[1] > 0 ? out_shape[1] : 0,
-         ksize[0], ksize[1], stride[0], stride[1], pad[0], pad[1], dil[0], dil[1], ksize[0] * ksize[1], batch,
-         n_in_dev};
+  const Geom3 q = pad3(ndim, in_shape, out_shape, ksize, stride, pad, dil);
+  const Geom g = make_geom(q, ndim, batch, n_in_dev);
+  WFSP_REQUIRE(g.kvol <= WFSP_MAX_KVOL, "kernel volume %d > %d", g.kvol, WFSP_MAX_KVOL);
   WFSP_REQUIRE(n_in * int64_t(g.kvol) < int64_t(kRankInf), "n_in * kvol too large for 31-bit ranks");
-  WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * out_h * out_w too large");
+  WFSP_REQUIRE(int64_t(batch) * q.out_vol < int64_t(0xfffffff0u), "batch * output volume too large");
   cudaStream_t st = as_stream(stream);
-  Plan p = make_plan(n_in, batch, g.out_h, g.out_w, g.kvol);
+  Plan p = make_plan(n_in, batch, q.out_vol, g.kvol);
   if (workspace_bytes < p.total) return set_error(WFSP_EWORKSPACE, "rulebook workspace %zu < %zu", workspace_bytes, p.total);
   char* ws = static_cast<char*>(workspace);
   Table t{reinterpret_cast<int32_t*>(ws + p.off_vals), reinterpret_cast<uint32_t*>(ws + p.off_keys),
@@ -595,19 +633,19 @@ extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, const in
                 : run_conv<false>(indices, n_in, g, t, p, ws, out_indices, out_cap, pairs, pair_num, n_out, st);
 }
 
-extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
-                                  const int* shape,
-                                  const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num,
-                                  void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
-  const int one[2] = {1, 1};
-  const int pad[2] = {ksize[0] / 2, ksize[1] / 2};
-  if (int rc = check_geom(ksize, one, pad, dil)) return rc;
+int rulebook_subm_impl(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                       const int* shape, const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num,
+                       void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  const int one[3] = {1, 1, 1};
+  const int pad[3] = {ksize[0] / 2, ksize[1] / 2, ndim > 2 ? ksize[2] / 2 : 0};
+  if (int rc = check_geom(ndim, ksize, one, pad, dil)) return rc;
   WFSP_REQUIRE(n_in >= 0 && batch >= 0, "negative sizes");
-  Geom g{shape[0], shape[1], shape[0], shape[1], ksize[0], ksize[1], 1, 1, pad[0], pad[1], dil[0], dil[1],
-         ksize[0] * ksize[1], batch, n_in_dev};
-  WFSP_REQUIRE(int64_t(batch) * g.out_h * g.out_w < int64_t(0xfffffff0u), "batch * h * w too large");
+  const Geom3 q = pad3(ndim, shape, shape, ksize, one, pad, dil);
+  const Geom g = make_geom(q, ndim, batch, n_in_dev);
+  WFSP_REQUIRE(g.kvol <= WFSP_MAX_KVOL, "kernel volume %d > %d", g.kvol, WFSP_MAX_KVOL);
+  WFSP_REQUIRE(int64_t(batch) * q.out_vol < int64_t(0xfffffff0u), "batch * volume too large");
   cudaStream_t st = as_stream(stream);
-  Plan p = make_plan(n_in, batch, g.out_h, g.out_w, g.kvol);
+  Plan p = make_plan(n_in, batch, q.out_vol, g.kvol);
   if (workspace_bytes < p.total) return set_error(WFSP_EWORKSPACE, "rulebook workspace %zu < %zu", workspace_bytes, p.total);
   char* ws = static_cast<char*>(workspace);
   Table t{reinterpret_cast<int32_t*>(ws + p.off_vals), reinterpret_cast<uint32_t*>(ws + p.off_keys),
@@ -621,6 +659,52 @@ extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, const in
   WFSP_CHECK_CUDA(cudaMemsetAsync(pairs, 0xff, size_t(2) * g.kvol * n_in * 4, st));
   return p.hash ? run_subm<true>(indices, n_in, g, t, p, ws, pairs, pair_num, st)
                 : run_subm<false>(indices, n_in, g, t, p, ws, pairs, pair_num, st);
+}
+
+}  // namespace
+}  // namespace wfsp
+
+using namespace wfsp;
+
+extern "C" int wfsp_conv_out_shape(const int* in_shape, const int* ksize, const int* stride, const int* pad,
+                                   const int* dil, int* out_shape) {
+  return out_shape_nd(2, in_shape, ksize, stride, pad, dil, out_shape);
+}
+
+extern "C" int wfsp_conv_out_shape_nd(int ndim, const int* in_shape, const int* ksize, const int* stride,
+                                      const int* pad, const int* dil, int* out_shape) {
+  WFSP_REQUIRE(ndim == 2 || ndim == 3, "ndim %d: only 2-d and 3-d", ndim);
+  return out_shape_nd(ndim, in_shape, ksize, stride, pad, dil, out_shape);
+}
+
+extern "C" size_t wfsp_rulebook_workspace_bytes(int64_t n_in, int batch, const int* out_shape, const int* ksize) {
+  return make_plan(n_in, batch, int64_t(out_shape[0]) * out_shape[1], ksize[0] * ksize[1]).total;
+}
+
+extern "C" size_t wfsp_rulebook_workspace_bytes_nd(int ndim, int64_t n_in, int batch, const int* out_shape,
+                                                   const int* ksize) {
+  int64_t vol = 1;
+  int kvol = 1;
+  for (int i = 0; i < ndim && i < 3; ++i) { vol *= out_shape[i] > 0 ? out_shape[i] : 0; kvol *= ksize[i]; }
+  return make_plan(n_in, batch, vol, kvol).total;
+}
+
+extern "C" int wfsp_rulebook_conv(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                                  const int* in_shape,
+                                  const int* ksize, const int* stride, const int* pad, const int* dil,
+                                  int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
+                                  int32_t* n_out, void* workspace, size_t workspace_bytes,
+                                  wfsp_stream_t stream) {
+  return rulebook_conv_impl(2, indices, n_in, n_in_dev, batch, in_shape, ksize, stride, pad, dil, out_indices, out_cap,
+                            pairs, pair_num, n_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int wfsp_rulebook_subm(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int batch,
+                                  const int* shape,
+                                  const int* ksize, const int* dil, int32_t* pairs, int32_t* pair_num,
+                                  void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return rulebook_subm_impl(2, indices, n_in, n_in_dev, batch, shape, ksize, dil, pairs, pair_num, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_num, int kvol, int64_t pair_pitch,
@@ -638,28 +722,31 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
   return WFSP_OK;
 }
 
-
 // Rulebook + neighbour tables in one call (what a layer needs before its first convolution).  Small
-// inputs (<= 1024 rows, direct table, kernel volume <= 256) take the single-launch path; everything else
-// runs the phase kernels above followed by rb_tables.
-extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int64_t n_in_hint, int batch,
-                                   const int* in_shape, const int* ksize, const int* stride, const int* pad,
-                                   const int* dil, int subm, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
-                                   int32_t* pair_num, int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in,
-                                   int32_t* dup_flag, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+// inputs (up to kSmallMaxRows expected live rows, direct table, kernel volume <= 256) take the single-launch
+// path; everything else runs the phase kernels above followed by rb_tables.  ndim 2: index rows (b, x, y);
+// ndim 3: (b, x, y, t).
+extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                                      int64_t n_in_hint, int batch, const int* in_shape, const int* ksize,
+                                      const int* stride, const int* pad, const int* dil, int subm,
+                                      int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
+                                      int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag,
+                                      void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(ndim == 2 || ndim == 3, "ndim %d: only 2-d and 3-d rulebooks", ndim);
   WFSP_REQUIRE(pair_num && dup_flag, "null output");
   WFSP_REQUIRE(n_in == 0 || (pairs && nbr_out && nbr_in), "null output");
   WFSP_REQUIRE(subm || n_out, "regular convolution needs n_out");
-  const int one[2] = {1, 1};
-  const int spad[2] = {ksize[0] / 2, ksize[1] / 2};
+  const int one[3] = {1, 1, 1};
+  const int spad[3] = {ksize[0] / 2, ksize[1] / 2, ndim > 2 ? ksize[2] / 2 : 0};
   const int* st_ = subm ? one : stride;
   const int* pd_ = subm ? spad : pad;
-  if (int rc = check_geom(ksize, st_, pd_, dil)) return rc;
-  int out_shape[2] = {in_shape[0], in_shape[1]};
-  if (!subm) wfsp_conv_out_shape(in_shape, ksize, stride, pad, dil, out_shape);
-  const int oh = out_shape[0] > 0 ? out_shape[0] : 0, ow = out_shape[1] > 0 ? out_shape[1] : 0;
-  const int kvol = ksize[0] * ksize[1];
-  const int64_t cells = int64_t(batch) * oh * ow;
+  if (int rc = check_geom(ndim, ksize, st_, pd_, dil)) return rc;
+  int out_shape[3] = {in_shape[0], in_shape[1], ndim > 2 ? in_shape[2] : 1};
+  if (!subm) out_shape_nd(ndim, in_shape, ksize, stride, pad, dil, out_shape);
+  const Geom3 q = pad3(ndim, in_shape, out_shape, ksize, st_, pd_, dil);
+  const int kvol = q.kvol;
+  WFSP_REQUIRE(kvol <= WFSP_MAX_KVOL, "kernel volume %d > %d", kvol, WFSP_MAX_KVOL);
+  const int64_t cells = int64_t(batch) * q.out_vol;
   cudaStream_t st = as_stream(stream);
   // expected live rows: the capacity, or the caller's hint where only the device knows the count (graph path);
   // a wrong hint only costs time (the single-launch builder walks the live rows in rounds of 1024)
@@ -667,8 +754,7 @@ extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const i
   if (n_in > 0 && live <= kSmallMaxRows && n_in <= kSmallMaxCap && kvol <= 256 && !g_force_hash && cells > 0 && cells <= (int64_t(1) << 20) &&
       n_in * int64_t(kvol) < int64_t(kRankInf)) {
     WFSP_REQUIRE(workspace_bytes >= size_t(cells > 0 ? cells : 1) * 4, "rulebook workspace too small");
-    Geom g{in_shape[0], in_shape[1], oh, ow, ksize[0], ksize[1], st_[0], st_[1], pd_[0], pd_[1], dil[0], dil[1], kvol,
-           batch, n_in_dev};
+    const Geom g = make_geom(q, ndim, batch, n_in_dev);
     size_t smem = size_t(kvol) * (kSmallWarps + 1) * sizeof(int);
     const bool in_smem = smem + size_t(cells) * 4 <= size_t(200) * 1024;
     if (in_smem) smem += size_t(cells) * 4;
@@ -694,12 +780,22 @@ extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const i
   }
   int rc;
   if (subm)
-    rc = wfsp_rulebook_subm(indices, n_in, n_in_dev, batch, in_shape, ksize, dil, pairs, pair_num, workspace, workspace_bytes,
-                            stream);
+    rc = rulebook_subm_impl(ndim, indices, n_in, n_in_dev, batch, in_shape, ksize, dil, pairs, pair_num, workspace,
+                            workspace_bytes, stream);
   else
-    rc = wfsp_rulebook_conv(indices, n_in, n_in_dev, batch, in_shape, ksize, stride, pad, dil, out_indices, out_cap, pairs,
-                            pair_num, n_out, workspace, workspace_bytes, stream);
+    rc = rulebook_conv_impl(ndim, indices, n_in, n_in_dev, batch, in_shape, ksize, stride, pad, dil, out_indices,
+                            out_cap, pairs, pair_num, n_out, workspace, workspace_bytes, stream);
   if (rc) return rc;
   WFSP_CHECK_CUDA(cudaMemsetAsync(dup_flag, 0, 4, st));
   return wfsp_rulebook_tables(pairs, pair_num, kvol, n_in, n_in, subm ? n_in : out_cap, nbr_out, nbr_in, dup_flag, stream);
+}
+
+extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int64_t n_in_hint, int batch,
+                                   const int* in_shape, const int* ksize, const int* stride, const int* pad,
+                                   const int* dil, int subm, int32_t* out_indices, int64_t out_cap, int32_t* pairs,
+                                   int32_t* pair_num, int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in,
+                                   int32_t* dup_flag, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return wfsp_rulebook_build_nd(2, indices, n_in, n_in_dev, n_in_hint, batch, in_shape, ksize, stride, pad, dil, subm,
+                                out_indices, out_cap, pairs, pair_num, n_out, nbr_out, nbr_in, dup_flag, workspace,
+                                workspace_bytes, stream);
 }

@@ -25,7 +25,7 @@ from . import fused, ops
 from .ops import Rulebook, get_conv_output_size, get_indice_pairs  # noqa: F401
 
 __all__ = ["SparseConvTensor", "SparseModule", "SparseConvolution", "SparseConv2d", "SubMConv2d",
-           "SparseInverseConv2d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode", "set_fused"]
+           "SparseInverseConv2d", "SparseConv3d", "SubMConv3d", "SparseInverseConv3d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode", "set_fused"]
 
 _math_mode = os.environ.get("WFSP_MATH", "bf16")
 assert _math_mode in ("bf16", "fp32")
@@ -49,7 +49,8 @@ class SparseConvTensor:
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None, n_rows=None):
         """features [N, C]; indices int32 [N, 3] = (batch, x, y); spatial_shape e.g. [14, 11]
         (list / numpy array); batch_size int or 0-dim tensor (as the reference passes,
-        src/models/SPConvNet.py:51,63).
+        src/models/SPConvNet.py:51,63).  The 3-d variant (net_type "3DConvolution", SPConvNet.py:42-49) has
+        indices [N, 4] = (batch, x, y, t) and spatial_shape [14, 11, n_samples].
 
         n_rows (extension, graph path): int32 device scalar with the live row count; features /
         indices are then capacity-sized buffers, nothing downstream reads the count back to the host
@@ -76,6 +77,14 @@ class SparseConvTensor:
         return None
 
     def dense(self, channels_first=True):
+        if len(self.spatial_shape) == 3:
+            # [B, C, H, W, T] is [B, C, H, W*T] with the last two coordinates merged: same scatter kernel
+            h, w, t = self.spatial_shape
+            i = self.indices
+            merged = torch.stack([i[:, 0], i[:, 1], i[:, 2] * t + i[:, 3]], dim=1).contiguous()
+            out = Fsp.ToDenseFunction.apply(self.features, merged, self.batch_size, h, w * t, self.n_rows)
+            out = out.view(out.shape[0], out.shape[1], h, w, t)
+            return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
         h, w = self.spatial_shape
         out = Fsp.ToDenseFunction.apply(self.features, self.indices, self.batch_size, h, w, self.n_rows)
         if not channels_first:
@@ -97,8 +106,9 @@ class SparseConvolution(SparseModule):
                  fused_bn=False, use_hash=False):
         super().__init__()
         assert groups == 1
-        if ndim != 2:
-            raise NotImplementedError("only 2-d sparse convolutions are implemented (the 14x11 segment grid)")
+        if ndim not in (2, 3):
+            raise NotImplementedError("2-d (the 14x11 segment grid) and 3-d (14x11xsamples) sparse convolutions "
+                                      "are implemented")
         if transposed:
             raise NotImplementedError("SparseConvTranspose is not used by the reference models")
 
@@ -187,26 +197,46 @@ class SparseInverseConv2d(SparseConvolution):
         super().__init__(2, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key)
 
 
+class SparseConv3d(SparseConvolution):
+    """3-d counterpart (src/utils/ModelValidation.py:24-31 lists it; net_type "3DConvolution",
+    src/models/SPConvNet.py:42-49).  Weight [kH, kW, kT, Cin, Cout]; same kernels, 3-d rulebook."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, use_hash=False):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         indice_key=indice_key, use_hash=use_hash)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, use_hash=False):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key, use_hash=use_hash)
+
+
+class SparseInverseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key, bias=True):
+        super().__init__(3, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key)
+
+
 def _not_implemented(name):
     class _Stub(SparseModule):
         def __init__(self, *args, **kwargs):
             raise NotImplementedError(
                 "%s is listed by src/utils/ModelValidation.py:24-31 but constructed by no shipped config; "
-                "only the 2-d layers of the 14x11 grid are implemented" % name)
+                "the 2-d and 3-d regular / submanifold / inverse layers are implemented" % name)
     _Stub.__name__ = name
     return _Stub
 
 
 SparseConv1d = _not_implemented("SparseConv1d")
-SparseConv3d = _not_implemented("SparseConv3d")
 SparseConv4d = _not_implemented("SparseConv4d")
-SubMConv3d = _not_implemented("SubMConv3d")
 SparseConvTranspose2d = _not_implemented("SparseConvTranspose2d")
 SparseConvTranspose3d = _not_implemented("SparseConvTranspose3d")
 
 
 class ToDense(SparseModule):
-    """SparseConvTensor -> dense [B, C, H, W]."""
+    """SparseConvTensor -> dense [B, C, H, W] (3-d: [B, C, H, W, T])."""
 
     def forward(self, x):
         return x.dense()

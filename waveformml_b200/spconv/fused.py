@@ -19,6 +19,7 @@ modules, unknown modules) falls back to the per-layer path in SparseSequential.f
 """
 import ctypes
 
+import numpy as np
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -138,6 +139,18 @@ def _bn_ws(lib, n, c, dev):
     return torch.empty((lib.wfsp_bn_workspace_bytes(n, c),), dtype=torch.uint8, device=dev)
 
 
+def _dense_geometry(t, idx=None):
+    """(H, W, index rows [n, 3]) for the ToDense kernels; a 3-d tensor is scattered as [B, C, H, W*T] with its last
+    two coordinates merged (the memory layout of [B, C, H, W, T])."""
+    if len(t.spatial_shape) == 2:
+        return t.spatial_shape[0], t.spatial_shape[1], (t.indices.contiguous() if idx is None else idx)
+    h, w, d = t.spatial_shape
+    if idx is None:
+        i = t.indices
+        idx = torch.stack([i[:, 0], i[:, 1], i[:, 2] * d + i[:, 3]], dim=1).contiguous()
+    return h, w * d, idx
+
+
 class FusedStackFunction(Function):
     @staticmethod
     def forward(ctx, plan, x, holder, features, *params):
@@ -156,7 +169,7 @@ class FusedStackFunction(Function):
             # ---- every layer's weights -> bf16 tensor-core layouts, one launch
             jobs, offs, total = [], [], 0
             for bi, b in enumerate(blocks):
-                kvol = 1 if b.conv.conv1x1 else int(b.conv.kernel_size[0] * b.conv.kernel_size[1])
+                kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
                 cin, cout = b.conv.in_channels, b.conv.out_channels
                 f_off = total
                 total += lib.wfsp_prepared_weight_bytes(kvol, cin, cout)
@@ -167,7 +180,7 @@ class FusedStackFunction(Function):
                 offs.append((f_off, d_off))
             wbuf = torch.empty((total,), dtype=torch.uint8, device=dev)
             for bi, b in enumerate(blocks):
-                kvol = 1 if b.conv.conv1x1 else int(b.conv.kernel_size[0] * b.conv.kernel_size[1])
+                kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
                 cin, cout = b.conv.in_channels, b.conv.out_channels
                 w = params[4 * bi]
                 assert w.dtype == torch.float32 and w.is_contiguous()
@@ -286,13 +299,13 @@ class FusedStackFunction(Function):
             ctx.need_in_grad, ctx.in_dtype = need_in_grad, features.dtype
             ctx.final = cur
             if plan.to_dense:
-                h, w = cur.spatial_shape
+                h, w, ctx.dense_idx = _dense_geometry(cur)
                 n, c = out32.shape
                 dense = torch.empty((cur.batch_size, c, h, w), dtype=torch.float32, device=dev)
                 table = torch.empty((max(cur.batch_size * h * w, 1),), dtype=torch.int32, device=dev)
-                _lib.check(lib.wfsp_to_dense(_lib.ptr(out32), _lib.ptr(cur.indices.contiguous()), n, _lib.ptr(cur.n_rows),
+                _lib.check(lib.wfsp_to_dense(_lib.ptr(out32), _lib.ptr(ctx.dense_idx), n, _lib.ptr(cur.n_rows),
                                              c, cur.batch_size, h, w, _lib.ptr(dense), _lib.ptr(table), st()))
-                return dense
+                return dense.view(cur.batch_size, c, *cur.spatial_shape)
             return out32
 
     @staticmethod
@@ -309,9 +322,9 @@ class FusedStackFunction(Function):
             final = ctx.final
             if plan.to_dense:
                 n, c = saved[-1][6], blocks[-1].conv.out_channels
-                h, w = final.spatial_shape
+                h, w, _ = _dense_geometry(final, ctx.dense_idx)
                 dy = torch.empty((n, c), dtype=torch.float32, device=dev)
-                _lib.check(lib.wfsp_to_dense_bwd(_lib.ptr(g), _lib.ptr(final.indices.contiguous()), n,
+                _lib.check(lib.wfsp_to_dense_bwd(_lib.ptr(g), _lib.ptr(ctx.dense_idx), n,
                                                  _lib.ptr(final.n_rows), c, final.batch_size, h, w, _lib.ptr(dy), st()))
             else:
                 dy = g

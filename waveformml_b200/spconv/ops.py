@@ -7,12 +7,15 @@ import torch
 from .. import _lib
 
 
-def _list2(v):
+def _listn(v, nd=2):
     if isinstance(v, (int, np.integer)):
-        return [int(v), int(v)]
+        return [int(v)] * nd
     v = [int(x) for x in v]
-    assert len(v) == 2, "only 2-d sparse convolutions are implemented"
+    assert len(v) == nd, "expected %d values per geometry argument, got %r" % (nd, v)
     return v
+
+
+_list2 = _listn
 
 
 def get_conv_output_size(input_size, kernel_size, stride, padding, dilation):
@@ -68,15 +71,18 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     _lib.require_cuda(indices)
     if indices.dtype != torch.int32:
         raise RuntimeError("indices must be int32 (got %s)" % indices.dtype)
-    assert indices.dim() == 2 and indices.shape[1] == 3, "indices must be [N, 3] = (batch, x, y)"
-    indices = indices.contiguous()
-    ksize, stride, padding, dilation = _list2(ksize), _list2(stride), _list2(padding), _list2(dilation)
     spatial_shape = [int(s) for s in spatial_shape]
+    nd = len(spatial_shape)
+    assert nd in (2, 3), "2-d (14x11 grid) and 3-d (14x11xsamples) sparse convolutions are implemented"
+    assert indices.dim() == 2 and indices.shape[1] == nd + 1, "indices must be [N, %d] = (batch, x, y%s)" % (
+        nd + 1, ", t" if nd == 3 else "")
+    indices = indices.contiguous()
+    ksize, stride, padding, dilation = (_listn(v, nd) for v in (ksize, stride, padding, dilation))
     for s, d in zip(stride, dilation):
         assert s == 1 or d == 1, "don't support this."
     batch_size = int(batch_size)
     dev = indices.device
-    N, K = indices.shape[0], ksize[0] * ksize[1]
+    N, K = indices.shape[0], int(np.prod(ksize))
     static = n_rows is not None
     if subm:
         out_shape = list(spatial_shape)
@@ -84,8 +90,8 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
         out_shape = get_conv_output_size(spatial_shape, ksize, stride, padding, dilation)
     pairs = torch.empty((2, K, N), dtype=torch.int32, device=dev)
     pair_num = torch.empty((K,), dtype=torch.int32, device=dev)
-    oshape_c = _lib.ints([max(o, 0) for o in out_shape])
-    ws_bytes = lib.wfsp_rulebook_workspace_bytes(N, batch_size, oshape_c, _lib.ints(ksize))
+    oshape_c = _lib.ints([max(o, 0) for o in out_shape], nd)
+    ws_bytes = lib.wfsp_rulebook_workspace_bytes_nd(nd, N, batch_size, oshape_c, _lib.ints(ksize, nd))
     ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     n_in_dev = n_rows if static else None
     n_out_dev = None
@@ -93,29 +99,30 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     n_hint = hints.get(n_rows) if static else 0  # expected live rows: picks the builder, never the result
     dup = torch.empty((1,), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
+
+    def build(subm_flag, out_indices, out_cap, n_out_t, nbr_out):
+        geom = [_lib.ints(v, nd) for v in (spatial_shape, ksize, stride, padding, dilation)]
+        tail = (subm_flag, _lib.ptr(out_indices), out_cap, _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t),
+                _lib.ptr(nbr_out), _lib.ptr(nbr_in), _lib.ptr(dup), _lib.ptr(ws), ws.numel(), _lib.stream())
+        head = (_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size)
+        if nd == 2:  # the 14x11 grid keeps its own entry point
+            return lib.wfsp_rulebook_build(*head, *geom, *tail)
+        return lib.wfsp_rulebook_build_nd(nd, *head, *geom, *tail)
+
     with torch.cuda.device(dev):
         if subm:
             nbr_out = torch.empty((N, K), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size,
-                                               _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
-                                               _lib.ints(padding), _lib.ints(dilation), 1, None, N, _lib.ptr(pairs),
-                                               _lib.ptr(pair_num), None, _lib.ptr(nbr_out), _lib.ptr(nbr_in),
-                                               _lib.ptr(dup), _lib.ptr(ws), ws.numel(), _lib.stream()))
+            _lib.check(build(1, None, N, None, nbr_out))
             outids, n_out = indices, N
             n_out_dev = n_in_dev
         else:
-            cells = batch_size * max(out_shape[0], 0) * max(out_shape[1], 0)
+            cells = batch_size * int(np.prod([max(o, 0) for o in out_shape]))
             cap = max(1, min(N * K, cells))
-            outbuf = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+            outbuf = torch.empty((cap, nd + 1), dtype=torch.int32, device=dev)
             n_out_t = torch.empty((1,), dtype=torch.int32, device=dev)
             # nbr_out is sized at the bound: its live rows are known only on the device
             nbr_cap = torch.empty((cap, K), dtype=torch.int32, device=dev)
-            _lib.check(lib.wfsp_rulebook_build(_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size,
-                                               _lib.ints(spatial_shape), _lib.ints(ksize), _lib.ints(stride),
-                                               _lib.ints(padding), _lib.ints(dilation), 0, _lib.ptr(outbuf), cap,
-                                               _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t),
-                                               _lib.ptr(nbr_cap), _lib.ptr(nbr_in), _lib.ptr(dup), _lib.ptr(ws),
-                                               ws.numel(), _lib.stream()))
+            _lib.check(build(0, outbuf, cap, n_out_t, nbr_cap))
             if static:
                 n_out, outids, n_out_dev, nbr_out = cap, outbuf, n_out_t, nbr_cap
             else:
@@ -133,8 +140,9 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padd
     """Upstream-compatible signature; returns (outids, indice_pairs [2,K,N], indice_pair_num [K])."""
     if transpose:
         raise NotImplementedError("transposed sparse convolution is not used by the reference models")
-    ks = _list2(ksize)
-    pad = [k // 2 for k in ks] if subm else _list2(padding)
-    st = [1, 1] if subm else _list2(stride)
+    nd = len(spatial_shape)
+    ks = _listn(ksize, nd)
+    pad = [k // 2 for k in ks] if subm else _listn(padding, nd)
+    st = [1] * nd if subm else _listn(stride, nd)
     rb = build_rulebook(indices, batch_size, spatial_shape, ks, st, pad, dilation, subm)
     return rb.outids, rb.pairs, rb.pair_num
