@@ -39,13 +39,20 @@ struct Geom {
   int kh, kw, kt, sh, sw, st, ph, pw, pt, dh, dw, dt;
   int kvol, batch, cols;
   const int32_t* n_dev;  // live row count (graph path); NULL = the host count is exact
+  uint32_t mh, mw, mt;   // ceil(2^32 / stride) per dimension (0 for stride 1): division by multiplication
 };
 
-// every kernel tap in ascending offset order k = (kx * kw + ky) * kt + kz
-#define WFSP_FOR_TAPS(g, kx, ky, kz)        \
-  for (int kx = 0; kx < (g).kh; ++kx)       \
-    for (int ky = 0; ky < (g).kw; ++ky)     \
-      for (int kz = 0; kz < (g).kt; ++kz)
+// n / s for 0 <= n < 2^32 / s with m = ceil(2^32 / s)  (m == 0: s == 1).  The rulebook kernels of a
+// 64-event batch are instruction-fetch bound (a single CTA running cold code once), so the integer
+// divisions -- some twenty instructions each when the divisor is a run-time value -- are kept out of them.
+__device__ __forceinline__ int fast_div(int n, uint32_t m) { return m ? int(__umulhi(uint32_t(n), m)) : n; }
+
+// every kernel tap in ascending offset order k = (kx * kw + ky) * kt + kz.  Not unrolled on purpose: the
+// bodies are long and the compiler would otherwise emit 4 x 4 x 4 copies of each.
+#define WFSP_FOR_TAPS(g, kx, ky, kz)                             \
+  _Pragma("unroll 1") for (int kx = 0; kx < (g).kh; ++kx)        \
+    _Pragma("unroll 1") for (int ky = 0; ky < (g).kw; ++ky)      \
+      _Pragma("unroll 1") for (int kz = 0; kz < (g).kt; ++kz)
 #define WFSP_TAP(g, kx, ky, kz) (((kx) * (g).kw + (ky)) * (g).kt + (kz))
 
 struct Table {
@@ -85,11 +92,13 @@ __device__ __forceinline__ int table_find(const Table& t, uint32_t key) {
 
 // bit kk of the result is set iff kernel tap kk along one dimension maps input coordinate `c`
 // onto an existing output coordinate:  c = o*s - p + kk*d  with 0 <= o < out
-__device__ __forceinline__ uint32_t tap_mask(int c, int k, int s, int p, int d, int out) {
+__device__ __forceinline__ uint32_t tap_mask(int c, int k, int s, uint32_t magic, int p, int d, int out) {
   uint32_t m = 0;
+#pragma unroll 1
   for (int kk = 0; kk < k; ++kk) {
-    int num = c + p - kk * d;
-    if (num >= 0 && (num % s) == 0 && (num / s) < out) m |= 1u << kk;
+    const int num = c + p - kk * d;
+    const int q = fast_div(num < 0 ? 0 : num, magic);
+    if (num >= 0 && q * s == num && q < out) m |= 1u << kk;
   }
   return m;
 }
@@ -114,9 +123,9 @@ __device__ __forceinline__ Row load_row(const int32_t* __restrict__ indices, int
     r.ok = r.b >= 0 && r.b < g.batch && r.x >= 0 && r.x < g.in_h && r.y >= 0 && r.y < g.in_w && r.z >= 0 &&
            r.z < g.in_t;
     if (r.ok) {
-      r.mx = tap_mask(r.x, g.kh, g.sh, g.ph, g.dh, g.out_h);
-      r.my = tap_mask(r.y, g.kw, g.sw, g.pw, g.dw, g.out_w);
-      r.mz = tap_mask(r.z, g.kt, g.st, g.pt, g.dt, g.out_t);
+      r.mx = tap_mask(r.x, g.kh, g.sh, g.mh, g.ph, g.dh, g.out_h);
+      r.my = tap_mask(r.y, g.kw, g.sw, g.mw, g.pw, g.dw, g.out_w);
+      r.mz = g.kt > 1 ? tap_mask(r.z, g.kt, g.st, g.mt, g.pt, g.dt, g.out_t) : 1u;
     }
   }
   return r;
@@ -138,9 +147,10 @@ __device__ __forceinline__ uint32_t in_key(const Geom& g, int b, int x, int y, i
 }
 
 __device__ __forceinline__ uint32_t out_key(const Row& r, const Geom& g, int kx, int ky, int kz, Pos& o) {
-  o.x = (r.x + g.ph - kx * g.dh) / g.sh;
-  o.y = (r.y + g.pw - ky * g.dw) / g.sw;
-  o.z = (r.z + g.pt - kz * g.dt) / g.st;
+  // only called for taps whose mask bits are set: the numerators are non-negative multiples of the strides
+  o.x = fast_div(r.x + g.ph - kx * g.dh, g.mh);
+  o.y = fast_div(r.y + g.pw - ky * g.dw, g.mw);
+  o.z = fast_div(r.z + g.pt - kz * g.dt, g.mt);
   return uint32_t(((r.b * g.out_h + o.x) * g.out_w + o.y) * g.out_t + o.z);
 }
 
@@ -343,6 +353,15 @@ __global__ void __launch_bounds__(kBlock) rb_tables(const int32_t* __restrict__ 
 // neighbour tables, so no memset nodes are needed.  The number of rounds follows the LIVE row count, so a
 // capacity-sized graph buffer costs nothing.  A 64-event batch of the reference's detector (a few hundred
 // hits) is launch-latency bound: this replaces ~11 graph nodes per rulebook by one.
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += up;
+  }
+  return v;
+}
+
 constexpr int kSmallBlock = 1024;
 constexpr int kSmallWarps = kSmallBlock / 32;
 constexpr int64_t kSmallMaxRows = 2048;   // live rows (two rounds): beyond this the multi-kernel phases win
@@ -370,20 +389,31 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   const int rounds = (live + kSmallBlock - 1) / kSmallBlock;
   // phase 0: initialise.  The -1 padding of the pair arrays is part of the upstream-visible result; with
   // device-side counts it is written for the live rows only (nothing reads the capacity tail).
-  for (int64_t i = tid; i < cells; i += kSmallBlock) table[i] = SUBM ? -1 : kRankInf;
+  // (plain counted loops, not unrolled: this kernel runs once, cold, in one CTA -- its cost is fetching its code)
+  const int ncells = int(cells);
+#pragma unroll 1
+  for (int i = tid; i < ncells; i += kSmallBlock) table[i] = SUBM ? -1 : kRankInf;
   if (!g.n_dev) {
-    for (int64_t i = tid; i < int64_t(2) * K * n; i += kSmallBlock) pairs[i] = -1;
+#pragma unroll 1
+    for (int i = tid; i < 2 * K * n; i += kSmallBlock) pairs[i] = -1;
   } else {  // rows [0, live) of every (side, offset) list; the capacity tail stays unspecified
-    for (int64_t i = tid; i < int64_t(2) * K * live; i += kSmallBlock) pairs[(i / live) * n + (i % live)] = -1;
+#pragma unroll 1
+    for (int c = warp; c < 2 * K; c += kSmallWarps)
+#pragma unroll 1
+      for (int i = lane; i < live; i += 32) pairs[c * n + i] = -1;
   }
-  for (int64_t i = tid; i < int64_t(live) * K; i += kSmallBlock) nbr_in[i] = -1;
+#pragma unroll 1
+  for (int i = tid; i < live * K; i += kSmallBlock) nbr_in[i] = -1;
+#pragma unroll 1
   for (int k = tid; k < K; k += kSmallBlock) s_kbase[k] = 0;
   if (tid == 0) { *dup_flag = 0; s_base = 0; }
   __syncthreads();
+  const Row r0 = load_row(indices, n, tid, g);  // round 0 (all there is up to 1024 rows) reads its row once
   // phase 1: claim cells
+#pragma unroll 1
   for (int rd = 0; rd < rounds; ++rd) {
     const int j = rd * kSmallBlock + tid;
-    Row r = load_row(indices, n, j, g);
+    Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
     if (!r.ok) continue;
     if (SUBM) {
       atomicMax(&table[in_key(g, r.b, r.x, r.y, r.z)], j);
@@ -399,91 +429,93 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   int64_t rows_out = live;
   if (!SUBM) {
     // phase 2: first touchers -> output rows in rank order, round after round
+#pragma unroll 1
     for (int rd = 0; rd < rounds; ++rd) {
       const int j = rd * kSmallBlock + tid;
-      Row r = load_row(indices, n, j, g);
+      Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
       int first = 0;
       WFSP_FOR_TAPS(g, kx, ky, kz) {
-          int slot = 0, val;
-      Pos o;
-          if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz)) ++first;
-        }
-      int incl = first;
-      for (int o = 1; o < 32; o <<= 1) {
-        int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
+        int slot = 0, val;
+        Pos o;
+        if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz))
+          ++first;
       }
+      const int incl = warp_incl_scan(first, lane);
       if (lane == 31) s_warp[warp] = incl;
       __syncthreads();
-      int off = s_base + incl - first;
-      for (int w = 0; w < warp; ++w) off += s_warp[w];
+      // every warp scans the 32 per-warp totals itself (one smem read + five shuffles instead of a serial sum)
+      const int wtot = warp_incl_scan(s_warp[lane], lane);
+      int off = s_base + incl - first + (warp ? __shfl_sync(0xffffffffu, wtot, warp - 1) : 0);
+      const int total = s_base + __shfl_sync(0xffffffffu, wtot, 31);
       // a first toucher only rewrites its own cells, and nobody else's test `== own rank` can succeed on them
       if (first) {
         WFSP_FOR_TAPS(g, kx, ky, kz) {
-            int slot = 0, val;
-      Pos o;
-            if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz)) {
-              if (off < out_cap) {
-                store_pos(out_indices, off, g, r.b, o);
-              }
-              table[slot] = -off - 1;
-              ++off;
-            }
+          int slot = 0, val;
+          Pos o;
+          if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz)) {
+            if (off < out_cap) store_pos(out_indices, off, g, r.b, o);
+            table[slot] = -off - 1;
+            ++off;
           }
+        }
       }
       __syncthreads();
-      if (tid == kSmallBlock - 1) s_base = off;  // inclusive end of the last thread = total so far
+      if (tid == 0) s_base = total;
       __syncthreads();
     }
     rows_out = s_base;
     if (tid == 0) *n_out = s_base;
   }
   if (rows_out > out_cap) rows_out = out_cap;
-  for (int64_t i = tid; i < rows_out * K; i += kSmallBlock) nbr_out[i] = -1;
+#pragma unroll 1
+  for (int i = tid; i < int(rows_out) * K; i += kSmallBlock) nbr_out[i] = -1;
   __syncthreads();
   // phase 3: per-offset compaction in ascending input order
   const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
   for (int rd = 0; rd < rounds; ++rd) {
     const int j = rd * kSmallBlock + tid;
-    Row r = load_row(indices, n, j, g);
+    Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
     WFSP_FOR_TAPS(g, kx, ky, kz) {
-        int slot = 0, val = 0;
+      int slot = 0, val = 0;
       Pos o;
-        bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
-        unsigned bal = __ballot_sync(0xffffffffu, v);
-        if (lane == 0) s_dyn[(WFSP_TAP(g, kx, ky, kz)) * kSmallWarps + warp] = __popc(bal);
-      }
+      const bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
+      const unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_dyn[WFSP_TAP(g, kx, ky, kz) * kSmallWarps + warp] = __popc(bal);
+    }
     __syncthreads();
-    for (int k = tid; k < K; k += kSmallBlock) {
-      int run = s_kbase[k];
-      for (int w = 0; w < kSmallWarps; ++w) {
-        const int c = s_dyn[k * kSmallWarps + w];
-        s_dyn[k * kSmallWarps + w] = run;
-        run += c;
-      }
-      s_kbase[k] = run;
+    // warp w turns the 32 per-warp counts of offsets w, w + 32, ... into running positions
+#pragma unroll 1
+    for (int k = warp; k < K; k += kSmallWarps) {
+      const int c = s_dyn[k * kSmallWarps + lane];
+      const int incl = warp_incl_scan(c, lane);
+      const int base = s_kbase[k];
+      __syncwarp();
+      s_dyn[k * kSmallWarps + lane] = base + incl - c;
+      if (lane == 31) s_kbase[k] = base + incl;
     }
     __syncthreads();
     WFSP_FOR_TAPS(g, kx, ky, kz) {
-        const int k = WFSP_TAP(g, kx, ky, kz);
-        int slot = 0, val = 0;
+      const int k = WFSP_TAP(g, kx, ky, kz);
+      int slot = 0, val = 0;
       Pos o;
-        bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
-        unsigned bal = __ballot_sync(0xffffffffu, v);
-        if (v) {
-          const int pos = s_dyn[k * kSmallWarps + warp] + __popc(bal & lt);
-          const int o = SUBM ? val : -table[slot] - 1;
-          pairs[(int64_t(0) * K + k) * n + pos] = j;
-          pairs[(int64_t(1) * K + k) * n + pos] = o;
-          nbr_in[int64_t(j) * K + k] = o;
-          if (o < out_cap) {
-            const int prev = atomicExch(&nbr_out[int64_t(o) * K + k], j);
-            if (prev != -1) *dup_flag = 1;
-          }
+      const bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
+      const unsigned bal = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        const int pos = s_dyn[k * kSmallWarps + warp] + __popc(bal & lt);
+        const int o_row = SUBM ? val : -table[slot] - 1;
+        pairs[(int64_t(0) * K + k) * n + pos] = j;
+        pairs[(int64_t(1) * K + k) * n + pos] = o_row;
+        nbr_in[int64_t(j) * K + k] = o_row;
+        if (o_row < out_cap) {
+          const int prev = atomicExch(&nbr_out[int64_t(o_row) * K + k], j);
+          if (prev != -1) *dup_flag = 1;
         }
       }
+    }
     __syncthreads();
   }
+#pragma unroll 1
   for (int k = tid; k < K; k += kSmallBlock) pair_num[k] = s_kbase[k];
 }
 
@@ -566,8 +598,11 @@ Geom3 pad3(int ndim, const int* in_shape, const int* out_shape, const int* ksize
 }
 
 Geom make_geom(const Geom3& q, int ndim, int batch, const int32_t* n_dev) {
+  uint32_t magic[3];
+  for (int i = 0; i < 3; ++i) magic[i] = q.s[i] > 1 ? uint32_t(((uint64_t(1) << 32) + q.s[i] - 1) / q.s[i]) : 0u;
   return Geom{q.in[0], q.in[1], q.in[2], q.out[0], q.out[1], q.out[2], q.k[0], q.k[1], q.k[2], q.s[0], q.s[1], q.s[2],
-              q.p[0], q.p[1], q.p[2], q.d[0], q.d[1], q.d[2], q.kvol, batch, ndim + 1, n_dev};
+              q.p[0], q.p[1], q.p[2], q.d[0], q.d[1], q.d[2], q.kvol, batch, ndim + 1, n_dev, magic[0], magic[1],
+              magic[2]};
 }
 
 template <bool HASH>
