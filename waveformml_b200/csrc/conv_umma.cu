@@ -7,10 +7,13 @@
 //              128-byte-swizzled shared-memory tiles, then cp.async.mbarrier.arrive.noinc on the stage's
 //              "full" barrier and move on -- they never wait for data, so up to `stages` slices are in
 //              flight per CTA.  Sixteen warps (four per scheduler) because a lone producer warp per
-//              scheduler was instruction-issue bound (ncu: ~0.27 IPC).  The weight slice of the apply
-//              kernel arrives by ONE cp.async.bulk of a pre-swizzled block (thread 0, expect_tx);
-//   warp 16    one elected lane waits on "full", issues tcgen05.mma (K=16 each) accumulating in TMEM and
-//              tcgen05.commit's to the stage's "free" barrier;
+//              scheduler was instruction-issue bound (ncu: ~0.27 IPC);
+//   warp 16    MMA issuer.  The whole warp walks the pipeline with converged control flow and ONE ELECTED lane
+//              issues the four tcgen05.mma (K=16 each, accumulating in TMEM) of a slice and tcgen05.commit's to
+//              the stage's "free" barrier.  (A lone `lane == 0` branch made the compiler wrap every tcgen05
+//              instruction in a loop over the active lanes and move each descriptor through R2UR: ~100 cycles
+//              per MMA, which WAS the cost of a small launch -- cycle trace in DESIGN.md.)
+//   warp 17    apply kernel only: one cp.async.bulk per stage brings the pre-swizzled weight slice (expect_tx);
 //   warps 0-7  epilogue after the last commit: tcgen05.ld -> registers -> shared-memory tile -> coalesced
 //              global rows (warps w and w+4 share TMEM lane quarter w and take alternate column chunks).
 //
@@ -36,10 +39,12 @@ namespace {
 
 using namespace umma;
 
-constexpr int kProducerWarps = 16;  // two per scheduler: a lone producer warp per scheduler was instruction-issue bound
+constexpr int kProducerWarps = 16;  // four per scheduler; eight were measured equal on small launches and slower on the large ones
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 32;  // + the MMA issuer warp
 constexpr int kMmaWarp = kProducerWarps;
+constexpr int kWeightWarp = kMmaWarp + 1;          // conv_apply only: issues the bulk copy of every weight slice
+constexpr int kApplyThreads = kThreads + 32;
 constexpr int kEpiWarps = 8;  // producer warps 0..7 drain TMEM (pairs w, w+4 share lane quarter w)
 constexpr int kRowStep = kProducerThreads / 8;   // tile rows covered by one pass of the producers (8 threads per row)
 constexpr int kRowsPerThread = 128 / kRowStep;   // rows of a 128-row tile per producer thread
@@ -60,9 +65,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 // arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-charged at init)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cp_async_arrive_noinc_u32(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) { cp_async_arrive_noinc_u32(smem_u32(bar)); }
 
 // ---- weight preparation: fp32 [kvol][c_red][c_dst] (or transposed) -> bf16 tiles
 // [kvol][kc_pad/64][n_pad][64], zero padded, each row's eight 16-byte chunks already permuted by the
@@ -181,15 +187,17 @@ __device__ __forceinline__ void init_pipe(PipeBarriers& b, uint32_t full_count) 
 }
 
 // one arrival on `bar` that also announces `bytes` of bulk-copy traffic to wait for
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+
 // TMA bulk copy (no tensor map): `bytes` contiguous bytes global -> shared, completion counted on `bar`
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_copy_g2s_u32(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+
 
 // TMEM -> registers (thread = row) -> the warp's shared-memory tile -> global, the warp writing whole row
 // segments so the stores are coalesced whatever the channel count (float4 / float2 / scalar by the
@@ -231,7 +239,7 @@ struct ApplyParams {
 // them, so the weights -- the larger half of the operand traffic when the channel counts are a few
 // hundred -- cross L2 -> SM once per rblk row blocks.  Accumulators: rblk x n_tile fp32 columns of TMEM.
 template <int RB>
-__global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyParams pp) {
+__global__ void __launch_bounds__(kApplyThreads) conv_apply_umma_kernel(const ApplyParams pp) {
   ApplyParams p = pp;
   if (p.n_src_dev) p.n_src = *p.n_src_dev;
   if (p.n_dst_dev) p.n_dst = *p.n_dst_dev;
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(RB * p.acc_stride));
   const bool staged = p.nbr != nullptr && p.staged;
 
-  for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kThreads) s_active[i] = 0;
+  for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kApplyThreads) s_active[i] = 0;
   if (tid == 0) init_pipe(bars, kProducerThreads + 1);
   if (warp == kMmaWarp) {
     tmem_alloc(&s_tmem, tmem_cols);
@@ -270,16 +278,16 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
     const int total = rb_live * kTileM * p.kvol;
     const int limit = rows_left * p.kvol;
     const int32_t* base = p.nbr + row0 * p.kvol;
-    for (int i0 = tid; i0 < total; i0 += kThreads * 8) {
+    for (int i0 = tid; i0 < total; i0 += kApplyThreads * 8) {
       int v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = i0 + j * kThreads;
+        const int i = i0 + j * kApplyThreads;
         v[j] = i < limit ? __ldg(base + i) : -1;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = i0 + j * kThreads;
+        const int i = i0 + j * kApplyThreads;
         if (i < total) {
           const int vv = v[j] >= p.n_src ? -1 : v[j];
           if (staged) s_nbr[i] = vv;
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
   for (int w = 0; w < (p.kvol + 31) / 32; ++w) n_active += __popc(s_active[w]);
   const int total_iters = n_active * num_kb;
   const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&bars.full[0]), free0 = smem_u32(&bars.free_[0]);  // barrier s is 8 s bytes further
 
   if (warp < kProducerWarps) {
     // ------------------------------------------------------------------ producers
@@ -309,9 +318,6 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
     const int rsub = tid >> 3;  // this thread covers tile rows rsub + kRowStep*i
     const uint32_t off0 = sw128_offset(uint32_t(rsub), uint32_t(c16));
     const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;  // slices in which the chunk is inside the row
-    int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
-    if (n_lim > p.n_tile) n_lim = p.n_tile;
-    const uint32_t b_bytes = uint32_t(n_lim) * 128u;
     const size_t a_row_bytes = size_t(p.c_pad) * 2;
     const char* src_c = reinterpret_cast<const char*>(p.src) + c16 * 16;
     int s = 0, it = 0;
@@ -341,14 +347,9 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
             rows[rb * kRowsPerThread + i] = v;
           }
         }
-        const char* wk = reinterpret_cast<const char*>(p.wt) + ((size_t(k) * num_kb) * p.n_pad + n0) * 128;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          if (it >= p.stages) mbar_wait(&bars.free_[s], ph ^ 1u);
+          if (it >= p.stages) mbar_wait_u32(free0 + 8u * s, ph ^ 1u);
           const uint32_t sa = smem0 + uint32_t(s) * stage_bytes;
-          if (tid == 0) {
-            mbar_arrive_expect_tx(&bars.full[s], b_bytes);
-            bulk_copy_g2s(sa + a_bytes, wk + size_t(kb) * p.n_pad * 128, b_bytes, &bars.full[s]);
-          }
           const bool col_ok = kb < kb_lim;
 #pragma unroll
           for (int rb = 0; rb < RB; ++rb) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
               }
             }
           }
-          cp_async_arrive_noinc(&bars.full[s]);
+          cp_async_arrive_noinc_u32(full0 + 8u * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -427,28 +428,61 @@ __global__ void __launch_bounds__(kThreads) conv_apply_umma_kernel(const ApplyPa
         __syncwarp();
       }
     }
-  } else if (lane == 0) {
+  } else if (warp == kWeightWarp) {
+    // ------------------------------------------------------------------ weight slices
+    // One bulk copy (cp.async.bulk) per pipeline stage drops the pre-swizzled [n_tile][64] slice of the current
+    // (offset, 64-channel block) behind the gathered rows.  A warp of its own: the copy's operands live on the
+    // uniform datapath, which a lane of a (divergent) gather warp can only reach through register moves.
+    int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
+    if (n_lim > p.n_tile) n_lim = p.n_tile;
+    const uint32_t b_bytes = uint32_t(n_lim) * 128u;
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int kw = 0; kw < (p.kvol + 31) / 32; ++kw) {
+      uint32_t mask = s_active[kw];
+      while (mask) {
+        const int k = kw * 32 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const char* wk = reinterpret_cast<const char*>(p.wt) + ((size_t(k) * num_kb) * p.n_pad + n0) * 128;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          if (it >= p.stages) mbar_wait_u32(free0 + 8u * s, ph ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx_u32(full0 + 8u * s, b_bytes);
+            bulk_copy_g2s_u32(smem0 + uint32_t(s) * stage_bytes + a_bytes, wk + size_t(kb) * p.n_pad * 128, b_bytes, full0 + 8u * s);
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp walks the pipeline (converged control flow keeps the descriptor arithmetic on the uniform
+    // datapath); one elected lane issues.  The descriptors of the four K=16 steps of a slice differ only in
+    // their start-address field: +32 bytes = +2 in the low word.
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
+    const uint64_t desc_hi = make_desc_sw128(0, 16, 1024);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < total_iters; ++it) {
-      mbar_wait(&bars.full[s], ph);
+      mbar_wait_u32(full0 + 8u * s, ph);
       fence_proxy_async_smem();
       tc_fence_after();
       const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
-      for (int rb = 0; rb < rb_live; ++rb) {
+      if (elect_one()) {
+        const uint64_t bdesc0 = desc_hi | uint64_t((b_addr >> 4) & 0x3fffu);
+        for (int rb = 0; rb < rb_live; ++rb) {
+          const uint64_t adesc0 = desc_hi | uint64_t(((a_addr + rb * kABytes) >> 4) & 0x3fffu);
 #pragma unroll
-        for (int kk = 0; kk < kSliceK / 16; ++kk) {
-          const uint64_t adesc = make_desc_sw128(a_addr + rb * kABytes + kk * 32, 16, 1024);
-          const uint64_t bdesc = make_desc_sw128(b_addr + kk * 32, 16, 1024);
-          mma_bf16(tmem + uint32_t(rb * p.acc_stride), adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kSliceK / 16; ++kk)
+            mma_bf16(tmem + uint32_t(rb * p.acc_stride), adesc0 + 2 * kk, bdesc0 + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
+        mma_commit_u32(free0 + 8u * s);
       }
-      mma_commit(&bars.free_[s]);
+      __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
-    if (total_iters > 0) mma_commit(&bars.done);
+    if (total_iters > 0 && elect_one()) mma_commit(&bars.done);
   }
   __syncwarp();
   tc_fence_before();
@@ -622,29 +656,34 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
         __syncwarp();
       }
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane)
     const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 1, 1);
+    // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO); the K=16 steps of a slice
+    // are 2048 B apart = +128 in the descriptor's start-address field
+    const uint64_t desc_hi = make_desc_sw128(0, 8192, 1024);
+    const uint32_t full0 = smem_u32(&bars.full[0]), free0 = smem_u32(&bars.free_[0]);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
-      mbar_wait(&bars.full[s], ph);
+      mbar_wait_u32(full0 + 8u * s, ph);
       fence_proxy_async_smem();
       tc_fence_after();
       const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
-      for (int mt = 0; mt < mt_live; ++mt) {
+      if (elect_one()) {
+        const uint64_t bdesc0 = desc_hi | uint64_t((b_addr >> 4) & 0x3fffu);
+        for (int mt = 0; mt < mt_live; ++mt) {
+          const uint64_t adesc0 = desc_hi | uint64_t(((a_addr + mt * 16384) >> 4) & 0x3fffu);
 #pragma unroll
-        for (int kk = 0; kk < kSliceK / 16; ++kk) {
-          // MN-major: 64-channel panels 8192 B apart (LBO), 8-pair groups 1024 B apart (SBO)
-          const uint64_t adesc = make_desc_sw128(a_addr + mt * 16384 + kk * 2048, 8192, 1024);
-          const uint64_t bdesc = make_desc_sw128(b_addr + kk * 2048, 8192, 1024);
-          mma_bf16(tmem + uint32_t(mt * p.acc_stride), adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kSliceK / 16; ++kk)
+            mma_bf16(tmem + uint32_t(mt * p.acc_stride), adesc0 + 128 * kk, bdesc0 + 128 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
+        mma_commit_u32(free0 + 8u * s);
       }
-      mma_commit(&bars.free_[s]);
+      __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
-    if (iters > 0) mma_commit(&bars.done);
+    if (iters > 0 && elect_one()) mma_commit(&bars.done);
   }
   __syncwarp();
   tc_fence_before();
@@ -777,7 +816,7 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
     case RB:                                                                                                         \
       WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                            kSmemOptIn));                                                             \
-      conv_apply_umma_kernel<RB><<<grid, kThreads, smem, st>>>(p);                                                   \
+      conv_apply_umma_kernel<RB><<<grid, kApplyThreads, smem, st>>>(p);                                                   \
       break;
     WFSP_LAUNCH_APPLY(1) WFSP_LAUNCH_APPLY(2) WFSP_LAUNCH_APPLY(3) WFSP_LAUNCH_APPLY(4)
 #undef WFSP_LAUNCH_APPLY

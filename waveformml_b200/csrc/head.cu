@@ -99,10 +99,13 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   float* s_w2 = s_h1 + B * hp;
   float* s_dl = s_w2 + C * hp;
   float* s_lg = s_dl + B * C;
+#pragma unroll 1
   for (int i = tid; i < B * H1; i += nt) s_h1[(i / H1) * hp + i % H1] = h1[i];
+#pragma unroll 1
   for (int i = tid; i < C * H1; i += nt) s_w2[(i / H1) * hp + i % H1] = w2[i];
   __syncthreads();
   // logits = h1 w2^T + b2
+#pragma unroll 1
   for (int i = tid; i < B * C; i += nt) {
     const int b = i / C, c = i % C;
     float s = b2 ? b2[c] : 0.f;
@@ -116,15 +119,19 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   __syncthreads();
   // cross entropy (mean over the batch) and dlogits = (softmax - onehot) / B
   float lsum = 0.f;
+#pragma unroll 1
   for (int b = tid; b < B; b += nt) {
     const float* lr = s_lg + b * C;
     float m = lr[0];
+#pragma unroll 1
     for (int c = 1; c < C; ++c) m = fmaxf(m, lr[c]);
     float z = 0.f;
+#pragma unroll 1
     for (int c = 0; c < C; ++c) z += expf(lr[c] - m);
     const float lse = m + logf(z);
     const int y = int(labels[b]);
     lsum += lse - lr[y];
+#pragma unroll 1
     for (int c = 0; c < C; ++c) {
       const float d = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) / float(B);
       s_dl[b * C + c] = d;
@@ -136,10 +143,12 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
+#pragma unroll 1
     for (int w = 0; w < (nt + 31) / 32; ++w) t += s_red[w];
     *loss = t / float(B);
   }
   // dW2[c][h] = sum_b dlogits[b][c] h1[b][h];  db2[c] = sum_b dlogits[b][c]
+#pragma unroll 1
   for (int i = tid; i < C * H1; i += nt) {
     const int c = i / H1, h = i % H1;
     float s = 0.f;
@@ -147,15 +156,19 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
     for (int b = 0; b < B; ++b) s += s_dl[b * C + c] * s_h1[b * hp + h];
     dw2[i] = s;
   }
+#pragma unroll 1
   for (int c = tid; c < C; c += nt) {
     float s = 0.f;
+#pragma unroll 1
     for (int b = 0; b < B; ++b) s += s_dl[b * C + c];
     db2[c] = s;
   }
   // dh1[b][h] = sum_c dlogits[b][c] w2[c][h]
+#pragma unroll 1
   for (int i = tid; i < B * H1; i += nt) {
     const int b = i / H1, h = i % H1;
     float s = 0.f;
+#pragma unroll 1
     for (int c = 0; c < C; ++c) s += s_dl[b * C + c] * s_w2[c * hp + h];
     dh1[i] = s;
   }

@@ -112,14 +112,17 @@ struct Row {
 __device__ __forceinline__ Row load_row(const int32_t* __restrict__ indices, int64_t n, int64_t j,
                                         const Geom& g) {
   Row r;
-  r.ok = j < (g.n_dev ? int64_t(*g.n_dev) : n);
   r.b = r.x = r.y = r.z = 0;
   r.mx = r.my = r.mz = 0;
-  if (r.ok) {
+  // rows up to the capacity n are readable: fetch the coordinates alongside the live count, not after it
+  if (j < n) {
     r.b = indices[g.cols * j + 0];
     r.x = indices[g.cols * j + 1];
     r.y = indices[g.cols * j + 2];
     if (g.cols > 3) r.z = indices[g.cols * j + 3];
+  }
+  r.ok = j < (g.n_dev ? int64_t(*g.n_dev) : n) && j < n;
+  if (r.ok) {
     r.ok = r.b >= 0 && r.b < g.batch && r.x >= 0 && r.x < g.in_h && r.y >= 0 && r.y < g.in_w && r.z >= 0 &&
            r.z < g.in_t;
     if (r.ok) {
@@ -472,6 +475,7 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   __syncthreads();
   // phase 3: per-offset compaction in ascending input order
   const unsigned lt = (1u << lane) - 1u;
+  int dup = 0;  // becomes non-zero if a (row, offset) slot of nbr_out was already taken: duplicate coordinates
 #pragma unroll 1
   for (int rd = 0; rd < rounds; ++rd) {
     const int j = rd * kSmallBlock + tid;
@@ -507,14 +511,13 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
         pairs[(int64_t(0) * K + k) * n + pos] = j;
         pairs[(int64_t(1) * K + k) * n + pos] = o_row;
         nbr_in[int64_t(j) * K + k] = o_row;
-        if (o_row < out_cap) {
-          const int prev = atomicExch(&nbr_out[int64_t(o_row) * K + k], j);
-          if (prev != -1) *dup_flag = 1;
-        }
+        // the previous occupants are only looked at after the loop: the exchanges of one row overlap
+        if (o_row < out_cap) dup |= atomicExch(&nbr_out[int64_t(o_row) * K + k], j) + 1;
       }
     }
     __syncthreads();
   }
+  if (dup) *dup_flag = 1;
 #pragma unroll 1
   for (int k = tid; k < K; k += kSmallBlock) pair_num[k] = s_kbase[k];
 }

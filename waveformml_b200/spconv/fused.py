@@ -198,6 +198,13 @@ class FusedStackFunction(Function):
                 _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
                 w_ready = torch.cuda.Event()
                 w_ready.record(side2)
+                # BatchNorm step counters: one multi-tensor add here instead of one launch per layer on the main stream
+                counters = [b.bn.num_batches_tracked for b in blocks
+                            if b.bn is not None and b.bn.training and b.bn.num_batches_tracked is not None]
+                if counters:
+                    torch._foreach_add_(counters, 1)
+                side2_done = torch.cuda.Event()
+                side2_done.record(side2)
 
             # ---- input activations -> bf16 once
             n0, c0 = feats.shape
@@ -264,8 +271,6 @@ class FusedStackFunction(Function):
                         bn = b.bn
                         mean = torch.empty((cout,), dtype=torch.float32, device=dev)
                         invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
-                        if bn.training and bn.num_batches_tracked is not None:
-                            bn.num_batches_tracked.add_(1)
                         if n_dst and partials is not None:
                             _lib.check(lib.wfsp_bn_relu_fwd_stats(
                                 _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), hint, cout, _lib.ptr(partials), _lib.ptr(bn.weight),
@@ -293,6 +298,7 @@ class FusedStackFunction(Function):
                 saved.append((a16, keep_x, mean, invstd, rb, cur.indices.shape[0], n_dst, n_src_dev, n_dst_dev, hint))
                 cur, a16, out32 = nxt, y16, y32
 
+            main.wait_event(side2_done)
             holder["tensor"] = cur  # geometry of the stack's output
             ctx.plan, ctx.saved, ctx.offs, ctx.wbuf = plan, saved, offs, wbuf
             ctx.params = params
