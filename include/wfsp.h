@@ -89,6 +89,15 @@ int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype,
                     const int64_t* item_offset, int64_t n_items, float scale, int32_t* indices_bxy,
                     void* feats, int feats_dtype, int64_t feats_pitch, wfsp_stream_t stream);
 
+/* Staging of one batch into the capacity-sized input buffers of a captured step (the graph path's
+ * counterpart of `.to(device)` in HDF5Dataset._concat_range, src/datasets/HDF5Dataset.py:340-346):
+ * copies up to three device buffers (coords, waveforms, labels; a NULL source skips its slot) and
+ * writes the live row count, in ONE launch -- at 64 events four separate copies cost more than any
+ * kernel of the step.  All pointers are device pointers; byte counts need no alignment. */
+int wfsp_stage_inputs(void* dst0, const void* src0, size_t bytes0, void* dst1, const void* src1,
+                      size_t bytes1, void* dst2, const void* src2, size_t bytes2, int32_t* n_rows_dev,
+                      int32_t n_rows, wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2) Rulebook builder.  Bit-exact with the CPU path of upstream ops.get_indice_pairs, which
  * every spconv.SparseConv2d / SubMConv2d with kernel volume > 1 reaches

@@ -96,3 +96,28 @@ def test_pack_bf16_operand_format_padding(cuda_device):
         assert tuple(f16.shape) == (n, pitch)
         assert torch.equal(f16[:, :c], f32.bfloat16())
         assert bool((f16[:, c:] == 0).all())
+
+
+def test_stage_inputs_copies_bit_exact(cuda_device):
+    """wfsp_stage_inputs: three copies + the live row count in one launch; odd byte counts, unaligned
+    pointers (a slice starting at an odd element), an empty and a skipped slot."""
+    from waveformml_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    src = [torch.randint(-2 ** 15, 2 ** 15, (4097,), dtype=torch.int16, generator=g).to(cuda_device)[1:],  # 2-byte aligned only
+           torch.randint(0, 255, (100003,), dtype=torch.uint8, generator=g).to(cuda_device),
+           torch.randint(0, 2 ** 31 - 1, (777, 3), dtype=torch.int32, generator=g).to(cuda_device)]
+    dst = [torch.full((s.numel() + 9,), 7, dtype=s.dtype, device=cuda_device) for s in src]
+    n_dev = torch.zeros((1,), dtype=torch.int32, device=cuda_device)
+    with torch.cuda.device(cuda_device):
+        _lib.check(lib.wfsp_stage_inputs(_lib.ptr(dst[0]), _lib.ptr(src[0]), src[0].numel() * 2,
+                                         _lib.ptr(dst[1]), _lib.ptr(src[1]), src[1].numel(),
+                                         _lib.ptr(dst[2]), _lib.ptr(src[2]), src[2].numel() * 4,
+                                         _lib.ptr(n_dev), 4321, _lib.stream()))
+    for d, s in zip(dst, src):
+        assert torch.equal(d[:s.numel()], s.reshape(-1)) and bool((d[s.numel():] == 7).all())
+    assert int(n_dev.item()) == 4321
+    with torch.cuda.device(cuda_device):  # skipped slots, count only
+        _lib.check(lib.wfsp_stage_inputs(None, None, 0, _lib.ptr(dst[1]), None, 5, None, None, 0, _lib.ptr(n_dev), 5,
+                                         _lib.stream()))
+    assert int(n_dev.item()) == 5 and torch.equal(dst[1][:src[1].numel()], src[1])

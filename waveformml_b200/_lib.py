@@ -30,6 +30,7 @@ SIGNATURES = {
                                   _vp, _sz, _vp]),
     "wfsp_rulebook_subm": (_int, [_vp, _i64, _vp, _int, _intp, _intp, _intp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_rulebook_tables": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "wfsp_stage_inputs": (_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _c.c_int32, _vp]),
     "wfsp_rulebook_build": (_int, [_vp, _i64, _vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _int, _vp, _i64, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wfsp_conv_out_shape_nd": (_int, [_int, _intp, _intp, _intp, _intp, _intp, _intp]),

@@ -271,8 +271,60 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, co
     p[i] = pv - lr * step;
   }
 }
+struct StageJobs {
+  char* dst[3];
+  const char* src[3];
+  size_t bytes[3];
+  int vec[3];  // 16-byte vectors usable (both pointers aligned)
+};
+
+// three independent copies in one grid: 16-byte vectors over the aligned body, bytes for the tail
+__global__ void __launch_bounds__(256) stage_inputs_kernel(StageJobs j, int32_t* __restrict__ n_dst, int32_t n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n_dst) *n_dst = n;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = size_t(gridDim.x) * blockDim.x;
+#pragma unroll 1
+  for (int s = 0; s < 3; ++s) {
+    if (j.bytes[s] == 0) continue;
+    const size_t body = j.vec[s] ? (j.bytes[s] & ~size_t(15)) : 0;
+    const uint4* sv = reinterpret_cast<const uint4*>(j.src[s]);
+    uint4* dv = reinterpret_cast<uint4*>(j.dst[s]);
+#pragma unroll 4
+    for (size_t i = tid; i < body / 16; i += nth) dv[i] = sv[i];
+#pragma unroll 1
+    for (size_t i = body + tid; i < j.bytes[s]; i += nth) j.dst[s][i] = j.src[s][i];
+  }
+}
+
 }  // namespace
 }  // namespace wfsp
+
+extern "C" int wfsp_stage_inputs(void* dst0, const void* src0, size_t bytes0, void* dst1, const void* src1, size_t bytes1,
+                                 void* dst2, const void* src2, size_t bytes2, int32_t* n_rows_dev, int32_t n_rows,
+                                 wfsp_stream_t stream) {
+  wfsp::StageJobs j{};
+  void* d[3] = {dst0, dst1, dst2};
+  const void* s[3] = {src0, src1, src2};
+  const size_t b[3] = {bytes0, bytes1, bytes2};
+  size_t total = 0;
+  for (int i = 0; i < 3; ++i) {
+    const bool on = s[i] != nullptr && b[i] > 0;
+    WFSP_REQUIRE(!on || d[i] != nullptr, "staging slot %d has a source but no destination", i);
+    j.dst[i] = static_cast<char*>(d[i]);
+    j.src[i] = static_cast<const char*>(s[i]);
+    j.bytes[i] = on ? b[i] : 0;
+    j.vec[i] = on && ((reinterpret_cast<uintptr_t>(d[i]) | reinterpret_cast<uintptr_t>(s[i])) & 15) == 0;
+    total += j.bytes[i];
+  }
+  if (total == 0 && n_rows_dev == nullptr) return WFSP_OK;
+  int64_t blocks = wfsp::ceil_div<int64_t>(int64_t(total / 16) + 1, 256 * 4);
+  const int64_t cap = int64_t(wfsp::sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  wfsp::stage_inputs_kernel<<<unsigned(blocks), 256, 0, wfsp::as_stream(stream)>>>(j, n_rows_dev, n_rows);
+  wfsp::count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
 
 extern "C" int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
                              int nesterov, float weight_decay, float grad_scale, wfsp_stream_t stream) {

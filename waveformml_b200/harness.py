@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from . import batcher, spconv
+from . import _lib, batcher, spconv
 from .synth import MAX_RANGE_INV
 
 
@@ -186,6 +186,19 @@ class GraphTrainStep(TrainStep):
         n = coords.shape[0]
         if n > self.row_capacity:
             raise ValueError("batch has %d rows, graph capacity is %d" % (n, self.row_capacity))
+        dev = self.coords.device
+        if (coords.device == dev and wave.device == dev and target.device == dev and coords.dtype == self.coords.dtype
+                and wave.dtype == self.wave.dtype and target.dtype == self.target.dtype and coords.is_contiguous()
+                and wave.is_contiguous() and target.is_contiguous() and target.numel() <= self.target.numel()):
+            # batch already in HBM: one launch stages all three buffers and the live row count
+            lib = _lib.load()
+            with torch.cuda.device(dev):
+                _lib.check(lib.wfsp_stage_inputs(
+                    _lib.ptr(self.coords), _lib.ptr(coords), coords.numel() * coords.element_size(),
+                    _lib.ptr(self.wave), _lib.ptr(wave), wave.numel() * wave.element_size(),
+                    _lib.ptr(self.target), _lib.ptr(target), target.numel() * target.element_size(),
+                    _lib.ptr(self.n_rows), n, _lib.stream()))
+            return
         self.coords[:n].copy_(coords, non_blocking=True)
         self.wave[:n].copy_(wave, non_blocking=True)
         self.target[:target.shape[0]].copy_(target, non_blocking=True)
