@@ -88,3 +88,31 @@ def test_fused_and_per_layer_agree_with_facade_bn(cuda_device):
         assert float(y.detach().min()) < 0  # the last layer has no activation
         outs.append(y.detach())
     torch.testing.assert_close(outs[0], outs[1], rtol=5e-3, atol=5e-3 * float(outs[1].abs().max()))
+
+
+def test_dimension_3_matches_dense_convolutions(cuda_device):
+    """SCNet.py:53-55 (net_type "3DConvolution"): coords (x, y, t, batch), spatial size [14, 11, n_samples]."""
+    from waveformml_b200.synth import make_events_3d
+    torch.manual_seed(6)
+    B, T, C = 9, 10, 2
+    ev = make_events_3d(B, n_samples=T, seed=12)
+    coords = torch.from_numpy(ev["coords"]).long()
+    feats = torch.rand(coords.shape[0], C)
+    dense = torch.zeros(B, C, 14, 11, T)
+    dense[coords[:, 3], :, coords[:, 0], coords[:, 1], coords[:, 2]] = feats
+    sub = scn.SubmanifoldConvolution(3, C, 8, 3, False)
+    conv = scn.Convolution(3, 8, 6, [3, 3, 2], [1, 1, 2], False)
+    net = scn.Sequential(sub, conv, scn.SparseToDense(3, 6)).to(cuda_device)
+    spconv.set_math_mode("fp32")
+    try:
+        y = net(scn.InputLayer(3, [14, 11, T], mode=0)([coords.to(cuda_device), feats.to(cuda_device)]))
+    finally:
+        spconv.set_math_mode("bf16")
+
+    def w3(c):
+        k = c.filter_size
+        return c.weight.detach().cpu().view(k[0], k[1], k[2], c.nIn, c.nOut).permute(4, 3, 0, 1, 2).contiguous()
+    mask = (dense.abs().sum(1, keepdim=True) > 0).float()
+    ref = F.conv3d(F.conv3d(dense, w3(sub), None, padding=1) * mask, w3(conv), None, stride=[1, 1, 2])
+    assert tuple(y.shape) == tuple(ref.shape) == (B, 6, 12, 9, 5)
+    torch.testing.assert_close(y.detach().cpu(), ref, rtol=1e-4, atol=1e-5)

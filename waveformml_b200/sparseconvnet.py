@@ -4,6 +4,7 @@ The reference can build its 2-d classifier with facebookresearch/SparseConvNet i
 (src/models/SCNet.py:62-77, config/examples/OPs3ns_SCNet.json:22-66, src/utils/ModelValidation.py:16-18):
 
     scn.InputLayer(2, spatial_size, mode=0)          coords arrive batch-LAST: (x, y, batch) int64
+                                                     (dimension 3, SCNet.py:53-55: (x, y, t, batch), size [14, 11, ns])
     scn.Convolution(dim, nIn, nOut, filter_size, filter_stride, bias)
     scn.SubmanifoldConvolution(dim, nIn, nOut, filter_size, bias)
     scn.BatchNormReLU(nPlanes) / scn.BatchNormalization(nPlanes) / scn.ReLU()
@@ -38,8 +39,8 @@ class InputLayer(nn.Module):
 
     def __init__(self, dimension, spatial_size, mode=3):
         super().__init__()
-        if dimension != 2:
-            raise NotImplementedError("only the 2-d 14x11 segment grid is implemented")
+        if dimension not in (2, 3):
+            raise NotImplementedError("the 2-d 14x11 segment grid and the 3-d 14x11xsamples grid are implemented")
         if mode != 0:
             raise NotImplementedError("InputLayer mode %d (duplicate coordinates) is not used by the reference" % mode)
         self.dimension, self.mode = dimension, mode
@@ -48,21 +49,22 @@ class InputLayer(nn.Module):
     def forward(self, x):
         coords, feats = x[0], x[1]
         batch_size = x[2] if len(x) > 2 else int(coords[:, -1].max()) + 1
-        idx = coords[:, [2, 0, 1]].to(torch.int32).contiguous()
+        d = self.dimension  # batch-last (x, y[, t], batch) -> batch-first, as SCNet.forward / SPConvNet.forward permute
+        idx = coords[:, [d] + list(range(d))].to(torch.int32).contiguous()
         return spconv.SparseConvTensor(feats, idx, self.spatial_size, batch_size)
 
 
 class _SCNConv(spconv.SparseConvolution):
     def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, subm, groups=1):
-        if dimension != 2:
-            raise NotImplementedError("only 2-d sparse convolutions are implemented")
+        if dimension not in (2, 3):
+            raise NotImplementedError("2-d and 3-d sparse convolutions are implemented (SCNet.py:51-55)")
         assert groups == 1
         fs = _tup(filter_size, dimension)
         st = _tup(filter_stride, dimension)
-        super().__init__(2, nIn, nOut, fs, st, 0, 1, 1, bias, subm=subm, indice_key=None)
+        super().__init__(dimension, nIn, nOut, fs, st, 0, 1, 1, bias, subm=subm, indice_key=None)
         self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
         self.filter_size, self.filter_stride = fs, st
-        self.filter_volume = int(fs[0] * fs[1])
+        self.filter_volume = int(math.prod(fs))
         # SparseConvNet parameter layout and init: [filter_volume, nIn, nOut], N(0, sqrt(2 / (nIn * volume)))
         std = math.sqrt(2.0 / nIn / self.filter_volume)
         self.weight = nn.Parameter(torch.empty(self.filter_volume, nIn, nOut).normal_(0, std))
@@ -81,7 +83,7 @@ class Convolution(_SCNConv):
 class SubmanifoldConvolution(_SCNConv):
     def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
         super().__init__(dimension, nIn, nOut, filter_size, 1, bias, True, groups)
-        self.indice_key = "scn_subm%dx%d" % tuple(self.filter_size)  # same-size submanifold layers share a rulebook
+        self.indice_key = "scn_subm" + "x".join(str(k) for k in self.filter_size)  # same-size submanifold layers share a rulebook
 
 
 class BatchNormalization(nn.BatchNorm1d):
