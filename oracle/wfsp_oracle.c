@@ -18,7 +18,10 @@
  *   - src/engineering/PSDDataModule.py:10-20 (collate_fn: running event offset)
  *   - src/datasets/HDF5Dataset.py:15-17,345-346 (normalisation by 1/(2^14-1))
  * plus the hand-derived known-answer vectors of SURVEY.md A.6 and the dense-conv identities of
- * A.5 (tests/test_oracle.py).
+ * A.5 (tests/test_oracle.py).  The rulebook functions take the number of spatial dimensions at run
+ * time (2: the 14x11 grid; 3: net_type "3DConvolution", src/models/SPConvNet.py:42-49); the 3-d case
+ * is pinned the same way -- conv3d / conv_transpose3d identities, a hand KAT, rulebook invariants and
+ * "a 3-d problem of depth 1 is the 2-d problem" (tests/test_oracle_3d.py).
  *
  * Everything here is single-threaded scalar C on purpose: it is the checker, not the product.
  */

@@ -114,3 +114,48 @@ def test_kat_3d_two_voxels():
     assert outids[1].tolist() == [0, 1, 1, 0] and pairs[1, 1, :2].tolist() == [1, 0]
     # 8 candidates per voxel, 4 shared cells (z overlap) -> 12 distinct outputs
     assert outids.shape[0] == 12
+
+
+@pytest.mark.parametrize("k,s,p,d", [([3, 3, 3], [1, 1, 1], [0, 0, 0], [1, 1, 1]), ([3, 2, 5], [2, 1, 2], [1, 0, 2], [1, 1, 1]),
+                                     ([2, 3, 3], [1, 1, 1], [1, 2, 0], [1, 2, 3]), ([1, 1, 4], [1, 1, 3], [0, 0, 1], [1, 1, 1])])
+def test_rulebook_invariants_3d(k, s, p, d):
+    """Every pair (input j, output o, offset (kx,ky,kt)) satisfies in = out*s - p + k*d per dimension; outputs are
+    unique and created in first-touch order (walking inputs in order, offsets ascending); the pairs of one offset
+    are in ascending input order with no input repeated; counts match the number of valid candidates."""
+    B = 5
+    indices, _ = _voxels(B, 7, 1)
+    outids, pairs, num = osp.get_indice_pairs(indices, B, SHAPE, k, s, p, d, False)
+    out_shape = osp.get_conv_output_size(SHAPE, k, s, p, d)
+    K = int(np.prod(k))
+    inn, out = indices.numpy().astype(np.int64), outids.numpy().astype(np.int64)
+    assert len({tuple(r) for r in out.tolist()}) == out.shape[0]
+    assert (out[:, 1:] >= 0).all() and (out[:, 1:] < np.array(out_shape)).all()
+    first_touch = {}
+    total = 0
+    for kk in range(K):
+        kv = np.unravel_index(kk, k)
+        n = int(num[kk])
+        total += n
+        ji, oi = pairs[0, kk, :n].numpy(), pairs[1, kk, :n].numpy()
+        assert (pairs[:, kk, n:] == -1).all()
+        assert (np.diff(ji) > 0).all()
+        for j, o in zip(ji, oi):
+            assert inn[j, 0] == out[o, 0]
+            for dim in range(3):
+                assert inn[j, 1 + dim] == out[o, 1 + dim] * s[dim] - p[dim] + kv[dim] * d[dim]
+            rank = int(j) * K + kk
+            first_touch[int(o)] = min(first_touch.get(int(o), rank), rank)
+    # brute-force candidate count
+    expect = 0
+    for row in inn:
+        for kk in range(K):
+            kv = np.unravel_index(kk, k)
+            ok = True
+            for dim in range(3):
+                num_ = row[1 + dim] + p[dim] - kv[dim] * d[dim]
+                if num_ < 0 or num_ % s[dim] or num_ // s[dim] >= out_shape[dim]:
+                    ok = False
+            expect += ok
+    assert total == expect
+    order = [first_touch[o] for o in range(out.shape[0])]
+    assert order == sorted(order)  # output rows are numbered in the order they are first touched
