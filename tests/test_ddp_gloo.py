@@ -99,3 +99,23 @@ def test_flat_grads_are_views():
     assert float(grads.flat.abs().sum()) > 0
     grads.zero()
     assert all(float(p.grad.abs().sum()) == 0 for p in model.parameters())
+
+
+def test_shard_events_by_rows_balances_hits():
+    """Row-balanced contiguous sharding (load imbalance): a partition of the events, in order, whose
+    per-rank row counts are within one event's rows of the ideal split."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for n, world in [(64, 2), (64, 8), (1024, 8), (10, 4), (3, 8), (8, 8), (1, 2)]:
+        rows = np.clip(1 + rng.poisson(2.0, size=n), 1, 10)
+        rows[: n // 4] *= 6  # a skewed head: equal event counts would overload rank 0
+        spans = harness.shard_events_by_rows(rows, world)
+        assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(lo <= hi for lo, hi in spans)
+        if n >= world:
+            assert all(hi > lo for lo, hi in spans)
+            per = [int(rows[lo:hi].sum()) for lo, hi in spans]
+            ideal = rows.sum() / world
+            assert max(per) <= ideal + 2 * rows.max(), (n, world, per)
+            by_events = [int(rows[lo:hi].sum()) for lo, hi in (harness.shard_events(n, r, world) for r in range(world))]
+            assert max(per) <= max(by_events)

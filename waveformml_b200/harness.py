@@ -31,6 +31,33 @@ def shard_events(n_events, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_events_by_rows(event_rows, world):
+    """Contiguous event ranges balanced by ROWS (hits) instead of event counts -- SURVEY.md 8e: the conv work of a
+    rank follows its rows, and hit multiplicities are skewed (1-10 hits per event in the reference's data).
+
+    event_rows: rows of every event of the global batch, in batch order.  Returns `world` (lo, hi) event ranges
+    that partition [0, n_events): boundary r is the event index where the running row count first reaches
+    r / world of the total (every rank keeps at least one event while events remain).  Events stay whole and in
+    order, so event ids stay rank-local after subtracting `lo`, exactly as with shard_events."""
+    import numpy as np
+    rows = np.asarray(event_rows, dtype=np.int64)
+    n = int(rows.shape[0])
+    cum = np.concatenate([[0], np.cumsum(rows)])
+    total = int(cum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(cum, target, side="left"))
+        # the boundary that leaves the running count closest to the target
+        if b > 0 and abs(cum[b - 1] - target) <= abs(cum[min(b, n)] - target):
+            b -= 1
+        b = max(b, bounds[-1] + (1 if bounds[-1] < n else 0))   # at least one event per rank while any remain
+        b = min(b, n - (world - r)) if n >= world else min(b, n)  # ... and one left for every later rank
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
 class FlatGrads:
     """All parameter gradients live in one flat fp32 buffer (param.grad are views into it), so the
     data-parallel exchange is a single all-reduce of ~4 MB, issued once after backward."""
