@@ -51,7 +51,7 @@ enum wfsp_math {
   WFSP_MATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (kind::f16)  */
 };
 
-#define WFSP_VERSION 100
+#define WFSP_VERSION 200
 #define WFSP_MAX_KVOL 1024
 
 int wfsp_version(void);
@@ -63,10 +63,9 @@ int wfsp_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host)
 int wfsp_set_option(const char* name, int value);
 /* number of CUDA kernels this library has launched in the calling process (monotonic) */
 unsigned long long wfsp_kernel_launches(void);
-/* test hook for the TMA gather path: rows idx128[0..127] (any value; rows outside [0, rows) read as
- * zero) x channels [c0, c0+64) of the bf16 matrix [rows][pitch] -> out_bf16 [128][64] */
-int wfsp_selftest_gather4(const void* src_bf16, int64_t rows, int channels, int64_t pitch,
-                          const int32_t* idx128, int c0, void* out_bf16, wfsp_stream_t stream);
+/* hex digest of the sources (csrc/ + this header) the library was compiled from; the Python loader compares it
+ * with the tree it runs in and rebuilds (or refuses) when they differ -- a stale binary never gets tested */
+const char* wfsp_source_hash(void);
 
 /* ---------------------------------------------------------------------------------------------
  * (1) Sparse-tensor batcher.

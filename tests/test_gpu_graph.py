@@ -232,3 +232,48 @@ def test_graph_path_z_regressor(cuda_device):
             assert _l2(b.grad, a.grad) < 5e-3, (k, _l2(b.grad, a.grad))
     finally:
         spconv.set_math_mode("bf16")
+
+
+def test_graph_path_reports_duplicate_inputs(cuda_device):
+    """The captured step cannot raise on duplicate (event, x, y) rows; the flag of every captured rulebook is
+    readable after a replay (dup_flag must reach the user)."""
+    B = 8
+    torch.manual_seed(5)
+    model = stacks.PSDClassifier().to(cuda_device).train()
+    coords, wave, labels = _psd_inputs(B, 11, cuda_device)
+    step = harness.GraphTrainStep(model, "psd", B, B * 10, 300, capture_update=False)
+    step.load(coords, wave, labels)
+    step.capture()
+    step.run()
+    assert step.duplicate_inputs() is False
+    bad = coords.clone()
+    bad[1] = bad[0]  # two hits in the same cell of the same event
+    step.load(bad, wave, labels)
+    step.run()
+    assert step.duplicate_inputs() is True
+    step.load(coords, wave, labels)
+    step.run()
+    assert step.duplicate_inputs() is False
+
+
+def test_two_backwards_accumulate_outside_write_through(cuda_device):
+    """FlatGrads attaches write-through targets, but only TrainStep.forward_backward (one backward over zeroed
+    gradients) may use them: two plain backwards must ACCUMULATE like torch.autograd."""
+    B = 12
+    torch.manual_seed(6)
+    model = stacks.PSDClassifier().to(cuda_device).train()
+    grads = harness.FlatGrads(model.parameters())
+    coords, wave, labels = _psd_inputs(B, 13, cuda_device)
+    idx, feats = batcher.pack_batch(coords, wave)
+    crit = nn.CrossEntropyLoss()
+    grads.zero()
+    crit(model([idx, feats, B]), labels).backward()
+    once = grads.flat.clone()
+    crit(model([idx, feats, B]), labels).backward()
+    twice = grads.flat.clone()
+    # BatchNorm running statistics moved between the passes but training-mode outputs do not depend on them
+    assert _l2(twice, 2 * once) < 1e-5
+    # and the write-through step still produces the single-backward gradient
+    step = harness.TrainStep(model, "psd")
+    step.forward_backward(idx, feats, labels, B)
+    assert _l2(step.grads.flat, once) < 1e-5

@@ -130,9 +130,18 @@ def test_unsorted_input_first_touch_order(cuda_device):
 def test_duplicate_coordinates_flagged(cuda_device):
     idx = torch.tensor([(0, 5, 5), (0, 5, 5), (0, 6, 6)], dtype=torch.int32)
     ref = osp.get_indice_pairs(idx, 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], False)
-    rb = ops.build_rulebook(idx.to(cuda_device), 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], False)
+    rb = ops.build_rulebook(idx.to(cuda_device), 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], False,
+                            check_duplicates=False)
     assert torch.equal(rb.pairs.cpu(), ref[1]) and torch.equal(rb.outids.cpu(), ref[0])  # the rulebook itself is exact
     assert int(rb.dup_flag.item()) == 1
+    # default: the eager path raises (upstream would SUM the duplicates; silently keeping one is not acceptable)
     with pytest.raises(RuntimeError, match="duplicate"):
-        ops.build_rulebook(idx.to(cuda_device), 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], False,
-                           check_duplicates=True)
+        ops.build_rulebook(idx.to(cuda_device), 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], False)
+    with pytest.raises(RuntimeError, match="duplicate"):
+        ops.build_rulebook(idx.to(cuda_device), 1, [14, 11], [3, 3], [1, 1], [0, 0], [1, 1], True)
+    # ... and through the layer API the reference calls
+    import spconv
+    layer = spconv.SparseConv2d(4, 4, 3, 1, 0, bias=False).to(cuda_device)
+    x = spconv.SparseConvTensor(torch.ones(3, 4, device=cuda_device), idx.to(cuda_device), [14, 11], 1)
+    with pytest.raises(RuntimeError, match="duplicate"):
+        layer(x)

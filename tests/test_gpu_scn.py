@@ -116,3 +116,59 @@ def test_dimension_3_matches_dense_convolutions(cuda_device):
     ref = F.conv3d(F.conv3d(dense, w3(sub), None, padding=1) * mask, w3(conv), None, stride=[1, 1, 2])
     assert tuple(y.shape) == tuple(ref.shape) == (B, 6, 12, 9, 5)
     torch.testing.assert_close(y.detach().cpu(), ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fused_on", [True, False])
+def test_submanifold_layers_either_side_of_a_stride(cuda_device, fused_on):
+    """The canonical SparseConvNet pattern SubmanifoldConvolution -> Convolution(stride 2) -> SubmanifoldConvolution
+    with ONE filter size: the second submanifold layer must get the rulebook of the strided active set, not the
+    cached one of the input resolution (shared `scn_subm3x3` key)."""
+    torch.manual_seed(8)
+    B = 19
+    coords, feats, dense = _batch(B, 6, 21, cuda_device)
+    s1 = scn.SubmanifoldConvolution(2, 6, 8, 3, False)
+    cv = scn.Convolution(2, 8, 8, 2, 2, False)
+    s2 = scn.SubmanifoldConvolution(2, 8, 5, 3, False)
+    net = scn.Sequential(s1, cv, s2, scn.SparseToDense(2, 5)).to(cuda_device)
+    spconv.set_math_mode("fp32")
+    spconv.set_fused(fused_on)
+    try:
+        y = net(scn.InputLayer(2, [14, 11], mode=0)([coords, feats]))
+    finally:
+        spconv.set_math_mode("bf16")
+        spconv.set_fused(True)
+    m0 = (dense.abs().sum(1, keepdim=True) > 0).float()
+    a = F.conv2d(dense, _w(s1), None, padding=1) * m0
+    b = F.conv2d(a, _w(cv), None, stride=2)
+    m1 = (F.conv2d(m0, torch.ones(1, 1, 2, 2), None, stride=2) > 0).float()  # active iff the receptive field holds an input
+    ref = F.conv2d(b * m1, _w(s2), None, padding=1) * m1
+    assert tuple(y.shape) == tuple(ref.shape) == (B, 5, 7, 5)
+    torch.testing.assert_close(y.detach().cpu(), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_shared_indice_key_across_resolutions_rebuilds(cuda_device):
+    """spconv layers: SubMConv2d('k') -> SparseConv2d(stride 2) -> SubMConv2d('k').  Upstream would reuse the first
+    rulebook for the third layer (wrong rows); the cache entry is validated against the input and rebuilt."""
+    import spconv as sp
+    torch.manual_seed(9)
+    B = 11
+    coords, feats, dense = _batch(B, 4, 33, cuda_device)
+    idx = coords[:, [2, 0, 1]].to(torch.int32).contiguous()
+    l1 = sp.SubMConv2d(4, 6, 3, bias=False, indice_key="k").to(cuda_device)
+    l2 = sp.SparseConv2d(6, 6, 3, 2, 1, bias=False).to(cuda_device)
+    l3 = sp.SubMConv2d(6, 3, 3, bias=False, indice_key="k").to(cuda_device)
+    sp.set_math_mode("fp32")
+    try:
+        x = sp.SparseConvTensor(feats, idx, [14, 11], B)
+        y = l3(l2(l1(x))).dense()
+    finally:
+        sp.set_math_mode("bf16")
+
+    def w(c):
+        return c.weight.detach().cpu().permute(3, 2, 0, 1).contiguous()
+    m0 = (dense.abs().sum(1, keepdim=True) > 0).float()
+    a = F.conv2d(dense, w(l1), None, padding=1) * m0
+    b = F.conv2d(a, w(l2), None, stride=2, padding=1)
+    m1 = (F.conv2d(m0, torch.ones(1, 1, 3, 3), None, stride=2, padding=1) > 0).float()
+    ref = F.conv2d(b * m1, w(l3), None, padding=1) * m1
+    torch.testing.assert_close(y.detach().cpu(), ref, rtol=1e-4, atol=1e-5)

@@ -22,7 +22,7 @@ SIGNATURES = {
     "wfsp_device_info": (_int, [_intp, _intp, _intp]),
     "wfsp_set_option": (_int, [_c.c_char_p, _int]),
     "wfsp_kernel_launches": (_c.c_ulonglong, []),
-    "wfsp_selftest_gather4": (_int, [_vp, _i64, _int, _i64, _vp, _int, _vp, _vp]),
+    "wfsp_source_hash": (_c.c_char_p, []),
     "wfsp_batch_pack": (_int, [_vp, _vp, _int, _i64, _vp, _int, _vp, _vp, _i64, _f32, _vp, _vp, _int, _i64, _vp]),
     "wfsp_conv_out_shape": (_int, [_intp] * 6),
     "wfsp_rulebook_workspace_bytes": (_sz, [_i64, _int, _intp, _intp]),
@@ -88,18 +88,28 @@ class WfspError(RuntimeError):
     pass
 
 
+EXPECTED_VERSION = 200  # include/wfsp.h WFSP_VERSION: bumped with every change of the C ABI
+
+
 def load():
-    """Loads libwfsp.so (building it with nvcc first if the .so is absent).  Raises on failure."""
+    """Loads libwfsp.so.  The library must have been compiled from the sources of THIS tree (digest check,
+    build.source_hash): a missing or stale binary is rebuilt with nvcc first, and if that is impossible the load
+    fails -- a stale .so called through new ctypes signatures would corrupt memory silently."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    if _build._stale():
         _build.build()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype, fn.argtypes = res, args
+    if lib.wfsp_version() != EXPECTED_VERSION:
+        raise WfspError("libwfsp.so has ABI version %d, the bindings expect %d" % (lib.wfsp_version(), EXPECTED_VERSION))
+    if lib.wfsp_source_hash().decode() != _build.source_hash():
+        raise WfspError("libwfsp.so was built from other sources (%s, tree is %s)"
+                        % (lib.wfsp_source_hash().decode(), _build.source_hash()))
     _lib = lib
     return lib
 

@@ -75,6 +75,11 @@ using namespace wfsp;
 
 extern "C" int wfsp_version(void) { return WFSP_VERSION; }
 
+#ifndef WFSP_SOURCE_HASH
+#define WFSP_SOURCE_HASH "unknown"
+#endif
+extern "C" const char* wfsp_source_hash(void) { return WFSP_SOURCE_HASH; }
+
 extern "C" const char* wfsp_last_error(void) { return error_buffer(); }
 
 extern "C" unsigned long long wfsp_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }

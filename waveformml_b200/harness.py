@@ -70,7 +70,8 @@ class FlatGrads:
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            # one backward per step: the fused sparse stack writes these gradients in place (spconv/fused.py)
+            # inside spconv.fused.grad_write_through() (one backward per step over zeroed gradients) the fused
+            # sparse stack and head write these gradients in place; outside it autograd accumulates as usual
             p._wfsp_grad_out = p.grad
             off += p.numel()
 
@@ -173,8 +174,10 @@ class TrainStep:
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev
         try:
-            loss = self.loss(indices, feats, target, batch_size, n_rows)
-            loss.backward()
+            # one backward over freshly zeroed gradients: the fused kernels write straight into the flat buffer
+            with spconv.fused.grad_write_through():
+                loss = self.loss(indices, feats, target, batch_size, n_rows)
+                loss.backward()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return loss
@@ -284,12 +287,22 @@ class GraphTrainStep(TrainStep):
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.wfsp_kernel_launches()
         hints.start("replay")
+        from .spconv import ops as _ops
+        del _ops.graph_dup_flags[:]
         try:
             with torch.cuda.graph(self.graph):
                 self.loss_out = self._body()
         finally:
             hints.stop()
+        self._dup_flags = list(_ops.graph_dup_flags)  # one int32 per captured rulebook, rewritten by every replay
+        del _ops.graph_dup_flags[:]
         self.launches_per_replay = int(lib.wfsp_kernel_launches() - n0)  # libwfsp kernels in one replay
+
+    def duplicate_inputs(self):
+        """True if the batch of the LAST replay held duplicate (event, x, y) rows (a host readback: call it when
+        validating data, not every step).  The eager path raises at rulebook construction instead."""
+        flags = getattr(self, "_dup_flags", [])
+        return bool(flags) and bool(torch.stack([f.reshape(()) for f in flags]).ne(0).any().item())
 
     def run(self):
         if self.graph is None:

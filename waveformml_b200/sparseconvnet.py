@@ -83,7 +83,14 @@ class Convolution(_SCNConv):
 class SubmanifoldConvolution(_SCNConv):
     def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
         super().__init__(dimension, nIn, nOut, filter_size, 1, bias, True, groups)
-        self.indice_key = "scn_subm" + "x".join(str(k) for k in self.filter_size)  # same-size submanifold layers share a rulebook
+        # same-size submanifold layers AT ONE RESOLUTION share a rulebook: the key is completed with the input's
+        # spatial shape at run time (geometry), so the layers before and after a strided Convolution never collide
+        self._key_base = "scn_subm" + "x".join(str(k) for k in self.filter_size)
+        self.indice_key = self._key_base
+
+    def geometry(self, input):
+        self.indice_key = self._key_base + "@" + "x".join(str(int(s)) for s in input.spatial_shape)
+        return super().geometry(input)
 
 
 class BatchNormalization(nn.BatchNorm1d):

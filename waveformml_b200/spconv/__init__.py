@@ -156,7 +156,7 @@ class SparseConvolution(SparseModule):
             assert rb.kvol == int(np.prod(self.kernel_size)), \
                 "inverse conv must have same kernel size as its couple conv"
             return rb, rb.indices, rb.spatial_shape, rb.n_in_dev
-        if self.indice_key is not None and datas is not None:
+        if self.indice_key is not None and datas is not None and self._rulebook_matches(datas, input):
             rb = datas
         else:
             pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
@@ -166,6 +166,15 @@ class SparseConvolution(SparseModule):
             input.indice_dict[self.indice_key] = rb
         out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
         return rb, rb.outids, out_spatial_shape, rb.n_out_dev
+
+    def _rulebook_matches(self, rb, input):
+        """A cached rulebook is reused only if it was built for THIS input: same index tensor, grid and kernel
+        volume.  Upstream reuses whatever sits under the key; with a key shared across resolutions (submanifold ->
+        strided -> submanifold with one key) that reads neighbour tables of the wrong active set and indexes past
+        the feature buffer.  Here a mismatch rebuilds (and re-caches) instead."""
+        idx = input.indices
+        return (rb.kvol == int(np.prod(self.kernel_size)) and rb.indices.shape == idx.shape
+                and rb.indices.data_ptr() == idx.data_ptr() and list(rb.spatial_shape) == list(input.spatial_shape))
 
     def forward(self, input):
         assert isinstance(input, SparseConvTensor)

@@ -231,7 +231,12 @@ class BatchNormReLUFunction(Function):
 
 def batch_norm_relu(x, n_rows, bn, relu):
     """Applies the nn.BatchNorm1d module `bn` (+ ReLU) to the live rows of x."""
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if bn.momentum is None:
+        # torch's cumulative moving average needs 1 / num_batches_tracked on the host every step: not expressible
+        # in a captured launch, and silently substituting 0.1 would change the running statistics
+        raise NotImplementedError("BatchNorm1d(momentum=None) (cumulative average) is not supported on the "
+                                  "device-counted path; use a fixed momentum")
+    momentum = bn.momentum
     training = bn.training or bn.running_mean is None
     if bn.training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)

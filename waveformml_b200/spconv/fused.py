@@ -110,12 +110,34 @@ def compile_stack(modules, sparse_conv_cls, to_dense_cls):
     return Plan(blocks, to_dense)
 
 
+_write_through = 0
+
+
+class grad_write_through:
+    """Context manager: inside it, the fused kernels may OVERWRITE `param._wfsp_grad_out` with the gradient and hand
+    None to autograd.  That is only right when the step runs exactly one backward over freshly zeroed gradients and
+    no parameter is shared between two fused nodes (harness.TrainStep.forward_backward) -- so it is opt-in per step;
+    everywhere else (gradient accumulation over micro-batches, retain_graph, shared parameters) the kernels return
+    fresh tensors and torch.autograd accumulates as usual."""
+
+    def __enter__(self):
+        global _write_through
+        _write_through += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _write_through
+        _write_through -= 1
+        return False
+
+
 def _grad_target(param, shape, dev):
     """Where a parameter gradient is written.  A training harness that owns a flat gradient buffer and
     runs ONE backward per step can attach `param._wfsp_grad_out` (a contiguous fp32 view of the parameter's
-    shape, e.g. harness.FlatGrads): the kernel then writes the gradient there and autograd gets None -- no
-    accumulation kernel per parameter.  Otherwise a fresh tensor is returned to autograd as usual."""
-    tgt = getattr(param, "_wfsp_grad_out", None) if param is not None else None
+    shape, e.g. harness.FlatGrads) and run the step inside `grad_write_through()`: the kernel then writes the
+    gradient there and autograd gets None -- no accumulation kernel per parameter.  Otherwise a fresh tensor is
+    returned to autograd as usual."""
+    tgt = getattr(param, "_wfsp_grad_out", None) if (param is not None and _write_through > 0) else None
     if tgt is not None and tgt.dtype == torch.float32 and tgt.is_contiguous() and tgt.numel() == param.numel() \
             and tgt.device == dev:
         return tgt.view(shape), True
@@ -336,6 +358,12 @@ class FusedStackFunction(Function):
                 dy = g
             main, side = torch.cuda.current_stream(), _side_stream(dev)
             side_used = False
+            # Tensors the side stream reads (the bf16 gradient of every block) must outlive the loop: the caching
+            # allocator only knows the stream a block was ALLOCATED on, so a g16 dropped here could be handed to the
+            # next iteration's main-stream buffers while wgrad on `side` still reads it (inside a capture the same
+            # aliasing would be baked into the graph with no edge between the branches).  They are released after
+            # main has waited for the side stream.
+            cross_stream = []
             for bi in range(len(blocks) - 1, -1, -1):
                 b = blocks[bi]
                 conv = b.conv
@@ -345,6 +373,7 @@ class FusedStackFunction(Function):
                 w_p, bias_p, gamma_p, beta_p = params[4 * bi: 4 * bi + 4]
                 want_bias = bias_p is not None and ctx.needs_input_grad[4 + 4 * bi + 1]
                 g16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
+                cross_stream.append(g16)
                 dx32 = torch.empty((n_dst, cout), dtype=torch.float32, device=dev) if want_bias else None
                 if b.bn is not None:
                     dgam, gam_through = _grad_target(gamma_p, (cout,), dev)
@@ -410,6 +439,7 @@ class FusedStackFunction(Function):
                 joined = torch.cuda.Event()
                 joined.record(side)
                 main.wait_event(joined)
+            del cross_stream  # main is ordered after every side-stream reader now
             d_feats = None
             if ctx.need_in_grad:
                 d_feats = dy if ctx.in_dtype == torch.float32 else dy.to(ctx.in_dtype)

@@ -59,8 +59,17 @@ class Rulebook:
         return self.pairs.shape[1]
 
 
+# Duplicate (batch, x, y[, t]) rows in the input.  Upstream's gather / scatter-add sums all contributors of an
+# (output, offset); the output-stationary neighbour tables keep one, so duplicates are an ERROR here, not a silent
+# difference: the eager path raises at rulebook construction (the flag rides on the row-count readback), the graph
+# path cannot read anything back, so every rulebook built with device-side counts appends its flag to
+# `graph_dup_flags` (harness.GraphTrainStep.duplicate_inputs() reads them after a replay).
+check_duplicates_default = True
+graph_dup_flags = []
+
+
 def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=False,
-                   check_duplicates=False, n_rows=None):
+                   check_duplicates=None, n_rows=None):
     """Builds pairs + neighbour tables on the GPU.
 
     Eager path (n_rows None): one host readback (n_out) for a regular conv, none for a submanifold
@@ -97,7 +106,10 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     n_out_dev = None
     from .functional import hints
     n_hint = hints.get(n_rows) if static else 0  # expected live rows: picks the builder, never the result
-    dup = torch.empty((1,), dtype=torch.int32, device=dev)
+    if check_duplicates is None:
+        check_duplicates = check_duplicates_default
+    meta = torch.empty((2,), dtype=torch.int32, device=dev)  # [n_out, duplicate flag]: ONE readback on the eager path
+    dup = meta[1:2]
     nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
 
     def build(subm_flag, out_indices, out_cap, n_out_t, nbr_out):
@@ -119,20 +131,27 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
             cells = batch_size * int(np.prod([max(o, 0) for o in out_shape]))
             cap = max(1, min(N * K, cells))
             outbuf = torch.empty((cap, nd + 1), dtype=torch.int32, device=dev)
-            n_out_t = torch.empty((1,), dtype=torch.int32, device=dev)
+            n_out_t = meta[0:1]
             # nbr_out is sized at the bound: its live rows are known only on the device
             nbr_cap = torch.empty((cap, K), dtype=torch.int32, device=dev)
             _lib.check(build(0, outbuf, cap, n_out_t, nbr_cap))
             if static:
                 n_out, outids, n_out_dev, nbr_out = cap, outbuf, n_out_t, nbr_cap
             else:
-                n_out = int(n_out_t.item())  # the one readback per rulebook (output tensor shapes need it)
+                n_out, dup_host = meta.tolist()  # the one readback per rulebook (output tensor shapes need it)
                 outids, nbr_out = outbuf[:n_out], nbr_cap[:n_out]
-    if check_duplicates and not static and int(dup.item()) != 0:
-        raise RuntimeError("duplicate (batch, x, y) coordinates in the input: not supported by the "
-                           "output-stationary kernels")
+                if check_duplicates and dup_host != 0:
+                    raise RuntimeError(_DUP_MESSAGE)
+    if static:
+        graph_dup_flags.append(dup)
+    elif subm and check_duplicates and N > 0 and int(dup.item()) != 0:
+        raise RuntimeError(_DUP_MESSAGE)
     return Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup,
                     n_in_dev, n_out_dev)
+
+
+_DUP_MESSAGE = ("duplicate (batch, x, y) coordinates in the input: upstream spconv would sum their contributions, the "
+                "output-stationary kernels keep one -- de-duplicate the hits (or sum their features) before the batcher")
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
