@@ -12,6 +12,12 @@ timed step, barrier + synchronize on both sides of the timed loop, max over rank
 batch resident in HBM; `e2e` starts from pinned host buffers (H2D inside the timed region) and ends
 with the loss read back to the host.
 
+Besides the contract keys the line carries: `roofline` (dominant conv launch of the headline workload, timed
+alone, against the BURST tensor peak / the copy bandwidth), `large` (the throughput-bound configuration C5 =
+1024 full-grid events per GPU: ms_per_step, value, e2e, its own roofline and per-kernel fractions),
+`sustained` (>= 2000 replays), `rotating` (8 distinct batches with different row counts through the one
+captured graph), `cpu_baseline`, `clocks`, `gpu_launches`.
+
 --impl reference times the reference's CPU path (restated spconv-1.2.1 CPU algorithm: oracle/) on the
 host cores, same model / batch / metric.
 """
@@ -60,7 +66,20 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--large-batch", type=int, default=1024,
+                    help="also time the throughput-bound configuration (C5, this many full-grid events per GPU) and "
+                         "report it under `large`; 0 = skip")
+    ap.add_argument("--sustained", type=int, default=2000, help="replays of the `sustained` figure; 0 = skip")
+    ap.add_argument("--rotate", type=int, default=8, help="distinct batches of the `rotating` figure; <= 1 = skip")
     return ap.parse_args()
+
+
+def config_of(args, world, rows):
+    """`config` names the WORKLOAD only and is identical in both arms (ours / reference); how each arm executes it
+    is under `implementation` / `cpu_baseline`."""
+    return {"workload": WORKLOADS[args.workload][0], "events_per_gpu": args.batch,
+            "global_events_per_step": world * args.batch, "rows_per_gpu": int(rows),
+            "l2": "GPU arm: flushed with a 256 MB write before every timed step"}
 
 
 def make_batch(args, rank):
@@ -213,12 +232,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][0], "events_per_step": args.batch,
-                   "rows": int(batch["coords"].shape[0])},
+        "config": config_of(args, int(os.environ.get("WORLD_SIZE", "1")), batch["coords"].shape[0]),
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d full training steps of %d events (restated spconv-1.2.1 CPU algorithm: C hash "
-                                   "rulebook + per-offset gather/torch.mm/scatter-add, torch-CPU BN/ReLU/Linear/SGD); "
-                                   "thread count = fastest of {1,4,16,64,all} on this host (%d cores)"
+                         "sample": "%d full training steps of ONE rank's %d events on one process (restated spconv-1.2.1 "
+                                   "CPU algorithm: C hash rulebook + per-offset gather/torch.mm/scatter-add, torch-CPU "
+                                   "BN/ReLU/Linear/SGD); thread count = fastest of {1,4,16,64,all} on this host (%d cores)"
                                    % (len(times), args.batch, os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -326,9 +344,152 @@ def conv_breakdown(model, idx, feats, batch_size, flush, reps=10):
     return rows, e
 
 
+def roofline_of(row, pk, ms_per_step, traffic_key, note=None):
+    """roofline object for ONE isolated kernel launch (CUDA events, L2 flushed): the denominator is the BURST
+    tensor peak (a kernel timed alone), `frac_sustained` rides along; HBM-bound launches use the copy bandwidth."""
+    ai = row["flops"] / row["bytes"]
+    ridge = pk["tflops_burst"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    tf, gb = row["flops"] / row["s"] / 1e12, row["bytes"] / row["s"] / 1e9
+    if ai >= ridge:
+        roof = {"bound": "tensor", "achieved": tf, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
+                "frac": tf / pk["tflops_burst"], "frac_sustained": tf / pk["tflops_sustained"]}
+    else:
+        roof = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / pk["hbm_gbs"]}
+    # DRAM bytes of the same launch from the committed `ncu --set full` capture (profiles/r*_traffic.json, made by
+    # scripts/ncu_traffic.py); null if that capture does not exist
+    roof["traffic"] = None
+    roof["algorithmic_bytes"] = row["bytes"]
+    roof["algorithmic_flops"] = row["flops"]
+    for fname in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", fname)))
+            parts = row["name"].split()
+            ent = tr[traffic_key][parts[0] + " " + parts[-1]]
+            roof["traffic"] = ent["dram_bytes"]
+            roof["traffic_source"] = "profiles/%s (ncu --set full, %s)" % (fname, ent["kernel"])
+            break
+        except Exception:
+            pass
+    roof["kernel"] = row["name"] + " (" + row["kernel"] + ")"
+    roof["kernel_ms"] = row["s"] * 1e3
+    roof["share_of_step"] = row["s"] * 1e3 / ms_per_step
+    roof["peak_source"] = pk["source"]
+    roof["tensor_tflops"], roof["hbm_gbs"] = tf, gb
+    roof["timing"] = "isolated launch, CUDA events on the launching stream, L2 flushed, mean of 10"
+    if note:
+        roof["note"] = note
+    return roof
+
+
+class GpuWorkload:
+    """One (workload, events per GPU) configuration on this rank: model, captured step, host + device batches."""
+
+    def __init__(self, args, workload, B, rank, world, dev, n_batches=1):
+        from waveformml_b200 import harness, stacks
+        from waveformml_b200.synth import make_events
+        self.args, self.workload, self.B, self.rank, self.world, self.dev = args, workload, B, rank, world, dev
+        full = WORKLOADS[workload][1]
+        torch.manual_seed(0)
+        self.model = stacks.PSDClassifier().to(dev).train()
+        # batch 0 is THE batch of the headline numbers (seed 1234 + rank); the others only feed `rotating`
+        self.batches = [make_events(B, n_samples=150, seed=1234 + rank + 1000 * i, full_grid=full) for i in range(n_batches)]
+        self.batch = self.batches[0]
+        rows_per_event = 154 if full else 10  # multiplicity is clipped to 10 hits/event
+        self.capacity = B * rows_per_event
+        if args.mode == "graph":
+            self.step = harness.GraphTrainStep(self.model, "psd", B, self.capacity, 300)
+        else:
+            self.step = harness.TrainStep(self.model, "psd")
+        self.host = [tuple(torch.from_numpy(b[k]).pin_memory() for k in ("coords", "wave", "labels")) for b in self.batches]
+        self.devb = [tuple(t.to(dev) for t in h) for h in self.host]
+        self.rows = int(self.batch["coords"].shape[0])
+
+    def capture(self):
+        from waveformml_b200 import harness
+        if self.args.mode != "graph":
+            return
+        self.step.load(*self.devb[0])
+        try:
+            self.step.capture()
+        except Exception as exc:  # e.g. a collective that cannot be captured: keep the update outside the graph
+            if self.world == 1:
+                raise
+            sys.stderr.write("full-step capture failed (%s); capturing forward+backward only\n" % exc)
+            self.step = harness.GraphTrainStep(self.model, "psd", self.B, self.capacity, 300, capture_update=False)
+            self.step.load(*self.devb[0])
+            self.step.capture()
+
+    # one step with the batch already resident in HBM
+    def step_resident(self, i=0):
+        from waveformml_b200 import batcher
+        c, w, y = self.devb[i % len(self.devb)]
+        if self.args.mode == "graph":
+            self.step.load(c, w, y)  # one launch: device-to-device into the graph's static buffers
+            return self.step.run()
+        idx, feats = batcher.pack_batch(c, w)
+        return self.step.step(idx, feats, y, self.B)
+
+    def h2d_bytes(self):
+        c, w, y = self.host[0]
+        return int(c.numel() * c.element_size() + w.numel() * w.element_size() + y.numel() * y.element_size())
+
+
+def timed_steps(fn, steps, flush, sync_all):
+    """CUDA events on the launching stream around every step, L2 flushed before each; returns total ms."""
+    evs = []
+    sync_all()
+    for i in range(steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(i)
+        b.record()
+        evs.append((a, b))
+    sync_all()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+
+def time_e2e(wl, steps, flush, sync_all):
+    """End to end through the public API: pinned host buffers -> device -> step -> loss on the host.  Graph mode
+    uses GraphTrainStep.prefetch (double-buffered staging on a copy stream): the timed region of step i holds the
+    H2D copy of batch i+1 (overlapped with the compute of step i), the staging launch, the replay and the D2H read
+    of the loss -- one H2D and one D2H per step, K of each over K steps."""
+    from waveformml_b200 import batcher
+    step, dev = wl.step, wl.dev
+    nb = len(wl.host)
+
+    if wl.args.mode == "graph":
+        step.prefetch(*wl.host[0])
+
+        def one(i):
+            out = step.run()                       # consumes the pending prefetch
+            step.prefetch(*wl.host[(i + 1) % nb])  # next batch: copy stream, overlaps this step
+            return float(out.item())
+    else:
+        def one(i):
+            c, w, y = (t.to(dev, non_blocking=True) for t in wl.host[i % nb])
+            idx, feats = batcher.pack_batch(c, w)
+            return float(step.step(idx, feats, y, wl.B).item())
+
+    for i in range(2):
+        one(i)
+    sync_all()
+    total = 0.0
+    for i in range(steps):
+        flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        one(i)
+        total += time.perf_counter() - t0
+    sync_all()
+    if wl.args.mode == "graph" and step._pending is not None:
+        step._consume_prefetch()  # leave no batch pending
+    return total * 1e3
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from waveformml_b200 import _lib, batcher, harness, spconv, stacks
+    from waveformml_b200 import _lib, batcher, spconv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -341,159 +502,150 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     spconv.set_math_mode(args.math)
-    torch.manual_seed(0)
-    model = stacks.PSDClassifier().to(dev).train()
-    batch = make_batch(args, rank)
-    B = args.batch
-    rows_per_event = 154 if WORKLOADS[args.workload][1] else 10  # multiplicity is clipped to 10 hits/event
-    if args.mode == "graph":
-        step = harness.GraphTrainStep(model, "psd", B, B * rows_per_event, 300)
-    else:
-        step = harness.TrainStep(model, "psd")
-    h_coords = torch.from_numpy(batch["coords"]).pin_memory()
-    h_wave = torch.from_numpy(batch["wave"]).pin_memory()
-    h_labels = torch.from_numpy(batch["labels"]).pin_memory()
-    d_coords, d_wave, d_labels = h_coords.to(dev), h_wave.to(dev), h_labels.to(dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
         flush_buf.zero_()
-
-    if args.mode == "graph":
-        def step_resident():
-            step.load(d_coords, d_wave, d_labels)  # device-to-device into the graph's static buffers
-            return step.run()
-
-        def step_e2e():
-            step.load(h_coords, h_wave, h_labels)  # async H2D from pinned memory
-            return float(step.run().item())
-
-        step.load(d_coords, d_wave, d_labels)
-        try:
-            step.capture()
-        except Exception as exc:  # e.g. a collective that cannot be captured: keep the update outside the graph
-            if world == 1:
-                raise
-            sys.stderr.write("full-step capture failed (%s); capturing forward+backward only\n" % exc)
-            step = harness.GraphTrainStep(model, "psd", B, B * rows_per_event, 300, capture_update=False)
-            step.load(d_coords, d_wave, d_labels)
-            step.capture()
-        n0 = lib.wfsp_kernel_launches()
-    else:
-        def step_resident():
-            idx, feats = batcher.pack_batch(d_coords, d_wave)
-            return step.step(idx, feats, d_labels, B)
-
-        def step_e2e():
-            c = h_coords.to(dev, non_blocking=True)
-            w = h_wave.to(dev, non_blocking=True)
-            y = h_labels.to(dev, non_blocking=True)
-            idx, feats = batcher.pack_batch(c, w)
-            return float(step.step(idx, feats, y, B).item())
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
+    def reduce_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    B = args.batch
+    wl = GpuWorkload(args, args.workload, B, rank, world, dev, n_batches=args.rotate if args.mode == "graph" else 1)
+    wl.capture()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        wl.step_resident()
     sync_all()
 
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.wfsp_kernel_launches()
-    evs = []
-    sync_all()
-    for _ in range(args.steps):
-        flush()
+    dev_ms = timed_steps(lambda i: wl.step_resident(0), args.steps, flush, sync_all)
+    launches = lib.wfsp_kernel_launches() - launches0
+    if args.mode == "graph":  # kernels replayed by the graph + the staging launch of every step
+        launches = (wl.step.launches_per_replay + 1) * args.steps
+    e2e_ms = time_e2e(wl, args.steps, flush, sync_all)
+
+    # sustained: many more steps than the driver's K (the K-step region is a few ms and noise-prone); same
+    # per-step event timing with the L2 flush, plus the back-to-back rate without flushes
+    extra = {}
+    if args.sustained > 0:
+        sus_ms = timed_steps(lambda i: wl.step_resident(0), args.sustained, flush, sync_all)
+        sync_all()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step_resident()
+        for _ in range(args.sustained):
+            wl.step_resident(0)
         b.record()
-        evs.append((a, b))
-    sync_all()
-    launches = lib.wfsp_kernel_launches() - launches0
-    if args.mode == "graph":  # kernels replayed by the graph: count what one captured step enqueued
-        launches = step.launches_per_replay * args.steps
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-
-    # end to end: pinned host buffers -> device -> step -> loss on the host
-    for _ in range(2):
-        step_e2e()
-    sync_all()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step_e2e()
-        e2e_s += time.perf_counter() - t0
-    sync_all()
+        sync_all()
+        bb_ms = a.elapsed_time(b)
+        sus_ms, bb_ms = reduce_max([sus_ms, bb_ms])
+        extra["sustained"] = {"replays": args.sustained, "ms_per_step": sus_ms / args.sustained,
+                              "value": world * B / (sus_ms / args.sustained * 1e-3),
+                              "ms_per_step_back_to_back_no_flush": bb_ms / args.sustained,
+                              "value_back_to_back_no_flush": world * B / (bb_ms / args.sustained * 1e-3)}
+    # rotating: >= 8 DISTINCT batches (different row counts) through the ONE captured graph whose launch shapes were
+    # recorded from batch 0 -- what a real epoch pays when the hints do not match the batch
+    if args.mode == "graph" and args.rotate > 1:
+        rot_steps = max(args.steps, 4 * args.rotate)
+        for i in range(args.rotate):
+            wl.step_resident(i)
+        rot_ms = timed_steps(lambda i: wl.step_resident(i), rot_steps, flush, sync_all)
+        (rot_ms,) = reduce_max([rot_ms])
+        rws = [int(b["coords"].shape[0]) for b in wl.batches]
+        extra["rotating"] = {"batches": args.rotate, "steps": rot_steps, "rows_min": min(rws), "rows_max": max(rws),
+                             "hint_rows": rws[0], "ms_per_step": rot_ms / rot_steps,
+                             "value": world * B / (rot_ms / rot_steps * 1e-3)}
     clocks = sampler.stop()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = reduce_max([dev_ms, e2e_ms])
     ms_per_step = dev_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
 
     line = {
         "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.math == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][0], "events_per_gpu": B, "global_events_per_step": world * B,
-                   "rows_per_gpu": int(d_coords.shape[0]), "parallelism": "dp%d (events sharded by rank, NCCL "
-                   "all-reduce of the flat 4.2 MB gradient)" % world, "l2": "flushed with a 256 MB write before every timed step",
-                   "math": "bf16 operands / fp32 accumulate (tcgen05)" if args.math == "bf16" else "fp32 CUDA cores",
-                   "execution": ("whole step replayed from one CUDA graph, row counts on the device, no host readback"
-                                 if args.mode == "graph" else "eager, exact shapes, one readback per rulebook")},
-        "e2e": {"value": e2e_value, "unit": "events/s",
-                "h2d_bytes_per_step": int(h_coords.numel() * 4 + h_wave.numel() * 2 + h_labels.numel() * 8),
-                "d2h_bytes_per_step": 4},
+        "config": config_of(args, world, wl.rows),
+        "implementation": {
+            "parallelism": "dp%d (events sharded by rank, rank-local rulebooks and BatchNorm, NCCL all-reduce of the "
+                           "flat 4.2 MB gradient inside the captured step)" % world,
+            "math": "bf16 operands / fp32 accumulate (tcgen05)" if args.math == "bf16" else "fp32 CUDA cores",
+            "execution": ("whole step replayed from one CUDA graph, row counts on the device, no host readback"
+                          if args.mode == "graph" else "eager, exact shapes, one readback per rulebook"),
+            "e2e": "double-buffered pinned-host -> device staging on a copy stream (GraphTrainStep.prefetch), loss "
+                   "read back every step"},
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    line.update(extra)
 
+    pk = peaks()
     if rank == 0 and not args.no_breakdown:
-        pk = peaks()
-        idx, feats = batcher.pack_batch(d_coords, d_wave)
-        rows, _ = conv_breakdown(model, idx, feats, B, flush)
+        c, w, _ = wl.devb[0]
+        idx, feats = batcher.pack_batch(c, w)
+        rows, _ = conv_breakdown(wl.model, idx, feats, B, flush)
         tot = sum(r["s"] for r in rows)
         top = max(rows, key=lambda r: r["s"])
-        ai = top["flops"] / top["bytes"]
-        ridge = pk["tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)
-        if ai >= ridge:
-            roof = {"bound": "tensor", "achieved": top["flops"] / top["s"] / 1e12, "peak": pk["tflops_sustained"], "unit": "TFLOP/s"}
-        else:
-            roof = {"bound": "hbm", "achieved": top["bytes"] / top["s"] / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        # DRAM bytes of the same launch from the committed `ncu --set full` capture of this command line
-        # (profiles/r1_traffic.json, made by scripts/ncu_traffic.py); null if that capture does not exist
-        roof["traffic"] = None
-        roof["algorithmic_bytes"] = top["bytes"]
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            parts = top["name"].split()
-            ent = tr["%s_%d" % (args.workload, B)][parts[0] + " " + parts[-1]]
-            roof["traffic"] = ent["dram_bytes"]
-            roof["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, %s)" % ent["kernel"]
-        except Exception:
-            pass
-        roof["kernel"] = top["name"] + " (" + top["kernel"] + ")"
-        roof["kernel_ms"] = top["s"] * 1e3
-        roof["share_of_step"] = top["s"] * 1e3 / ms_per_step
-        roof["peak_source"] = pk["source"]
-        roof["tensor_tflops"] = top["flops"] / top["s"] / 1e12
-        roof["hbm_gbs"] = top["bytes"] / top["s"] / 1e9
-        line["roofline"] = roof
+        note = None
+        if args.workload == "C2" and B <= 256:
+            note = ("%d rows: every launch of this configuration is latency-bound (microseconds of ideal work); the "
+                    "throughput-bound configuration is reported under `large`" % wl.rows)
+        line["roofline"] = roofline_of(top, pk, ms_per_step, "%s_%d" % (args.workload, B), note)
         line["conv_kernels"] = [{"name": r["name"], "ms": r["s"] * 1e3, "tflops": r["flops"] / r["s"] / 1e12,
                                  "gbs": r["bytes"] / r["s"] / 1e9} for r in rows]
         line["conv_kernels_share_of_step"] = tot * 1e3 / ms_per_step
 
+    # ---- the throughput-bound configuration (C5: full-grid events, 1024 per GPU): the only one of BASELINE.json's
+    # configs whose kernels can approach a roofline; same step, same timing rules, reported inside the same line
+    if args.large_batch > 0 and not (args.workload == "C5" and B == args.large_batch):
+        lw = GpuWorkload(args, "C5", args.large_batch, rank, world, dev)
+        lw.capture()
+        for _ in range(3):
+            lw.step_resident()
+        l_steps = max(10, min(args.steps, 30))
+        l_ms = timed_steps(lambda i: lw.step_resident(0), l_steps, flush, sync_all)
+        l_e2e = time_e2e(lw, l_steps, flush, sync_all)
+        l_ms, l_e2e = reduce_max([l_ms, l_e2e])
+        lb = args.large_batch
+        large = {"workload": WORKLOADS["C5"][0], "events_per_gpu": lb, "global_events_per_step": world * lb,
+                 "rows_per_gpu": lw.rows, "steps": l_steps, "ms_per_step": l_ms / l_steps,
+                 "value": world * lb / (l_ms / l_steps * 1e-3), "unit": "events/s",
+                 "e2e": {"value": world * lb / (l_e2e / l_steps * 1e-3), "unit": "events/s",
+                         "h2d_bytes_per_step": lw.h2d_bytes(), "d2h_bytes_per_step": 4},
+                 "l2": "inputs and activations exceed L2 (>= 96 MB of waveforms per step); flushed as well"}
+        if rank == 0 and not args.no_breakdown:
+            c, w, _ = lw.devb[0]
+            idx, feats = batcher.pack_batch(c, w)
+            rows, _ = conv_breakdown(lw.model, idx, feats, lb, flush)
+            top = max(rows, key=lambda r: r["s"])
+            large["roofline"] = roofline_of(top, pk, l_ms / l_steps, "C5_%d" % lb)
+            large["conv_kernels"] = [
+                {"name": r["name"], "ms": r["s"] * 1e3, "tflops": r["flops"] / r["s"] / 1e12, "gbs": r["bytes"] / r["s"] / 1e9,
+                 "frac_burst": r["flops"] / r["s"] / 1e12 / pk["tflops_burst"], "frac_hbm": r["bytes"] / r["s"] / 1e9 / pk["hbm_gbs"]}
+                for r in rows]
+            large["conv_kernels_share_of_step"] = sum(r["s"] for r in rows) * 1e3 / (l_ms / l_steps)
+            # ideal step time of this configuration: max of tensor and HBM time
+            fl = sum(r["flops"] for r in rows)
+            by = sum(r["bytes"] for r in rows)
+            ideal_ms = max(fl / (pk["tflops_burst"] * 1e12), by / (pk["hbm_gbs"] * 1e9)) * 1e3
+            large["step_vs_ideal"] = {"conv_flops": fl, "conv_bytes": by, "ideal_ms": ideal_ms,
+                                      "frac": ideal_ms / (l_ms / l_steps)}
+        line["large"] = large
+    wl_cpu_model, wl_cpu_batch = wl.model, wl.batch
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cstep = cpu_step_fn(cpu_reference_model(model), batch, model.n_linear)
+        cstep = cpu_step_fn(cpu_reference_model(wl_cpu_model), wl_cpu_batch, wl_cpu_model.n_linear)
         pick_cpu_threads(cstep)
         times = time_cpu(cstep, args.cpu_seconds)
         cms = float(np.mean(times))

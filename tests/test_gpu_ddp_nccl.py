@@ -1,0 +1,34 @@
+"""Multi-GPU parity on hardware (VERDICT r1 missing #4): after one NCCL step every rank holds
+identical parameters, equal to a single-process run that feeds the shards sequentially and averages the gradients.
+Needs >= 2 GPUs on the box (`gpurun --gpus 2`); on a one-GPU box it is skipped -- the gloo world-size-2 test of the
+host logic is tests/test_ddp_gloo.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2])
+def test_nccl_step_equals_sequential_shards(world):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "ddp_nccl_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(res.stdout[-2000:])
+    sys.stderr.write(res.stderr[-2000:])
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ddp_nccl_parity" in res.stdout

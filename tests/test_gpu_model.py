@@ -36,7 +36,10 @@ def _rel(a, b):
 # (math mode, oracle operand rounding, gradient tolerance (norm-wise), loss tolerance (relative))
 MODES = [("fp32", None, 1e-3, 1e-4),       # exact-fp32 kernels vs the fp32 oracle
          ("bf16", "bf16", 1e-2, 1e-3),     # tcgen05 kernels vs the oracle with bf16-rounded GEMM operands
-         ("bf16", None, 0.2, 1e-2)]        # tcgen05 kernels vs the fp32 oracle: the stated bf16 tolerance
+         ("bf16", None, 0.2, 1e-2)]        # tcgen05 kernels vs the fp32 oracle: a sanity cap only -- the bound that
+                                           # is JUSTIFIED BY DATA is in tests/test_gpu_large.py
+                                           # (test_bf16_vs_fp32_gap_is_the_operand_rounding: the oracle's own
+                                           # gradients move by the same ~8 % when its operands are rounded to bf16)
 MODE_IDS = ["fp32", "bf16-vs-emulated", "bf16-vs-fp32"]
 
 

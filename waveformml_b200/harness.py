@@ -209,6 +209,7 @@ class GraphTrainStep(TrainStep):
         self.capture_update = capture_update
         self.graph = None
         self.loss_out = None
+        self._stage, self._pending = None, None
 
     def load(self, coords, wave, target):
         """coords int32 [n,3] (x, y, event), wave [n,C], target [B] (psd) or [n] (z); host (pinned for an
@@ -221,18 +222,59 @@ class GraphTrainStep(TrainStep):
                 and wave.dtype == self.wave.dtype and target.dtype == self.target.dtype and coords.is_contiguous()
                 and wave.is_contiguous() and target.is_contiguous() and target.numel() <= self.target.numel()):
             # batch already in HBM: one launch stages all three buffers and the live row count
-            lib = _lib.load()
-            with torch.cuda.device(dev):
-                _lib.check(lib.wfsp_stage_inputs(
-                    _lib.ptr(self.coords), _lib.ptr(coords), coords.numel() * coords.element_size(),
-                    _lib.ptr(self.wave), _lib.ptr(wave), wave.numel() * wave.element_size(),
-                    _lib.ptr(self.target), _lib.ptr(target), target.numel() * target.element_size(),
-                    _lib.ptr(self.n_rows), n, _lib.stream()))
+            self._stage_device(coords, wave, target, n)
             return
         self.coords[:n].copy_(coords, non_blocking=True)
         self.wave[:n].copy_(wave, non_blocking=True)
         self.target[:target.shape[0]].copy_(target, non_blocking=True)
         self.n_rows.fill_(n)  # the value travels as a kernel argument: no host buffer to race with
+
+    def _stage_device(self, coords, wave, target, n):
+        """One launch copies a device-resident batch into the graph's static buffers and sets the live row count."""
+        lib = _lib.load()
+        with torch.cuda.device(self.coords.device):
+            _lib.check(lib.wfsp_stage_inputs(
+                _lib.ptr(self.coords), _lib.ptr(coords), n * 3 * coords.element_size(),
+                _lib.ptr(self.wave), _lib.ptr(wave), n * wave.shape[1] * wave.element_size(),
+                _lib.ptr(self.target), _lib.ptr(target), target.numel() * target.element_size(),
+                _lib.ptr(self.n_rows), n, _lib.stream()))
+
+    def prefetch(self, coords, wave, target):
+        """Double-buffered input staging (the DataLoader `pin_memory` + `non_blocking` pattern): the pinned host
+        batch is copied to one of two device staging sets on a COPY stream, so the transfer of batch i+1 overlaps the
+        compute of batch i; the next run() waits for the copy and moves it into the graph's buffers with one launch.
+        At most one batch is pending; a staging set is reused only after the step that consumed it has read it."""
+        n = coords.shape[0]
+        if n > self.row_capacity:
+            raise ValueError("batch has %d rows, graph capacity is %d" % (n, self.row_capacity))
+        dev = self.coords.device
+        if self._stage is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [{"coords": torch.empty_like(self.coords), "wave": torch.empty_like(self.wave),
+                            "target": torch.empty_like(self.target), "ready": None, "free": None} for _ in range(2)]
+            self._stage_i = 0
+        slot = self._stage[self._stage_i]
+        self._stage_i ^= 1
+        cs = self._copy_stream
+        if slot["free"] is not None:
+            cs.wait_event(slot["free"])
+        nt = target.shape[0]
+        with torch.cuda.stream(cs):
+            slot["coords"][:n].copy_(coords, non_blocking=True)
+            slot["wave"][:n].copy_(wave, non_blocking=True)
+            slot["target"][:nt].copy_(target, non_blocking=True)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(cs)
+        slot["n"], slot["nt"] = n, nt
+        self._pending = slot
+
+    def _consume_prefetch(self):
+        slot, self._pending = self._pending, None
+        main = torch.cuda.current_stream()
+        main.wait_event(slot["ready"])
+        self._stage_device(slot["coords"], slot["wave"], slot["target"][:slot["nt"]], slot["n"])
+        slot["free"] = torch.cuda.Event()
+        slot["free"].record(main)
 
     def _body(self):
         # bf16 math + fused stack: the batcher writes the tensor-core operand format directly
@@ -305,6 +347,8 @@ class GraphTrainStep(TrainStep):
         return bool(flags) and bool(torch.stack([f.reshape(()) for f in flags]).ne(0).any().item())
 
     def run(self):
+        if self._pending is not None:
+            self._consume_prefetch()
         if self.graph is None:
             self.capture()
         self.graph.replay()
