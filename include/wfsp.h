@@ -51,7 +51,7 @@ enum wfsp_math {
   WFSP_MATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (kind::f16)  */
 };
 
-#define WFSP_VERSION 200
+#define WFSP_VERSION 201
 #define WFSP_MAX_KVOL 1024
 
 int wfsp_version(void);
@@ -61,6 +61,11 @@ int wfsp_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host)
 /* tuning / test knobs; "rulebook_force_hash" = 1 forces the open-addressing coordinate hash even
  * when the dense grid table would be used */
 int wfsp_set_option(const char* name, int value);
+/* Debugging aid: while device_buffer (>= 128 + 2048 uint64) is set, tile (0, 0) of every wfsp_conv_apply_bf16[_ex]
+ * launch stamps clock64() at its phase boundaries (slot 15 of each cluster rank: %globaltimer at entry), and every live
+ * CTA of the first 1024 writes %globaltimer at entry / exit to slots 128 + 2 * linear block id (+1).  NULL switches it
+ * off (the default; costs one predicate per phase). */
+int wfsp_debug_trace(unsigned long long* device_buffer);
 /* number of CUDA kernels this library has launched in the calling process (monotonic) */
 unsigned long long wfsp_kernel_launches(void);
 /* hex digest of the sources (csrc/ + this header) the library was compiled from; the Python loader compares it
@@ -82,6 +87,8 @@ const char* wfsp_source_hash(void);
  *   item_offset  int64 [n_items]   event offset added to each item (0 for item 0)
  *   indices_bxy  int32 [n_rows,3] = (global event, x, y)                       (output)
  *   feats        [n_rows, feats_pitch] of feats_dtype, value = wave * scale    (output)
+ *   Either output may be NULL (with its input): the two halves are independent, so a caller may issue them
+ *   on different streams (the rulebooks only wait for the indices).
  */
 int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int wave_dtype, int64_t n_rows,
                     const int32_t* n_rows_dev, int n_chan, const int64_t* item_rows,
@@ -297,6 +304,37 @@ int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const int32_t* n_s
                          float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint,
                          int c_dst, float* bn_partials, wfsp_stream_t stream);
 
+/* wfsp_conv_apply_bf16 with the optional fused epilogues / launch options of the bf16-resident stack (fused.py);
+ * a zeroed struct (or NULL) is plain wfsp_conv_apply_bf16 without bn_partials.
+ *   bn_partials   as above (forward: statistics of the BatchNorm that FOLLOWS this convolution,
+ *                 src/models/SPConvBlocks.py:505-508).
+ *   bwd_*         dgrad only: the output of this call is the gradient dy arriving at a BatchNorm(+ReLU) whose
+ *                 input was bwd_x [n_dst, c_dst] with saved statistics bwd_mean / bwd_invstd and affine parameters
+ *                 bwd_gamma / bwd_beta (may be NULL).  The epilogue then also writes, per chunk of 32 destination
+ *                 rows, bwd_partials [ceil(n_dst / 32)][2][c_dst] = (sum dy', sum dy' * xhat) with dy' = dy masked
+ *                 by the ReLU -- the two reductions of BatchNorm backward, taken from the tile while it is on
+ *                 chip, so wfsp_bn_relu_bwd_parts needs no reduction pass over (x, dy).  Buffer size:
+ *                 wfsp_bn_partials_bytes(n_dst, c_dst).
+ *   k_split       0 = automatic.  Small launches (a handful of tiles) are bound by the serial walk of each CTA over
+ *                 (kernel offset x 64-channel slice); there a thread-block cluster of up to 8 CTAs splits that
+ *                 loop and the partial accumulators are added through distributed shared memory in rank order
+ *                 (deterministic).  1 = never split; 2 / 4 / 8 = force (tests). */
+typedef struct wfsp_conv_epilogue {
+  float* bn_partials;
+  const float* bwd_x;
+  const float* bwd_mean;
+  const float* bwd_invstd;
+  const float* bwd_gamma;
+  const float* bwd_beta;
+  float* bwd_partials;
+  int bwd_relu;
+  int k_split;
+} wfsp_conv_epilogue;
+int wfsp_conv_apply_bf16_ex(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
+                            const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,
+                            float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                            int c_dst, const wfsp_conv_epilogue* epilogue, wfsp_stream_t stream);
+
 /* wfsp_conv_wgrad on bf16 rows (a = layer input, b = gradient of the layer output) */
 int wfsp_conv_wgrad_bf16(const void* a_bf16, int64_t n_a, const int32_t* n_a_dev, int c_a,
                          const void* b_bf16, int64_t n_b, const int32_t* n_b_dev, int c_b,
@@ -331,6 +369,15 @@ int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const in
                        int64_t n_rows_hint, int c, const float* gamma, const float* beta, const float* save_mean,
                        const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
                        float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+
+/* BatchNorm1d(+ReLU) backward whose two reductions were already taken by the dgrad epilogue
+ * (wfsp_conv_epilogue.bwd_partials, chunks of WFSP_BN_CHUNK_ROWS rows): fold the partials (fixed order, double
+ * precision) into d_gamma / d_beta and stream dx / dx_bf16 -- one pass over (x, dy) instead of two. */
+int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
+                           int64_t n_rows_hint, int c, const float* gamma, const float* beta,
+                           const float* save_mean, const float* save_invstd, int relu,
+                           const float* bwd_partials, float* dx, void* dx_bf16, float* d_gamma,
+                           float* d_beta, wfsp_stream_t stream);
 
 /* a convolution followed by nn.ReLU (or nothing) without BatchNorm: y = relu?(x), and its backward
  * dx = dy * (x > 0 or no relu), with the same optional outputs */

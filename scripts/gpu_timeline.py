@@ -11,6 +11,11 @@ from waveformml_b200.synth import make_events
 wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 dev = torch.device("cuda", 0)
+from waveformml_b200 import _lib
+for kv in os.environ.get("WFSP_OPTIONS", "").split(","):  # e.g. WFSP_OPTIONS=apply_k_split=4,apply_split_stages=3
+    if kv:
+        k, v = kv.split("=")
+        _lib.check(_lib.load().wfsp_set_option(k.encode(), int(v)))
 torch.manual_seed(0)
 model = stacks.PSDClassifier().to(dev).train()
 batch = make_events(B, n_samples=150, seed=1234, full_grid=(wl == "C5"))

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, n), "libwfsp.so does not export %s" % n
         assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.wfsp_version() == 200
+    assert lib.wfsp_version() == _lib.EXPECTED_VERSION
 
 
 def test_host_only_helpers():

@@ -18,6 +18,7 @@ _intp = _c.POINTER(_c.c_int)
 # name -> (restype, argtypes); must list every symbol include/wfsp.h declares
 SIGNATURES = {
     "wfsp_version": (_int, []),
+    "wfsp_debug_trace": (_int, [_vp]),
     "wfsp_last_error": (_c.c_char_p, []),
     "wfsp_device_info": (_int, [_intp, _intp, _intp]),
     "wfsp_set_option": (_int, [_c.c_char_p, _int]),
@@ -54,6 +55,9 @@ SIGNATURES = {
     "wfsp_prep_weights": (_int, [_vp, _int, _vp]),
     "wfsp_cast_rows_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp]),
     "wfsp_conv_apply_bf16": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "wfsp_conv_apply_bf16_ex": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "wfsp_bn_relu_bwd_parts": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                                      _vp]),
     "wfsp_bn_partials_bytes": (_sz, [_i64, _int]),
     "wfsp_bn_relu_fwd_stats": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp,
                                       _vp, _vp, _vp]),
@@ -81,6 +85,28 @@ class PrepJob(ctypes.Structure):
     _fields_ = [("weight", ctypes.c_void_p), ("out", ctypes.c_void_p), ("kvol", ctypes.c_int), ("c_red", ctypes.c_int),
                 ("c_dst", ctypes.c_int), ("transpose_w", ctypes.c_int)]
 
+
+class ConvEpilogue(ctypes.Structure):
+    """struct wfsp_conv_epilogue (include/wfsp.h)"""
+    _fields_ = [("bn_partials", ctypes.c_void_p), ("bwd_x", ctypes.c_void_p), ("bwd_mean", ctypes.c_void_p),
+                ("bwd_invstd", ctypes.c_void_p), ("bwd_gamma", ctypes.c_void_p), ("bwd_beta", ctypes.c_void_p),
+                ("bwd_partials", ctypes.c_void_p), ("bwd_relu", ctypes.c_int), ("k_split", ctypes.c_int)]
+
+
+def conv_epilogue(bn_partials=None, bwd=None, k_split=0):
+    """bwd = (x, mean, invstd, gamma, beta, relu, partials) tensors of the BatchNorm whose dy this dgrad produces."""
+    def a(t):
+        return None if t is None else t.data_ptr()
+    e = ConvEpilogue()
+    e.bn_partials = a(bn_partials)
+    if bwd is not None:
+        x, mean, invstd, gamma, beta, relu, partials = bwd
+        e.bwd_x, e.bwd_mean, e.bwd_invstd, e.bwd_gamma, e.bwd_beta = a(x), a(mean), a(invstd), a(gamma), a(beta)
+        e.bwd_relu, e.bwd_partials = int(relu), a(partials)
+    e.k_split = int(k_split)
+    return e
+
+
 _lib = None
 
 
@@ -88,7 +114,7 @@ class WfspError(RuntimeError):
     pass
 
 
-EXPECTED_VERSION = 200  # include/wfsp.h WFSP_VERSION: bumped with every change of the C ABI
+EXPECTED_VERSION = 201  # include/wfsp.h WFSP_VERSION: bumped with every change of the C ABI
 
 
 def load():

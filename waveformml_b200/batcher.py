@@ -20,7 +20,7 @@ def item_tables(item_rows, item_events, device):
 
 
 def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RANGE_INV, out_dtype=torch.float32,
-               n_rows=None, tables=None):
+               n_rows=None, tables=None, feats_stream=None):
     """coords_xye int32 [N,3] = (x, y, event id local to its item) and wave int16|f32 [N,C], both on
     the GPU, items concatenated.  item_rows [n_items+1] row offsets and item_events [n_items] events
     per item (host lists / tensors); omitted = a single item.  Returns (indices int32 [N,3] =
@@ -28,7 +28,9 @@ def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RAN
 
     Graph path: n_rows = int32 device scalar with the live row count (the inputs are capacity-sized
     static buffers) and tables = item_tables(...) prepared once, so nothing is copied from the host
-    inside a captured region."""
+    inside a captured region.  feats_stream: run the waveform half on that stream (it must already be ordered after
+    the inputs; the caller joins it before reading `features`) -- the indices, which the rulebooks wait for, are then
+    not queued behind the much larger waveform conversion."""
     lib = _lib.load()
     _lib.require_cuda(coords_xye, wave)
     dev = wave.device
@@ -50,9 +52,18 @@ def pack_batch(coords_xye, wave, item_rows=None, item_events=None, scale=MAX_RAN
     alloc = torch.empty if (pitch == c or c % 4 == 0) else torch.zeros  # the vector kernel zeroes the padding itself
     feats = alloc((n, pitch), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), _lib.ptr(wave), wdt, n, _lib.ptr(n_rows), c,
-                                       _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), _lib.ptr(indices),
-                                       _lib.ptr(feats), odt, pitch, _lib.stream()))
+        if feats_stream is None:
+            _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), _lib.ptr(wave), wdt, n, _lib.ptr(n_rows), c,
+                                           _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), _lib.ptr(indices),
+                                           _lib.ptr(feats), odt, pitch, _lib.stream()))
+        else:
+            _lib.check(lib.wfsp_batch_pack(_lib.ptr(coords_xye), None, wdt, n, _lib.ptr(n_rows), c,
+                                           _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), _lib.ptr(indices),
+                                           None, odt, pitch, _lib.stream()))
+            with torch.cuda.stream(feats_stream):
+                _lib.check(lib.wfsp_batch_pack(None, _lib.ptr(wave), wdt, n, _lib.ptr(n_rows), c,
+                                               _lib.ptr(rows_d), _lib.ptr(offs_d), n_items, float(scale), None,
+                                               _lib.ptr(feats), odt, pitch, _lib.stream()))
     return indices, feats
 
 

@@ -34,6 +34,10 @@ int sm_count() {
 
 void set_force_hash(int v);
 void set_force_rblk(int v);
+void set_auto_ksplit(int v);
+void set_split_stages(int v);
+void set_split_wide(int v);
+void set_trace(unsigned long long* p);
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
@@ -62,8 +66,8 @@ int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st);
 int cast_rows_bf16(const float* src, int64_t n, const int32_t* n_dev, int c, void* dst16, cudaStream_t st);
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
                            const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, float* stats,
-                           cudaStream_t st);
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                           const wfsp_conv_epilogue* ep, cudaStream_t st);
 int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const __nv_bfloat16* b16, int64_t n_b, int c_b,
                            const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol,
                            int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
@@ -97,7 +101,15 @@ extern "C" int wfsp_device_info(int* sm, int* major, int* minor) {
 extern "C" int wfsp_set_option(const char* name, int value) {
   if (strcmp(name, "rulebook_force_hash") == 0) { set_force_hash(value); return WFSP_OK; }
   if (strcmp(name, "apply_row_blocks") == 0) { set_force_rblk(value); return WFSP_OK; }
+  if (strcmp(name, "apply_k_split") == 0) { set_auto_ksplit(value); return WFSP_OK; }
+  if (strcmp(name, "apply_split_stages") == 0) { set_split_stages(value); return WFSP_OK; }
+  if (strcmp(name, "apply_split_wide") == 0) { set_split_wide(value); return WFSP_OK; }
   return set_error(WFSP_EINVAL, "unknown option %s", name);
+}
+
+extern "C" int wfsp_debug_trace(unsigned long long* device_buffer) {
+  set_trace(device_buffer);
+  return WFSP_OK;
 }
 
 extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math) {
@@ -164,9 +176,23 @@ extern "C" int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const i
   WFSP_REQUIRE(n_src >= 0 && n_dst >= 0 && c_red >= 1 && c_dst >= 1, "bad conv sizes");
   WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
   WFSP_REQUIRE(nbr != nullptr || (kvol == 1 && n_src == n_dst), "identity map needs kvol == 1 and n_src == n_dst");
+  wfsp_conv_epilogue ep{};
+  ep.bn_partials = bn_partials;
   return conv_apply_umma_launch(static_cast<const __nv_bfloat16*>(src_bf16), n_src, c_red,
                                 static_cast<const __nv_bfloat16*>(weight_prepared), bias, nbr, kvol, dst, n_dst, c_dst,
-                                n_src_dev, n_dst_dev, n_dst_hint, bn_partials, as_stream(stream));
+                                n_src_dev, n_dst_dev, n_dst_hint, &ep, as_stream(stream));
+}
+
+extern "C" int wfsp_conv_apply_bf16_ex(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
+                                       const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,
+                                       float* dst, int64_t n_dst, const int32_t* n_dst_dev, int64_t n_dst_hint, int c_dst,
+                                       const wfsp_conv_epilogue* epilogue, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_src >= 0 && n_dst >= 0 && c_red >= 1 && c_dst >= 1, "bad conv sizes");
+  WFSP_REQUIRE(kvol >= 1 && kvol <= WFSP_MAX_KVOL, "kvol %d out of range", kvol);
+  WFSP_REQUIRE(nbr != nullptr || (kvol == 1 && n_src == n_dst), "identity map needs kvol == 1 and n_src == n_dst");
+  return conv_apply_umma_launch(static_cast<const __nv_bfloat16*>(src_bf16), n_src, c_red,
+                                static_cast<const __nv_bfloat16*>(weight_prepared), bias, nbr, kvol, dst, n_dst, c_dst,
+                                n_src_dev, n_dst_dev, n_dst_hint, epilogue, as_stream(stream));
 }
 
 extern "C" int wfsp_conv_wgrad_bf16(const void* a_bf16, int64_t n_a, const int32_t* n_a_dev, int c_a, const void* b_bf16,

@@ -356,26 +356,55 @@ __global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* __restrict__ part, int64_t n_cap,
+// grid (channel groups, S): block (g, seg) folds segment seg of the partial list (chunks of `chunk_rows` rows); with
+// S > 1 the last block of a channel group to finish (ticket) adds the S segment results in segment order -- the
+// same scheme as bn_finalize_stats, so the sums do not depend on scheduling.
+__global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* __restrict__ part, int chunk_rows, int64_t n_cap,
                                                        const int32_t* __restrict__ n_dev, int c,
-                                                       float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+                                                       float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                                                       double* __restrict__ inter, unsigned* __restrict__ tickets) {
   __shared__ double r0[kFinLanes][kCh], r1[kFinLanes][kCh];
+  __shared__ unsigned s_ticket;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
+  const int S = gridDim.y, seg = blockIdx.y;
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t nblk = n > 0 ? (n + kRowsBwd - 1) / kRowsBwd : 0;
+  const int64_t nblk = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0;
+  const int64_t per = (nblk + S - 1) / S;
+  const int64_t lo = seg * per, hi = lo + per < nblk ? lo + per : nblk;
   double s0 = 0.0, s1 = 0.0;
   if (ch < c) {
 #pragma unroll 4
-    for (int64_t b = ty; b < nblk; b += kFinLanes) {
+    for (int64_t b = lo + ty; b < hi; b += kFinLanes) {
       s0 += part[(b * 2 + 0) * c + ch];
       s1 += part[(b * 2 + 1) * c + ch];
     }
   }
   r0[ty][tx] = s0; r1[ty][tx] = s1;
   __syncthreads();
+  if (ty == 0)
+    for (int l = 1; l < kFinLanes; ++l) { s0 += r0[l][tx]; s1 += r1[l][tx]; }
+  if (S > 1) {
+    if (ty == 0 && ch < c) {
+      inter[(int64_t(seg) * 2 + 0) * c + ch] = s0;
+      inter[(int64_t(seg) * 2 + 1) * c + ch] = s1;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tx == 0 && ty == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+    __syncthreads();
+    if (s_ticket != unsigned(S - 1)) return;
+    __threadfence();
+    if (tx == 0 && ty == 0) tickets[blockIdx.x] = 0u;
+    if (ty == 0 && ch < c) {
+      s0 = 0.0; s1 = 0.0;
+      for (int sg = 0; sg < S; ++sg) {
+        s0 += __ldcg(&inter[(int64_t(sg) * 2 + 0) * c + ch]);
+        s1 += __ldcg(&inter[(int64_t(sg) * 2 + 1) * c + ch]);
+      }
+    }
+  }
   if (ty != 0 || ch >= c) return;
-  for (int l = 1; l < kFinLanes; ++l) { s0 += r0[l][tx]; s1 += r1[l][tx]; }
   d_beta[ch] = float(s0);
   d_gamma[ch] = float(s1);
 }
@@ -388,11 +417,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                                     const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                                                     int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
-                                                    int rows_per_cta) {
+                                                    int rows_per_cta, const float* __restrict__ part, int chunk_rows,
+                                                    float* __restrict__ d_gamma_out, float* __restrict__ d_beta_out) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
   uint32_t* dx16w = reinterpret_cast<uint32_t*>(dx16);
+  // fused small path: the (few) per-chunk sums of the dgrad epilogue are folded by every CTA for its own use --
+  // same order everywhere, so all CTAs hold bit-identical sums -- and CTA 0 records d_gamma / d_beta (c <= 512)
+  __shared__ float s_db[512], s_dg[512];
+  if (part) {
+    const int64_t nblk = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0;
+    for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y) {
+      double a = 0.0, q = 0.0;
+      for (int64_t b = 0; b < nblk; ++b) {
+        a += part[(b * 2 + 0) * c + ch];
+        q += part[(b * 2 + 1) * c + ch];
+      }
+      s_db[ch] = float(a); s_dg[ch] = float(q);
+      if (blockIdx.x == 0) { d_beta_out[ch] = float(a); d_gamma_out[ch] = float(q); }
+    }
+    __syncthreads();
+    d_beta = s_db; d_gamma = s_dg;
+  }
   for (int pc = threadIdx.x; pc < ppr; pc += blockDim.x) {
     const int ch = pc << 1;
     float m[2] = {0.f, 0.f}, is[2] = {1.f, 1.f}, g[2] = {1.f, 1.f}, b[2] = {0.f, 0.f}, db[2] = {0.f, 0.f}, dg[2] = {0.f, 0.f};
@@ -819,12 +866,55 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
     bn_bwd_partial<true><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   else
     bn_bwd_partial<false><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
-  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, n_rows, n_rows_dev, c, d_gamma, d_beta);
+  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, kRowsBwd, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr, nullptr);
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
-    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows));
+    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   else
-    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows));
+    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   count_launches(3);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
+                                      int64_t n_rows_hint, int c, const float* gamma, const float* beta,
+                                      const float* save_mean, const float* save_invstd, int relu,
+                                      const float* bwd_partials, float* dx, void* dx_bf16, float* d_gamma, float* d_beta,
+                                      wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1 && bwd_partials != nullptr && d_gamma != nullptr && d_beta != nullptr,
+               "bad batch-norm arguments");
+  WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "batch norm backward needs at least one output");
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* dx16 = static_cast<__nv_bfloat16*>(dx_bf16);
+  if (n_rows == 0) {
+    WFSP_CHECK_CUDA(cudaMemsetAsync(d_gamma, 0, size_t(c) * 4, st));
+    WFSP_CHECK_CUDA(cudaMemsetAsync(d_beta, 0, size_t(c) * 4, st));
+    return WFSP_OK;
+  }
+  const int64_t live = (n_rows_dev != nullptr && n_rows_hint > 0 && n_rows_hint < n_rows) ? n_rows_hint : n_rows;
+  const bool v2 = vec2_ok(c, x, dy) && vec2_ok(c, dx, dx);
+  if (live <= kFoldRows && c <= 512) {  // ONE launch: every CTA folds the few partials of its channels itself
+    if (v2)
+      bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+    else
+      bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return WFSP_OK;
+  }
+  const int64_t chunks = ceil_div<int64_t>(n_rows, WFSP_BN_CHUNK_ROWS);
+  char* scratch = reinterpret_cast<char*>(const_cast<float*>(bwd_partials)) + align_up(size_t(chunks) * 2 * c * sizeof(float), 256);
+  const int S = fin_segments(chunks);
+  double* inter = reinterpret_cast<double*>(scratch);
+  unsigned* tickets = reinterpret_cast<unsigned*>(scratch + size_t(kFinSegMax) * 2 * c * sizeof(double));
+  if (S > 1) WFSP_CHECK_CUDA(cudaMemsetAsync(tickets, 0, 1024, st));
+  bn_bwd_finalize<<<dim3(unsigned(ceil_div(c, kCh)), unsigned(S)), dim3(kCh, kFinLanes), 0, st>>>(
+      bwd_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, d_gamma, d_beta, inter, tickets);
+  if (v2)
+    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+  else
+    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+  count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
@@ -863,11 +953,11 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
     bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows));
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   else
     bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows));
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

@@ -229,10 +229,90 @@ struct ApplyParams {
   const __nv_bfloat16* wt; int n_pad, kc_pad;
   const float* bias; const int32_t* nbr; int kvol;
   float* dst; int64_t n_dst; int c_dst;
-  int n_tile, stages, rblk, acc_stride, staged;
+  int n_tile, stages, rblk, acc_stride, staged, nbr_bytes;
   const int32_t* n_src_dev; const int32_t* n_dst_dev;
   float* stats;  // optional [ceil(n_dst/32)][2][c_dst]: per 32-row chunk (mean, M2) of every output column
+  // optional (dgrad): this output is the dy of a BatchNorm(+ReLU) whose input was bwd_x -- per 32-row chunk
+  // [chunk][2][c_dst] sums of dy' and dy' * xhat (dy' = dy masked by the ReLU), so BatchNorm backward needs no
+  // reduction pass over (x, dy)
+  const float* bwd_x; const float* bwd_mean; const float* bwd_invstd; const float* bwd_gamma; const float* bwd_beta;
+  float* bwd_part; int bwd_relu;
+  int ksplit;  // CTAs of a thread-block cluster (along z) that split the (offset, channel slice) loop of one tile
+  unsigned long long* trace;  // debugging aid (wfsp_debug_trace): clock64 stamps of tile (0, 0)'s phases, 16 per cluster rank
 };
+#define WFSP_TRACE(slot)                                                                     \
+  do {                                                                                       \
+    if (p.trace != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)                \
+      p.trace[krank * 16 + (slot)] = (unsigned long long)clock64();                          \
+  } while (0)
+
+// ---- thread-block cluster helpers (split reduction of small launches)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_u32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// What happens to one finished 32-row x (16|32)-column block of the output, sitting in the warp's shared-memory
+// tile: optional BatchNorm statistics of the chunk, optional BatchNorm-backward partial sums, then the coalesced
+// store of the rows (+bias).
+__device__ __forceinline__ void finish_block(const ApplyParams& p, const float* tile, int64_t grow0 /* first row */,
+                                             int rmax, int cc /* first column */, int ncols, int vec, int lane) {
+  if (rmax <= 0) return;
+  if (p.stats != nullptr && lane < ncols && cc + lane < p.c_dst) {
+    // BatchNorm statistics of this 32-row chunk, straight from the tile (saves the pass that would
+    // re-read the output from HBM): shifted sums -> (mean, M2), merged later by bn_finalize_stats
+    const int ccol = cc + lane;
+    const float bv = p.bias ? __ldg(p.bias + ccol) : 0.f;
+    const float K = tile[lane];
+    float sd = 0.f, sq = 0.f;
+    for (int r = 0; r < rmax; ++r) {
+      const float d = tile[r * kEpiPitch + lane] - K;
+      sd += d;
+      sq += d * d;
+    }
+    const float cnt = float(rmax);
+    float* sp = p.stats + (grow0 >> 5) * 2 * p.c_dst + ccol;
+    sp[0] = K + bv + sd / cnt;
+    sp[p.c_dst] = fmaxf(sq - sd * sd / cnt, 0.f);
+  }
+  if (p.bwd_part != nullptr && lane < ncols && cc + lane < p.c_dst) {
+    const int ccol = cc + lane;
+    const float m = __ldg(p.bwd_mean + ccol), is = __ldg(p.bwd_invstd + ccol);
+    const float g = p.bwd_gamma ? __ldg(p.bwd_gamma + ccol) : 1.f, b = p.bwd_beta ? __ldg(p.bwd_beta + ccol) : 0.f;
+    const float* xp = p.bwd_x + grow0 * p.c_dst + ccol;
+    float s0 = 0.f, s1 = 0.f;
+    for (int r0 = 0; r0 < rmax; r0 += 8) {
+      float xv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xv[u] = (r0 + u < rmax) ? __ldg(xp + int64_t(r0 + u) * p.c_dst) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r0 + u < rmax) {
+          const float xh = (xv[u] - m) * is;
+          float d = tile[(r0 + u) * kEpiPitch + lane];
+          if (p.bwd_relu && xh * g + b <= 0.f) d = 0.f;
+          s0 += d;
+          s1 += d * xh;
+        }
+      }
+    }
+    float* sp = p.bwd_part + (grow0 >> 5) * 2 * p.c_dst + ccol;
+    sp[0] = s0;
+    sp[p.c_dst] = s1;
+  }
+  float* o = p.dst + grow0 * p.c_dst + cc;
+  const float* bias = p.bias ? p.bias + cc : nullptr;
+  if (vec == 4) store_tile_rows<4>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
+  else if (vec == 2) store_tile_rows<2>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
+  else store_tile_rows<1>(tile, o, p.c_dst, rmax, ncols, p.c_dst - cc, bias, lane);
+}
 
 // A CTA owns rblk (1..4) consecutive 128-row blocks of destination rows and one column tile.  Every
 // pipeline stage holds the gathered A slice of each row block plus ONE weight slice shared by all of
@@ -490,6 +570,362 @@ __global__ void __launch_bounds__(kApplyThreads) conv_apply_umma_kernel(const Ap
   if (warp == kMmaWarp) tmem_dealloc(tmem, tmem_cols);
 }
 
+// Small launches: the same tile walk, but the (offset, slice) loop of a tile is split over the CTAs of a thread-block
+// cluster (SPLIT), the grid covers only the EXPECTED live rows and the kernel loops over tiles.  Kept apart from the
+// throughput kernel above: under its 96-register budget any extra live value costs the hot loops there.
+template <int RB, bool SPLIT>
+__global__ void __launch_bounds__(kApplyThreads) conv_apply_split_kernel(const ApplyParams pp) {
+  ApplyParams p = pp;
+  if (p.n_src_dev) p.n_src = *p.n_src_dev;
+  if (p.n_dst_dev) p.n_dst = *p.n_dst_dev;
+  constexpr int kTileRows = kTileM * RB;
+  if (int64_t(blockIdx.x) * kTileRows >= p.n_dst) return;  // nothing live for this CTA (uniform over a cluster: same blockIdx.x)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PipeBarriers bars;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_active[WFSP_MAX_KVOL / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int ks = SPLIT ? p.ksplit : 1, krank = SPLIT ? int(blockIdx.z) : 0;  // cluster (1, 1, ks): rank = blockIdx.z
+  WFSP_TRACE(0);
+  if (p.trace != nullptr && tid == 0) {  // %globaltimer at entry: slot 15 of tile (0, 0)'s ranks, and every CTA's from slot 128
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    if (blockIdx.x == 0 && blockIdx.y == 0) p.trace[krank * 16 + 15] = gt;
+    const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (lin < 1024) p.trace[128 + 2 * lin] = gt;
+  }
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = uint32_t(RB) * kABytes;
+  const uint32_t stage_bytes = a_bytes + uint32_t(p.n_tile) * 128u;
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem + uint32_t(p.stages) * stage_bytes);
+  const uint32_t tmem_cols = tmem_cols_pow2(uint32_t(RB * p.acc_stride));
+  const bool staged = p.nbr != nullptr && p.staged;
+  const int num_kb = p.kc_pad / kSliceK;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&bars.full[0]), free0 = smem_u32(&bars.free_[0]);  // barrier s is 8 s bytes further
+  const bool al16 = (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(p.dst) & 7) == 0;
+  const int vec = ((p.c_dst & 3) == 0 && al16) ? 4 : (((p.c_dst & 1) == 0 && al8) ? 2 : 1);
+  const int ncc = (p.n_tile + 31) / 32;  // 32-column chunks of the tile (the last may be 16 wide)
+  constexpr int kBlockFloats = 32 * kEpiPitch;
+  // split launches: the blocks other CTAs of the cluster push here live behind the neighbour tile (never aliased
+  // with the pipeline stages: a fast peer pushes while this CTA is still in its main loop)
+  float* park = reinterpret_cast<float*>(smem + uint32_t(p.stages) * stage_bytes + uint32_t(p.nbr_bytes));
+
+  if (warp == kMmaWarp) {
+    tmem_alloc(&s_tmem, tmem_cols);
+    tmem_relinquish();
+  }
+
+  // The grid covers the EXPECTED live rows (launch-shape hint); whatever lies beyond is taken by further trips of
+  // this loop, so a wrong hint costs time, never rows.
+  for (int64_t tile_i = blockIdx.x; tile_i * kTileRows < p.n_dst; tile_i += gridDim.x) {
+    const int64_t row0 = tile_i * kTileRows;
+    const int rows_left = int(p.n_dst - row0 < int64_t(kTileRows) ? p.n_dst - row0 : int64_t(kTileRows));
+    const int rb_live = (rows_left + kTileM - 1) / kTileM;  // row blocks with at least one live row
+    for (int i = tid; i < WFSP_MAX_KVOL / 32; i += kApplyThreads) s_active[i] = 0;
+    if (tid == 0) init_pipe(bars, kProducerThreads + 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    WFSP_TRACE(1);
+
+    // neighbour tile of this CTA: which kernel offsets are active, and (small kernels) a smem copy.
+    // Loads are issued eight at a time before any is used: one memory round trip per batch.
+    if (p.nbr) {
+      const int total = rb_live * kTileM * p.kvol;
+      const int limit = rows_left * p.kvol;
+      const int32_t* base = p.nbr + row0 * p.kvol;
+      uint32_t mine = 0;  // kernel volumes up to 32: the warp ORs its bits and ONE lane updates the shared mask
+      for (int i0 = tid; i0 < total; i0 += kApplyThreads * 8) {
+        int v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * kApplyThreads;
+          v[j] = i < limit ? __ldg(base + i) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * kApplyThreads;
+          if (i < total) {
+            const int vv = v[j] >= p.n_src ? -1 : v[j];
+            if (staged) s_nbr[i] = vv;
+            if (vv >= 0) {
+              const int k = i % p.kvol;
+              if (p.kvol <= 32) mine |= 1u << k;
+              else atomicOr(&s_active[k >> 5], 1u << (k & 31));
+            }
+          }
+        }
+      }
+      if (p.kvol <= 32) {
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicOr(&s_active[0], mine);
+      }
+    } else if (tid == 0) {
+      s_active[0] = 1u;
+    }
+    __syncthreads();
+
+    int n_active = 0;
+    for (int w = 0; w < (p.kvol + 31) / 32; ++w) n_active += __popc(s_active[w]);
+    const int total_iters = n_active * num_kb;
+    // this CTA's share of the flattened (active offset, 64-channel slice) loop; every CTA of a cluster sees the same
+    // neighbour tile, hence the same total
+    const int it_lo = SPLIT ? total_iters * krank / ks : 0;
+    const int it_hi = SPLIT ? total_iters * (krank + 1) / ks : total_iters;
+    const int my_iters = it_hi - it_lo;
+    WFSP_TRACE(2);
+
+    if (warp < kProducerWarps) {
+      // ------------------------------------------------------------------ producers
+      // A: 16-byte cp.async of this thread's chunk of 8 rows per row block (rows rsub + 16 i are 2048 B
+      // apart in the swizzled tile); B: the weight warp issues one bulk copy of the pre-swizzled weight slice.
+      const int c16 = tid & 7;    // 16-byte chunk inside the 128-byte slice row
+      const int rsub = tid >> 3;  // this thread covers tile rows rsub + kRowStep*i
+      const uint32_t off0 = sw128_offset(uint32_t(rsub), uint32_t(c16));
+      const int kb_lim = (p.c_pad - c16 * 8 + kSliceK - 1) / kSliceK;  // slices in which the chunk is inside the row
+      const size_t a_row_bytes = size_t(p.c_pad) * 2;
+      const char* src_c = reinterpret_cast<const char*>(p.src) + c16 * 16;
+      int s = 0, it = 0, g = 0;
+      uint32_t ph = 0;
+      for (int kw = 0; kw < (p.kvol + 31) / 32 && g < it_hi; ++kw) {
+        uint32_t mask = s_active[kw];
+        while (mask && g < it_hi) {
+          const int k = kw * 32 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          if (g + num_kb <= it_lo) { g += num_kb; continue; }  // another CTA of the cluster takes this offset
+          int rows[RB * kRowsPerThread];
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) {
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; ++i) {
+              const int r = rb * kTileM + rsub + kRowStep * i;
+              int v = -1;
+              if (rb < rb_live) {
+                if (!p.nbr) {
+                  v = r < rows_left ? int(row0 + r) : -1;
+                } else if (staged) {
+                  v = s_nbr[r * p.kvol + k];
+                } else if (r < rows_left) {
+                  v = __ldg(p.nbr + (row0 + r) * p.kvol + k);
+                  if (v >= p.n_src) v = -1;
+                }
+              }
+              rows[rb * kRowsPerThread + i] = v;
+            }
+          }
+          const int kb0 = g < it_lo ? it_lo - g : 0;
+          const int kb1 = g + num_kb > it_hi ? it_hi - g : num_kb;
+          g += num_kb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            if (it >= p.stages) mbar_wait_u32(free0 + 8u * s, ph ^ 1u);
+            const uint32_t sa = smem0 + uint32_t(s) * stage_bytes;
+            const bool col_ok = kb < kb_lim;
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+              if (rb < rb_live) {
+#pragma unroll
+                for (int i = 0; i < kRowsPerThread; ++i) {
+                  const int v = rows[rb * kRowsPerThread + i];
+                  const bool ok = col_ok && v >= 0;
+                  cp_async16(sa + off0 + rb * kABytes + i * (kRowStep * 128), src_c + (ok ? size_t(v) * a_row_bytes + kb * 128 : size_t(0)),
+                             ok ? 16u : 0u);
+                }
+              }
+            }
+            cp_async_arrive_noinc_u32(full0 + 8u * s);
+            ++it;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+      // The pipeline's stage memory is free once `done` has fired: the epilogue stages its blocks there.
+      WFSP_TRACE(3);
+      if (my_iters > 0) {
+        mbar_wait(&bars.done, 0);
+        tc_fence_after();
+      }
+      WFSP_TRACE(4);
+    } else if (warp == kWeightWarp) {
+      // ------------------------------------------------------------------ weight slices
+      // One bulk copy (cp.async.bulk) per pipeline stage drops the pre-swizzled [n_tile][64] slice of the current
+      // (offset, 64-channel block) behind the gathered rows.  A warp of its own: the copy's operands live on the
+      // uniform datapath, which a lane of a (divergent) gather warp can only reach through register moves.
+      int n_lim = p.n_pad - n0;  // the last column tile may overhang the padded weights
+      if (n_lim > p.n_tile) n_lim = p.n_tile;
+      const uint32_t b_bytes = uint32_t(n_lim) * 128u;
+      int s = 0, it = 0, g = 0;
+      uint32_t ph = 0;
+      for (int kw = 0; kw < (p.kvol + 31) / 32 && g < it_hi; ++kw) {
+        uint32_t mask = s_active[kw];
+        while (mask && g < it_hi) {
+          const int k = kw * 32 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          if (g + num_kb <= it_lo) { g += num_kb; continue; }
+          const char* wk = reinterpret_cast<const char*>(p.wt) + ((size_t(k) * num_kb) * p.n_pad + n0) * 128;
+          const int kb0 = g < it_lo ? it_lo - g : 0;
+          const int kb1 = g + num_kb > it_hi ? it_hi - g : num_kb;
+          g += num_kb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            if (it >= p.stages) mbar_wait_u32(free0 + 8u * s, ph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx_u32(full0 + 8u * s, b_bytes);
+              bulk_copy_g2s_u32(smem0 + uint32_t(s) * stage_bytes + a_bytes, wk + size_t(kb) * p.n_pad * 128, b_bytes, full0 + 8u * s);
+            }
+            __syncwarp();
+            ++it;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------ MMA issuer
+      // The whole warp walks the pipeline (converged control flow keeps the descriptor arithmetic on the uniform
+      // datapath); one elected lane issues.  The descriptors of the four K=16 steps of a slice differ only in
+      // their start-address field: +32 bytes = +2 in the low word.
+      const uint32_t idesc = make_idesc_bf16(kTileM, uint32_t(p.n_tile), 0, 0);
+      const uint64_t desc_hi = make_desc_sw128(0, 16, 1024);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_iters; ++it) {
+        mbar_wait_u32(full0 + 8u * s, ph);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint32_t a_addr = smem0 + uint32_t(s) * stage_bytes, b_addr = a_addr + a_bytes;
+        if (elect_one()) {
+          const uint64_t bdesc0 = desc_hi | uint64_t((b_addr >> 4) & 0x3fffu);
+          for (int rb = 0; rb < rb_live; ++rb) {
+            const uint64_t adesc0 = desc_hi | uint64_t(((a_addr + rb * kABytes) >> 4) & 0x3fffu);
+#pragma unroll
+            for (int kk = 0; kk < kSliceK / 16; ++kk)
+              mma_bf16(tmem + uint32_t(rb * p.acc_stride), adesc0 + 2 * kk, bdesc0 + 2 * kk, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit_u32(free0 + 8u * s);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (my_iters > 0 && elect_one()) mma_commit(&bars.done);
+    }
+
+    // ------------------------------------------------------------------ epilogue (warps 0..7)
+    // TMEM -> registers (thread = row) -> a 32 x 32 block in shared memory.  Warps w and w+4 share TMEM lane
+    // quarter w (a warp may only read lanes 32*(warp%4)..+31): they take alternate 32-column chunks of it.
+    auto load_acc = [&](int rb, int col, int ncols, uint32_t (&acc)[32]) {  // this warp's lane quarter of row block rb
+      if (my_iters > 0) {
+        const uint32_t taddr = tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(rb * p.acc_stride + col);
+        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        if (ncols > 16) tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[16]));
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0u;
+      }
+    };
+    float* tile = reinterpret_cast<float*>(smem) + (warp % kEpiWarps) * kBlockFloats;
+    if (!SPLIT) {
+      if (warp < kEpiWarps) {
+        for (int rb = 0; rb < rb_live; ++rb) {
+          const int wr0 = rb * kTileM + (warp & 3) * 32;  // first row of this warp's block inside the CTA tile
+          int rmax = rows_left - wr0;
+          if (rmax > 32) rmax = 32;
+          for (int col = (warp >> 2) * 32; col < p.n_tile; col += 64) {
+            const int ncols = p.n_tile - col < 32 ? p.n_tile - col : 32;  // 16 or 32
+            uint32_t acc[32];
+            load_acc(rb, col, ncols, acc);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (4 * q < ncols)
+                *reinterpret_cast<uint4*>(tile + lane * kEpiPitch + 4 * q) = make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            __syncwarp();
+            finish_block(p, tile, row0 + wr0, rmax, n0 + col, ncols, vec, lane);
+            __syncwarp();
+          }
+        }
+      }
+    } else {
+      // Split reduction.  The tile's 32 x 32 blocks are dealt out round-robin over the CTAs of the cluster; every
+      // CTA PUSHES its partial of a block into a slot of the owner's shared memory (remote stores do not stall),
+      // one cluster barrier, then the owner adds the ks slots IN RANK ORDER (fixed summation order, no atomics)
+      // from its own shared memory and finishes the block as above.
+      if (warp < kEpiWarps) {
+        for (int rb = 0; rb < rb_live; ++rb)
+          for (int cc = warp >> 2; cc < ncc; cc += 2) {
+            const int ncols = p.n_tile - cc * 32 < 32 ? p.n_tile - cc * 32 : 32;
+            uint32_t acc[32];
+            load_acc(rb, cc * 32, ncols, acc);
+            const int u = (rb * 4 + (warp & 3)) * ncc + cc;
+            const uint32_t slot = smem_u32(park + ((u / ks) * ks + krank) * kBlockFloats + lane * kEpiPitch);
+            const uint32_t remote = map_to_cta(slot, uint32_t(u % ks));
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (4 * q < ncols) st_cluster_u32x4(remote + 16u * q, acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+          }
+      }
+      WFSP_TRACE(5);
+      __syncwarp();
+      cluster_sync_all();
+      WFSP_TRACE(6);
+      if (warp < kEpiWarps) {
+        const int units = rb_live * 4 * ncc;
+        for (int j = warp; krank + ks * j < units; j += kEpiWarps) {
+          const int u = krank + ks * j;
+          const int cc = u % ncc, rq = (u / ncc) & 3, rb = u / (4 * ncc);
+          const int ncols = p.n_tile - cc * 32 < 32 ? p.n_tile - cc * 32 : 32;
+          const int wr0 = rb * kTileM + rq * 32;
+          int rmax = rows_left - wr0;
+          if (rmax > 32) rmax = 32;
+          if (rmax > 0) {
+            // lane -> rows (lane >> 3) + 4 i, four columns from 4 (lane & 7)
+            const int c4 = (lane & 7) * 4;
+            const float* slot0 = park + (j * ks) * kBlockFloats + (lane >> 3) * kEpiPitch + c4;
+            if (c4 < ncols) {
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h) {  // two batches of four 16-byte loads per slot (register budget)
+                const float* sl = slot0 + h * 16 * kEpiPitch;
+                float4 acc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = *reinterpret_cast<const float4*>(sl + i * 4 * kEpiPitch);
+                for (int src = 1; src < ks; ++src) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 t = *reinterpret_cast<const float4*>(sl + src * kBlockFloats + i * 4 * kEpiPitch);
+                    acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  *reinterpret_cast<float4*>(tile + ((lane >> 3) + 16 * h + 4 * i) * kEpiPitch + c4) = acc[i];
+              }
+            }
+            __syncwarp();
+            finish_block(p, tile, row0 + wr0, rmax, n0 + cc * 32, ncols, vec, lane);
+            __syncwarp();
+          }
+        }
+      }
+      WFSP_TRACE(7);
+    }
+    WFSP_TRACE(8);
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    // a further trip (wrong launch-shape hint only): peers must have summed this trip's slots before anyone pushes again
+    if (SPLIT && (tile_i + gridDim.x) * kTileRows < p.n_dst) cluster_sync_all();
+  }
+  if (warp == kMmaWarp) tmem_dealloc(s_tmem, tmem_cols);
+  WFSP_TRACE(9);
+  if (p.trace != nullptr && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    const unsigned lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (lin < 1024) p.trace[128 + 2 * lin + 1] = gt;
+  }
+}
+
 struct WgradParams {
   const __nv_bfloat16* a; int64_t n_a; int c_a, ca_pad;
   const __nv_bfloat16* b; int64_t n_b; int c_b, cb_pad;
@@ -694,6 +1130,9 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_umma_kernel(const WgradPa
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 int g_force_rblk = 0;  // tuning knob (wfsp_set_option "apply_row_blocks"): 0 = cost model
+int g_auto_ksplit = 4;  // wfsp_set_option "apply_k_split": 0 = never split the reduction over a cluster, else the largest split
+int g_split_wide = 0;    // wfsp_set_option "apply_split_wide": split launches take the widest column tiles (fewest MMA instructions)
+int g_split_stages = 4;  // wfsp_set_option "apply_split_stages": ring depth of split launches (each CTA walks few slices)
 
 // column tiling of the destination channels: as few tiles as possible (<= 256 columns each) when
 // there are enough row tiles to fill the machine, narrower tiles (down to 32 columns) when there are
@@ -732,6 +1171,11 @@ int pick_stages(int stage_bytes, int extra_bytes, bool alone = false) {
 }  // namespace
 
 void set_force_rblk(int v) { g_force_rblk = v; }
+void set_auto_ksplit(int v) { g_auto_ksplit = v == 1 ? 8 : v; }
+void set_split_stages(int v) { g_split_stages = v; }
+void set_split_wide(int v) { g_split_wide = v; }
+unsigned long long* g_trace = nullptr;
+void set_trace(unsigned long long* p) { g_trace = p; }
 
 size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) {
   return apply_plan(kvol, n_src, c_red, c_dst).total;
@@ -739,8 +1183,8 @@ size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) 
 
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
                            const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, float* stats,
-                           cudaStream_t st);
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                           const wfsp_conv_epilogue* ep, cudaStream_t st);
 
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
@@ -770,53 +1214,133 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
 // bf16 activations [n_src, round_up(c_red, 8)] and prepared weights in, fp32 [n_dst, c_dst] out
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
                            const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
-                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint, float* stats,
-                           cudaStream_t st) {
+                           const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
+                           const wfsp_conv_epilogue* ep, cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
   ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
   const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
-  int n_tile, n_tiles;
-  choose_column_tiles(a.n_pad, ceil_div<int64_t>(live, kTileM), n_tile, n_tiles);
-  ApplyParams p{};
-  p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
-  p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst; p.n_tile = n_tile;
-  p.n_src_dev = n_src_dev; p.n_dst_dev = n_dst_dev;
-  p.stats = stats;
-  p.acc_stride = round_up(n_tile, 32);
-  // Row blocking: rblk 128-row blocks per CTA share every weight slice.  Modelled cost of a launch =
-  // rounds of CTAs over the SMs x (operand KB a CTA moves + a per-CTA prologue / epilogue term); the weight
-  // slice (n_tile * 128 B per stage) is amortised over rblk blocks, the rounds quantise.  Only worth it
-  // when the row blocks exceed one round -- small problems keep rblk = 1 and as many CTAs as possible.
   const int64_t row_blocks = ceil_div<int64_t>(live, kTileM);
   const int iters_est = kvol * (a.kc_pad / kSliceK);
-  int best_r = 1;
-  double best_cost = 1e300;
-  for (int r = 1; r <= kMaxRowBlocks; ++r) {
-    if (r * p.acc_stride > 512) break;
-    const int stage_b = r * kABytes + n_tile * 128;
-    const int nbr_b = (nbr != nullptr && kvol <= kNbrStageK) ? r * kTileM * kvol * 4 : 0;
-    if (2 * stage_b + nbr_b + 1024 > kSmemMax) break;
-    const int64_t ctas = ceil_div<int64_t>(row_blocks, r) * n_tiles;
-    const double rounds = double(ceil_div<int64_t>(ctas, sm_count()));
-    const double cost = rounds * (double(iters_est) * (r * 16.0 + n_tile / 8.0) + 48.0 * r + 48.0);
-    if (cost < best_cost * 0.97) { best_cost = cost; best_r = r; }
+  ApplyParams p{};
+  p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
+  p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst;
+  p.n_src_dev = n_src_dev; p.n_dst_dev = n_dst_dev;
+  p.trace = g_trace;
+  if (ep) {
+    p.stats = ep->bn_partials;
+    if (ep->bwd_partials) {
+      if (!ep->bwd_x || !ep->bwd_mean || !ep->bwd_invstd)
+        return set_error(WFSP_EINVAL, "bwd_partials needs bwd_x, bwd_mean and bwd_invstd");
+      p.bwd_x = ep->bwd_x; p.bwd_mean = ep->bwd_mean; p.bwd_invstd = ep->bwd_invstd; p.bwd_gamma = ep->bwd_gamma;
+      p.bwd_beta = ep->bwd_beta; p.bwd_part = ep->bwd_partials; p.bwd_relu = ep->bwd_relu;
+    }
   }
-  if (g_force_rblk > 0 && g_force_rblk <= kMaxRowBlocks && g_force_rblk * p.acc_stride <= 512) best_r = g_force_rblk;
-  p.rblk = best_r;
-  const int stage_bytes = p.rblk * kABytes + n_tile * 128;
-  p.staged = (nbr != nullptr && kvol <= kNbrStageK) ? 1 : 0;
-  const int nbr_bytes = p.staged ? p.rblk * kTileM * kvol * 4 : 0;
-  const bool alone = ceil_div<int64_t>(row_blocks, p.rblk) * n_tiles <= sm_count();
-  p.stages = pick_stages(stage_bytes, nbr_bytes + 1024, alone);
-  const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + 1024;
+  // Split reduction over a thread-block cluster (small launches only): the largest split that leaves every CTA
+  // at least three pipeline slices while the launch still fits one round of the machine.
+  int ksplit = 1;
+  const int want_split = ep ? ep->k_split : 0;
+  if (want_split == 0) {
+    const int t_min = (a.n_pad + 255) / 256;
+    for (int ks = 8; ks > 1; ks >>= 1)
+      if (ks <= g_auto_ksplit && iters_est >= 3 * ks && row_blocks * t_min * ks <= sm_count()) { ksplit = ks; break; }
+  } else if (want_split == 2 || want_split == 4 || want_split == 8) {
+    ksplit = want_split;
+  }
+  const size_t block_bytes = size_t(32) * kEpiPitch * sizeof(float);
+  int n_tile = 0, n_tiles = 0, nbr_bytes = 0, stage_bytes = 0;
+  size_t park_bytes = 0;
+  for (;; ksplit = 1) {  // second trip: the split does not fit the shared memory, plain launch
+    choose_column_tiles(a.n_pad, row_blocks * ksplit, n_tile, n_tiles);
+    if (ksplit > 1 && g_split_wide) {
+      // issuing a tcgen05.mma costs about the same whatever its N: a split launch takes the fewest, widest column
+      // tiles (its parallelism comes from the split), which also gathers every row once instead of once per tile
+      n_tiles = (a.n_pad + 255) / 256;
+      n_tile = round_up((a.n_pad + n_tiles - 1) / n_tiles, 16);
+    }
+    p.n_tile = n_tile;
+    p.acc_stride = round_up(n_tile, 32);
+    // Row blocking: rblk 128-row blocks per CTA share every weight slice.  Modelled cost of a launch =
+    // rounds of CTAs over the SMs x (operand KB a CTA moves + a per-CTA prologue / epilogue term); the weight
+    // slice (n_tile * 128 B per stage) is amortised over rblk blocks, the rounds quantise.  Only worth it
+    // when the row blocks exceed one round -- small problems keep rblk = 1 and as many CTAs as possible.
+    int best_r = 1;
+    double best_cost = 1e300;
+    const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr;  // conv_apply_split_kernel: one row block per CTA
+    for (int r = 1; r <= (tile_loop_kernel ? 1 : kMaxRowBlocks); ++r) {
+      if (r * p.acc_stride > 512) break;
+      const int stage_b = r * kABytes + n_tile * 128;
+      const int nbr_b = (nbr != nullptr && kvol <= kNbrStageK) ? r * kTileM * kvol * 4 : 0;
+      if (2 * stage_b + nbr_b + 1024 > kSmemMax) break;
+      const int64_t ctas = ceil_div<int64_t>(row_blocks, r) * n_tiles;
+      const double rounds = double(ceil_div<int64_t>(ctas, sm_count()));
+      const double cost = rounds * (double(iters_est) * (r * 16.0 + n_tile / 8.0) + 48.0 * r + 48.0);
+      if (cost < best_cost * 0.97) { best_cost = cost; best_r = r; }
+    }
+    if (!tile_loop_kernel && g_force_rblk > 0 && g_force_rblk <= kMaxRowBlocks && g_force_rblk * p.acc_stride <= 512) best_r = g_force_rblk;
+    p.rblk = best_r;
+    stage_bytes = p.rblk * kABytes + n_tile * 128;
+    p.staged = (nbr != nullptr && kvol <= kNbrStageK) ? 1 : 0;
+    nbr_bytes = p.staged ? p.rblk * kTileM * kvol * 4 : 0;
+    const bool alone = ceil_div<int64_t>(row_blocks, p.rblk) * n_tiles * ksplit <= sm_count();
+    park_bytes = 0;
+    if (ksplit == 1) {
+      p.stages = pick_stages(stage_bytes, nbr_bytes + 1024, alone);
+      break;
+    }
+    // a split CTA walks only a few slices: a shallow ring; behind it the slots its peers push their partial blocks
+    // into (ks slots for every block this CTA finishes); the ring must also hold one block per epilogue warp
+    const int units = p.rblk * 4 * ((n_tile + 31) / 32);
+    park_bytes = size_t(ceil_div(units, ksplit)) * ksplit * block_bytes;
+    int stages = g_split_stages < 2 ? 2 : g_split_stages;
+    while (stages > 2 && size_t(stages) * stage_bytes + nbr_bytes + park_bytes + 1024 > size_t(kSmemMax)) --stages;
+    while (size_t(stages) * stage_bytes < kEpiWarps * block_bytes) ++stages;
+    p.stages = stages;
+    if (size_t(stages) * stage_bytes + nbr_bytes + park_bytes + 1024 <= size_t(kSmemMax)) break;
+  }
+  p.ksplit = ksplit;
+  p.nbr_bytes = nbr_bytes;
+  const size_t smem = size_t(p.stages) * stage_bytes + nbr_bytes + park_bytes + 1024;
   if (smem > size_t(227) * 1024) return set_error(WFSP_EUNSUPPORTED, "conv_apply tile needs %zu B of shared memory", smem);
-  dim3 grid(unsigned(ceil_div<int64_t>(n_dst, int64_t(kTileM) * p.rblk)), unsigned(n_tiles));
+  // grid: the tiles of the EXPECTED live rows plus half as many again (the kernel loops over whatever lies beyond)
+  const int64_t tile_rows = int64_t(kTileM) * p.rblk;
+  int64_t grid_x = ceil_div<int64_t>(n_dst, tile_rows);
+  const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr;
+  if (tile_loop_kernel && live < n_dst) {
+    const int64_t want = ceil_div<int64_t>(live + live / 2, tile_rows);
+    if (want < grid_x) grid_x = want;
+  }
+  const dim3 grid{unsigned(grid_x), unsigned(n_tiles), unsigned(ksplit)};
+  if (tile_loop_kernel && ksplit == 1) {
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_split_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+    conv_apply_split_kernel<1, false><<<grid, kApplyThreads, smem, st>>>(p);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return WFSP_OK;
+  }
+  if (ksplit > 1) {
+    WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_split_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kApplyThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = unsigned(ksplit);
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WFSP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_apply_split_kernel<1, true>, p));
+    count_launches(1);
+    return WFSP_OK;
+  }
   switch (p.rblk) {
 #define WFSP_LAUNCH_APPLY(RB)                                                                                        \
     case RB:                                                                                                         \
       WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_umma_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                            kSmemOptIn));                                                             \
-      conv_apply_umma_kernel<RB><<<grid, kApplyThreads, smem, st>>>(p);                                                   \
+      conv_apply_umma_kernel<RB><<<grid, kApplyThreads, smem, st>>>(p);                                            \
       break;
     WFSP_LAUNCH_APPLY(1) WFSP_LAUNCH_APPLY(2) WFSP_LAUNCH_APPLY(3) WFSP_LAUNCH_APPLY(4)
 #undef WFSP_LAUNCH_APPLY

@@ -204,10 +204,16 @@ extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int 
   WFSP_REQUIRE(feats_dtype == WFSP_F32 || feats_dtype == WFSP_BF16, "feats dtype must be f32 or bf16");
   cudaStream_t st = as_stream(stream);
   if (n_rows == 0) return WFSP_OK;
-  pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, n_rows_dev, item_rows,
-                                                                               item_offset, n_items, indices_bxy);
-  count_launches(1);
-  WFSP_CHECK_LAUNCH();
+  // either half may be skipped (NULL output): the two are independent, so a caller can put them on different streams
+  if (indices_bxy != nullptr) {
+    WFSP_REQUIRE(coords_xye != nullptr, "indices requested without coordinates");
+    pack_indices_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(coords_xye, n_rows, n_rows_dev, item_rows,
+                                                                                 item_offset, n_items, indices_bxy);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+  }
+  if (feats == nullptr) return WFSP_OK;
+  WFSP_REQUIRE(wave != nullptr, "features requested without waveforms");
   if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_F32)
     return launch_pack_feats<int16_t, float>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
   if (wave_dtype == WFSP_I16 && feats_dtype == WFSP_BF16)

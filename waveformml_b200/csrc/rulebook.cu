@@ -23,6 +23,7 @@ namespace wfsp {
 
 static int g_force_hash = 0;
 void set_force_hash(int v) { g_force_hash = v; }
+extern unsigned long long* g_trace;  // conv_umma.cu (wfsp_debug_trace)
 
 namespace {
 
@@ -376,7 +377,10 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
                                                         int32_t* __restrict__ out_indices, int64_t out_cap,
                                                         int32_t* __restrict__ pairs, int32_t* __restrict__ pair_num,
                                                         int32_t* __restrict__ n_out, int32_t* __restrict__ nbr_out,
-                                                        int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag) {
+                                                        int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag,
+                                                        unsigned long long* trace) {
+#define WFSP_RB_TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[slot] = (unsigned long long)clock64(); } while (0)
+  WFSP_RB_TRACE(0);
   extern __shared__ int s_dyn[];  // [K][kSmallWarps] per-warp pair counts / prefixes, [K] running bases, [cells] table
   __shared__ int s_warp[kSmallWarps];
   __shared__ int s_base;
@@ -390,6 +394,7 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   const int n = int(n_cap);
   const int live = g.n_dev ? min(int(*g.n_dev), n) : n;
   const int rounds = (live + kSmallBlock - 1) / kSmallBlock;
+  WFSP_RB_TRACE(1);
   // phase 0: initialise.  The -1 padding of the pair arrays is part of the upstream-visible result; with
   // device-side counts it is written for the live rows only (nothing reads the capacity tail).
   // (plain counted loops, not unrolled: this kernel runs once, cold, in one CTA -- its cost is fetching its code)
@@ -411,6 +416,7 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   for (int k = tid; k < K; k += kSmallBlock) s_kbase[k] = 0;
   if (tid == 0) { *dup_flag = 0; s_base = 0; }
   __syncthreads();
+  WFSP_RB_TRACE(2);
   const Row r0 = load_row(indices, n, tid, g);  // round 0 (all there is up to 1024 rows) reads its row once
   // phase 1: claim cells
 #pragma unroll 1
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
     }
   }
   __syncthreads();
+  WFSP_RB_TRACE(3);
   int64_t rows_out = live;
   if (!SUBM) {
     // phase 2: first touchers -> output rows in rank order, round after round
@@ -436,16 +443,23 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
     for (int rd = 0; rd < rounds; ++rd) {
       const int j = rd * kSmallBlock + tid;
       Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
+      // a warp whose 32 rows all lie beyond the live count skips the tap loops (the CTA runs on ONE SM: with a few
+      // hundred live rows most of its 32 warps would otherwise spend its issue slots on rows that do not exist)
+      const bool warp_live = rd * kSmallBlock + warp * 32 < live;
       int first = 0;
-      WFSP_FOR_TAPS(g, kx, ky, kz) {
-        int slot = 0, val;
-        Pos o;
-        if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz))
-          ++first;
+      if (warp_live) {
+        WFSP_FOR_TAPS(g, kx, ky, kz) {
+          int slot = 0, val;
+          Pos o;
+          if (candidate<false, false>(r, g, t, kx, ky, kz, slot, val, o) && table[slot] == j * K + WFSP_TAP(g, kx, ky, kz))
+            ++first;
+        }
       }
+      WFSP_RB_TRACE(8);
       const int incl = warp_incl_scan(first, lane);
       if (lane == 31) s_warp[warp] = incl;
       __syncthreads();
+      WFSP_RB_TRACE(9);
       // every warp scans the 32 per-warp totals itself (one smem read + five shuffles instead of a serial sum)
       const int wtot = warp_incl_scan(s_warp[lane], lane);
       int off = s_base + incl - first + (warp ? __shfl_sync(0xffffffffu, wtot, warp - 1) : 0);
@@ -462,6 +476,7 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
           }
         }
       }
+      WFSP_RB_TRACE(10);
       __syncthreads();
       if (tid == 0) s_base = total;
       __syncthreads();
@@ -470,9 +485,11 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
     if (tid == 0) *n_out = s_base;
   }
   if (rows_out > out_cap) rows_out = out_cap;
+  WFSP_RB_TRACE(4);
 #pragma unroll 1
   for (int i = tid; i < int(rows_out) * K; i += kSmallBlock) nbr_out[i] = -1;
   __syncthreads();
+  WFSP_RB_TRACE(5);
   // phase 3: per-offset compaction in ascending input order
   const unsigned lt = (1u << lane) - 1u;
   int dup = 0;  // becomes non-zero if a (row, offset) slot of nbr_out was already taken: duplicate coordinates
@@ -480,14 +497,22 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   for (int rd = 0; rd < rounds; ++rd) {
     const int j = rd * kSmallBlock + tid;
     Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
-    WFSP_FOR_TAPS(g, kx, ky, kz) {
-      int slot = 0, val = 0;
-      Pos o;
-      const bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
-      const unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (lane == 0) s_dyn[WFSP_TAP(g, kx, ky, kz) * kSmallWarps + warp] = __popc(bal);
+    const bool warp_live = rd * kSmallBlock + warp * 32 < live;  // (see phase 2)
+    if (warp_live) {
+      WFSP_FOR_TAPS(g, kx, ky, kz) {
+        int slot = 0, val = 0;
+        Pos o;
+        const bool v = candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o);
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        if (lane == 0) s_dyn[WFSP_TAP(g, kx, ky, kz) * kSmallWarps + warp] = __popc(bal);
+      }
+    } else {
+#pragma unroll 1
+      for (int k = lane; k < K; k += 32) s_dyn[k * kSmallWarps + warp] = 0;
     }
+    WFSP_RB_TRACE(11);
     __syncthreads();
+    WFSP_RB_TRACE(12);
     // warp w turns the 32 per-warp counts of offsets w, w + 32, ... into running positions
 #pragma unroll 1
     for (int k = warp; k < K; k += kSmallWarps) {
@@ -499,6 +524,8 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
       if (lane == 31) s_kbase[k] = base + incl;
     }
     __syncthreads();
+    WFSP_RB_TRACE(13);
+    if (warp_live) {
     WFSP_FOR_TAPS(g, kx, ky, kz) {
       const int k = WFSP_TAP(g, kx, ky, kz);
       int slot = 0, val = 0;
@@ -515,11 +542,16 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
         if (o_row < out_cap) dup |= atomicExch(&nbr_out[int64_t(o_row) * K + k], j) + 1;
       }
     }
+    }
+    WFSP_RB_TRACE(14);
     __syncthreads();
   }
+  WFSP_RB_TRACE(6);
   if (dup) *dup_flag = 1;
 #pragma unroll 1
   for (int k = tid; k < K; k += kSmallBlock) pair_num[k] = s_kbase[k];
+  WFSP_RB_TRACE(7);
+#undef WFSP_RB_TRACE
 }
 
 struct Plan {
@@ -802,7 +834,7 @@ extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t 
       WFSP_CHECK_CUDA(cudaFuncSetAttribute(rb_small<SUBM, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                            208 * 1024));                                                        \
       rb_small<SUBM, SM><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, tab, cells, OUT, CAP, pairs, pair_num,  \
-                                                       NOUT, nbr_out, nbr_in, dup_flag);                         \
+                                                       NOUT, nbr_out, nbr_in, dup_flag, g_trace);                \
     } while (0)
     if (subm) {
       if (in_smem) WFSP_RB_SMALL(true, true, nullptr, n_in, nullptr);

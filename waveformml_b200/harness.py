@@ -165,8 +165,9 @@ class TrainStep:
             return self.criterion(out, target)
         return segment_l1_loss(indices, out, target, self.model.spatial_size, batch_size, n_rows)
 
-    def forward_backward(self, indices, feats, target, batch_size, n_rows=None):
-        self.grads.zero()
+    def forward_backward(self, indices, feats, target, batch_size, n_rows=None, zero=True):
+        if zero:
+            self.grads.zero()
         # bf16 math mode = tensor-core operands with fp32 accumulation everywhere: the dense head's library
         # GEMMs (batches too large for the fused head) then run as TF32 tensor-core GEMMs instead of fp32 SIMT
         # ones (85 -> ~10 us for Linear(4480,116) at 1024 events).  fp32 mode keeps exact fp32 products.
@@ -189,76 +190,114 @@ class TrainStep:
 
 
 class GraphTrainStep(TrainStep):
-    """One CUDA graph per model: static input buffers of `row_capacity` rows and `batch_size` events;
+    """One CUDA graph per input set: static input buffers of `row_capacity` rows and `batch_size` events;
     `load()` copies a batch in (async from pinned host memory or device to device), `run()` replays
     the captured step.  Any batch with at most `row_capacity` rows and exactly `batch_size` events
-    reuses the same graph -- the live row count is data, not shape."""
+    reuses the same graph -- the live row count is data, not shape.
+
+    n_buffers = 2 double-buffers the INPUTS: two input sets, each with its own captured graph over the same
+    parameters / optimiser state, so `prefetch()` copies the next pinned host batch straight into the idle set on a
+    copy stream while the current step runs -- no staging copy, no extra launch between the copy and the replay (the
+    DataLoader `pin_memory` + `non_blocking` pattern of the reference's Lightning loop, src/utils/util.py:229-236)."""
 
     def __init__(self, model, task, batch_size, row_capacity, n_chan, wave_dtype=torch.int16, scale=MAX_RANGE_INV,
-                 capture_update=True, **kw):
+                 capture_update=True, n_buffers=1, **kw):
         super().__init__(model, task, **kw)
         dev = self.grads.flat.device
         self.batch_size, self.row_capacity, self.scale = int(batch_size), int(row_capacity), scale
-        self.coords = torch.zeros((row_capacity, 3), dtype=torch.int32, device=dev)
-        self.wave = torch.zeros((row_capacity, n_chan), dtype=wave_dtype, device=dev)
         tshape = (batch_size,) if task == "psd" else (row_capacity,)
-        self.target = torch.zeros(tshape, dtype=torch.int64 if task == "psd" else torch.float32, device=dev)
-        self.n_rows = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self._n_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.sets = []
+        for _ in range(max(1, int(n_buffers))):
+            self.sets.append({
+                "coords": torch.zeros((row_capacity, 3), dtype=torch.int32, device=dev),
+                "wave": torch.zeros((row_capacity, n_chan), dtype=wave_dtype, device=dev),
+                "target": torch.zeros(tshape, dtype=torch.int64 if task == "psd" else torch.float32, device=dev),
+                "n_rows": torch.zeros((1,), dtype=torch.int32, device=dev),
+                "n_host": torch.zeros((1,), dtype=torch.int32).pin_memory() if dev.type == "cuda" else None,
+                "graph": None, "loss": None, "dup_flags": [], "ready": None, "done": None})
+        self.cur = 0  # the set the next run() replays
         self.tables = batcher.item_tables([0, row_capacity], [0], dev)
         self.capture_update = capture_update
-        self.graph = None
         self.loss_out = None
         self._stage, self._pending = None, None
+        self._copy_stream = None
 
-    def load(self, coords, wave, target):
+    # the first input set under the names the single-buffer interface always had
+    coords = property(lambda self: self.sets[0]["coords"])
+    wave = property(lambda self: self.sets[0]["wave"])
+    target = property(lambda self: self.sets[0]["target"])
+    n_rows = property(lambda self: self.sets[0]["n_rows"])
+    graph = property(lambda self: self.sets[0]["graph"])
+
+    def load(self, coords, wave, target, buf=None):
         """coords int32 [n,3] (x, y, event), wave [n,C], target [B] (psd) or [n] (z); host (pinned for an
-        asynchronous copy) or device tensors."""
+        asynchronous copy) or device tensors.  Fills input set `buf` (default: the current one) and makes it the
+        one the next run() replays."""
         n = coords.shape[0]
         if n > self.row_capacity:
             raise ValueError("batch has %d rows, graph capacity is %d" % (n, self.row_capacity))
-        dev = self.coords.device
-        if (coords.device == dev and wave.device == dev and target.device == dev and coords.dtype == self.coords.dtype
-                and wave.dtype == self.wave.dtype and target.dtype == self.target.dtype and coords.is_contiguous()
-                and wave.is_contiguous() and target.is_contiguous() and target.numel() <= self.target.numel()):
+        if buf is not None:
+            self.cur = int(buf)
+        st = self.sets[self.cur]
+        dev = st["coords"].device
+        if (coords.device == dev and wave.device == dev and target.device == dev and coords.dtype == st["coords"].dtype
+                and wave.dtype == st["wave"].dtype and target.dtype == st["target"].dtype and coords.is_contiguous()
+                and wave.is_contiguous() and target.is_contiguous() and target.numel() <= st["target"].numel()):
             # batch already in HBM: one launch stages all three buffers and the live row count
-            self._stage_device(coords, wave, target, n)
+            self._stage_device(st, coords, wave, target, n)
             return
-        self.coords[:n].copy_(coords, non_blocking=True)
-        self.wave[:n].copy_(wave, non_blocking=True)
-        self.target[:target.shape[0]].copy_(target, non_blocking=True)
-        self.n_rows.fill_(n)  # the value travels as a kernel argument: no host buffer to race with
+        st["coords"][:n].copy_(coords, non_blocking=True)
+        st["wave"][:n].copy_(wave, non_blocking=True)
+        st["target"][:target.shape[0]].copy_(target, non_blocking=True)
+        st["n_rows"].fill_(n)  # the value travels as a kernel argument: no host buffer to race with
 
-    def _stage_device(self, coords, wave, target, n):
-        """One launch copies a device-resident batch into the graph's static buffers and sets the live row count."""
+    def _stage_device(self, st, coords, wave, target, n):
+        """One launch copies a device-resident batch into the set's static buffers and sets the live row count."""
         lib = _lib.load()
-        with torch.cuda.device(self.coords.device):
+        with torch.cuda.device(st["coords"].device):
             _lib.check(lib.wfsp_stage_inputs(
-                _lib.ptr(self.coords), _lib.ptr(coords), n * 3 * coords.element_size(),
-                _lib.ptr(self.wave), _lib.ptr(wave), n * wave.shape[1] * wave.element_size(),
-                _lib.ptr(self.target), _lib.ptr(target), target.numel() * target.element_size(),
-                _lib.ptr(self.n_rows), n, _lib.stream()))
+                _lib.ptr(st["coords"]), _lib.ptr(coords), n * 3 * coords.element_size(),
+                _lib.ptr(st["wave"]), _lib.ptr(wave), n * wave.shape[1] * wave.element_size(),
+                _lib.ptr(st["target"]), _lib.ptr(target), target.numel() * target.element_size(),
+                _lib.ptr(st["n_rows"]), n, _lib.stream()))
 
     def prefetch(self, coords, wave, target):
-        """Double-buffered input staging (the DataLoader `pin_memory` + `non_blocking` pattern): the pinned host
-        batch is copied to one of two device staging sets on a COPY stream, so the transfer of batch i+1 overlaps the
-        compute of batch i; the next run() waits for the copy and moves it into the graph's buffers with one launch.
-        At most one batch is pending; a staging set is reused only after the step that consumed it has read it."""
+        """Queues the pinned host batch for the NEXT run() on a copy stream, so its transfer overlaps the step that
+        is running.  With two input sets the copy lands directly in the idle set's buffers (after the last replay
+        that read them has finished); with one set it goes through two staging sets and run() moves it into the
+        graph's buffers with one launch.  At most one batch is pending."""
         n = coords.shape[0]
         if n > self.row_capacity:
             raise ValueError("batch has %d rows, graph capacity is %d" % (n, self.row_capacity))
-        dev = self.coords.device
-        if self._stage is None:
+        dev = self.sets[0]["coords"].device
+        if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage = [{"coords": torch.empty_like(self.coords), "wave": torch.empty_like(self.wave),
-                            "target": torch.empty_like(self.target), "ready": None, "free": None} for _ in range(2)]
+        cs = self._copy_stream
+        nt = target.shape[0]
+        if len(self.sets) > 1:
+            nxt = (self.cur + 1) % len(self.sets)
+            st = self.sets[nxt]
+            if st["done"] is not None:
+                cs.wait_event(st["done"])  # the replay that last read this set
+            st["n_host"][0] = n
+            with torch.cuda.stream(cs):
+                st["coords"][:n].copy_(coords, non_blocking=True)
+                st["wave"][:n].copy_(wave, non_blocking=True)
+                st["target"][:nt].copy_(target, non_blocking=True)
+                st["n_rows"].copy_(st["n_host"], non_blocking=True)
+                st["ready"] = torch.cuda.Event()
+                st["ready"].record(cs)
+            self._pending = ("set", nxt)
+            return
+        if self._stage is None:
+            s0 = self.sets[0]
+            self._stage = [{"coords": torch.empty_like(s0["coords"]), "wave": torch.empty_like(s0["wave"]),
+                            "target": torch.empty_like(s0["target"]), "ready": None, "free": None} for _ in range(2)]
             self._stage_i = 0
         slot = self._stage[self._stage_i]
         self._stage_i ^= 1
-        cs = self._copy_stream
         if slot["free"] is not None:
             cs.wait_event(slot["free"])
-        nt = target.shape[0]
         with torch.cuda.stream(cs):
             slot["coords"][:n].copy_(coords, non_blocking=True)
             slot["wave"][:n].copy_(wave, non_blocking=True)
@@ -266,22 +305,49 @@ class GraphTrainStep(TrainStep):
             slot["ready"] = torch.cuda.Event()
             slot["ready"].record(cs)
         slot["n"], slot["nt"] = n, nt
-        self._pending = slot
+        self._pending = ("stage", slot)
+
+    def pending_ready(self):
+        """Event after the H2D copies of the pending prefetch (the host may reuse its pinned buffers once it fired)."""
+        kind, what = self._pending
+        return self.sets[what]["ready"] if kind == "set" else what["ready"]
 
     def _consume_prefetch(self):
-        slot, self._pending = self._pending, None
+        (kind, what), self._pending = self._pending, None
         main = torch.cuda.current_stream()
+        if kind == "set":
+            self.cur = what
+            main.wait_event(self.sets[what]["ready"])
+            return
+        slot = what
         main.wait_event(slot["ready"])
-        self._stage_device(slot["coords"], slot["wave"], slot["target"][:slot["nt"]], slot["n"])
+        self._stage_device(self.sets[self.cur], slot["coords"], slot["wave"], slot["target"][:slot["nt"]], slot["n"])
         slot["free"] = torch.cuda.Event()
         slot["free"].record(main)
 
-    def _body(self):
+    def _body(self, st=None):
+        st = self.sets[self.cur] if st is None else st
         # bf16 math + fused stack: the batcher writes the tensor-core operand format directly
         direct = spconv.get_math_mode() == "bf16" and spconv.fused.is_enabled()
-        idx, feats = batcher.pack_batch(self.coords, self.wave, scale=self.scale, n_rows=self.n_rows,
-                                        tables=self.tables, out_dtype=torch.bfloat16 if direct else torch.float32)
-        loss = self.forward_backward(idx, feats, self.target, self.batch_size, self.n_rows)
+        # The rulebooks wait for the indices only, the first convolution for the features and the prepared weights:
+        # the (larger) waveform conversion and the weight preparation run on side streams from the very start of the
+        # step, the indices go first on the main stream (parallel branches of the captured graph).
+        side = None
+        if st["coords"].is_cuda:
+            main = torch.cuda.current_stream()
+            side = spconv.fused._side_stream(st["coords"].device, 2)
+            side.wait_stream(main)
+            spconv.fused.prepare_stacks(self.model)
+        idx, feats = batcher.pack_batch(st["coords"], st["wave"], scale=self.scale, n_rows=st["n_rows"],
+                                        tables=self.tables, out_dtype=torch.bfloat16 if direct else torch.float32,
+                                        feats_stream=side)
+        if side is not None:
+            with torch.cuda.stream(side):
+                self.grads.zero()  # off the main stream too: the first gradient is written long after the join below
+            feats_ready = torch.cuda.Event()
+            feats_ready.record(side)
+            feats._wfsp_ready = feats_ready  # the first consumer on the main stream waits for it (fused.py)
+        loss = self.forward_backward(idx, feats, st["target"], self.batch_size, st["n_rows"], zero=side is None)
         if self.capture_update:
             self._update()
         return loss.detach()
@@ -317,41 +383,52 @@ class GraphTrainStep(TrainStep):
         side.wait_stream(torch.cuda.current_stream())
         from . import _lib
         from .spconv.functional import hints
+        first = self.sets[self.cur]
         with torch.cuda.stream(side):
             # warm-up on a side stream (allocator, cuBLAS handles, NCCL) before capture; the first pass also
             # records the live row counts of the loaded batch as launch-shape hints (see LaunchHints)
             for i in range(3):
                 hints.start("record" if i == 0 else "replay")
-                self._body()
+                self._body(first)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         lib = _lib.load()
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = lib.wfsp_kernel_launches()
-        hints.start("replay")
         from .spconv import ops as _ops
-        del _ops.graph_dup_flags[:]
-        try:
-            with torch.cuda.graph(self.graph):
-                self.loss_out = self._body()
-        finally:
-            hints.stop()
-        self._dup_flags = list(_ops.graph_dup_flags)  # one int32 per captured rulebook, rewritten by every replay
-        del _ops.graph_dup_flags[:]
-        self.launches_per_replay = int(lib.wfsp_kernel_launches() - n0)  # libwfsp kernels in one replay
+        for st in self.sets:
+            if st is not first:  # every set is captured over the batch the hints were recorded from
+                for k in ("coords", "wave", "target", "n_rows"):
+                    st[k].copy_(first[k])
+            st["graph"] = torch.cuda.CUDAGraph()
+            n0 = lib.wfsp_kernel_launches()
+            hints.start("replay")
+            del _ops.graph_dup_flags[:]
+            try:
+                with torch.cuda.graph(st["graph"]):
+                    st["loss"] = self._body(st)
+            finally:
+                hints.stop()
+            st["dup_flags"] = list(_ops.graph_dup_flags)  # one int32 per captured rulebook, rewritten by every replay
+            del _ops.graph_dup_flags[:]
+            self.launches_per_replay = int(lib.wfsp_kernel_launches() - n0)  # libwfsp kernels in one replay
+        self.loss_out = first["loss"]
 
     def duplicate_inputs(self):
         """True if the batch of the LAST replay held duplicate (event, x, y) rows (a host readback: call it when
         validating data, not every step).  The eager path raises at rulebook construction instead."""
-        flags = getattr(self, "_dup_flags", [])
+        flags = self.sets[self.cur]["dup_flags"]
         return bool(flags) and bool(torch.stack([f.reshape(()) for f in flags]).ne(0).any().item())
 
     def run(self):
         if self._pending is not None:
             self._consume_prefetch()
-        if self.graph is None:
+        st = self.sets[self.cur]
+        if st["graph"] is None:
             self.capture()
-        self.graph.replay()
+        st["graph"].replay()
+        if len(self.sets) > 1:
+            st["done"] = torch.cuda.Event()
+            st["done"].record(torch.cuda.current_stream())
         if not self.capture_update:
             self._update()
+        self.loss_out = st["loss"]
         return self.loss_out

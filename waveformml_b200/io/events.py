@@ -309,7 +309,7 @@ def feed(step, batches, on_loss=None):
         pw[:n].copy_(torch.from_numpy(np.ascontiguousarray(w)))
         py[:len(y)].copy_(torch.from_numpy(np.ascontiguousarray(y)).to(py.dtype))
         step.prefetch(pc[:n], pw[:n], py[:len(y)])
-        copied[k % 3] = step._pending["ready"]
+        copied[k % 3] = step.pending_ready()
 
     it = iter(batches)
     nxt = next(it, None)

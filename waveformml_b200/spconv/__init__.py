@@ -305,10 +305,17 @@ class SparseSequential(SparseModule):
             # whole stack as one autograd node with bf16-resident operands (fused.py); None = not covered
             plan = fused.compile_stack([m for _, m in mods], SparseConvolution, ToDense)
             if plan is not None:
+                plan.prepared = self.__dict__.pop("_wfsp_prepared", None)
                 for k, module in mods:
                     if is_spconv_module(module):
                         self._sparity_dict[k] = input.sparity
                 return fused.run(plan, input)
+        # per-layer path from here on; work a caller started early on side streams for the fused path is joined first
+        stale = self.__dict__.pop("_wfsp_prepared", None)
+        if stale is not None:
+            torch.cuda.current_stream().wait_event(stale["done"])
+        if isinstance(input, SparseConvTensor) and getattr(input.features, "_wfsp_ready", None) is not None:
+            torch.cuda.current_stream().wait_event(input.features._wfsp_ready)
         first = next((m for _, m in mods if isinstance(m, SparseConvolution)), None)
         if (first is not None and isinstance(input, SparseConvTensor) and input.features is not None
                 and fused.is_operand_format(input.features, first.in_channels)

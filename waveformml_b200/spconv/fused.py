@@ -31,6 +31,11 @@ _enabled = True
 # BatchNorm statistics come from the convolution epilogue (per-32-row partials) whenever the output has more
 # rows than this; small outputs then normalise in ONE launch that folds the few partials itself
 _STATS_FUSE_MIN_ROWS = 0
+# The dgrad epilogue can also take the two reductions of the previous block's BatchNorm backward (sum dy', sum dy' xhat;
+# wfsp_conv_epilogue.bwd_partials + wfsp_bn_relu_bwd_parts).  Measured on B200 and left OFF: the epilogue of these
+# kernels is not overlapped with the next tile's main loop (one CTA per SM), so the extra pass over x is exposed --
+# C5@1024: 3x3 dgrad 156 -> 451 us against 141 us of bn_bwd_partial saved; 64 events: dgrad +9 us against -2.5 us.
+_BWD_PARTS = False
 
 
 def set_fused(flag):
@@ -63,6 +68,7 @@ class Block:
 class Plan:
     def __init__(self, blocks, to_dense):
         self.blocks, self.to_dense = blocks, to_dense
+        self.prepared = None  # weight preparation already launched for this step (prepare_stacks)
 
     def params(self):
         out = []
@@ -173,6 +179,82 @@ def _dense_geometry(t, idx=None):
     return h, w * d, idx
 
 
+def _param_key(params):
+    return tuple(0 if p is None else p.data_ptr() for p in params[0::4])
+
+
+def _prep_weights(plan, params, need_in_grad, dev, fork):
+    """Launches the preparation of every layer's weights (forward + dgrad layouts, one launch) on the second side
+    stream, ordered after `fork`; the BatchNorm step counters ride along.  Returns the buffers and events."""
+    lib = _lib.load()
+    blocks = plan.blocks
+    st = _lib.stream
+    jobs, offs, total = [], [], 0
+    for bi, b in enumerate(blocks):
+        kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
+        cin, cout = b.conv.in_channels, b.conv.out_channels
+        f_off = total
+        total += lib.wfsp_prepared_weight_bytes(kvol, cin, cout)
+        d_off = None
+        if bi > 0 or need_in_grad:
+            d_off = total
+            total += lib.wfsp_prepared_weight_bytes(kvol, cout, cin)
+        offs.append((f_off, d_off))
+    wbuf = torch.empty((total,), dtype=torch.uint8, device=dev)
+    for bi, b in enumerate(blocks):
+        kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
+        cin, cout = b.conv.in_channels, b.conv.out_channels
+        w = params[4 * bi]
+        assert w.dtype == torch.float32 and w.is_contiguous()
+        f_off, d_off = offs[bi]
+        jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + f_off, kvol, cin, cout, 0))
+        if d_off is not None:
+            jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + d_off, kvol, cout, cin, 1))
+    arr = (_lib.PrepJob * len(jobs))(*jobs)
+    # the weights do not depend on this step's data: prepared on a side stream, beside the batcher / the input cast
+    side2 = _side_stream(dev, 1)
+    with torch.cuda.stream(side2):
+        side2.wait_event(fork)
+        _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
+        w_ready = torch.cuda.Event()
+        w_ready.record(side2)
+        # BatchNorm step counters: one multi-tensor add here instead of one launch per layer on the main stream
+        counters = [b.bn.num_batches_tracked for b in blocks
+                    if b.bn is not None and b.bn.training and b.bn.num_batches_tracked is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)
+        side2_done = torch.cuda.Event()
+        side2_done.record(side2)
+    return {"wbuf": wbuf, "offs": offs, "w_ready": w_ready, "done": side2_done, "need_in_grad": need_in_grad,
+            "key": _param_key(params)}
+
+
+def prepare_stacks(model):
+    """Called at the very start of a training step (harness.GraphTrainStep._body): starts the weight preparation of
+    every fused sparse stack of `model` now, beside the batcher, instead of when the stack's forward is reached.  The
+    next forward of each stack picks the result up (and falls back to preparing itself if anything changed)."""
+    from . import SparseSequential, SparseConvolution, ToDense, get_math_mode
+    if not (_enabled and torch.is_grad_enabled()):
+        return
+    for seq in model.modules():
+        if not isinstance(seq, SparseSequential):
+            continue
+        mods = list(seq._modules.values())
+        if not all((m.math or get_math_mode()) == "bf16" for m in mods if isinstance(m, SparseConvolution)):
+            continue
+        plan = compile_stack(mods, SparseConvolution, ToDense)
+        if plan is None:
+            continue
+        params = plan.params()
+        w0 = params[0]
+        if not w0.is_cuda:
+            continue
+        with torch.cuda.device(w0.device):
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream())
+            seq._wfsp_prepared = _prep_weights(plan, params, False, w0.device, fork)
+
+
 class FusedStackFunction(Function):
     @staticmethod
     def forward(ctx, plan, x, holder, features, *params):
@@ -188,45 +270,20 @@ class FusedStackFunction(Function):
         st = _lib.stream
         need_in_grad = features.requires_grad and not ready16
         with torch.cuda.device(dev):
-            # ---- every layer's weights -> bf16 tensor-core layouts, one launch
-            jobs, offs, total = [], [], 0
-            for bi, b in enumerate(blocks):
-                kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
-                cin, cout = b.conv.in_channels, b.conv.out_channels
-                f_off = total
-                total += lib.wfsp_prepared_weight_bytes(kvol, cin, cout)
-                d_off = None
-                if bi > 0 or need_in_grad:
-                    d_off = total
-                    total += lib.wfsp_prepared_weight_bytes(kvol, cout, cin)
-                offs.append((f_off, d_off))
-            wbuf = torch.empty((total,), dtype=torch.uint8, device=dev)
-            for bi, b in enumerate(blocks):
-                kvol = 1 if b.conv.conv1x1 else int(np.prod(b.conv.kernel_size))
-                cin, cout = b.conv.in_channels, b.conv.out_channels
-                w = params[4 * bi]
-                assert w.dtype == torch.float32 and w.is_contiguous()
-                f_off, d_off = offs[bi]
-                jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + f_off, kvol, cin, cout, 0))
-                if d_off is not None:
-                    jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + d_off, kvol, cout, cin, 1))
-            arr = (_lib.PrepJob * len(jobs))(*jobs)
-            # the weights do not depend on this step's data: prepared on the side stream, beside the input cast
-            main, side, side2 = torch.cuda.current_stream(), _side_stream(dev), _side_stream(dev, 1)
+            # ---- every layer's weights -> bf16 tensor-core layouts, one launch (already under way if the caller
+            # announced the step early: prepare_stacks)
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
             fork = torch.cuda.Event()
             fork.record(main)
-            with torch.cuda.stream(side2):
-                side2.wait_event(fork)
-                _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
-                w_ready = torch.cuda.Event()
-                w_ready.record(side2)
-                # BatchNorm step counters: one multi-tensor add here instead of one launch per layer on the main stream
-                counters = [b.bn.num_batches_tracked for b in blocks
-                            if b.bn is not None and b.bn.training and b.bn.num_batches_tracked is not None]
-                if counters:
-                    torch._foreach_add_(counters, 1)
-                side2_done = torch.cuda.Event()
-                side2_done.record(side2)
+            prep = plan.prepared
+            if prep is None or prep["need_in_grad"] != need_in_grad or prep["key"] != _param_key(params):
+                if prep is not None:
+                    main.wait_event(prep["done"])  # an early preparation that does not fit this call: just join it
+                prep = _prep_weights(plan, params, need_in_grad, dev, fork)
+            wbuf, offs, w_ready, side2_done = prep["wbuf"], prep["offs"], prep["w_ready"], prep["done"]
+            ready_ev = getattr(features, "_wfsp_ready", None)
+            if ready_ev is not None:  # features written on another stream (harness: waveform conversion beside the indices)
+                main.wait_event(ready_ev)
 
             # ---- input activations -> bf16 once
             n0, c0 = feats.shape
@@ -278,10 +335,11 @@ class FusedStackFunction(Function):
                 hint = 0
                 if n_dst:
                     hint = Fsp.hints.get(n_dst_dev)
-                    _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
-                                                        ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
-                                                        _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
-                                                        hint, cout, _lib.ptr(partials), st()))
+                    ep = _lib.conv_epilogue(bn_partials=partials)
+                    _lib.check(lib.wfsp_conv_apply_bf16_ex(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
+                                                           ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
+                                                           _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
+                                                           hint, cout, ctypes.byref(ep), st()))
                 # ---- BatchNorm / ReLU -> next operand (bf16) or the stack's output (fp32)
                 y32 = y16 = mean = invstd = None
                 if b.bn is not None or b.relu:
@@ -364,6 +422,7 @@ class FusedStackFunction(Function):
             # aliasing would be baked into the graph with no edge between the branches).  They are released after
             # main has waited for the side stream.
             cross_stream = []
+            dy_parts = None  # BatchNorm-backward partial sums of `dy`, when the dgrad that produced it took them
             for bi in range(len(blocks) - 1, -1, -1):
                 b = blocks[bi]
                 conv = b.conv
@@ -378,11 +437,17 @@ class FusedStackFunction(Function):
                 if b.bn is not None:
                     dgam, gam_through = _grad_target(gamma_p, (cout,), dev)
                     dbet, bet_through = _grad_target(beta_p, (cout,), dev)
-                    ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
-                    _lib.check(lib.wfsp_bn_relu_bwd_x(
-                        _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), dst_hint, cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
-                        _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
-                        _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
+                    if dy_parts is not None:
+                        _lib.check(lib.wfsp_bn_relu_bwd_parts(
+                            _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), dst_hint, cout, _lib.ptr(gamma_p),
+                            _lib.ptr(beta_p), _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dy_parts),
+                            _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam), _lib.ptr(dbet), st()))
+                    else:
+                        ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
+                        _lib.check(lib.wfsp_bn_relu_bwd_x(
+                            _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), dst_hint, cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
+                            _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
+                            _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
                     if gamma_p is not None and not gam_through:
                         grads[4 * bi + 2] = dgam
                     if beta_p is not None and not bet_through:
@@ -429,12 +494,22 @@ class FusedStackFunction(Function):
                 if bi > 0 or ctx.need_in_grad:
                     nbr_t = None if rb is None else (rb.nbr_out if conv.inverse else rb.nbr_in)
                     dy = torch.empty((n_in, cin), dtype=torch.float32, device=dev)
+                    dy_parts = None
                     if n_in:
                         hint = Fsp.hints.get(n_src_dev)
-                        _lib.check(lib.wfsp_conv_apply_bf16(_lib.ptr(g16), n_dst, _lib.ptr(n_dst_dev), cout,
-                                                            ctypes.c_void_p(wbuf.data_ptr() + offs[bi][1]), None,
-                                                            _lib.ptr(nbr_t), kvol, _lib.ptr(dy), n_in, _lib.ptr(n_src_dev),
-                                                            hint, cin, None, st()))
+                        # this dy arrives at the previous block's BatchNorm: its two reductions (sum dy', sum dy' xhat)
+                        # are taken from the dgrad tile while it is on chip
+                        bwd = None
+                        if bi > 0 and blocks[bi - 1].bn is not None and _BWD_PARTS and cin <= 512:
+                            pb = blocks[bi - 1]
+                            p_xf, p_mean, p_invstd = saved[bi - 1][1], saved[bi - 1][2], saved[bi - 1][3]
+                            dy_parts = torch.empty((lib.wfsp_bn_partials_bytes(n_in, cin),), dtype=torch.uint8, device=dev)
+                            bwd = (p_xf, p_mean, p_invstd, params[4 * (bi - 1) + 2], params[4 * (bi - 1) + 3], pb.relu, dy_parts)
+                        ep = _lib.conv_epilogue(bwd=bwd)
+                        _lib.check(lib.wfsp_conv_apply_bf16_ex(_lib.ptr(g16), n_dst, _lib.ptr(n_dst_dev), cout,
+                                                               ctypes.c_void_p(wbuf.data_ptr() + offs[bi][1]), None,
+                                                               _lib.ptr(nbr_t), kvol, _lib.ptr(dy), n_in, _lib.ptr(n_src_dev),
+                                                               hint, cin, ctypes.byref(ep), st()))
             if side_used:
                 joined = torch.cuda.Event()
                 joined.record(side)
