@@ -204,8 +204,10 @@ __device__ __forceinline__ void stats_from_partials(const PartStats& ps, int64_t
   }
 }
 
-template <bool VEC2>
-__global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int64_t n_cap,
+// FOLD: the fused small path (statistics folded from the partials by every CTA); the streaming variant is kept lean
+// (<= 64 registers, four CTAs per SM) -- these kernels are bound by the bytes they keep in flight.
+template <bool VEC2, bool FOLD>
+__global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_apply(const float* __restrict__ x, int64_t n_cap,
                                                 const int32_t* __restrict__ n_dev, int c,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -214,9 +216,9 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
   const int64_t n = live_rows(n_cap, n_dev);
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
   uint32_t* y16w = reinterpret_cast<uint32_t*>(y16);
-  if (int64_t(blockIdx.x) * rows_per_cta >= n && !(ps.part && blockIdx.x == 0)) return;
-  __shared__ float s_m[512], s_is[512];  // fused small path: statistics of this CTA's channels (c <= 512)
-  if (ps.part && n > 0) {
+  if (int64_t(blockIdx.x) * rows_per_cta >= n && !(FOLD && blockIdx.x == 0)) return;
+  __shared__ float s_m[FOLD ? 512 : 1], s_is[FOLD ? 512 : 1];  // fused small path: statistics of this CTA's channels (c <= 512)
+  if (FOLD && n > 0) {
     for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y)
       stats_from_partials(ps, n, c, ch, s_m[ch], s_is[ch], blockIdx.x == 0);
     __syncthreads();
@@ -227,8 +229,8 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
     const bool on[2] = {ch < c, ch + 1 < c};
 #pragma unroll
     for (int e = 0; e < 2; ++e)
-      if ((mean || ps.part) && on[e]) {
-        if (ps.part) { m[e] = s_m[ch + e]; is[e] = s_is[ch + e]; }
+      if ((mean || FOLD) && on[e]) {
+        if (FOLD) { m[e] = s_m[ch + e]; is[e] = s_is[ch + e]; }
         else { m[e] = mean[ch + e]; is[e] = invstd[ch + e]; }
         if (gamma) g[e] = gamma[ch + e];
         if (beta) b[e] = beta[ch + e];
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
           for (int e = 0; e < 2; ++e) {
             if (on[e]) {
               float tv = xv[u][e];
-              if (mean || ps.part) tv = (tv - m[e]) * is[e] * g[e] + b[e];
+              if (mean || FOLD) tv = (tv - m[e]) * is[e] * g[e] + b[e];
               if (relu && tv < 0.f) tv = 0.f;
               v[e] = tv;
             }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(256) bn_apply(const float* __restrict__ x, int
 // parameters in registers, float2 accesses when VEC2), thread y strides over the chunk's rows with four rows in
 // flight; a warp reads 256 contiguous bytes per row.  grid = row chunks of kRowsBwd, block = apply_block(c).
 template <bool VEC2>
-__global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256, 4) bn_bwd_partial(const float* __restrict__ x, const float* __restrict__ dy,
                                                       int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -362,14 +364,16 @@ __global__ void __launch_bounds__(256) bn_bwd_partial(const float* __restrict__ 
 __global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* __restrict__ part, int chunk_rows, int64_t n_cap,
                                                        const int32_t* __restrict__ n_dev, int c,
                                                        float* __restrict__ d_gamma, float* __restrict__ d_beta,
-                                                       double* __restrict__ inter, unsigned* __restrict__ tickets) {
+                                                       double* __restrict__ inter, unsigned* __restrict__ tickets,
+                                                       int nblk_fixed /* >= 0: length of the partial list (one entry per CTA
+                                                                         of the streaming kernel), else derived from the rows */) {
   __shared__ double r0[kFinLanes][kCh], r1[kFinLanes][kCh];
   __shared__ unsigned s_ticket;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * kCh + tx;
   const int S = gridDim.y, seg = blockIdx.y;
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t nblk = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0;
+  const int64_t nblk = nblk_fixed >= 0 ? int64_t(nblk_fixed) : (n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0);
   const int64_t per = (nblk + S - 1) / S;
   const int64_t lo = seg * per, hi = lo + per < nblk ? lo + per : nblk;
   double s0 = 0.0, s1 = 0.0;
@@ -410,8 +414,8 @@ __global__ void __launch_bounds__(kCh * kFinLanes) bn_bwd_finalize(const float* 
 }
 
 // same thread mapping as bn_apply; mean == nullptr means "no normalisation" (plain ReLU backward)
-template <bool VEC2>
-__global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
+template <bool VEC2, bool FOLD>
+__global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
                                                     int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -425,8 +429,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply(const float* __restrict__ x,
   uint32_t* dx16w = reinterpret_cast<uint32_t*>(dx16);
   // fused small path: the (few) per-chunk sums of the dgrad epilogue are folded by every CTA for its own use --
   // same order everywhere, so all CTAs hold bit-identical sums -- and CTA 0 records d_gamma / d_beta (c <= 512)
-  __shared__ float s_db[512], s_dg[512];
-  if (part) {
+  __shared__ float s_db[FOLD ? 512 : 1], s_dg[FOLD ? 512 : 1];
+  if (FOLD) {
     const int64_t nblk = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 0;
     for (int ch = threadIdx.y * blockDim.x + threadIdx.x; ch < c; ch += blockDim.x * blockDim.y) {
       double a = 0.0, q = 0.0;
@@ -736,6 +740,22 @@ inline dim3 apply_block(int c) {
 }
 
 }  // namespace
+
+// bn_stream.cu: the same passes fed by bulk copies (large row counts)
+bool bn_stream_ok(int c, int arrays, const void* x, const void* dy);
+int bn_stream_grid(int64_t n_rows, int chunk_rows);
+int bn_stream_chunk_rows(int c, int arrays);
+int bn_stream_fwd_apply(const float* x, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma, const float* beta,
+                        const float* mean, const float* invstd, int relu, float* y, void* y16, cudaStream_t st);
+int bn_stream_bwd_partial(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
+                          const float* beta, const float* mean, const float* invstd, int relu, float* part, int* n_part,
+                          cudaStream_t st);
+int bn_stream_bwd_apply(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
+                        const float* beta, const float* mean, const float* invstd, const float* d_gamma, const float* d_beta,
+                        int relu, float* dx, void* dx16, cudaStream_t st);
+constexpr int64_t kStreamMinRows = 32768;  // (expected live) rows from which the bulk-copy fed passes are used
+static int g_bn_stream = 1;                // wfsp_set_option "bn_stream": 0 = register-load kernels everywhere
+void set_bn_stream(int v) { g_bn_stream = v; }
 }  // namespace wfsp
 
 using namespace wfsp;
@@ -785,9 +805,9 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     count_launches(1);
   }
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -808,9 +828,9 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
     // few chunks: every CTA of the apply kernel folds the partials of its channels itself -- ONE launch
     const PartStats ps{bn_partials, WFSP_BN_CHUNK_ROWS, eps, momentum, running_mean, running_var, save_mean, save_invstd};
     if (vec2_ok(c, x, y))
-      bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
+      bn_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
     else
-      bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
+      bn_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -820,10 +840,14 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
   if (int rc = launch_finalize(bn_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, eps, momentum, running_mean,
                                running_var, save_mean, save_invstd, scratch, st))
     return rc;
+  if (g_bn_stream && live >= kStreamMinRows && bn_stream_ok(c, 1, x, nullptr) && (y == nullptr || vec2_ok(c, y, y))) {
+    count_launches(1);
+    return bn_stream_fwd_apply(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, st);
+  }
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -861,16 +885,27 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
     return set_error(WFSP_EWORKSPACE, "batch-norm workspace too small");
   float* part = static_cast<float*>(workspace);
+  if (g_bn_stream && live >= kStreamMinRows && n_rows >= int64_t(sm_count()) * kRowsBwd && bn_stream_ok(c, 2, x, dy) &&
+      (dx == nullptr || vec2_ok(c, dx, dx))) {
+    int n_part = 0;
+    if (int rc = bn_stream_bwd_partial(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part, &n_part, st))
+      return rc;
+    bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, 1, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr,
+                                                                      nullptr, n_part);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+    return bn_stream_bwd_apply(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, st);
+  }
   const unsigned pgrid = unsigned(ceil_div<int64_t>(n_rows, kRowsBwd));
   if (vec2_ok(c, x, dy))
     bn_bwd_partial<true><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
   else
     bn_bwd_partial<false><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
-  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, kRowsBwd, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr, nullptr);
+  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, kRowsBwd, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr, nullptr, -1);
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
-    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   else
-    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -895,9 +930,9 @@ extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n
   const bool v2 = vec2_ok(c, x, dy) && vec2_ok(c, dx, dx);
   if (live <= kFoldRows && c <= 512) {  // ONE launch: every CTA folds the few partials of its channels itself
     if (v2)
-      bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+      bn_bwd_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
     else
-      bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+      bn_bwd_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -909,11 +944,11 @@ extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n
   unsigned* tickets = reinterpret_cast<unsigned*>(scratch + size_t(kFinSegMax) * 2 * c * sizeof(double));
   if (S > 1) WFSP_CHECK_CUDA(cudaMemsetAsync(tickets, 0, 1024, st));
   bn_bwd_finalize<<<dim3(unsigned(ceil_div(c, kCh)), unsigned(S)), dim3(kCh, kFinLanes), 0, st>>>(
-      bwd_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, d_gamma, d_beta, inter, tickets);
+      bwd_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, d_gamma, d_beta, inter, tickets, -1);
   if (v2)
-    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   else
-    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -935,10 +970,10 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
   if (vec2_ok(c, x, y))
-    bn_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
   else
-    bn_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
   count_launches(1);
   WFSP_CHECK_LAUNCH();
@@ -951,11 +986,11 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "needs at least one output");
   if (n_rows == 0) return WFSP_OK;
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
-    bn_bwd_apply<true><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
         static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   else
-    bn_bwd_apply<false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
+    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
         static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
   count_launches(1);

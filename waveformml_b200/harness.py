@@ -176,9 +176,13 @@ class TrainStep:
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev
         try:
             # one backward over freshly zeroed gradients: the fused kernels write straight into the flat buffer
-            with spconv.fused.grad_write_through():
+            with spconv.fused.grad_write_through(zeroed=True):
                 loss = self.loss(indices, feats, target, batch_size, n_rows)
-                loss.backward()
+                # d(loss)/d(loss) = 1 from a persistent tensor: autograd would otherwise launch a fill for it every step
+                if (getattr(self, "_one", None) is None or self._one.device != loss.device or self._one.dtype != loss.dtype
+                        or self._one.shape != loss.shape):
+                    self._one = torch.ones(loss.shape, dtype=loss.dtype, device=loss.device)
+                loss.backward(gradient=self._one)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return loss

@@ -117,6 +117,7 @@ def compile_stack(modules, sparse_conv_cls, to_dense_cls):
 
 
 _write_through = 0
+_write_through_zeroed = False  # the write-through targets were zeroed before this backward (grad_write_through(zeroed=True))
 
 
 class grad_write_through:
@@ -126,14 +127,20 @@ class grad_write_through:
     everywhere else (gradient accumulation over micro-batches, retain_graph, shared parameters) the kernels return
     fresh tensors and torch.autograd accumulates as usual."""
 
+    def __init__(self, zeroed=False):
+        self.zeroed = zeroed
+
     def __enter__(self):
-        global _write_through
+        global _write_through, _write_through_zeroed
         _write_through += 1
+        self._prev = _write_through_zeroed
+        _write_through_zeroed = bool(self.zeroed)
         return self
 
     def __exit__(self, *exc):
-        global _write_through
+        global _write_through, _write_through_zeroed
         _write_through -= 1
+        _write_through_zeroed = self._prev
         return False
 
 
@@ -484,9 +491,12 @@ class FusedStackFunction(Function):
                     g_ready.record(main)
                     with torch.cuda.stream(side):
                         side.wait_event(g_ready)
+                        # write-through target = the harness' flat gradient buffer, zeroed at the start of the step: the
+                        # split reduction adds into it directly (no memset node per wgrad)
                         _lib.check(lib.wfsp_conv_wgrad_bf16(_lib.ptr(a16), n_in, _lib.ptr(n_src_dev), cin, _lib.ptr(g16),
                                                             n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(pa), _lib.ptr(pb),
-                                                            _lib.ptr(pn), kvol, pitch, hint, _lib.ptr(dw), 0, st()))
+                                                            _lib.ptr(pn), kvol, pitch, hint, _lib.ptr(dw),
+                                                            1 if (w_through and _write_through_zeroed) else 0, st()))
                     side_used = True
                     if not w_through:
                         grads[4 * bi] = dw.view(w_p.shape)
