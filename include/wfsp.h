@@ -178,6 +178,20 @@ int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t n_in, const
                            int32_t* nbr_in, int32_t* dup_flag, void* workspace, size_t workspace_bytes,
                            wfsp_stream_t stream);
 
+/* wfsp_rulebook_build_nd in two launches, for callers that overlap the backward half of a rulebook with the forward
+ * pass (waveformml_b200/spconv/fused.py): phases = 1 (FRONT) produces out_indices, *n_out and nbr_out -- all the forward
+ * convolution and the next layer's rulebook wait for; phases = 2 (BACK, same arguments, any stream ordered after the
+ * front call) produces pairs, pair_num, nbr_in and dup_flag; phases = 3 = everything (= wfsp_rulebook_build_nd).  Only
+ * the single-launch builder (small inputs) is split: otherwise the FRONT call builds everything and sets *built_all
+ * (host int, may be NULL) and the BACK call returns immediately. */
+int wfsp_rulebook_build_phased(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                               int64_t n_in_hint, int batch, const int* in_shape_host,
+                               const int* ksize_host, const int* stride_host, const int* pad_host,
+                               const int* dil_host, int subm, int32_t* out_indices, int64_t out_cap,
+                               int32_t* pairs, int32_t* pair_num, int32_t* n_out, int32_t* nbr_out,
+                               int32_t* nbr_in, int32_t* dup_flag, void* workspace, size_t workspace_bytes,
+                               int phases, int* built_all, wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (3) Gather-GEMM forward / dgrad / wgrad.  Replaces upstream indice_conv /
  * indice_conv_backward reached from spconv.SparseConv2d / SubMConv2d / SparseInverseConv2d

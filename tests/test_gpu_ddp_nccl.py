@@ -27,7 +27,7 @@ def _free_port():
 def test_nccl_step_equals_sequential_shards(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "ddp_nccl_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     sys.stdout.write(res.stdout[-2000:])
     sys.stderr.write(res.stderr[-2000:])
     assert res.returncode == 0, res.stderr[-2000:]

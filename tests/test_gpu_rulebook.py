@@ -145,3 +145,48 @@ def test_duplicate_coordinates_flagged(cuda_device):
     x = spconv.SparseConvTensor(torch.ones(3, 4, device=cuda_device), idx.to(cuda_device), [14, 11], 1)
     with pytest.raises(RuntimeError, match="duplicate"):
         layer(x)
+
+
+@pytest.mark.parametrize("k,s,p,d,subm", [(3, 1, 0, 1, False), (3, 1, 1, 1, False), (2, 1, 0, 1, False), (3, 2, 1, 1, False),
+                                          (3, 1, 1, 1, True), (5, 1, 2, 1, True)])
+def test_front_back_split_equals_whole(cuda_device, k, s, p, d, subm):
+    """Graph path: the rulebook built in two launches (FRONT: output rows + nbr_out, what the forward pass waits for;
+    BACK: pairs, nbr_in, counts, duplicate flag, beside the forward pass) is bit-identical to the single launch, on
+    capacity-sized buffers with the live count on the device; duplicates are still flagged by the BACK half."""
+    from waveformml_b200.spconv.functional import hints
+    dev = cuda_device
+    for dup in (False, True):
+        idx = _indices(37, 11)
+        n = idx.shape[0]
+        if dup:
+            idx[5] = idx[4]
+        cap = n + 40
+        buf = torch.zeros(cap, 3, dtype=torch.int32)
+        buf[:n] = idx
+        n_dev = torch.tensor([n], dtype=torch.int32, device=dev)
+        pad = [k // 2] * 2 if subm else [p, p]
+        st = [1, 1] if subm else [s, s]
+        res = []
+        for front_only in (False, True):
+            hints.start("record")
+            try:
+                rb = ops.build_rulebook(buf.to(dev), 37, [14, 11], [k, k], st, pad, [d, d], subm, n_rows=n_dev,
+                                        front_only=front_only)
+            finally:
+                hints.stop()
+            del ops.graph_dup_flags[:]
+            if front_only:
+                assert rb._pending, "the single-launch builder should have left its BACK half pending"
+                front = (rb.outids.clone(), rb.nbr_out.clone(), rb.n_out_dev.clone())
+                rb.finish()
+                torch.cuda.synchronize()
+                assert all(torch.equal(a, b) for a, b in zip(front, (rb.outids, rb.nbr_out, rb.n_out_dev))), \
+                    "the BACK half must not touch the FRONT half's results"
+            n_out = int(rb.n_out_dev)
+            res.append((rb.outids[:n_out].cpu(), rb.nbr_out[:n_out].cpu(), rb.pairs[:, :, :n].cpu(), rb.pair_num.cpu(),
+                        rb.nbr_in[:n].cpu(), int(rb.dup_flag.item()), n_out))
+        whole, split = res
+        if not dup:  # (with duplicate rows the contested nbr_out slots legitimately depend on which store lands last)
+            for a, b in zip(whole, split):
+                assert torch.equal(a, b) if torch.is_tensor(a) else a == b
+        assert whole[5] == split[5] == (1 if dup else 0)

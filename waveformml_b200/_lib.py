@@ -38,6 +38,8 @@ SIGNATURES = {
     "wfsp_rulebook_workspace_bytes_nd": (_sz, [_int, _i64, _int, _intp, _intp]),
     "wfsp_rulebook_build_nd": (_int, [_int, _vp, _i64, _vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _int, _vp,
                                       _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "wfsp_rulebook_build_phased": (_int, [_int, _vp, _i64, _vp, _i64, _int, _intp, _intp, _intp, _intp, _intp, _int, _vp,
+                                          _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _int, _intp, _vp]),
     "wfsp_conv_apply_workspace_bytes": (_sz, [_int, _i64, _int, _int, _int]),
     "wfsp_conv_apply": (_int, [_vp, _i64, _vp, _int, _vp, _int, _vp, _vp, _int, _vp, _i64, _vp, _i64, _int, _int, _vp,
                                _sz, _vp]),

@@ -378,7 +378,10 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
                                                         int32_t* __restrict__ pairs, int32_t* __restrict__ pair_num,
                                                         int32_t* __restrict__ n_out, int32_t* __restrict__ nbr_out,
                                                         int32_t* __restrict__ nbr_in, int32_t* __restrict__ dup_flag,
-                                                        unsigned long long* trace) {
+                                                        unsigned long long* trace, int phases) {
+  // phases: 3 = the whole rulebook; 1 = FRONT only -- output rows + nbr_out, what the forward convolution (and the next
+  // rulebook) waits for; 2 = BACK only -- pair lists, nbr_in, pair counts, duplicate check, what backward needs: it
+  // rebuilds the coordinate table from the output rows of the front launch and runs beside the forward pass.
 #define WFSP_RB_TRACE(slot) do { if (trace != nullptr && threadIdx.x == 0) trace[slot] = (unsigned long long)clock64(); } while (0)
   WFSP_RB_TRACE(0);
   extern __shared__ int s_dyn[];  // [K][kSmallWarps] per-warp pair counts / prefixes, [K] running bases, [cells] table
@@ -399,28 +402,40 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   // device-side counts it is written for the live rows only (nothing reads the capacity tail).
   // (plain counted loops, not unrolled: this kernel runs once, cold, in one CTA -- its cost is fetching its code)
   const int ncells = int(cells);
+  const bool front = (phases & 1) != 0, back = (phases & 2) != 0;
 #pragma unroll 1
-  for (int i = tid; i < ncells; i += kSmallBlock) table[i] = SUBM ? -1 : kRankInf;
-  if (!g.n_dev) {
+  for (int i = tid; i < ncells; i += kSmallBlock) table[i] = (SUBM || !front) ? -1 : kRankInf;
+  if (back) {
+    if (!g.n_dev) {
 #pragma unroll 1
-    for (int i = tid; i < 2 * K * n; i += kSmallBlock) pairs[i] = -1;
-  } else {  // rows [0, live) of every (side, offset) list; the capacity tail stays unspecified
+      for (int i = tid; i < 2 * K * n; i += kSmallBlock) pairs[i] = -1;
+    } else {  // rows [0, live) of every (side, offset) list; the capacity tail stays unspecified
 #pragma unroll 1
-    for (int c = warp; c < 2 * K; c += kSmallWarps)
+      for (int c = warp; c < 2 * K; c += kSmallWarps)
 #pragma unroll 1
-      for (int i = lane; i < live; i += 32) pairs[c * n + i] = -1;
+        for (int i = lane; i < live; i += 32) pairs[c * n + i] = -1;
+    }
+#pragma unroll 1
+    for (int i = tid; i < live * K; i += kSmallBlock) nbr_in[i] = -1;
   }
 #pragma unroll 1
-  for (int i = tid; i < live * K; i += kSmallBlock) nbr_in[i] = -1;
-#pragma unroll 1
   for (int k = tid; k < K; k += kSmallBlock) s_kbase[k] = 0;
-  if (tid == 0) { *dup_flag = 0; s_base = 0; }
+  if (tid == 0) { if (back) *dup_flag = 0; s_base = 0; }
   __syncthreads();
   WFSP_RB_TRACE(2);
   const Row r0 = load_row(indices, n, tid, g);  // round 0 (all there is up to 1024 rows) reads its row once
   // phase 1: claim cells
+  if (!SUBM && !front) {
+    // BACK only: the front launch already numbered the output rows; cell of output row r <- -r - 1
+    const int n_o = min(int(*n_out), int(out_cap));
 #pragma unroll 1
-  for (int rd = 0; rd < rounds; ++rd) {
+    for (int i = tid; i < n_o; i += kSmallBlock) {
+      const int32_t* q = out_indices + g.cols * i;
+      table[((q[0] * g.out_h + q[1]) * g.out_w + q[2]) * g.out_t + (g.cols > 3 ? q[3] : 0)] = -i - 1;
+    }
+  }
+#pragma unroll 1
+  for (int rd = 0; rd < ((SUBM || front) ? rounds : 0); ++rd) {
     const int j = rd * kSmallBlock + tid;
     Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
     if (!r.ok) continue;
@@ -437,7 +452,8 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   __syncthreads();
   WFSP_RB_TRACE(3);
   int64_t rows_out = live;
-  if (!SUBM) {
+  if (!SUBM && !front) rows_out = *n_out;
+  if (!SUBM && front) {
     // phase 2: first touchers -> output rows in rank order, round after round
 #pragma unroll 1
     for (int rd = 0; rd < rounds; ++rd) {
@@ -486,10 +502,31 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
   }
   if (rows_out > out_cap) rows_out = out_cap;
   WFSP_RB_TRACE(4);
+  if (front) {
 #pragma unroll 1
-  for (int i = tid; i < int(rows_out) * K; i += kSmallBlock) nbr_out[i] = -1;
+    for (int i = tid; i < int(rows_out) * K; i += kSmallBlock) nbr_out[i] = -1;
+  }
   __syncthreads();
   WFSP_RB_TRACE(5);
+  if (!back) {
+    // FRONT only: the output-stationary table straight from the coordinate table (no compaction needed for it)
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int j = rd * kSmallBlock + tid;
+      if (rd * kSmallBlock + warp * 32 >= live) continue;
+      Row r = rd == 0 ? r0 : load_row(indices, n, j, g);
+      WFSP_FOR_TAPS(g, kx, ky, kz) {
+        int slot = 0, val = 0;
+        Pos o;
+        if (candidate<false, SUBM>(r, g, t, kx, ky, kz, slot, val, o)) {
+          const int o_row = SUBM ? val : -table[slot] - 1;
+          if (o_row < out_cap) nbr_out[int64_t(o_row) * K + WFSP_TAP(g, kx, ky, kz)] = j;
+        }
+      }
+    }
+    WFSP_RB_TRACE(6);
+    return;
+  }
   // phase 3: per-offset compaction in ascending input order
   const unsigned lt = (1u << lane) - 1u;
   int dup = 0;  // becomes non-zero if a (row, offset) slot of nbr_out was already taken: duplicate coordinates
@@ -539,7 +576,10 @@ __global__ void __launch_bounds__(kSmallBlock) rb_small(const int32_t* __restric
         pairs[(int64_t(1) * K + k) * n + pos] = o_row;
         nbr_in[int64_t(j) * K + k] = o_row;
         // the previous occupants are only looked at after the loop: the exchanges of one row overlap
-        if (o_row < out_cap) dup |= atomicExch(&nbr_out[int64_t(o_row) * K + k], j) + 1;
+        if (o_row < out_cap) {
+          if (front) dup |= atomicExch(&nbr_out[int64_t(o_row) * K + k], j) + 1;
+          else dup |= int(nbr_out[int64_t(o_row) * K + k] != j);  // the front launch's table: another row took the slot
+        }
       }
     }
     }
@@ -796,13 +836,16 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
 // inputs (up to kSmallMaxRows expected live rows, direct table, kernel volume <= 256) take the single-launch
 // path; everything else runs the phase kernels above followed by rb_tables.  ndim 2: index rows (b, x, y);
 // ndim 3: (b, x, y, t).
-extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
-                                      int64_t n_in_hint, int batch, const int* in_shape, const int* ksize,
-                                      const int* stride, const int* pad, const int* dil, int subm,
-                                      int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
-                                      int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag,
-                                      void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+extern "C" int wfsp_rulebook_build_phased(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                                          int64_t n_in_hint, int batch, const int* in_shape, const int* ksize,
+                                          const int* stride, const int* pad, const int* dil, int subm,
+                                          int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
+                                          int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag,
+                                          void* workspace, size_t workspace_bytes, int phases, int* built_all,
+                                          wfsp_stream_t stream) {
   WFSP_REQUIRE(ndim == 2 || ndim == 3, "ndim %d: only 2-d and 3-d rulebooks", ndim);
+  WFSP_REQUIRE(phases >= 1 && phases <= 3, "phases must be 1 (front), 2 (back) or 3 (all)");
+  if (built_all) *built_all = 0;
   WFSP_REQUIRE(pair_num && dup_flag, "null output");
   WFSP_REQUIRE(n_in == 0 || (pairs && nbr_out && nbr_in), "null output");
   WFSP_REQUIRE(subm || n_out, "regular convolution needs n_out");
@@ -834,7 +877,7 @@ extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t 
       WFSP_CHECK_CUDA(cudaFuncSetAttribute(rb_small<SUBM, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                            208 * 1024));                                                        \
       rb_small<SUBM, SM><<<1, kSmallBlock, smem, st>>>(indices, n_in, g, tab, cells, OUT, CAP, pairs, pair_num,  \
-                                                       NOUT, nbr_out, nbr_in, dup_flag, g_trace);                \
+                                                       NOUT, nbr_out, nbr_in, dup_flag, g_trace, phases);        \
     } while (0)
     if (subm) {
       if (in_smem) WFSP_RB_SMALL(true, true, nullptr, n_in, nullptr);
@@ -848,6 +891,10 @@ extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t 
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
   }
+  // the multi-kernel builders are not split: a FRONT request builds everything (and says so), a BACK request after
+  // that has nothing left to do
+  if (phases == 2) return WFSP_OK;
+  if (built_all) *built_all = 1;
   int rc;
   if (subm)
     rc = rulebook_subm_impl(ndim, indices, n_in, n_in_dev, batch, in_shape, ksize, dil, pairs, pair_num, workspace,
@@ -858,6 +905,17 @@ extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t 
   if (rc) return rc;
   WFSP_CHECK_CUDA(cudaMemsetAsync(dup_flag, 0, 4, st));
   return wfsp_rulebook_tables(pairs, pair_num, kvol, n_in, n_in, subm ? n_in : out_cap, nbr_out, nbr_in, dup_flag, stream);
+}
+
+extern "C" int wfsp_rulebook_build_nd(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
+                                      int64_t n_in_hint, int batch, const int* in_shape, const int* ksize,
+                                      const int* stride, const int* pad, const int* dil, int subm,
+                                      int32_t* out_indices, int64_t out_cap, int32_t* pairs, int32_t* pair_num,
+                                      int32_t* n_out, int32_t* nbr_out, int32_t* nbr_in, int32_t* dup_flag,
+                                      void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return wfsp_rulebook_build_phased(ndim, indices, n_in, n_in_dev, n_in_hint, batch, in_shape, ksize, stride, pad, dil, subm,
+                                    out_indices, out_cap, pairs, pair_num, n_out, nbr_out, nbr_in, dup_flag, workspace,
+                                    workspace_bytes, 3, nullptr, stream);
 }
 
 extern "C" int wfsp_rulebook_build(const int32_t* indices, int64_t n_in, const int32_t* n_in_dev, int64_t n_in_hint, int batch,

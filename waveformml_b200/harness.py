@@ -85,11 +85,53 @@ class FlatGrads:
 
     def all_reduce_sum(self, group=None):
         """SUM only; returns the factor (1 / world size) that turns it into the mean -- FlatSGD folds it into
-        the update instead of spending a kernel on the division."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            return 1.0 / dist.get_world_size(group)
-        return 1.0
+        the update instead of spending a kernel on the division.  Ranges already exchanged during backward
+        (early_reduce) are skipped; the side-stream exchanges are joined."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return 1.0
+        done = sorted(getattr(self, "_early", []))
+        pos, total = 0, self.flat.numel()
+        for lo, hi, _ in done + [(total, total, None)]:
+            if lo > pos:
+                dist.all_reduce(self.flat[pos:lo], op=dist.ReduceOp.SUM, group=group)
+            pos = max(pos, hi)
+        main = torch.cuda.current_stream() if self.flat.is_cuda else None
+        for _, _, ev in done:
+            if ev is not None:
+                main.wait_event(ev)
+        self._early = []
+        return 1.0 / dist.get_world_size(group)
+
+    def offsets(self):
+        if getattr(self, "_off", None) is None:
+            self._off, off = {}, 0
+            for p in self.params:
+                self._off[id(p)] = (off, off + p.numel())
+                off += p.numel()
+        return self._off
+
+    def early_reduce(self, params, events, group=None):
+        """Called from backward (spconv.fused.grads_ready_hook / head.grads_ready_hook) when the gradients of `params`
+        are final: if they form one contiguous range of the flat buffer, its all-reduce is issued NOW on a
+        communication stream (ordered after `events`), overlapping the rest of the backward pass."""
+        if not self.flat.is_cuda:
+            return
+        off = self.offsets()
+        rng = sorted(off[id(p)] for p in params if id(p) in off)
+        if not rng or any(rng[i][1] != rng[i + 1][0] for i in range(len(rng) - 1)):
+            return  # not contiguous: left to the final exchange
+        lo, hi = rng[0][0], rng[-1][1]
+        if any(not (hi <= a or lo >= b) for a, b, _ in getattr(self, "_early", [])):
+            return
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=self.flat.device)
+        with torch.cuda.stream(self._comm):
+            for ev in events:
+                self._comm.wait_event(ev)
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        self._early = getattr(self, "_early", []) + [(lo, hi, done)]
 
 
 class FlatSGD:
@@ -165,7 +207,9 @@ class TrainStep:
             return self.criterion(out, target)
         return segment_l1_loss(indices, out, target, self.model.spatial_size, batch_size, n_rows)
 
-    def forward_backward(self, indices, feats, target, batch_size, n_rows=None, zero=True):
+    def forward_backward(self, indices, feats, target, batch_size, n_rows=None, zero=True, overlap_exchange=False):
+        """loss + gradients.  overlap_exchange (only when _update() follows, i.e. from step()): gradient buckets that
+        are final early are all-reduced during backward; a bare forward_backward never communicates."""
         if zero:
             self.grads.zero()
         # bf16 math mode = tensor-core operands with fp32 accumulation everywhere: the dense head's library
@@ -174,6 +218,12 @@ class TrainStep:
         tf32 = self.grads.flat.is_cuda and spconv.get_math_mode() == "bf16"
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev
+        from . import head as _head
+        overlap = (overlap_exchange and self.grads.flat.is_cuda and isinstance(self.opt, FlatSGD) and dist.is_available()
+                   and dist.is_initialized() and dist.get_world_size(self.group) > 1)
+        if overlap:  # gradient buckets are exchanged as soon as they are final (head first, then the later conv blocks)
+            hook = lambda params, events: self.grads.early_reduce(params, events, self.group)
+            spconv.fused.grads_ready_hook, _head.grads_ready_hook = hook, hook
         try:
             # one backward over freshly zeroed gradients: the fused kernels write straight into the flat buffer
             with spconv.fused.grad_write_through(zeroed=True):
@@ -185,10 +235,11 @@ class TrainStep:
                 loss.backward(gradient=self._one)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
+            spconv.fused.grads_ready_hook, _head.grads_ready_hook = None, None
         return loss
 
     def step(self, indices, feats, target, batch_size, n_rows=None):
-        loss = self.forward_backward(indices, feats, target, batch_size, n_rows)
+        loss = self.forward_backward(indices, feats, target, batch_size, n_rows, overlap_exchange=True)
         self._update()
         return loss.detach()
 
@@ -351,7 +402,8 @@ class GraphTrainStep(TrainStep):
             feats_ready = torch.cuda.Event()
             feats_ready.record(side)
             feats._wfsp_ready = feats_ready  # the first consumer on the main stream waits for it (fused.py)
-        loss = self.forward_backward(idx, feats, st["target"], self.batch_size, st["n_rows"], zero=side is None)
+        loss = self.forward_backward(idx, feats, st["target"], self.batch_size, st["n_rows"], zero=side is None,
+                                     overlap_exchange=self.capture_update)
         if self.capture_update:
             self._update()
         return loss.detach()

@@ -14,6 +14,8 @@ from torch.autograd import Function
 from . import _lib
 from .spconv.fused import _grad_target
 
+grads_ready_hook = None  # see spconv.fused.grads_ready_hook: called when the head's parameter gradients are final
+
 MAX_BATCH = 256   # one CTA reduces over the batch (staged in shared memory): beyond this the library GEMMs win
 MAX_HIDDEN = 128
 MAX_CLASSES = 64
@@ -85,6 +87,10 @@ class HeadCEFunction(Function):
             torch.mm(dh1s.t(), x, out=dw1)
             if dx is not None:
                 torch.mm(dh1s, w1, out=dx)
+        if grads_ready_hook is not None and w1_thr and w2_thr and b1_thr and b2_thr:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            grads_ready_hook([q for q in (w1_p, b1_p, w2_p, b2_p) if q is not None], [ev])
         return (dx, None if w1_thr else dw1, None if b1_thr else db1, None if w2_thr else dw2, None if b2_thr else db2,
                 None)
 

@@ -88,9 +88,9 @@ class SubmanifoldConvolution(_SCNConv):
         self._key_base = "scn_subm" + "x".join(str(k) for k in self.filter_size)
         self.indice_key = self._key_base
 
-    def geometry(self, input):
+    def geometry(self, input, front_only=False):
         self.indice_key = self._key_base + "@" + "x".join(str(int(s)) for s in input.spatial_shape)
-        return super().geometry(input)
+        return super().geometry(input, front_only=front_only)
 
 
 class BatchNormalization(nn.BatchNorm1d):

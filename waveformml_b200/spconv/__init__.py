@@ -142,7 +142,7 @@ class SparseConvolution(SparseModule):
             self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.dilation,
             self.subm, self.inverse, self.indice_key)
 
-    def geometry(self, input):
+    def geometry(self, input, front_only=False):
         """Rulebook lookup / construction for this layer on `input` (upstream conv.py forward: reuse the
         entry cached under indice_key, else build and cache it -- also under key None).  Returns
         (rulebook or None for the 1x1 shortcut, output indices, output spatial shape, device row count
@@ -162,7 +162,7 @@ class SparseConvolution(SparseModule):
             pad = [k // 2 for k in self.kernel_size] if self.subm else self.padding
             stride = [1] * self.ndim if self.subm else self.stride
             rb = ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape, self.kernel_size, stride,
-                                    pad, self.dilation, self.subm, n_rows=input.n_rows)
+                                    pad, self.dilation, self.subm, n_rows=input.n_rows, front_only=front_only)
             input.indice_dict[self.indice_key] = rb
         out_spatial_shape = input.spatial_shape if self.subm else rb.out_spatial_shape
         return rb, rb.outids, out_spatial_shape, rb.n_out_dev
@@ -180,6 +180,8 @@ class SparseConvolution(SparseModule):
         assert isinstance(input, SparseConvTensor)
         mode = self.math or _math_mode
         rb, outids, out_spatial_shape, out_rows = self.geometry(input)
+        if rb is not None:
+            rb.finish()
         out_features = Fsp.SparseConvFunction.apply(input.features, self.weight, self.bias, rb, self.inverse, mode,
                                                     input.n_rows if rb is None else None)
         out = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size, n_rows=out_rows)

@@ -157,6 +157,12 @@ def _grad_target(param, shape, dev):
     return torch.empty(shape, dtype=torch.float32, device=dev), False
 
 
+# Data-parallel training: a harness that exchanges gradients in buckets sets `grads_ready_hook(params, events)`; it is
+# called during backward as soon as the gradients of `params` are final, with the events (on the main / side stream)
+# after which they may be read -- so the exchange of the later layers overlaps the backward pass of the earlier ones
+# (the reference's DDP does the same with its gradient buckets, src/utils/util.py:233-236).
+grads_ready_hook = None
+
 _side_streams = {}
 
 
@@ -305,8 +311,12 @@ class FusedStackFunction(Function):
             geoms, gcur = [], x
             with torch.cuda.stream(side):
                 side.wait_event(fork)
+                # graph path: only what the forward pass waits for (output rows, nbr_out) is built here; the pair lists
+                # and nbr_in that backward needs follow on a third stream, beside the forward pass (an inverse
+                # convolution reads nbr_in in its FORWARD pass: such stacks build whole rulebooks)
+                split_rb = not any(b.conv.inverse for b in blocks)
                 for b in blocks:
-                    rb, outids, out_shape, out_rows = b.conv.geometry(gcur)
+                    rb, outids, out_shape, out_rows = b.conv.geometry(gcur, front_only=split_rb)
                     ready = torch.cuda.Event()
                     ready.record(side)
                     nxt = x.__class__(None, outids, out_shape, gcur.batch_size, n_rows=out_rows)
@@ -314,6 +324,16 @@ class FusedStackFunction(Function):
                     geoms.append((rb, outids, out_shape, out_rows, gcur, nxt, ready))
                     gcur = nxt
 
+            backs = [g[0] for g in geoms if g[0] is not None and getattr(g[0], "_pending", None)]
+            back_done = None
+            if backs:
+                side3 = _side_stream(dev, 3)
+                with torch.cuda.stream(side3):
+                    side3.wait_event(geoms[-1][6])
+                    for rb in backs:
+                        rb.finish()
+                    back_done = torch.cuda.Event()
+                    back_done.record(side3)
             main.wait_event(w_ready)
             saved, cur, out32 = [], x, None
             for bi, b in enumerate(blocks):
@@ -386,6 +406,8 @@ class FusedStackFunction(Function):
                 cur, a16, out32 = nxt, y16, y32
 
             main.wait_event(side2_done)
+            if back_done is not None:
+                main.wait_event(back_done)
             holder["tensor"] = cur  # geometry of the stack's output
             ctx.plan, ctx.saved, ctx.offs, ctx.wbuf = plan, saved, offs, wbuf
             ctx.params = params
@@ -500,6 +522,17 @@ class FusedStackFunction(Function):
                     side_used = True
                     if not w_through:
                         grads[4 * bi] = dw.view(w_p.shape)
+                if bi == 1 and grads_ready_hook is not None and _write_through > 0:
+                    # blocks >= 1 are final once their wgrads (side stream) and BatchNorm gradients (main) have run
+                    e_main, e_side = torch.cuda.Event(), torch.cuda.Event()
+                    e_main.record(main)
+                    e_side.record(side)
+                    done = [q for q in params[4:] if q is not None and q.requires_grad]
+                    # only if every one of them was written in place (a gradient handed back to autograd is accumulated
+                    # after this function returns): no conv bias in these blocks, write-through targets attached
+                    if (all(params[4 * j + 1] is None for j in range(1, len(blocks)))
+                            and all(getattr(q, "_wfsp_grad_out", None) is not None for q in done)):
+                        grads_ready_hook(done, [e_main, e_side])
                 # ---- dgrad -> dy of the previous block (or of the stack's input)
                 if bi > 0 or ctx.need_in_grad:
                     nbr_t = None if rb is None else (rb.nbr_out if conv.inverse else rb.nbr_in)

@@ -42,7 +42,14 @@ class Rulebook:
         self.nbr_out, self.nbr_in, self.dup_flag = nbr_out, nbr_in, dup_flag
         self.n_in_dev, self.n_out_dev = n_in_dev, n_out_dev
 
+    def finish(self):
+        """Launches the half of the rulebook that build_rulebook(front_only=True) left for later (no-op otherwise)."""
+        pend = getattr(self, "_pending", None)
+        while pend:
+            pend.pop()()
+
     def _tuple(self):
+        self.finish()
         return (self.outids, self.indices, self.pairs, self.pair_num, self.spatial_shape)
 
     def __iter__(self):
@@ -69,13 +76,17 @@ graph_dup_flags = []
 
 
 def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=False,
-                   check_duplicates=None, n_rows=None):
+                   check_duplicates=None, n_rows=None, front_only=False):
     """Builds pairs + neighbour tables on the GPU.
 
     Eager path (n_rows None): one host readback (n_out) for a regular conv, none for a submanifold
     conv; all results have exact shapes.  Graph path (n_rows = int32 device scalar, indices at
     capacity): no readback at all -- outputs are allocated at their upper bound
-    min(N*K, B*H'*W') and the live output count stays on the device."""
+    min(N*K, B*H'*W') and the live output count stays on the device.
+
+    front_only (graph path): only the half of the rulebook the forward pass waits for is built now (output rows,
+    n_out, nbr_out); the returned Rulebook carries `finish()`, which launches the other half (pairs, pair_num, nbr_in,
+    duplicate flag) on the current stream -- any stream ordered after this call -- and must run before backward."""
     lib = _lib.load()
     _lib.require_cuda(indices)
     if indices.dtype != torch.int32:
@@ -112,14 +123,26 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     dup = meta[1:2]
     nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
 
+    split = bool(front_only and static)
+    pending = []  # the BACK half, when it was left for later
+
     def build(subm_flag, out_indices, out_cap, n_out_t, nbr_out):
         geom = [_lib.ints(v, nd) for v in (spatial_shape, ksize, stride, padding, dilation)]
         tail = (subm_flag, _lib.ptr(out_indices), out_cap, _lib.ptr(pairs), _lib.ptr(pair_num), _lib.ptr(n_out_t),
-                _lib.ptr(nbr_out), _lib.ptr(nbr_in), _lib.ptr(dup), _lib.ptr(ws), ws.numel(), _lib.stream())
+                _lib.ptr(nbr_out), _lib.ptr(nbr_in), _lib.ptr(dup), _lib.ptr(ws), ws.numel())
         head = (_lib.ptr(indices), N, _lib.ptr(n_in_dev), n_hint, batch_size)
+        if split:
+            built_all = (_lib.ctypes.c_int * 1)(0)
+            rc = lib.wfsp_rulebook_build_phased(nd, *head, *geom, *tail, 1, built_all, _lib.stream())
+            if rc == 0 and not built_all[0]:
+                def finish():
+                    with torch.cuda.device(dev):
+                        _lib.check(lib.wfsp_rulebook_build_phased(nd, *head, *geom, *tail, 2, None, _lib.stream()))
+                pending.append(finish)
+            return rc
         if nd == 2:  # the 14x11 grid keeps its own entry point
-            return lib.wfsp_rulebook_build(*head, *geom, *tail)
-        return lib.wfsp_rulebook_build_nd(nd, *head, *geom, *tail)
+            return lib.wfsp_rulebook_build(*head, *geom, *tail, _lib.stream())
+        return lib.wfsp_rulebook_build_nd(nd, *head, *geom, *tail, _lib.stream())
 
     with torch.cuda.device(dev):
         if subm:
@@ -146,8 +169,11 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
         graph_dup_flags.append(dup)
     elif subm and check_duplicates and N > 0 and int(dup.item()) != 0:
         raise RuntimeError(_DUP_MESSAGE)
-    return Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup,
-                    n_in_dev, n_out_dev)
+    rb = Rulebook(outids, indices, pairs, pair_num, spatial_shape, out_shape, nbr_out, nbr_in, dup,
+                  n_in_dev, n_out_dev)
+    rb._keep = (ws,)  # the BACK half reuses the workspace
+    rb._pending = pending
+    return rb
 
 
 _DUP_MESSAGE = ("duplicate (batch, x, y) coordinates in the input: upstream spconv would sum their contributions, the "
