@@ -430,6 +430,16 @@ int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1, const flo
                      int n_class, float* h1, float* logits, float* loss, float* dlogits, float* dh1,
                      float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                      wfsp_stream_t stream);
+/* The tail of wfsp_head_ce_fwd for ANY batch size, for callers that computed h1 = x w1^T + b1 themselves (one plain GEMM:
+ * library): logits, mean cross-entropy, dlogits, dh1, dw2, db2 in ONE launch of ceil(batch / 32) CTAs; the batch
+ * reductions (loss, dw2, db2) are added in tile order by the last CTA to finish (deterministic).  *ticket: a device
+ * counter that is zero before the call and is left zero (allocate once, reuse).  Workspace:
+ * wfsp_head_tail_workspace_bytes(). */
+size_t wfsp_head_tail_workspace_bytes(int batch, int h1, int n_class);
+int wfsp_head_ce_tail(const float* h1, const float* w2, const float* b2, const int64_t* labels, int batch,
+                      int h1_dim, int n_class, float* logits, float* loss, float* dlogits, float* dh1,
+                      float* dw2, float* db2, void* workspace, size_t workspace_bytes, unsigned* ticket,
+                      wfsp_stream_t stream);
 /* backward split for callers with a GEMM library at hand: this entry does the small part (dh1_scaled = dh1 *
  * *grad_out, db1, dw2, db2); the caller then computes dw1 = dh1_scaled^T x and dx = dh1_scaled w1 as two
  * plain GEMMs (what waveformml_b200/head.py does with cuBLAS -- the all-in-one wfsp_head_bwd below is an

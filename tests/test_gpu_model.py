@@ -162,10 +162,12 @@ def test_flat_sgd_matches_torch_nesterov(cuda_device):
     assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in ours)  # parameters live in the flat buffer
 
 
-@pytest.mark.parametrize("B,k0,h1,C", [(64, 4480, 116, 3), (5, 70, 128, 2), (200, 333, 17, 64)])
+@pytest.mark.parametrize("B,k0,h1,C", [(64, 4480, 116, 3), (5, 70, 128, 2), (200, 333, 17, 64), (1024, 4480, 116, 3),
+                                       (300, 70, 33, 5), (257, 64, 128, 64)])
 def test_fused_head_matches_torch(cuda_device, B, k0, h1, C):
-    """wfsp_head_ce_fwd / wfsp_head_bwd == Linear . Linear . CrossEntropyLoss(mean) of torch: loss, input gradient
-    and all four parameter gradients, also under a non-unit incoming gradient."""
+    """wfsp_head_ce_fwd / wfsp_head_ce_tail / wfsp_head_bwd == Linear . Linear . CrossEntropyLoss(mean) of torch: loss,
+    input gradient and all four parameter gradients, also under a non-unit incoming gradient.  Batches above 256 take
+    the multi-CTA tail (Linear-1 as a library GEMM, exact fp32 here: TF32 is off outside the bf16 training step)."""
     from waveformml_b200 import head
     torch.manual_seed(B)
     lin = torch.nn.Sequential(torch.nn.Linear(k0, h1), torch.nn.Linear(h1, C)).to(cuda_device)

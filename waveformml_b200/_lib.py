@@ -72,6 +72,8 @@ SIGNATURES = {
     "wfsp_act_fwd": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_act_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_head_workspace_bytes": (_sz, [_int, _int, _int]),
+    "wfsp_head_tail_workspace_bytes": (_sz, [_int, _int, _int]),
+    "wfsp_head_ce_tail": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "wfsp_head_ce_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _sz, _vp]),
     "wfsp_head_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),

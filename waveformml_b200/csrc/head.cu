@@ -174,6 +174,101 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   }
 }
 
+// The same tail for ANY batch: CTA t owns batch rows [32 t, 32 t + 32).  Per-row results (logits, dlogits, dh1) are
+// final per CTA; the batch reductions (loss, dW2, db2) go through per-tile partials that the LAST CTA to finish (ticket)
+// adds in tile order -- deterministic, one launch.  h1 = x w1^T + b1 comes from the caller (a plain GEMM: library).
+// dynamic smem: h1 [TB][H1+1] | w2 [C][H1+1] | dlogits [TB][C] | logits [TB][C];  part: [tiles][C*H1 + C + 1]
+constexpr int kTailRows = 32;
+__global__ void __launch_bounds__(256) head_tail_tiles(const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       const int64_t* __restrict__ labels, int B, int H1, int C,
+                                                       const float* __restrict__ h1, float* __restrict__ logits,
+                                                       float* __restrict__ loss, float* __restrict__ dlogits,
+                                                       float* __restrict__ dh1, float* __restrict__ dw2, float* __restrict__ db2,
+                                                       float* __restrict__ part, unsigned* __restrict__ ticket) {
+  extern __shared__ float sm[];
+  __shared__ float s_red[16];
+  __shared__ unsigned s_ticket;
+  const int tid = threadIdx.x, nt = blockDim.x, hp = H1 + 1;
+  const int b0 = blockIdx.x * kTailRows, nb = min(kTailRows, B - b0), tiles = gridDim.x;
+  float* s_h1 = sm;
+  float* s_w2 = s_h1 + kTailRows * hp;
+  float* s_dl = s_w2 + C * hp;
+  float* s_lg = s_dl + kTailRows * C;
+  for (int i = tid; i < nb * H1; i += nt) s_h1[(i / H1) * hp + i % H1] = h1[int64_t(b0) * H1 + i];
+  for (int i = tid; i < C * H1; i += nt) s_w2[(i / H1) * hp + i % H1] = w2[i];
+  __syncthreads();
+  for (int i = tid; i < nb * C; i += nt) {
+    const int b = i / C, c = i % C;
+    float s = b2 ? b2[c] : 0.f;
+    const float* hr = s_h1 + b * hp;
+    const float* wr = s_w2 + c * hp;
+#pragma unroll 4
+    for (int h = 0; h < H1; ++h) s += hr[h] * wr[h];
+    s_lg[i] = s;
+    logits[int64_t(b0) * C + i] = s;
+  }
+  __syncthreads();
+  float lsum = 0.f;
+  for (int b = tid; b < nb; b += nt) {
+    const float* lr = s_lg + b * C;
+    float m = lr[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, lr[c]);
+    float z = 0.f;
+    for (int c = 0; c < C; ++c) z += expf(lr[c] - m);
+    const float lse = m + logf(z);
+    const int y = int(labels[b0 + b]);
+    lsum += lse - lr[y];
+    for (int c = 0; c < C; ++c) {
+      const float d = (expf(lr[c] - lse) - (c == y ? 1.f : 0.f)) / float(B);
+      s_dl[b * C + c] = d;
+      dlogits[int64_t(b0 + b) * C + c] = d;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
+  __syncthreads();
+  float* my = part + int64_t(blockIdx.x) * (C * H1 + C + 1);
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nt / 32; ++w) t += s_red[w];
+    my[C * H1 + C] = t;
+  }
+  for (int i = tid; i < C * H1; i += nt) {
+    const int c = i / H1, h = i % H1;
+    float s = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < nb; ++b) s += s_dl[b * C + c] * s_h1[b * hp + h];
+    my[i] = s;
+  }
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int b = 0; b < nb; ++b) s += s_dl[b * C + c];
+    my[C * H1 + c] = s;
+  }
+  for (int i = tid; i < nb * H1; i += nt) {
+    const int b = i / H1, h = i % H1;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += s_dl[b * C + c] * s_w2[c * hp + h];
+    dh1[int64_t(b0) * H1 + i] = s;
+  }
+  // last CTA: the batch reductions, in tile order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(tiles - 1)) return;
+  __threadfence();
+  if (tid == 0) *ticket = 0u;
+  const int per = C * H1 + C + 1;
+  for (int i = tid; i < per; i += nt) {
+    float s = 0.f;
+    for (int t = 0; t < tiles; ++t) s += __ldcg(part + int64_t(t) * per + i);
+    if (i < C * H1) dw2[i] = s;
+    else if (i < C * H1 + C) db2[i - C * H1] = s;
+    else *loss = s / float(B);
+  }
+}
+
 constexpr int kKB = 32;    // K-chunk of the backward kernel
 constexpr int kBB = 32;    // batch rows per tile of the backward kernel
 constexpr int kMaxH1 = 128;
@@ -298,6 +393,29 @@ extern "C" int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1
   WFSP_CHECK_CUDA(cudaFuncSetAttribute(head_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   head_tail<<<1, 1024, tail_smem, st>>>(w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2);
   count_launches(3);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+
+extern "C" size_t wfsp_head_tail_workspace_bytes(int batch, int h1, int n_class) {
+  const size_t tiles = size_t((batch + kTailRows - 1) / kTailRows);
+  return align_up(tiles * (size_t(n_class) * h1 + n_class + 1) * sizeof(float), 256);
+}
+
+extern "C" int wfsp_head_ce_tail(const float* h1, const float* w2, const float* b2, const int64_t* labels, int batch,
+                                 int h1_dim, int n_class, float* logits, float* loss, float* dlogits, float* dh1, float* dw2,
+                                 float* db2, void* workspace, size_t workspace_bytes, unsigned* ticket, wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 1 && h1_dim >= 1 && h1_dim <= kMaxH1 && n_class >= 1 && n_class <= 64,
+               "head sizes outside the supported range (hidden <= 128, classes <= 64)");
+  WFSP_REQUIRE(h1 && w2 && labels && logits && loss && dlogits && dh1 && dw2 && db2 && ticket, "null argument");
+  if (workspace == nullptr || workspace_bytes < wfsp_head_tail_workspace_bytes(batch, h1_dim, n_class))
+    return set_error(WFSP_EWORKSPACE, "head tail workspace too small");
+  const size_t smem = (size_t(kTailRows) * (h1_dim + 1) + size_t(n_class) * (h1_dim + 1) + size_t(2) * kTailRows * n_class) * sizeof(float);
+  WFSP_CHECK_CUDA(cudaFuncSetAttribute(head_tail_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  head_tail_tiles<<<unsigned((batch + kTailRows - 1) / kTailRows), 256, smem, as_stream(stream)>>>(
+      w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2, static_cast<float*>(workspace), ticket);
+  count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }

@@ -16,7 +16,9 @@ from .spconv.fused import _grad_target
 
 grads_ready_hook = None  # see spconv.fused.grads_ready_hook: called when the head's parameter gradients are final
 
-MAX_BATCH = 256   # one CTA reduces over the batch (staged in shared memory): beyond this the library GEMMs win
+MAX_BATCH = 256   # up to here the first Linear runs as our split-K launch + a one-CTA tail; beyond, Linear-1 is a library
+                  # GEMM (TF32 in bf16 math mode) and the tail (Linear-2, loss, small backward half) one multi-CTA launch
+_tickets = {}     # per device: the zero-initialised counter of wfsp_head_ce_tail (left zero by every call)
 MAX_HIDDEN = 128
 MAX_CLASSES = 64
 
@@ -30,7 +32,7 @@ def supported(linear, x, criterion=None):
                                       and criterion.ignore_index < 0):
         return False
     l1, l2 = linear[0], linear[1]
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] <= MAX_BATCH
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
             and l1.out_features <= MAX_HIDDEN and l2.out_features <= MAX_CLASSES and l1.in_features == x.shape[1]
             and l2.in_features == l1.out_features)
 
@@ -51,15 +53,30 @@ class HeadCEFunction(Function):
         dh1 = torch.empty((B, h1d), **f32)
         dw2 = torch.empty((C, h1d), **f32)
         db2 = torch.empty((C,), **f32)
-        ws_bytes = lib.wfsp_head_workspace_bytes(B, k0, h1d)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         labels = labels.contiguous()
         assert labels.dtype == torch.int64
         with torch.cuda.device(dev):
-            _lib.check(lib.wfsp_head_ce_fwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
-                                            _lib.ptr(labels), B, k0, h1d, C, _lib.ptr(h1), _lib.ptr(logits), _lib.ptr(loss),
-                                            _lib.ptr(dlogits), _lib.ptr(dh1), _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws),
-                                            ws_bytes, _lib.stream()))
+            if B <= MAX_BATCH:
+                ws_bytes = lib.wfsp_head_workspace_bytes(B, k0, h1d)
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                _lib.check(lib.wfsp_head_ce_fwd(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                                _lib.ptr(labels), B, k0, h1d, C, _lib.ptr(h1), _lib.ptr(logits),
+                                                _lib.ptr(loss), _lib.ptr(dlogits), _lib.ptr(dh1), _lib.ptr(dw2),
+                                                _lib.ptr(db2), _lib.ptr(ws), ws_bytes, _lib.stream()))
+            else:
+                if b1 is not None:
+                    torch.addmm(b1, x, w1.t(), out=h1)
+                else:
+                    torch.mm(x, w1.t(), out=h1)
+                key = (dev.type, dev.index)
+                if key not in _tickets:
+                    _tickets[key] = torch.zeros((1,), dtype=torch.int32, device=dev)
+                ws_bytes = lib.wfsp_head_tail_workspace_bytes(B, h1d, C)
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+                _lib.check(lib.wfsp_head_ce_tail(_lib.ptr(h1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(labels), B, h1d, C,
+                                                 _lib.ptr(logits), _lib.ptr(loss), _lib.ptr(dlogits), _lib.ptr(dh1),
+                                                 _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws), ws_bytes,
+                                                 _lib.ptr(_tickets[key]), _lib.stream()))
         ctx.save_for_backward(x, w1, dh1, dw2, db2)
         ctx.params = (w1, b1, w2, b2)
         ctx.logits = logits
