@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=64, help="events per GPU")
-    ap.add_argument("--math", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--math", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: sync-free capacity-sized step replayed from a CUDA graph; eager: exact shapes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -594,7 +594,9 @@ def run_ours(args):
         "implementation": {
             "parallelism": "dp%d (events sharded by rank, rank-local rulebooks and BatchNorm, NCCL all-reduce of the "
                            "flat 4.2 MB gradient inside the captured step)" % world,
-            "math": "bf16 operands / fp32 accumulate (tcgen05)" if args.math == "bf16" else "fp32 CUDA cores",
+            "math": {"bf16": "bf16 operands / fp32 accumulate (tcgen05)", "fp32": "fp32 CUDA cores",
+                     "bf16x3": "fp32-grade on tcgen05: hi/lo bf16 operand split, three products per pair, fp32 "
+                               "accumulate"}[args.math],
             "execution": ("whole step replayed from one CUDA graph, row counts on the device, no host readback"
                           if args.mode == "graph" else "eager, exact shapes, one readback per rulebook"),
             "e2e": "two input sets, each with its own captured graph: GraphTrainStep.prefetch copies the next pinned host "

@@ -48,7 +48,11 @@ enum wfsp_dtype { WFSP_F32 = 0, WFSP_BF16 = 1, WFSP_I16 = 2 };
 /* arithmetic of the channel contraction */
 enum wfsp_math {
   WFSP_MATH_FP32 = 0, /* fp32 FMA on CUDA cores, exact fp32 products                      */
-  WFSP_MATH_BF16 = 1  /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (kind::f16)  */
+  WFSP_MATH_BF16 = 1, /* bf16 operands, fp32 accumulate in TMEM, tcgen05.mma (kind::f16)  */
+  WFSP_MATH_BF16X3 = 2 /* fp32-grade results on the same tensor-core kernels: every operand is split into
+                          hi + lo bf16 parts and a w ~ hi hi + hi lo + lo hi is accumulated in fp32 (three
+                          times the reduction length; error ~2^-16 per product, vs 2^-9 for WFSP_MATH_BF16).
+                          The tensor-core counterpart of WFSP_MATH_FP32 for the tight-tolerance mode.    */
 };
 
 #define WFSP_VERSION 201

@@ -15,7 +15,7 @@ from waveformml_b200.synth import make_events
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": (1e-4, 1e-5), "bf16": (2e-2, 2e-2), "bf16_emulated": (2e-3, 2e-3)}
+TOL = {"fp32": (1e-4, 1e-5), "bf16x3": (1e-4, 1e-5), "bf16": (2e-2, 2e-2), "bf16_emulated": (2e-3, 2e-3)}
 
 
 def close(got, ref, mode, what=""):
@@ -92,7 +92,7 @@ def check_all(g, refs, mode, name, elementwise_fp32_ref=True):
     """fp32 mode: element-wise vs the fp32 oracle.  bf16 mode: element-wise (tight) vs the oracle
     that rounds operands to bf16, and vs the plain fp32 oracle either element-wise with the stated
     bf16 tolerance (single layers) or norm-wise (stacks with ReLU gates in between)."""
-    plan = [("fp32", "fp32")] if mode == "fp32" else [("bf16_emulated", "bf16_emulated")]
+    plan = [("fp32", mode)] if mode in ("fp32", "bf16x3") else [("bf16_emulated", "bf16_emulated")]
     if mode == "bf16" and elementwise_fp32_ref:
         plan.append(("fp32", "bf16"))
     for ref_name, tol in plan:
@@ -131,11 +131,12 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16_per_layer"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16_per_layer", "bf16x3"])
 @pytest.mark.parametrize("name,factory,cin", CASES, ids=[c[0] for c in CASES])
 def test_layer_parity(cuda_device, name, factory, cin, mode):
     """bf16: the stack runs as one fused node with bf16-resident operands (spconv/fused.py);
-    bf16_per_layer: the same kernels module by module through the fp32-in / fp32-out C entries."""
+    bf16_per_layer: the same kernels module by module through the fp32-in / fp32-out C entries;
+    bf16x3: the tensor-core kernels with hi/lo-split operands, held to the fp32 tolerance."""
     torch.manual_seed(sum(name.encode()))
     B = 19
     idx, feats = events(B, 21, cin)

@@ -120,7 +120,7 @@ def _psd_inputs(B, seed, dev):
             torch.from_numpy(ev["labels"]).to(dev))
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16x3"])
 def test_capacity_path_matches_eager_psd(cuda_device, mode):
     """Same weights, same batch: eager TrainStep (exact shapes, torch BatchNorm) vs the capacity-sized
     path with device-side counts (no graph yet) -- loss and every gradient."""

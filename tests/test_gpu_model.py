@@ -35,12 +35,19 @@ def _rel(a, b):
 
 # (math mode, oracle operand rounding, gradient tolerance (norm-wise), loss tolerance (relative))
 MODES = [("fp32", None, 1e-3, 1e-4),       # exact-fp32 kernels vs the fp32 oracle
+         ("bf16x3", None, 2e-2, 1e-4),     # tcgen05 kernels with hi/lo-split operands vs the fp32 oracle.  Per layer they
+                                           # are held to the fp32 tolerance (tests/test_gpu_conv.py; measured 4.5e-6
+                                           # relative vs float64, fp32 kernels 4e-7, bf16 2.3e-3: scripts/exp_x3_error.py).
+                                           # Whole-model GRADIENTS cross ReLU gates: a perturbation eps of the
+                                           # activations flips a fraction ~eps of the gates, each flip is a full-size
+                                           # error, so the norm-wise error goes like sqrt(eps) -- fp32 6e-4, bf16x3
+                                           # 7e-3, bf16 8e-2 on this batch -- while loss and activations stay at eps
          ("bf16", "bf16", 1e-2, 1e-3),     # tcgen05 kernels vs the oracle with bf16-rounded GEMM operands
          ("bf16", None, 0.2, 1e-2)]        # tcgen05 kernels vs the fp32 oracle: a sanity cap only -- the bound that
                                            # is JUSTIFIED BY DATA is in tests/test_gpu_large.py
                                            # (test_bf16_vs_fp32_gap_is_the_operand_rounding: the oracle's own
                                            # gradients move by the same ~8 % when its operands are rounded to bf16)
-MODE_IDS = ["fp32", "bf16-vs-emulated", "bf16-vs-fp32"]
+MODE_IDS = ["fp32", "bf16x3-vs-fp32", "bf16-vs-emulated", "bf16-vs-fp32"]
 
 
 @pytest.mark.parametrize("mode,rounding,tol,ltol", MODES, ids=MODE_IDS)

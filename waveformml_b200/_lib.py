@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwfsp.so")
 
 F32, BF16, I16 = 0, 1, 2
-MATH_FP32, MATH_BF16 = 0, 1
+MATH_FP32, MATH_BF16, MATH_BF16X3 = 0, 1, 2
 
 _c = ctypes
 _vp, _i64, _int, _sz, _f32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_size_t, _c.c_float

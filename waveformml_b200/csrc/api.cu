@@ -51,16 +51,16 @@ int conv_wgrad_simt(const float* a, int64_t n_a, int c_a, const float* b, int64_
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, const int32_t* n_a_dev, cudaStream_t st);
 // conv_umma.cu
-size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst);
+size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst, int split3);
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst,
                     void* ws, size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
-                    cudaStream_t st);
-size_t conv_wgrad_umma_workspace(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t pitch);
+                    int split3, cudaStream_t st);
+size_t conv_wgrad_umma_workspace(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t pitch, int split3);
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
-                    const int32_t* n_b_dev, int64_t pairs_hint, cudaStream_t st);
+                    const int32_t* n_b_dev, int64_t pairs_hint, int split3, cudaStream_t st);
 
 size_t prepared_weight_bytes(int kvol, int c_red, int c_dst);
 int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st);
@@ -115,7 +115,9 @@ extern "C" int wfsp_debug_trace(unsigned long long* device_buffer) {
 }
 
 extern "C" size_t wfsp_conv_apply_workspace_bytes(int kvol, int64_t n_src, int c_red, int c_dst, int math) {
-  return math == WFSP_MATH_BF16 ? conv_apply_umma_workspace(kvol, n_src, c_red, c_dst) : 0;
+  if (math == WFSP_MATH_BF16 || math == WFSP_MATH_BF16X3)
+    return conv_apply_umma_workspace(kvol, n_src, c_red, c_dst, math == WFSP_MATH_BF16X3);
+  return 0;
 }
 
 extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n_src_dev, int c_red,
@@ -128,15 +130,17 @@ extern "C" int wfsp_conv_apply(const float* src, int64_t n_src, const int32_t* n
   if (math == WFSP_MATH_FP32)
     return conv_apply_simt(src, n_src, c_red, weight, transpose_w, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev,
                            n_dst_dev, as_stream(stream));
-  if (math == WFSP_MATH_BF16)
+  if (math == WFSP_MATH_BF16 || math == WFSP_MATH_BF16X3)
     return conv_apply_umma(src, n_src, c_red, weight, transpose_w, bias, nbr, kvol, dst, n_dst, c_dst, workspace,
-                           workspace_bytes, n_src_dev, n_dst_dev, n_dst_hint, as_stream(stream));
+                           workspace_bytes, n_src_dev, n_dst_dev, n_dst_hint, math == WFSP_MATH_BF16X3, as_stream(stream));
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
 }
 
 extern "C" size_t wfsp_conv_wgrad_workspace_bytes(int kvol, int64_t n_a, int c_a, int64_t n_b, int c_b,
                                                   int64_t pair_pitch, int math) {
-  return math == WFSP_MATH_BF16 ? conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pair_pitch) : 0;
+  if (math == WFSP_MATH_BF16 || math == WFSP_MATH_BF16X3)
+    return conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pair_pitch, math == WFSP_MATH_BF16X3);
+  return 0;
 }
 
 extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_dev, int c_a, const float* b,
@@ -149,9 +153,10 @@ extern "C" int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_d
   if (math == WFSP_MATH_FP32)
     return conv_wgrad_simt(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
                            accumulate, n_a_dev, as_stream(stream));
-  if (math == WFSP_MATH_BF16)
+  if (math == WFSP_MATH_BF16 || math == WFSP_MATH_BF16X3)
     return conv_wgrad_umma(a, n_a, c_a, b, n_b, c_b, pair_a, pair_b, pair_num, kvol, pair_pitch, d_weight,
-                           accumulate, workspace, workspace_bytes, n_a_dev, n_b_dev, pairs_hint, as_stream(stream));
+                           accumulate, workspace, workspace_bytes, n_a_dev, n_b_dev, pairs_hint, math == WFSP_MATH_BF16X3,
+                           as_stream(stream));
   return set_error(WFSP_EINVAL, "unknown math mode %d", math);
 }
 

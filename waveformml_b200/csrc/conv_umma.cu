@@ -75,21 +75,42 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) { cp_async_
 // 128-byte swizzle (chunk ^ (row & 7)).  Rows n0 .. n0+n_tile of one (offset, 64-channel slice) are then
 // one contiguous block of n_tile * 128 bytes that a single bulk copy (cp.async.bulk) drops into shared
 // memory exactly as the UMMA descriptor expects it.
+// split3 (WFSP_MATH_BF16X3): the reduction is three segments of the real channel count c_red / 3 holding
+// hi(w), lo(w), hi(w) -- hi = w rounded to bf16, lo = (w - hi) rounded to bf16 -- against activations laid out as
+// [hi(a) | hi(a) | lo(a)]: a w ~ hi hi + hi lo + lo hi with fp32 accumulation (error ~2^-16 per product).
 __device__ __forceinline__ float prep_weight_value(const float* __restrict__ w, int64_t i, int c_red, int c_dst,
-                                                   int transpose_w, int n_pad, int num_kb) {
+                                                   int transpose_w, int n_pad, int num_kb, int split3 = 0) {
   const int e = int(i & 7), pc = int((i >> 3) & 7);
   int64_t t = i >> 6;
   const int n = int(t % n_pad);
   t /= n_pad;
   const int kb = int(t % num_kb), k = int(t / num_kb);
-  const int c = kb * 64 + ((pc ^ (n & 7)) << 3) + e;
+  int c = kb * 64 + ((pc ^ (n & 7)) << 3) + e;
   if (c >= c_red || n >= c_dst) return 0.f;
-  const float* wk = w + int64_t(k) * c_red * c_dst;
-  return transpose_w ? wk[int64_t(n) * c_red + c] : wk[int64_t(c) * c_dst + n];
+  int seg = 0, cr = c_red;
+  if (split3) { cr = c_red / 3; seg = c / cr; c -= seg * cr; }
+  const float* wk = w + int64_t(k) * cr * c_dst;
+  const float v = transpose_w ? wk[int64_t(n) * cr + c] : wk[int64_t(c) * c_dst + n];
+  if (!split3) return v;
+  const float hi = __bfloat162float(__float2bfloat16_rn(v));
+  return seg == 1 ? v - hi : hi;
 }
 
 // ---- activation cast: fp32 [n][c] -> bf16 [n][c_pad], zero padded; one 16-byte chunk per thread
-struct CastJob { const float* src; __nv_bfloat16* dst; int64_t n; int c, c_pad; const int32_t* n_dev; };
+// mode: 0 = round to bf16; 1 = [hi | hi | lo] over 3c channels (c_pad = pitch of 3c); 2 = hi only (= 0); 3 = lo only
+struct CastJob { const float* src; __nv_bfloat16* dst; int64_t n; int c, c_pad; const int32_t* n_dev; int mode; };
+
+__device__ __forceinline__ float cast_value(const CastJob& j, const float* row, int col) {
+  if (j.mode == 1) {
+    const int seg = col / j.c, cc = col - seg * j.c;
+    if (seg > 2) return 0.f;
+    const float v = __ldg(row + cc), hi = __bfloat162float(__float2bfloat16_rn(v));
+    return seg == 2 ? v - hi : hi;
+  }
+  if (col >= j.c) return 0.f;
+  const float v = __ldg(row + col);
+  return j.mode == 3 ? v - __bfloat162float(__float2bfloat16_rn(v)) : v;
+}
 
 __global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1) {
   const int64_t n0 = j0.n_dev ? int64_t(*j0.n_dev) : j0.n;
@@ -102,10 +123,10 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1) 
     const int cpr = j.c_pad >> 3;
     const int64_t row = ii / cpr;
     const int col = int(ii - row * cpr) << 3;
-    const float* s = j.src + row * j.c + col;
+    const float* s = j.src + row * j.c;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (col + e < j.c) ? __ldg(s + e) : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = cast_value(j, s, col + e);
     uint4 u;
     u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
@@ -117,12 +138,12 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(CastJob j0, CastJob j1) 
 // `prep_blocks` CTAs transpose / pad the weights, the rest cast the activation rows
 __global__ void __launch_bounds__(256) prep_and_cast_kernel(const float* __restrict__ w, int kvol, int c_red, int c_dst,
                                                             int transpose_w, __nv_bfloat16* __restrict__ wt, int n_pad,
-                                                            int kc_pad, int prep_blocks, CastJob job) {
+                                                            int kc_pad, int prep_blocks, CastJob job, int split3) {
   if (int(blockIdx.x) < prep_blocks) {
     const int num_kb = kc_pad / 64;
     const int64_t total = int64_t(kvol) * n_pad * kc_pad;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(prep_blocks) * blockDim.x)
-      wt[i] = __float2bfloat16_rn(prep_weight_value(w, i, c_red, c_dst, transpose_w, n_pad, num_kb));
+      wt[i] = __float2bfloat16_rn(prep_weight_value(w, i, c_red, c_dst, transpose_w, n_pad, num_kb, split3));
     return;
   }
   const int64_t n = job.n_dev ? int64_t(*job.n_dev) : job.n;
@@ -132,10 +153,10 @@ __global__ void __launch_bounds__(256) prep_and_cast_kernel(const float* __restr
   for (int64_t i = (int64_t(blockIdx.x) - prep_blocks) * blockDim.x + threadIdx.x; i < chunks; i += nb * blockDim.x) {
     const int64_t row = i / cpr;
     const int col = int(i - row * cpr) << 3;
-    const float* s = job.src + row * job.c + col;
+    const float* s = job.src + row * job.c;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (col + e < job.c) ? __ldg(s + e) : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = cast_value(job, s, col + e);
     uint4 u;
     u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(256) prep_weights_batch_kernel(const PrepBatch
 }
 
 int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
-  CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8, nullptr};
+  CastJob j1 = b ? *b : CastJob{nullptr, nullptr, 0, 8, 8, nullptr, 0};
   const int64_t c0 = a.n * (a.c_pad >> 3), c1 = j1.n * (j1.c_pad >> 3);
   if (c0 + c1 == 0) return WFSP_OK;
   int64_t blocks = ceil_div<int64_t>(c0 + c1, 256);
@@ -1177,8 +1198,8 @@ void set_split_wide(int v) { g_split_wide = v; }
 unsigned long long* g_trace = nullptr;
 void set_trace(unsigned long long* p) { g_trace = p; }
 
-size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst) {
-  return apply_plan(kvol, n_src, c_red, c_dst).total;
+size_t conv_apply_umma_workspace(int kvol, int64_t n_src, int c_red, int c_dst, int split3) {
+  return apply_plan(kvol, n_src, split3 ? 3 * c_red : c_red, c_dst).total;
 }
 
 int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, const __nv_bfloat16* wt,
@@ -1186,12 +1207,17 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
                            const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
                            const wfsp_conv_epilogue* ep, cudaStream_t st);
 
+// fp32 in / fp32 out entry: weight preparation + activation cast (one launch), then the tcgen05 kernel.  split3
+// (WFSP_MATH_BF16X3): the reduction runs over three bf16 segments per channel -- [hi(a) | hi(a) | lo(a)] against
+// [hi(w); lo(w); hi(w)] -- i.e. a w ~ hi hi + hi lo + lo hi accumulated in fp32: fp32-grade results (error ~2^-16 per
+// product) on the tensor cores, through the very same kernel with a three times longer reduction.
 int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* weight, int transpose_w,
                     const float* bias, const int32_t* nbr, int kvol, float* dst, int64_t n_dst, int c_dst, void* ws,
                     size_t ws_bytes, const int32_t* n_src_dev, const int32_t* n_dst_dev, int64_t n_dst_hint,
-                    cudaStream_t st) {
+                    int split3, cudaStream_t st) {
   if (n_dst == 0) return WFSP_OK;
-  ApplyPlan a = apply_plan(kvol, n_src, c_red, c_dst);
+  const int c_eff = split3 ? 3 * c_red : c_red;
+  ApplyPlan a = apply_plan(kvol, n_src, c_eff, c_dst);
   if (ws == nullptr || ws_bytes < a.total) return set_error(WFSP_EWORKSPACE, "conv_apply workspace %zu < %zu", ws_bytes, a.total);
   __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + a.off_act);
@@ -1199,15 +1225,15 @@ int conv_apply_umma(const float* src, int64_t n_src, int c_red, const float* wei
     const int64_t total = int64_t(kvol) * a.n_pad * a.kc_pad;
     int64_t prep_blocks = ceil_div<int64_t>(total, 256);
     if (prep_blocks > int64_t(sm_count()) * 8) prep_blocks = int64_t(sm_count()) * 8;
-    CastJob job{src, act, n_src, c_red, a.c_pad, n_src_dev};
+    CastJob job{src, act, n_src, c_red, a.c_pad, n_src_dev, split3 ? 1 : 0};
     int64_t cast_blocks = ceil_div<int64_t>(n_src * (a.c_pad >> 3) > 0 ? n_src * (a.c_pad >> 3) : 1, 256);
     if (cast_blocks > int64_t(sm_count()) * 16) cast_blocks = int64_t(sm_count()) * 16;
     prep_and_cast_kernel<<<unsigned(prep_blocks + cast_blocks), 256, 0, st>>>(
-        weight, kvol, c_red, c_dst, transpose_w, wt, a.n_pad, a.kc_pad, int(prep_blocks), job);
+        weight, kvol, c_eff, c_dst, transpose_w, wt, a.n_pad, a.kc_pad, int(prep_blocks), job, split3);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
   }
-  return conv_apply_umma_launch(act, n_src, c_red, wt, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev, n_dst_dev,
+  return conv_apply_umma_launch(act, n_src, c_eff, wt, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev, n_dst_dev,
                                 n_dst_hint, nullptr, st);
 }
 
@@ -1351,8 +1377,9 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
   return WFSP_OK;
 }
 
-size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t) {
-  return align_up(size_t(n_a) * round_up(c_a, 8) * 2, 256) + align_up(size_t(n_b) * round_up(c_b, 8) * 2, 256);
+size_t conv_wgrad_umma_workspace(int, int64_t n_a, int c_a, int64_t n_b, int c_b, int64_t, int split3) {
+  const size_t one = align_up(size_t(n_a) * round_up(c_a, 8) * 2, 256) + align_up(size_t(n_b) * round_up(c_b, 8) * 2, 256);
+  return split3 ? 2 * one : one;
 }
 
 int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const __nv_bfloat16* b16, int64_t n_b, int c_b,
@@ -1360,19 +1387,33 @@ int conv_wgrad_umma_launch(const __nv_bfloat16* a16, int64_t n_a, int c_a, const
                            int64_t pitch, float* d_weight, int accumulate, const int32_t* n_a_dev, int64_t pairs_hint,
                            cudaStream_t st);
 
+// split3: d_weight = hi(a)^T hi(b) + hi(a)^T lo(b) + lo(a)^T hi(b), three accumulating launches of the same kernel
 int conv_wgrad_umma(const float* a, int64_t n_a, int c_a, const float* b, int64_t n_b, int c_b,
                     const int32_t* pair_a, const int32_t* pair_b, const int32_t* pair_num, int kvol, int64_t pitch,
                     float* d_weight, int accumulate, void* ws, size_t ws_bytes, const int32_t* n_a_dev,
-                    const int32_t* n_b_dev, int64_t pairs_hint, cudaStream_t st) {
-  const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch);
+                    const int32_t* n_b_dev, int64_t pairs_hint, int split3, cudaStream_t st) {
+  const size_t need = conv_wgrad_umma_workspace(kvol, n_a, c_a, n_b, c_b, pitch, split3);
   if (need > 0 && (ws == nullptr || ws_bytes < need))
     return set_error(WFSP_EWORKSPACE, "conv_wgrad workspace %zu < %zu", ws_bytes, need);
   const int ca_pad = round_up(c_a, 8), cb_pad = round_up(c_b, 8);
-  __nv_bfloat16* a16 = static_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + align_up(size_t(n_a) * ca_pad * 2, 256));
-  CastJob ja{a, a16, n_a, c_a, ca_pad, n_a_dev}, jb{b, b16, n_b, c_b, cb_pad, n_b_dev};
+  const size_t a_bytes = align_up(size_t(n_a) * ca_pad * 2, 256), b_bytes = align_up(size_t(n_b) * cb_pad * 2, 256);
+  char* w8 = static_cast<char*>(ws);
+  __nv_bfloat16* a16 = reinterpret_cast<__nv_bfloat16*>(w8);
+  __nv_bfloat16* b16 = reinterpret_cast<__nv_bfloat16*>(w8 + a_bytes);
+  CastJob ja{a, a16, n_a, c_a, ca_pad, n_a_dev, split3 ? 2 : 0}, jb{b, b16, n_b, c_b, cb_pad, n_b_dev, split3 ? 2 : 0};
   if (int rc = launch_cast(ja, &jb, st)) return rc;
-  return conv_wgrad_umma_launch(a16, n_a, c_a, b16, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, accumulate,
+  if (!split3)
+    return conv_wgrad_umma_launch(a16, n_a, c_a, b16, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, accumulate,
+                                  n_a_dev, pairs_hint, st);
+  __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(w8 + a_bytes + b_bytes);
+  __nv_bfloat16* b_lo = reinterpret_cast<__nv_bfloat16*>(w8 + 2 * a_bytes + b_bytes);
+  CastJob la{a, a_lo, n_a, c_a, ca_pad, n_a_dev, 3}, lb{b, b_lo, n_b, c_b, cb_pad, n_b_dev, 3};
+  if (int rc = launch_cast(la, &lb, st)) return rc;
+  if (int rc = conv_wgrad_umma_launch(a16, n_a, c_a, b16, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, accumulate,
+                                      n_a_dev, pairs_hint, st)) return rc;
+  if (int rc = conv_wgrad_umma_launch(a16, n_a, c_a, b_lo, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, 1,
+                                      n_a_dev, pairs_hint, st)) return rc;
+  return conv_wgrad_umma_launch(a_lo, n_a, c_a, b16, n_b, c_b, pair_a, pair_b, pair_num, kvol, pitch, d_weight, 1,
                                 n_a_dev, pairs_hint, st);
 }
 
@@ -1472,7 +1513,7 @@ int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st) {
 }
 
 int cast_rows_bf16(const float* src, int64_t n, const int32_t* n_dev, int c, void* dst16, cudaStream_t st) {
-  CastJob j{src, static_cast<__nv_bfloat16*>(dst16), n, c, round_up(c, 8), n_dev};
+  CastJob j{src, static_cast<__nv_bfloat16*>(dst16), n, c, round_up(c, 8), n_dev, 0};
   return launch_cast(j, nullptr, st);
 }
 

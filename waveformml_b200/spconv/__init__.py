@@ -27,14 +27,17 @@ from .ops import Rulebook, get_conv_output_size, get_indice_pairs  # noqa: F401
 __all__ = ["SparseConvTensor", "SparseModule", "SparseConvolution", "SparseConv2d", "SubMConv2d",
            "SparseInverseConv2d", "SparseConv3d", "SubMConv3d", "SparseInverseConv3d", "ToDense", "SparseSequential", "ops", "set_math_mode", "get_math_mode", "set_fused"]
 
+MATH_MODES = ("bf16", "fp32", "bf16x3")
 _math_mode = os.environ.get("WFSP_MATH", "bf16")
-assert _math_mode in ("bf16", "fp32")
+assert _math_mode in MATH_MODES
 
 
 def set_math_mode(mode):
-    """'bf16': tcgen05 tensor cores, bf16 operands / fp32 accumulate.  'fp32': exact fp32 CUDA-core path."""
+    """'bf16': tcgen05 tensor cores, bf16 operands / fp32 accumulate.  'fp32': exact fp32 CUDA-core path.
+    'bf16x3': the tensor-core path at fp32-grade accuracy -- every operand split into hi + lo bf16 parts, three
+    products per pair accumulated in fp32 (WFSP_MATH_BF16X3): the tight-tolerance mode without leaving tcgen05."""
     global _math_mode
-    assert mode in ("bf16", "fp32")
+    assert mode in MATH_MODES
     _math_mode = mode
 
 

@@ -8,7 +8,7 @@ from torch.autograd import Function
 
 from .. import _lib
 
-_MATH = {"fp32": _lib.MATH_FP32, "bf16": _lib.MATH_BF16}
+_MATH = {"fp32": _lib.MATH_FP32, "bf16": _lib.MATH_BF16, "bf16x3": _lib.MATH_BF16X3}
 
 
 def _f32c(t):
