@@ -397,6 +397,34 @@ int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n_rows, cons
                            const float* bwd_partials, float* dx, void* dx_bf16, float* d_gamma,
                            float* d_beta, wfsp_stream_t stream);
 
+/* Training-mode nn.Dropout(p) behind a block's BatchNorm . ReLU (src/models/SPConvBlocks.py:375-376, 509-510), fused
+ * into the kernels that produce / consume the block's output.  Element (row, channel) is kept with probability 1 - p
+ * and scaled by 1 / (1 - p) (torch.nn.Dropout semantics); which elements are kept is a counter-based hash of
+ * (seed, *step_dev, salt, row * c + channel) -- the backward pass regenerates the mask, nothing is stored.  step_dev
+ * (device int64, may be NULL) lets a captured CUDA graph draw a fresh mask every replay: the caller advances it once
+ * per step.  The random stream is NOT torch's Philox stream (parity is distributional, as between any two seeds).
+ * wfsp_dropout_factors writes the factor (0 or 1 / (1 - p)) of every element of an [n_rows, c] tensor (tests). */
+typedef struct wfsp_dropout {
+  float p;
+  unsigned long long seed;
+  const void* step_dev;
+  unsigned salt;
+} wfsp_dropout;
+int wfsp_dropout_factors(const wfsp_dropout* drop, int64_t n_rows, int c, float* factors, wfsp_stream_t stream);
+/* wfsp_bn_relu_fwd_stats / wfsp_bn_relu_bwd_x with Dropout behind the ReLU (drop == NULL or p == 0: none).  Forward:
+ * y = dropout(relu?(bn(x))); backward: dy is first multiplied by the regenerated mask. */
+int wfsp_bn_relu_fwd_stats_ex(const float* x, int64_t n_rows, const int32_t* n_rows_dev,
+                              int64_t n_rows_hint, int c,
+                              const float* bn_partials, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps,
+                              int relu, float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                              const wfsp_dropout* drop, wfsp_stream_t stream);
+int wfsp_bn_relu_bwd_x_ex(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
+                          int64_t n_rows_hint, int c, const float* gamma, const float* beta, const float* save_mean,
+                          const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
+                          float* d_beta, void* workspace, size_t workspace_bytes, const wfsp_dropout* drop,
+                          wfsp_stream_t stream);
+
 /* a convolution followed by nn.ReLU (or nothing) without BatchNorm: y = relu?(x), and its backward
  * dx = dy * (x > 0 or no relu), with the same optional outputs */
 int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, int relu,

@@ -69,6 +69,11 @@ SIGNATURES = {
                                   _vp, _sz, _vp]),
     "wfsp_bn_relu_bwd_x": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                                   _sz, _vp]),
+    "wfsp_dropout_factors": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "wfsp_bn_relu_fwd_stats_ex": (_int, [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp,
+                                         _vp, _vp, _vp, _vp]),
+    "wfsp_bn_relu_bwd_x_ex": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                                     _sz, _vp, _vp]),
     "wfsp_act_fwd": (_int, [_vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_act_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _vp, _vp, _vp]),
     "wfsp_head_workspace_bytes": (_sz, [_int, _int, _int]),
@@ -95,6 +100,18 @@ class ConvEpilogue(ctypes.Structure):
     _fields_ = [("bn_partials", ctypes.c_void_p), ("bwd_x", ctypes.c_void_p), ("bwd_mean", ctypes.c_void_p),
                 ("bwd_invstd", ctypes.c_void_p), ("bwd_gamma", ctypes.c_void_p), ("bwd_beta", ctypes.c_void_p),
                 ("bwd_partials", ctypes.c_void_p), ("bwd_relu", ctypes.c_int), ("k_split", ctypes.c_int)]
+
+
+class Dropout(ctypes.Structure):
+    """struct wfsp_dropout (include/wfsp.h)"""
+    _fields_ = [("p", ctypes.c_float), ("seed", ctypes.c_ulonglong), ("step_dev", ctypes.c_void_p), ("salt", ctypes.c_uint)]
+
+
+def dropout_spec(p, seed, step_dev=None, salt=0):
+    d = Dropout()
+    d.p, d.seed, d.salt = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(salt)
+    d.step_dev = None if step_dev is None else step_dev.data_ptr()
+    return d
 
 
 def conv_epilogue(bn_partials=None, bwd=None, k_split=0):

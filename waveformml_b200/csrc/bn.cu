@@ -212,8 +212,9 @@ __global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_apply(const float* __res
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                 int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
-                                                const PartStats ps, int rows_per_cta) {
+                                                const PartStats ps, int rows_per_cta, const DropSpec drop) {
   const int64_t n = live_rows(n_cap, n_dev);
+  const unsigned long long dkey = drop.p > 0.f ? drop_key(drop) : 0ull;
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;  // channel pairs per (padded) row
   uint32_t* y16w = reinterpret_cast<uint32_t*>(y16);
   if (int64_t(blockIdx.x) * rows_per_cta >= n && !(FOLD && blockIdx.x == 0)) return;
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_apply(const float* __res
               float tv = xv[u][e];
               if (mean || FOLD) tv = (tv - m[e]) * is[e] * g[e] + b[e];
               if (relu && tv < 0.f) tv = 0.f;
+              if (drop.p > 0.f) tv *= drop_factor(dkey, drop.p, drop.scale, (unsigned long long)(r * c + ch + e));
               v[e] = tv;
             }
           }
@@ -286,9 +288,11 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_partial(const float* __restrict
                                                       int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                      int relu, float* __restrict__ part /* [nblk][2][c] */) {
+                                                      int relu, float* __restrict__ part /* [nblk][2][c] */,
+                                                      const DropSpec drop) {
   __shared__ float red[2][2][256];  // [sum kind][channel of the pair][thread]
   const int64_t n = live_rows(n_cap, n_dev);
+  const unsigned long long dkey = drop.p > 0.f ? drop_key(drop) : 0ull;
   const int64_t r0 = int64_t(blockIdx.x) * kRowsBwd;
   if (r0 >= n) return;
   const int64_t r_end = r0 + kRowsBwd < n ? r0 + kRowsBwd : n;
@@ -332,6 +336,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_partial(const float* __restrict
         for (int e = 0; e < 2; ++e) {
           const float xh = (xv[u][e] - m[e]) * is[e];
           float d = dv[u][e];
+          if (drop.p > 0.f && on[e])
+            d *= drop_factor(dkey, drop.p, drop.scale, (unsigned long long)((rb + int64_t(u) * blockDim.y) * c + ch + e));
           if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
           s0[e] += d;
           s1[e] += d * xh;
@@ -422,8 +428,10 @@ __global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_bwd_apply(const float* _
                                                     const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
                                                     int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
                                                     int rows_per_cta, const float* __restrict__ part, int chunk_rows,
-                                                    float* __restrict__ d_gamma_out, float* __restrict__ d_beta_out) {
+                                                    float* __restrict__ d_gamma_out, float* __restrict__ d_beta_out,
+                                                    const DropSpec drop) {
   const int64_t n = live_rows(n_cap, n_dev);
+  const unsigned long long dkey = drop.p > 0.f ? drop_key(drop) : 0ull;
   const int c_pad = (c + 7) & ~7, ppr = c_pad >> 1;
   const float inv_n = n > 0 ? 1.f / float(n) : 0.f;
   uint32_t* dx16w = reinterpret_cast<uint32_t*>(dx16);
@@ -486,6 +494,7 @@ __global__ void __launch_bounds__(256, FOLD ? 1 : 4) bn_bwd_apply(const float* _
           for (int e = 0; e < 2; ++e) {
             if (on[e]) {
               float d = dv[u][e];
+              if (drop.p > 0.f) d *= drop_factor(dkey, drop.p, drop.scale, (unsigned long long)(r * c + ch + e));
               if (mean) {
                 const float xh = (xv[u][e] - m[e]) * is[e];
                 if (relu && xh * g[e] + b[e] <= 0.f) d = 0.f;
@@ -634,9 +643,10 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
     const float* __restrict__ x, const float* __restrict__ dy, int64_t n_cap, const int32_t* __restrict__ n_dev, int c,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_,
     const float* __restrict__ invstd_, int relu, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
-    float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    float* __restrict__ d_gamma, float* __restrict__ d_beta, const DropSpec drop) {
   __shared__ float red[kRowLanes][kCh];
   __shared__ float part[2][kCh];
+  const unsigned long long dkey = drop.p > 0.f ? drop_key(drop) : 0ull;
   cg::cluster_group cluster = cg::this_cluster();
   const int64_t n = live_rows(n_cap, n_dev);
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -650,6 +660,7 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
     for (int64_t r = row0; r < n; r += rstep) {
       const float xh = (x[r * c + ch] - m) * is;
       float d = dy[r * c + ch];
+      if (drop.p > 0.f) d *= drop_factor(dkey, drop.p, drop.scale, (unsigned long long)(r * c + ch));
       if (relu && xh * g + b <= 0.f) d = 0.f;
       s[0] += d;
       s[1] += d * xh;
@@ -667,6 +678,7 @@ __global__ void __launch_bounds__(kCh * kRowLanes) bn_bwd_small(
   for (int64_t r = row0; r < n; r += rstep) {
     const float xh = (x[r * c + ch] - m) * is;
     float d = dy[r * c + ch];
+    if (drop.p > 0.f) d *= drop_factor(dkey, drop.p, drop.scale, (unsigned long long)(r * c + ch));
     if (relu && xh * g + b <= 0.f) d = 0.f;
     const float t = g * is * (d - s0 * inv_n - xh * s1 * inv_n);
     if (dx) dx[r * c + ch] = t;
@@ -746,13 +758,14 @@ bool bn_stream_ok(int c, int arrays, const void* x, const void* dy);
 int bn_stream_grid(int64_t n_rows, int chunk_rows);
 int bn_stream_chunk_rows(int c, int arrays);
 int bn_stream_fwd_apply(const float* x, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma, const float* beta,
-                        const float* mean, const float* invstd, int relu, float* y, void* y16, cudaStream_t st);
+                        const float* mean, const float* invstd, int relu, float* y, void* y16, const DropSpec& drop,
+                        cudaStream_t st);
 int bn_stream_bwd_partial(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
                           const float* beta, const float* mean, const float* invstd, int relu, float* part, int* n_part,
-                          cudaStream_t st);
+                          const DropSpec& drop, cudaStream_t st);
 int bn_stream_bwd_apply(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
                         const float* beta, const float* mean, const float* invstd, const float* d_gamma, const float* d_beta,
-                        int relu, float* dx, void* dx16, cudaStream_t st);
+                        int relu, float* dx, void* dx16, const DropSpec& drop, cudaStream_t st);
 constexpr int64_t kStreamMinRows = 32768;  // (expected live) rows from which the bulk-copy fed passes are used
 static int g_bn_stream = 1;                // wfsp_set_option "bn_stream": 0 = register-load kernels everywhere
 void set_bn_stream(int v) { g_bn_stream = v; }
@@ -805,19 +818,20 @@ extern "C" int wfsp_bn_relu_fwd_x(const float* x, int64_t n_rows, const int32_t*
     count_launches(1);
   }
   if (vec2_ok(c, x, y))
-    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows), DropSpec{});
   else
-    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows), DropSpec{});
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
 
-extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint, int c,
-                                      const float* bn_partials, const float* gamma, const float* beta,
-                                      float* running_mean, float* running_var, float momentum, float eps, int relu,
-                                      float* y, void* y_bf16, float* save_mean, float* save_invstd,
-                                      wfsp_stream_t stream) {
+extern "C" int wfsp_bn_relu_fwd_stats_ex(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint, int c,
+                                         const float* bn_partials, const float* gamma, const float* beta,
+                                         float* running_mean, float* running_var, float momentum, float eps, int relu,
+                                         float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                                         const wfsp_dropout* dropout, wfsp_stream_t stream) {
+  const DropSpec drop = make_drop(dropout);
   WFSP_REQUIRE(n_rows >= 0 && c >= 1 && bn_partials != nullptr, "bad batch-norm arguments");
   WFSP_REQUIRE(y != nullptr || y_bf16 != nullptr, "batch norm needs at least one output");
   if (n_rows == 0) return WFSP_OK;
@@ -828,9 +842,9 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
     // few chunks: every CTA of the apply kernel folds the partials of its channels itself -- ONE launch
     const PartStats ps{bn_partials, WFSP_BN_CHUNK_ROWS, eps, momentum, running_mean, running_var, save_mean, save_invstd};
     if (vec2_ok(c, x, y))
-      bn_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
+      bn_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows), drop);
     else
-      bn_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows));
+      bn_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, nullptr, nullptr, relu, y, y16, ps, apply_rows(n_rows), drop);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -842,15 +856,24 @@ extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int3
     return rc;
   if (g_bn_stream && live >= kStreamMinRows && bn_stream_ok(c, 1, x, nullptr) && (y == nullptr || vec2_ok(c, y, y))) {
     count_launches(1);
-    return bn_stream_fwd_apply(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, st);
+    return bn_stream_fwd_apply(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, drop, st);
   }
   if (vec2_ok(c, x, y))
-    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows), drop);
   else
-    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows));
+    bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, y, y16, PartStats{}, apply_rows(n_rows), drop);
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_fwd_stats(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint, int c,
+                                      const float* bn_partials, const float* gamma, const float* beta,
+                                      float* running_mean, float* running_var, float momentum, float eps, int relu,
+                                      float* y, void* y_bf16, float* save_mean, float* save_invstd,
+                                      wfsp_stream_t stream) {
+  return wfsp_bn_relu_fwd_stats_ex(x, n_rows, n_rows_dev, n_rows_hint, c, bn_partials, gamma, beta, running_mean, running_var,
+                                   momentum, eps, relu, y, y_bf16, save_mean, save_invstd, nullptr, stream);
 }
 
 extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, const float* gamma,
@@ -861,11 +884,13 @@ extern "C" int wfsp_bn_relu_fwd(const float* x, int64_t n_rows, const int32_t* n
                             relu, y, nullptr, save_mean, save_invstd, workspace, workspace_bytes, stream);
 }
 
-extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint,
-                                  int c,
-                                  const float* gamma, const float* beta, const float* save_mean,
-                                  const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
-                                  float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+extern "C" int wfsp_bn_relu_bwd_x_ex(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint,
+                                     int c,
+                                     const float* gamma, const float* beta, const float* save_mean,
+                                     const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
+                                     float* d_beta, void* workspace, size_t workspace_bytes, const wfsp_dropout* dropout,
+                                     wfsp_stream_t stream) {
+  const DropSpec drop = make_drop(dropout);
   WFSP_REQUIRE(n_rows >= 0 && c >= 1, "bad batch-norm sizes");
   WFSP_REQUIRE(dx != nullptr || dx_bf16 != nullptr, "batch norm backward needs at least one output");
   cudaStream_t st = as_stream(stream);
@@ -878,7 +903,7 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   const int64_t live = (n_rows_dev != nullptr && n_rows_hint > 0 && n_rows_hint < n_rows) ? n_rows_hint : n_rows;
   if (live <= kClusterRows && n_rows <= kSmallRows * 4) {
     WFSP_CHECK_CUDA(launch_cluster(bn_bwd_small, ceil_div((c + 7) & ~7, kCh), st, x, dy, n_rows, n_rows_dev, c, gamma, beta,
-                                   save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta));
+                                   save_mean, save_invstd, relu, dx, dx16, d_gamma, d_beta, drop));
     count_launches(1);
     return WFSP_OK;
   }
@@ -888,27 +913,35 @@ extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_row
   if (g_bn_stream && live >= kStreamMinRows && n_rows >= int64_t(sm_count()) * kRowsBwd && bn_stream_ok(c, 2, x, dy) &&
       (dx == nullptr || vec2_ok(c, dx, dx))) {
     int n_part = 0;
-    if (int rc = bn_stream_bwd_partial(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part, &n_part, st))
+    if (int rc = bn_stream_bwd_partial(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part, &n_part, drop, st))
       return rc;
     bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, 1, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr,
                                                                       nullptr, n_part);
     count_launches(1);
     WFSP_CHECK_LAUNCH();
-    return bn_stream_bwd_apply(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, st);
+    return bn_stream_bwd_apply(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, drop, st);
   }
   const unsigned pgrid = unsigned(ceil_div<int64_t>(n_rows, kRowsBwd));
   if (vec2_ok(c, x, dy))
-    bn_bwd_partial<true><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+    bn_bwd_partial<true><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part, drop);
   else
-    bn_bwd_partial<false><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part);
+    bn_bwd_partial<false><<<pgrid, apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, relu, part, drop);
   bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, kRowsBwd, n_rows, n_rows_dev, c, d_gamma, d_beta, nullptr, nullptr, -1);
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
-    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr, drop);
   else
-    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr, drop);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
+}
+
+extern "C" int wfsp_bn_relu_bwd_x(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev, int64_t n_rows_hint,
+                                  int c, const float* gamma, const float* beta, const float* save_mean,
+                                  const float* save_invstd, int relu, float* dx, void* dx_bf16, float* d_gamma,
+                                  float* d_beta, void* workspace, size_t workspace_bytes, wfsp_stream_t stream) {
+  return wfsp_bn_relu_bwd_x_ex(x, dy, n_rows, n_rows_dev, n_rows_hint, c, gamma, beta, save_mean, save_invstd, relu, dx, dx_bf16,
+                               d_gamma, d_beta, workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n_rows, const int32_t* n_rows_dev,
@@ -930,9 +963,9 @@ extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n
   const bool v2 = vec2_ok(c, x, dy) && vec2_ok(c, dx, dx);
   if (live <= kFoldRows && c <= 512) {  // ONE launch: every CTA folds the few partials of its channels itself
     if (v2)
-      bn_bwd_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+      bn_bwd_apply<true, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta, DropSpec{});
     else
-      bn_bwd_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta);
+      bn_bwd_apply<false, true><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, nullptr, nullptr, relu, dx, dx16, apply_rows(n_rows), bwd_partials, WFSP_BN_CHUNK_ROWS, d_gamma, d_beta, DropSpec{});
     count_launches(1);
     WFSP_CHECK_LAUNCH();
     return WFSP_OK;
@@ -946,9 +979,9 @@ extern "C" int wfsp_bn_relu_bwd_parts(const float* x, const float* dy, int64_t n
   bn_bwd_finalize<<<dim3(unsigned(ceil_div(c, kCh)), unsigned(S)), dim3(kCh, kFinLanes), 0, st>>>(
       bwd_partials, WFSP_BN_CHUNK_ROWS, n_rows, n_rows_dev, c, d_gamma, d_beta, inter, tickets, -1);
   if (v2)
-    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr, DropSpec{});
   else
-    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+    bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, st>>>(x, dy, n_rows, n_rows_dev, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, relu, dx, dx16, apply_rows(n_rows), nullptr, 0, nullptr, nullptr, DropSpec{});
   count_launches(2);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -962,6 +995,29 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
                             d_beta, workspace, workspace_bytes, stream);
 }
 
+namespace wfsp {
+namespace {
+__global__ void __launch_bounds__(256) dropout_factors_kernel(const DropSpec drop, int64_t total, float* __restrict__ out) {
+  const unsigned long long key = drop_key(drop);
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256)
+    out[i] = drop.p > 0.f ? drop_factor(key, drop.p, drop.scale, (unsigned long long)i) : 1.f;
+}
+}  // namespace
+}  // namespace wfsp
+
+extern "C" int wfsp_dropout_factors(const wfsp_dropout* dropout, int64_t n_rows, int c, float* factors, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1 && factors != nullptr, "bad dropout arguments");
+  WFSP_REQUIRE(dropout == nullptr || (dropout->p >= 0.f && dropout->p < 1.f), "dropout probability must be in [0, 1)");
+  const int64_t total = n_rows * c;
+  if (total == 0) return WFSP_OK;
+  int64_t blocks = ceil_div<int64_t>(total, 256);
+  if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
+  dropout_factors_kernel<<<unsigned(blocks), 256, 0, as_stream(stream)>>>(make_drop(dropout), total, factors);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
 // Activation-only blocks (a convolution followed by ReLU / nothing, no BatchNorm): the same streaming
 // kernels with the normalisation switched off.
 extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, int relu, float* y,
@@ -971,10 +1027,10 @@ extern "C" int wfsp_act_fwd(const float* x, int64_t n_rows, const int32_t* n_row
   if (n_rows == 0) return WFSP_OK;
   if (vec2_ok(c, x, y))
     bn_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows), DropSpec{});
   else
     bn_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
-        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows));
+        x, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, relu, y, static_cast<__nv_bfloat16*>(y_bf16), PartStats{}, apply_rows(n_rows), DropSpec{});
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
@@ -988,11 +1044,11 @@ extern "C" int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, con
   if (vec2_ok(c, x, dy) && vec2_ok(c, dx, dx))
     bn_bwd_apply<true, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr, DropSpec{});
   else
     bn_bwd_apply<false, false><<<apply_blocks(n_rows), apply_block(c), 0, as_stream(stream)>>>(
         x, dy, n_rows, n_rows_dev, c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, relu, dx,
-        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr);
+        static_cast<__nv_bfloat16*>(dx_bf16), apply_rows(n_rows), nullptr, 0, nullptr, nullptr, DropSpec{});
   count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;

@@ -52,6 +52,7 @@ struct StreamParams {
   int relu;
   float* out32; __nv_bfloat16* out16;  // kFwdApply: y; kBwdApply: dx
   float* part;                          // kBwdPartial: [gridDim.x][2][c] (sum dy', sum dy' xhat), one entry per CTA
+  DropSpec drop;                        // Dropout behind the ReLU (p == 0: none): forward scales y, backward scales dy
 };
 
 // the producer's view of chunk q of this CTA: rows [r0, r0 + rows)
@@ -121,6 +122,8 @@ __global__ void __launch_bounds__(kStThreads) bn_stream_kernel(const StreamParam
     }
   }
   float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;  // kBwdPartial: [sum kind][channel of the pair]
+  const bool dropping = p.drop.p > 0.f;
+  const unsigned long long dkey = dropping ? drop_key(p.drop) : 0ull;
   for (int64_t i = 0; i < my_chunks; ++i) {
     int64_t r0;
     int rows;
@@ -152,11 +155,19 @@ __global__ void __launch_bounds__(kStThreads) bn_stream_kernel(const StreamParam
           float v0 = x0, v1 = x1;
           if (norm) { v0 = (x0 - m0) * is0 * g0 + b0; v1 = (x1 - m1) * is1 * g1 + b1; }
           if (p.relu) { v0 = v0 < 0.f ? 0.f : v0; v1 = v1 < 0.f ? 0.f : v1; }
+          if (dropping) {
+            v0 *= drop_factor(dkey, p.drop.p, p.drop.scale, (unsigned long long)(gr * c + ch));
+            v1 *= drop_factor(dkey, p.drop.p, p.drop.scale, (unsigned long long)(gr * c + ch + 1));
+          }
           if (!on1) { v0 = 0.f; v1 = 0.f; }
           if (p.out32 && on1) *reinterpret_cast<float2*>(p.out32 + gr * c + ch) = make_float2(v0, v1);
           if (out16w) out16w[gr * ppr + pc] = st_pack_bf16x2(v0, v1);
         } else {
           const float xh0 = (x0 - m0) * is0, xh1 = (x1 - m1) * is1;
+          if (dropping) {
+            d0 *= drop_factor(dkey, p.drop.p, p.drop.scale, (unsigned long long)(gr * c + ch));
+            d1 *= drop_factor(dkey, p.drop.p, p.drop.scale, (unsigned long long)(gr * c + ch + 1));
+          }
           if (norm) {
             if (p.relu && xh0 * g0 + b0 <= 0.f) d0 = 0.f;
             if (p.relu && xh1 * g1 + b1 <= 0.f) d1 = 0.f;
@@ -234,8 +245,10 @@ static int launch_stream(StreamParams p, int arrays, int grid, cudaStream_t st) 
 }
 
 int bn_stream_fwd_apply(const float* x, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma, const float* beta,
-                        const float* mean, const float* invstd, int relu, float* y, void* y16, cudaStream_t st) {
+                        const float* mean, const float* invstd, int relu, float* y, void* y16, const DropSpec& drop,
+                        cudaStream_t st) {
   StreamParams p{};
+  p.drop = drop;
   p.x = x; p.n_cap = n_rows; p.n_dev = n_dev; p.c = c; p.chunk_rows = bn_stream_chunk_rows(c, 1);
   p.gamma = gamma; p.beta = beta; p.mean = mean; p.invstd = invstd; p.relu = relu;
   p.out32 = y; p.out16 = static_cast<__nv_bfloat16*>(y16);
@@ -245,8 +258,9 @@ int bn_stream_fwd_apply(const float* x, int64_t n_rows, const int32_t* n_dev, in
 // part: [grid][2][c] floats, grid = bn_stream_grid(n_rows, bn_stream_chunk_rows(c, 2)); returns the grid through *n_part
 int bn_stream_bwd_partial(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
                           const float* beta, const float* mean, const float* invstd, int relu, float* part, int* n_part,
-                          cudaStream_t st) {
+                          const DropSpec& drop, cudaStream_t st) {
   StreamParams p{};
+  p.drop = drop;
   p.x = x; p.dy = dy; p.n_cap = n_rows; p.n_dev = n_dev; p.c = c; p.chunk_rows = bn_stream_chunk_rows(c, 2);
   p.gamma = gamma; p.beta = beta; p.mean = mean; p.invstd = invstd; p.relu = relu; p.part = part;
   const int grid = bn_stream_grid(n_rows, p.chunk_rows);
@@ -256,8 +270,9 @@ int bn_stream_bwd_partial(const float* x, const float* dy, int64_t n_rows, const
 
 int bn_stream_bwd_apply(const float* x, const float* dy, int64_t n_rows, const int32_t* n_dev, int c, const float* gamma,
                         const float* beta, const float* mean, const float* invstd, const float* d_gamma, const float* d_beta,
-                        int relu, float* dx, void* dx16, cudaStream_t st) {
+                        int relu, float* dx, void* dx16, const DropSpec& drop, cudaStream_t st) {
   StreamParams p{};
+  p.drop = drop;
   p.x = x; p.dy = dy; p.n_cap = n_rows; p.n_dev = n_dev; p.c = c; p.chunk_rows = bn_stream_chunk_rows(c, 2);
   p.gamma = gamma; p.beta = beta; p.mean = mean; p.invstd = invstd; p.d_gamma = d_gamma; p.d_beta = d_beta; p.relu = relu;
   p.out32 = dx; p.out16 = static_cast<__nv_bfloat16*>(dx16);

@@ -59,10 +59,10 @@ def is_operand_format(features, channels):
 
 
 class Block:
-    __slots__ = ("conv", "bn", "relu")
+    __slots__ = ("conv", "bn", "relu", "drop")
 
     def __init__(self, conv):
-        self.conv, self.bn, self.relu = conv, None, False
+        self.conv, self.bn, self.relu, self.drop = conv, None, False, 0.0
 
 
 class Plan:
@@ -105,6 +105,13 @@ def compile_stack(modules, sparse_conv_cls, to_dense_cls):
             cur.relu = True
         elif isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and (not m.training or m.p == 0)):
             continue
+        elif isinstance(m, nn.Dropout):
+            # training-mode Dropout behind a block's BatchNorm(+ReLU) (SPConvBlocks.py:375-376, 509-510): fused into
+            # the kernel that writes the block's output; the backward kernels regenerate the mask
+            if (cur is None or cur.bn is None or cur.drop or not cur.bn.training or not (0.0 < m.p < 1.0)
+                    or cur.conv.out_channels > 512):
+                return None
+            cur.drop = float(m.p)
         elif isinstance(m, to_dense_cls):
             if i != n - 1 or cur is None:
                 return None
@@ -192,6 +199,19 @@ def _dense_geometry(t, idx=None):
     return h, w * d, idx
 
 
+_drop_steps = {}
+last_drop_seed = 0
+
+
+def _drop_step(dev):
+    """Per-device int64 counter mixed into every Dropout mask: advanced once per forward of a stack with Dropout (on
+    the device, so a replayed CUDA graph draws a fresh mask every step)."""
+    key = (dev.type, dev.index)
+    if key not in _drop_steps:
+        _drop_steps[key] = torch.zeros((1,), dtype=torch.int64, device=dev)
+    return _drop_steps[key]
+
+
 def _param_key(params):
     return tuple(0 if p is None else p.data_ptr() for p in params[0::4])
 
@@ -228,6 +248,8 @@ def _prep_weights(plan, params, need_in_grad, dev, fork):
     side2 = _side_stream(dev, 1)
     with torch.cuda.stream(side2):
         side2.wait_event(fork)
+        if any(b.drop for b in blocks):  # before w_ready: the first BatchNorm kernel must see this step's value
+            _drop_step(dev).add_(1)
         _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
         w_ready = torch.cuda.Event()
         w_ready.record(side2)
@@ -335,6 +357,9 @@ class FusedStackFunction(Function):
                     back_done = torch.cuda.Event()
                     back_done.record(side3)
             main.wait_event(w_ready)
+            drop_seed = 0
+            if any(b.drop for b in blocks):  # from torch's CPU generator: reproducible under torch.manual_seed
+                drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             saved, cur, out32 = [], x, None
             for bi, b in enumerate(blocks):
                 conv = b.conv
@@ -379,12 +404,14 @@ class FusedStackFunction(Function):
                         mean = torch.empty((cout,), dtype=torch.float32, device=dev)
                         invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
                         if n_dst and partials is not None:
-                            _lib.check(lib.wfsp_bn_relu_fwd_stats(
+                            spec = _lib.dropout_spec(b.drop, drop_seed, _drop_step(dev), bi) if b.drop else None
+                            _lib.check(lib.wfsp_bn_relu_fwd_stats_ex(
                                 _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), hint, cout, _lib.ptr(partials), _lib.ptr(bn.weight),
                                 _lib.ptr(bn.bias), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var),
                                 float(bn.momentum), float(bn.eps), int(b.relu), _lib.ptr(y32), _lib.ptr(y16),
-                                _lib.ptr(mean), _lib.ptr(invstd), st()))
+                                _lib.ptr(mean), _lib.ptr(invstd), None if spec is None else ctypes.byref(spec), st()))
                         elif n_dst:
+                            assert not b.drop, "Dropout needs the epilogue statistics path"
                             ws = _bn_ws(lib, n_dst, cout, dev)
                             _lib.check(lib.wfsp_bn_relu_fwd_x(
                                 _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), cout, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
@@ -410,6 +437,9 @@ class FusedStackFunction(Function):
                 main.wait_event(back_done)
             holder["tensor"] = cur  # geometry of the stack's output
             ctx.plan, ctx.saved, ctx.offs, ctx.wbuf = plan, saved, offs, wbuf
+            ctx.drop_seed = drop_seed
+            global last_drop_seed
+            last_drop_seed = drop_seed  # (tests: rebuild the masks of this forward with wfsp_dropout_factors)
             ctx.params = params
             ctx.need_in_grad, ctx.in_dtype = need_in_grad, features.dtype
             ctx.final = cur
@@ -473,10 +503,11 @@ class FusedStackFunction(Function):
                             _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam), _lib.ptr(dbet), st()))
                     else:
                         ws = _bn_ws(lib, max(n_dst, 1), cout, dev)
-                        _lib.check(lib.wfsp_bn_relu_bwd_x(
+                        spec = _lib.dropout_spec(b.drop, ctx.drop_seed, _drop_step(dev), bi) if b.drop else None
+                        _lib.check(lib.wfsp_bn_relu_bwd_x_ex(
                             _lib.ptr(xf), _lib.ptr(dy), n_dst, _lib.ptr(n_dst_dev), dst_hint, cout, _lib.ptr(gamma_p), _lib.ptr(beta_p),
                             _lib.ptr(mean), _lib.ptr(invstd), int(b.relu), _lib.ptr(dx32), _lib.ptr(g16), _lib.ptr(dgam),
-                            _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), st()))
+                            _lib.ptr(dbet), _lib.ptr(ws), ws.numel(), None if spec is None else ctypes.byref(spec), st()))
                     if gamma_p is not None and not gam_through:
                         grads[4 * bi + 2] = dgam
                     if beta_p is not None and not bet_through:
@@ -543,7 +574,7 @@ class FusedStackFunction(Function):
                         # this dy arrives at the previous block's BatchNorm: its two reductions (sum dy', sum dy' xhat)
                         # are taken from the dgrad tile while it is on chip
                         bwd = None
-                        if bi > 0 and blocks[bi - 1].bn is not None and _BWD_PARTS and cin <= 512:
+                        if bi > 0 and blocks[bi - 1].bn is not None and _BWD_PARTS and cin <= 512 and not blocks[bi - 1].drop:
                             pb = blocks[bi - 1]
                             p_xf, p_mean, p_invstd = saved[bi - 1][1], saved[bi - 1][2], saved[bi - 1][3]
                             dy_parts = torch.empty((lib.wfsp_bn_partials_bytes(n_in, cin),), dtype=torch.uint8, device=dev)
