@@ -444,6 +444,28 @@ int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_
                   float momentum, int nesterov, float weight_decay, float grad_scale,
                   wfsp_stream_t stream);
 
+/* The same update for data-parallel training (one process per GPU), fused with the gradient exchange over NVLink peer
+ * memory -- replaces NCCL all-reduce + optimiser step (src/utils/util.py:233-236: Lightning DDP).  The flat gradient
+ * and parameter buffers of every rank are peer-mapped; rank r sums shard r of all ranks' gradients in rank order
+ * (reduce-scatter), updates shard r of the parameters (momentum kept by rank r only), and stores the new values into
+ * every rank's parameter buffer (all-gather): ONE launch plus a one-warp launch that completes the closing barrier.
+ * All ranks end with bit-identical parameters.
+ *   peer_grads_dev / peer_params_dev / peer_flags_dev   DEVICE arrays of `world` pointers (this rank included) to the
+ *       peers' flat gradient buffers, flat parameter buffers and flag arrays (uint32 [2 * world], zero before the
+ *       first call on every rank)
+ *   flags    this rank's own flag array; state: LOCAL uint32 [4], zero before the first call (step epoch, CTA ticket, barrier pending)
+ *   grad_scale = 1 / world folds the data-parallel mean in; every rank must call this once per step.
+ *   wait_now = 1: the closing barrier is completed here (parameters final and gradients reusable when the stream
+ *       reaches the end of the call).  wait_now = 0: the caller completes it with wfsp_sgd_p2p_wait before anything
+ *       reads the parameters or overwrites the gradients -- e.g. at the START of the next step, where the other ranks'
+ *       stragglers are hidden behind that step's input handling. */
+int wfsp_sgd_step_p2p(float* params, const float* grads, float* momentum_buf, int64_t n, float lr,
+                      float momentum, int nesterov, float weight_decay, float grad_scale,
+                      const void* peer_grads_dev, const void* peer_params_dev,
+                      const void* peer_flags_dev, void* flags, void* state, int rank, int world,
+                      int wait_now, wfsp_stream_t stream);
+int wfsp_sgd_p2p_wait(void* flags, void* state, int world, wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (8) Dense classification head + loss.  SPConvNet flattens the ToDense output and applies
  * LinearBlock = Linear(k0, h1) . Linear(h1, n_class), no activation in between

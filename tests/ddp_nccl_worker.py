@@ -1,7 +1,8 @@
 """Worker of tests/test_gpu_ddp_nccl.py (launched with torch.distributed.run, one process per GPU).
 
-Every rank trains ONE captured step of the PSD classifier on its own shard of a global batch (rank-local rulebooks
-and BatchNorm, NCCL all-reduce of the flat gradient inside the graph, fused SGD with the 1/world mean).  Rank 0 then
+Every rank trains captured steps of the PSD classifier on its own shard of a global batch (rank-local rulebooks and
+BatchNorm; gradient exchange + SGD either as the fused peer-memory kernel wfsp_sgd_step_p2p or, with WFSP_P2P=0, as
+NCCL all-reduce of gradient buckets + fused SGD, both inside the graph).  Rank 0 then
 replays the same step WITHOUT communication -- shards fed sequentially through one process, gradients averaged --
 which is the parity statement of SURVEY.md 8e, and checks (i) every rank ended with bit-identical parameters,
 (ii) they equal the sequential-shard result."""
@@ -52,7 +53,7 @@ def main():
         step.capture()
         captured = False
     loss = float(step.run())
-    torch.cuda.synchronize()
+    step.finish()  # the peer-memory exchange completes its closing barrier lazily (next replay or finish())
     flat = step.opt.flat_p.detach().clone()
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
@@ -65,7 +66,7 @@ def main():
         # sequential-shard reference on this one process: same kernels, no communication
         ref = stacks.PSDClassifier().to(dev).train()
         ref.load_state_dict(init)
-        rstep = harness.TrainStep(ref, "psd", lr=0.02, momentum=0.98, nesterov=True)
+        rstep = harness.TrainStep(ref, "psd", lr=0.02, momentum=0.98, nesterov=True, data_parallel=False)
         acc = torch.zeros_like(rstep.grads.flat)
         for r in range(world):
             cr, wr, yr = (t.to(dev) for t in shard(r))
@@ -85,6 +86,20 @@ def main():
             ok, msg = False, "DDP parameters vs sequential shards: rel %.3e (update size %.3e)" % (rel, upd)
         print("ddp_nccl_parity world=%d events/rank=%d captured_allreduce=%s loss=%.6f rel_vs_sequential=%.3e "
               "update=%.3e ranks_identical=%s" % (world, B, captured, loss, rel, upd, ok or "differ" not in msg))
+    # two more replays (momentum now non-zero, barrier epochs advance): the ranks must stay bit-identical
+    for _ in range(2):
+        step.run()
+    step.finish()
+    flat = step.opt.flat_p.detach().clone()
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        for r in range(1, world):
+            if not torch.equal(gathered[0], gathered[r]):
+                ok, msg = False, "after 3 steps rank %d differs from rank 0" % r
+        if not torch.isfinite(gathered[0]).all():
+            ok, msg = False, "non-finite parameters after 3 steps"
+        print("exchange=%s" % ("peer-memory kernel" if getattr(step.opt, "p2p", None) is not None else "NCCL buckets"))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     if rank == 0 and not ok:

@@ -23,12 +23,14 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["peer_memory_kernel", "nccl_buckets"])
 @pytest.mark.parametrize("world", [2])
-def test_nccl_step_equals_sequential_shards(world):
+def test_nccl_step_equals_sequential_shards(world, p2p):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "ddp_nccl_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, WFSP_P2P=p2p))
     sys.stdout.write(res.stdout[-2000:])
     sys.stderr.write(res.stderr[-2000:])
     assert res.returncode == 0, res.stderr[-2000:]
     assert "ddp_nccl_parity" in res.stdout
+    assert ("exchange=peer-memory kernel" if p2p == "1" else "exchange=NCCL buckets") in res.stdout

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "rulebook.cu", "conv_simt.cu", "conv_umma.cu", "dense_pack.cu", "bn.cu", "bn_stream.cu", "head.cu", "edges.cu"]
+SOURCES = ["api.cu", "rulebook.cu", "conv_simt.cu", "conv_umma.cu", "dense_pack.cu", "bn.cu", "bn_stream.cu", "p2p_sgd.cu", "head.cu", "edges.cu"]
 LIB = os.path.join(HERE, "libwfsp.so")
 HEADER = os.path.join(ROOT, "include", "wfsp.h")
 

@@ -58,15 +58,51 @@ def shard_events_by_rows(event_rows, world):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
+class PeerBuffer:
+    """A tensor in peer-mapped (symmetric) memory: `tensor` is this rank's buffer, `ptrs_dev` a device array of the
+    `world` ranks' pointers to theirs (torch.distributed._symmetric_memory does the IPC plumbing)."""
+
+    def __init__(self, tensor, handle):
+        self.tensor, self.handle = tensor, handle
+        self.rank, self.world = handle.rank, handle.world_size
+        self.ptrs_dev = torch.tensor(list(handle.buffer_ptrs), dtype=torch.int64, device=tensor.device)
+
+
+def peer_buffer(numel, dtype, device, group=None):
+    """PeerBuffer of `numel` elements, or None when not applicable (single process, CPU, WFSP_P2P=0, or symmetric
+    memory unavailable -- the NCCL all-reduce path is used then)."""
+    import os
+    if group is False:
+        return None
+    if (device.type != "cuda" or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2
+            or os.environ.get("WFSP_P2P", "1") == "0"):
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        t = symm_mem.empty(max(int(numel), 4), dtype=dtype, device=device)
+        h = symm_mem.rendezvous(t, g)
+        return PeerBuffer(t[:numel], h)
+    except Exception as exc:  # noqa: BLE001 -- any failure here just selects the NCCL path
+        import sys
+        sys.stderr.write("peer-mapped buffers unavailable (%s: %s); gradients go through NCCL all-reduce\n"
+                         % (type(exc).__name__, exc))
+        return None
+
+
 class FlatGrads:
     """All parameter gradients live in one flat fp32 buffer (param.grad are views into it), so the
     data-parallel exchange is a single all-reduce of ~4 MB, issued once after backward."""
 
-    def __init__(self, params):
+    def __init__(self, params, group=None):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(total, dtype=torch.float32, device=p0.device)
+        # data-parallel on GPUs: the buffer lives in peer-mapped memory, so the fused exchange + optimiser kernel
+        # (wfsp_sgd_step_p2p) can read every rank's gradients over NVLink; otherwise an ordinary tensor
+        self.peers = peer_buffer(total, torch.float32, p0.device, group)
+        self.flat = self.peers.tensor if self.peers is not None else torch.zeros(total, dtype=torch.float32, device=p0.device)
+        self.flat.zero_()
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -139,9 +175,23 @@ class FlatSGD:
     over flat buffers (wfsp_sgd_step).  The parameters are re-homed into one flat fp32 buffer (each
     `param.data` becomes a view of it, values preserved), laid out like the FlatGrads buffer."""
 
-    def __init__(self, grads, lr, momentum=0.0, nesterov=False, weight_decay=0.0):
+    def __init__(self, grads, lr, momentum=0.0, nesterov=False, weight_decay=0.0, group=None):
         self.grads, self.lr, self.momentum, self.nesterov, self.weight_decay = grads, lr, momentum, nesterov, weight_decay
-        self.flat_p = torch.empty_like(grads.flat)
+        self.group = group
+        dev = grads.flat.device
+        # peer-mapped parameters + flags when the gradients are (all three or none: the ranks must agree)
+        self.p2p = None
+        if grads.peers is not None:
+            pp = peer_buffer(grads.flat.numel(), torch.float32, dev, group)
+            fl = peer_buffer(2 * grads.peers.world, torch.int32, dev, group)
+            ok = torch.tensor([1 if (pp is not None and fl is not None) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                fl.tensor.zero_()
+                self.p2p = {"params": pp, "flags": fl, "state": torch.zeros((4,), dtype=torch.int32, device=dev)}
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=group)  # every rank's flags are zero before anyone starts a step
+        self.flat_p = self.p2p["params"].tensor if self.p2p is not None else torch.empty_like(grads.flat)
         off = 0
         with torch.no_grad():
             for p in grads.params:
@@ -150,6 +200,31 @@ class FlatSGD:
                 p.data = view
                 off += p.numel()
         self.buf = torch.zeros_like(grads.flat)
+
+    def step_exchange(self, wait_now=True):
+        """Peer-memory path: gradient reduce-scatter + update + parameter all-gather in one launch (every rank calls it
+        once per step; no NCCL collective).  wait_now=False leaves the closing barrier to wait_exchange()."""
+        from . import _lib
+        lib = _lib.load()
+        g, q = self.grads.peers, self.p2p
+        with torch.cuda.device(self.flat_p.device):
+            _lib.check(lib.wfsp_sgd_step_p2p(
+                _lib.ptr(self.flat_p), _lib.ptr(self.grads.flat), _lib.ptr(self.buf), self.flat_p.numel(), float(self.lr),
+                float(self.momentum), int(self.nesterov), float(self.weight_decay), 1.0 / g.world, _lib.ptr(g.ptrs_dev),
+                _lib.ptr(q["params"].ptrs_dev), _lib.ptr(q["flags"].ptrs_dev), _lib.ptr(q["flags"].tensor),
+                _lib.ptr(q["state"]), g.rank, g.world, int(wait_now), _lib.stream()))
+        self.exchange_pending = not wait_now
+
+    def wait_exchange(self):
+        """Completes the closing barrier of a step_exchange(wait_now=False): every rank's parameter stores have landed
+        here and nobody reads this rank's gradients any more."""
+        from . import _lib
+        lib = _lib.load()
+        q = self.p2p
+        with torch.cuda.device(self.flat_p.device):
+            _lib.check(lib.wfsp_sgd_p2p_wait(_lib.ptr(q["flags"].tensor), _lib.ptr(q["state"]), self.grads.peers.world,
+                                             _lib.stream()))
+        self.exchange_pending = False
 
     def step(self, grad_scale=1.0):
         from . import _lib
@@ -180,19 +255,29 @@ def segment_l1_loss(indices, predictions, target, spatial_size, batch_size, n_ro
 
 
 class TrainStep:
-    def __init__(self, model, task="psd", lr=0.02, momentum=0.98, nesterov=True, group=None, fused_head=True):
+    def __init__(self, model, task="psd", lr=0.02, momentum=0.98, nesterov=True, group=None, fused_head=True,
+                 data_parallel=True):
+        """data_parallel=False: a purely local step even when torch.distributed is initialised (no peer-mapped buffers,
+        which every rank would have to create together; _update() then must not be used across ranks)."""
         assert task in ("psd", "z")
         self.model, self.task, self.group, self.fused_head = model, task, group, fused_head
-        self.grads = FlatGrads(model.parameters())
+        self.grads = FlatGrads(model.parameters(), group if data_parallel else False)
         if self.grads.flat.is_cuda:
-            self.opt = FlatSGD(self.grads, lr, momentum, nesterov)
+            self.opt = FlatSGD(self.grads, lr, momentum, nesterov, group=group if data_parallel else False)
         else:  # host-side tests of the plumbing (gloo): stock optimiser
             self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov, foreach=True)
         self.criterion = nn.CrossEntropyLoss()
 
     def _update(self):
         """gradient exchange + optimiser step"""
-        if isinstance(self.opt, FlatSGD):
+        import os
+        if os.environ.get("WFSP_NO_EXCHANGE") == "1" and isinstance(self.opt, FlatSGD):
+            self.opt.step(1.0)  # measurement aid: independent replicas, no gradient exchange at all
+        elif isinstance(self.opt, FlatSGD) and self.opt.p2p is not None:
+            # exchange + update over NVLink peer memory, no NCCL collective; the graph path completes the closing
+            # barrier at the start of the NEXT replay (other ranks' stragglers hide behind its input handling)
+            self.opt.step_exchange(wait_now=not getattr(self, "_defer_exchange_wait", False))
+        elif isinstance(self.opt, FlatSGD):
             self.opt.step(self.grads.all_reduce_sum(self.group))
         else:
             self.grads.all_reduce_mean(self.group)
@@ -219,7 +304,8 @@ class TrainStep:
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32 or prev
         from . import head as _head
-        overlap = (overlap_exchange and self.grads.flat.is_cuda and isinstance(self.opt, FlatSGD) and dist.is_available()
+        overlap = (overlap_exchange and self.grads.flat.is_cuda and isinstance(self.opt, FlatSGD)
+                   and self.opt.p2p is None and dist.is_available()
                    and dist.is_initialized() and dist.get_world_size(self.group) > 1)
         if overlap:  # gradient buckets are exchanged as soon as they are final (head first, then the later conv blocks)
             hook = lambda params, events: self.grads.early_reduce(params, events, self.group)
@@ -380,8 +466,21 @@ class GraphTrainStep(TrainStep):
         slot["free"] = torch.cuda.Event()
         slot["free"].record(main)
 
+    def finish(self):
+        """Completes the gradient exchange of the last run() (peer-memory path defers its closing barrier to the next
+        replay): call before reading parameters on the host / saving a checkpoint."""
+        opt = self.opt
+        if isinstance(opt, FlatSGD) and opt.p2p is not None:
+            opt.wait_exchange()  # idempotent on the device
+        torch.cuda.current_stream().synchronize()
+
     def _body(self, st=None):
         st = self.sets[self.cur] if st is None else st
+        p2p = isinstance(self.opt, FlatSGD) and self.opt.p2p is not None and self.capture_update
+        self._defer_exchange_wait = p2p
+        if p2p:
+            # closing barrier of the PREVIOUS step's exchange (the kernel returns at once if none is pending)
+            self.opt.wait_exchange()
         # bf16 math + fused stack: the batcher writes the tensor-core operand format directly
         direct = spconv.get_math_mode() == "bf16" and spconv.fused.is_enabled()
         # The rulebooks wait for the indices only, the first convolution for the features and the prepared weights:
@@ -432,7 +531,13 @@ class GraphTrainStep(TrainStep):
     def capture(self):
         snap = self._snapshot()  # the warm-up iterations below must not count as training steps
         self._capture()
+        self.finish()  # peers may still be storing the last warm-up step's parameters into this rank's buffer
+        if dist.is_available() and dist.is_initialized() and isinstance(self.opt, FlatSGD) and self.opt.p2p is not None:
+            dist.barrier(group=self.group)
         self._restore(snap)
+        if dist.is_available() and dist.is_initialized() and isinstance(self.opt, FlatSGD) and self.opt.p2p is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody starts a step before every rank has restored its parameters
 
     def _capture(self):
         side = torch.cuda.Stream()
