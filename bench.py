@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=64, help="events per GPU")
     ap.add_argument("--math", default="bf16", choices=["bf16", "fp32", "bf16x3"])
+    ap.add_argument("--no-math-modes", action="store_true", help="skip the bf16x3 / fp32 figures of the default line")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: sync-free capacity-sized step replayed from a CUDA graph; eager: exact shapes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -579,6 +580,30 @@ def run_ours(args):
         extra["rotating"] = {"batches": args.rotate, "steps": rot_steps, "rows_min": min(rws), "rows_max": max(rws),
                              "hint_rows": rws[0], "ms_per_step": rot_ms / rot_steps,
                              "value": world * B / (rot_ms / rot_steps * 1e-3)}
+    # the tight-tolerance mode on the same tensor-core kernels (WFSP_MATH_BF16X3: hi/lo bf16 operand split, fp32-grade
+    # results) and, for reference, the CUDA-core fp32 mode it replaces -- same workload, same timing rules
+    if args.mode == "graph" and args.math == "bf16" and world == 1 and not args.no_math_modes:
+        modes = {}
+        for m in ("bf16x3", "fp32"):
+            spconv.set_math_mode(m)
+            try:
+                mw = GpuWorkload(args, args.workload, B, rank, world, dev)
+                mw.capture()
+                mw.preload(0)
+                for _ in range(3):
+                    mw.step_resident()
+                m_steps = max(10, min(args.steps, 30))
+                m_ms = timed_steps(lambda i: mw.step_resident(), m_steps, flush, sync_all)
+                (m_ms,) = reduce_max([m_ms])
+                modes[m] = {"ms_per_step": m_ms / m_steps, "value": world * B / (m_ms / m_steps * 1e-3)}
+                if hasattr(mw.step, "finish"):
+                    mw.step.finish()
+                del mw
+            finally:
+                spconv.set_math_mode(args.math)
+        modes["bf16x3"]["what"] = "every GEMM operand split into hi + lo bf16, three tcgen05 products per pair, fp32 accumulate"
+        modes["fp32"]["what"] = "fp32 FMA on CUDA cores (exact fp32 products)"
+        extra["math_modes"] = modes
     clocks = sampler.stop()
 
     dev_ms, e2e_ms = reduce_max([dev_ms, e2e_ms])
