@@ -337,6 +337,28 @@ int wfsp_conv_apply_bf16(const void* src_bf16, int64_t n_src, const int32_t* n_s
  *                 (kernel offset x 64-channel slice); there a thread-block cluster of up to 8 CTAs splits that
  *                 loop and the partial accumulators are added through distributed shared memory in rank order
  *                 (deterministic).  1 = never split; 2 / 4 / 8 = force (tests). */
+struct wfsp_dropout;
+/* The BatchNorm1d(+ReLU, +Dropout) that FOLLOWS a convolution, finished inside the convolution's launch (small
+ * launches: all CTAs co-resident; a grid-wide barrier separates the statistics from the normalisation).  When the
+ * launch cannot take it (too many CTAs, large input) the library runs wfsp_bn_relu_fwd_stats_ex right behind the
+ * convolution instead: the caller gets the same results either way and never launches the BatchNorm itself.
+ * Fields as in wfsp_bn_relu_fwd_stats_ex; barrier: device uint32 [2], zero before the first use (reuse it). */
+typedef struct wfsp_bn_fuse {
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float momentum, eps;
+  int relu;
+  float* y;
+  void* y_bf16;
+  float* save_mean;
+  float* save_invstd;
+  const struct wfsp_dropout* dropout;
+  void* barrier;
+  int64_t n_rows_hint;
+} wfsp_bn_fuse;
+
 typedef struct wfsp_conv_epilogue {
   float* bn_partials;
   const float* bwd_x;
@@ -347,6 +369,7 @@ typedef struct wfsp_conv_epilogue {
   float* bwd_partials;
   int bwd_relu;
   int k_split;
+  const wfsp_bn_fuse* bn; /* needs bn_partials */
 } wfsp_conv_epilogue;
 int wfsp_conv_apply_bf16_ex(const void* src_bf16, int64_t n_src, const int32_t* n_src_dev, int c_red,
                             const void* weight_prepared, const float* bias, const int32_t* nbr, int kvol,

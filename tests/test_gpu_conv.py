@@ -149,8 +149,9 @@ def test_layer_parity(cuda_device, name, factory, cin, mode):
     check_all(g, refs, mode, name)
 
 
-@pytest.mark.parametrize("B,full", [(40, False), (160, True)], ids=["small", "24640_rows"])
-def test_fused_equals_per_layer(cuda_device, B, full):
+@pytest.mark.parametrize("B,full,bn_in_conv", [(40, False, 0), (160, True, 0), (40, False, 1), (100, False, 1)],
+                         ids=["small", "24640_rows", "small_bn_in_conv", "mid_bn_in_conv"])
+def test_fused_equals_per_layer(cuda_device, B, full, bn_in_conv):
     """The fused stack rounds the same values to bf16 at the same points as the per-layer path, so
     a conv-BN-ReLU stack must agree with it closely (outputs, input and parameter gradients, BN buffers).
     The large case crosses the row count above which BatchNorm statistics come from the convolution
@@ -167,9 +168,13 @@ def test_fused_equals_per_layer(cuda_device, B, full):
             spconv.SubMConv2d(12, 9, 3, bias=False, indice_key="subm0"), torch.nn.BatchNorm1d(9),
             spconv.ToDense()).to(cuda_device)
 
+    from waveformml_b200 import _lib
     res = []
     for fused_on in (True, False):
         spconv.set_fused(fused_on)
+        # bn_in_conv: the BatchNorm behind a small convolution launch is finished inside that launch (grid barrier;
+        # option apply_bn_fuse, off by default) -- same results as the stand-alone BatchNorm launch
+        _lib.check(_lib.load().wfsp_set_option(b"apply_bn_fuse", bn_in_conv if fused_on else 0))
         try:
             net = make()
             f = feats.clone().to(cuda_device).requires_grad_(True)
@@ -181,6 +186,7 @@ def test_fused_equals_per_layer(cuda_device, B, full):
                         [b.clone() for b in net.buffers()]))
         finally:
             spconv.set_fused(True)
+            _lib.check(_lib.load().wfsp_set_option(b"apply_bn_fuse", 0))
     (ya, fa, pa, ba), (yb, fb, pb, bb) = res
     # not bit-equal: the eager per-layer path normalises with torch's BatchNorm1d, whose statistics differ
     # from ours in the last fp32 bits, which can flip an occasional bf16 rounding of an activation

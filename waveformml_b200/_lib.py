@@ -102,7 +102,17 @@ class ConvEpilogue(ctypes.Structure):
     """struct wfsp_conv_epilogue (include/wfsp.h)"""
     _fields_ = [("bn_partials", ctypes.c_void_p), ("bwd_x", ctypes.c_void_p), ("bwd_mean", ctypes.c_void_p),
                 ("bwd_invstd", ctypes.c_void_p), ("bwd_gamma", ctypes.c_void_p), ("bwd_beta", ctypes.c_void_p),
-                ("bwd_partials", ctypes.c_void_p), ("bwd_relu", ctypes.c_int), ("k_split", ctypes.c_int)]
+                ("bwd_partials", ctypes.c_void_p), ("bwd_relu", ctypes.c_int), ("k_split", ctypes.c_int),
+                ("bn", ctypes.c_void_p)]
+
+
+class BnFuse(ctypes.Structure):
+    """struct wfsp_bn_fuse (include/wfsp.h)"""
+    _fields_ = [("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("running_mean", ctypes.c_void_p),
+                ("running_var", ctypes.c_void_p), ("momentum", ctypes.c_float), ("eps", ctypes.c_float),
+                ("relu", ctypes.c_int), ("y", ctypes.c_void_p), ("y_bf16", ctypes.c_void_p),
+                ("save_mean", ctypes.c_void_p), ("save_invstd", ctypes.c_void_p), ("dropout", ctypes.c_void_p),
+                ("barrier", ctypes.c_void_p), ("n_rows_hint", ctypes.c_int64)]
 
 
 class Dropout(ctypes.Structure):
@@ -117,11 +127,15 @@ def dropout_spec(p, seed, step_dev=None, salt=0):
     return d
 
 
-def conv_epilogue(bn_partials=None, bwd=None, k_split=0):
-    """bwd = (x, mean, invstd, gamma, beta, relu, partials) tensors of the BatchNorm whose dy this dgrad produces."""
+def conv_epilogue(bn_partials=None, bwd=None, k_split=0, bn=None):
+    """bwd = (x, mean, invstd, gamma, beta, relu, partials) tensors of the BatchNorm whose dy this dgrad produces.
+    bn = a BnFuse (kept alive by the returned object): the BatchNorm behind this convolution."""
     def a(t):
         return None if t is None else t.data_ptr()
     e = ConvEpilogue()
+    if bn is not None:
+        e._bn_keep = bn
+        e.bn = ctypes.addressof(bn)
     e.bn_partials = a(bn_partials)
     if bwd is not None:
         x, mean, invstd, gamma, beta, relu, partials = bwd

@@ -259,6 +259,16 @@ struct ApplyParams {
   const float* bwd_x; const float* bwd_mean; const float* bwd_invstd; const float* bwd_gamma; const float* bwd_beta;
   float* bwd_part; int bwd_relu;
   int ksplit;  // CTAs of a thread-block cluster (along z) that split the (offset, channel slice) loop of one tile
+  // optional (small launches, conv_apply_split_kernel): the BatchNorm(+ReLU, +Dropout) that follows this convolution,
+  // finished INSIDE the launch -- after a grid-wide barrier every CTA folds the statistics partials of its columns and
+  // normalises the blocks it produced (src/models/SPConvBlocks.py:505-510: conv . BatchNorm1d . ReLU . Dropout)
+  int bn_fuse, bn_relu;
+  const float* bn_gamma; const float* bn_beta;
+  float* bn_rmean; float* bn_rvar; float* bn_save_mean; float* bn_save_invstd;
+  float bn_eps, bn_momentum;
+  float* bn_y32; __nv_bfloat16* bn_y16;
+  unsigned* bn_bar;  // [2] {arrivals, generation}: zero before the first use, left consistent by every launch
+  DropSpec bn_drop;
   unsigned long long* trace;  // debugging aid (wfsp_debug_trace): clock64 stamps of tile (0, 0)'s phases, 16 per cluster rank
 };
 #define WFSP_TRACE(slot)                                                                     \
@@ -278,6 +288,87 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 }
 __device__ __forceinline__ void st_cluster_u32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Grid-wide barrier of the `expected` live CTAs of a launch whose CTAs are all co-resident (the host checks the
+// occupancy before it asks for a fused BatchNorm).  bar[0] counts arrivals and returns to zero, bar[1] is the
+// generation the waiters watch.  Bounded spin: a launch that could not become co-resident traps instead of hanging.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned gen = *reinterpret_cast<volatile unsigned*>(bar + 1);
+    if (atomicAdd(bar, 1u) == expected - 1u) {
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned*>(bar + 1) == gen) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Phase 2 of a fused BatchNorm: one 32-row x (16|32)-column block of the convolution output (written by this warp
+// before the grid barrier, so it comes back from L2) is normalised with the statistics folded from ALL chunks'
+// partials -- the same sums in the same order as bn_apply's fused small path (csrc/bn.cu: stats_from_partials), so the
+// result does not depend on which path ran -- and written as the next layer's bf16 operand (and / or fp32).
+__device__ __forceinline__ void bn_finish_block(const ApplyParams& p, int64_t grow0, int rmax, int cc, int ncols, int lane,
+                                                unsigned long long dkey) {
+  if (rmax <= 0) return;
+  const int c = p.c_dst, c_pad = (c + 7) & ~7;
+  const int ccol = cc + lane;
+  const bool on = lane < ncols && ccol < c;
+  float mean = 0.f, invstd = 0.f, g = 1.f, bt = 0.f;
+  if (on) {
+    const int64_t n = p.n_dst, nblk = (n + 31) / 32;
+    double a = 0.0, q = 0.0;
+#pragma unroll 4
+    for (int64_t b = 0; b < nblk; ++b) {
+      const double nb = double(b + 1 < nblk ? 32 : n - b * 32);
+      const double mb = __ldcg(p.stats + (b * 2 + 0) * c + ccol), m2b = __ldcg(p.stats + (b * 2 + 1) * c + ccol);
+      a += nb * mb;
+      q += m2b + nb * mb * mb;
+    }
+    const double cnt = double(n), mu = a / cnt;
+    double m2 = q - cnt * mu * mu;
+    if (m2 < 0.0) m2 = 0.0;
+    mean = float(mu);
+    invstd = float(1.0 / sqrt(m2 / cnt + double(p.bn_eps)));
+    if (grow0 == 0) {  // exactly one block per column starts at row 0: it records the statistics
+      p.bn_save_mean[ccol] = mean;
+      p.bn_save_invstd[ccol] = invstd;
+      if (p.bn_rmean) p.bn_rmean[ccol] = (1.f - p.bn_momentum) * p.bn_rmean[ccol] + p.bn_momentum * mean;
+      if (p.bn_rvar && cnt > 1.0) p.bn_rvar[ccol] = (1.f - p.bn_momentum) * p.bn_rvar[ccol] + p.bn_momentum * float(m2 / (cnt - 1.0));
+    }
+    if (p.bn_gamma) g = __ldg(p.bn_gamma + ccol);
+    if (p.bn_beta) bt = __ldg(p.bn_beta + ccol);
+  }
+  const bool pad = lane < ncols && ccol >= c && ccol < c_pad;  // zero padding of the bf16 operand rows
+  const float* xp = p.dst + grow0 * c + ccol;
+  for (int r0 = 0; r0 < rmax; r0 += 8) {
+    float xv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) xv[u] = (on && r0 + u < rmax) ? __ldcg(xp + int64_t(r0 + u) * c) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r0 + u >= rmax) continue;
+      const int64_t gr = grow0 + r0 + u;
+      if (on) {
+        float v = (xv[u] - mean) * invstd * g + bt;
+        if (p.bn_relu && v < 0.f) v = 0.f;
+        if (p.bn_drop.p > 0.f) v *= drop_factor(dkey, p.bn_drop.p, p.bn_drop.scale, (unsigned long long)(gr * c + ccol));
+        if (p.bn_y32) p.bn_y32[gr * c + ccol] = v;
+        if (p.bn_y16) p.bn_y16[gr * c_pad + ccol] = __float2bfloat16_rn(v);
+      } else if (pad && p.bn_y16) {
+        p.bn_y16[gr * c_pad + ccol] = __float2bfloat16_rn(0.f);
+      }
+    }
+  }
 }
 
 // What happens to one finished 32-row x (16|32)-column block of the output, sitting in the warp's shared-memory
@@ -938,6 +1029,40 @@ __global__ void __launch_bounds__(kApplyThreads) conv_apply_split_kernel(const A
     if (SPLIT && (tile_i + gridDim.x) * kTileRows < p.n_dst) cluster_sync_all();
   }
   if (warp == kMmaWarp) tmem_dealloc(s_tmem, tmem_cols);
+  if (p.bn_fuse) {
+    // ---- fused BatchNorm(+ReLU, +Dropout): every output block and every statistics partial of the layer is in
+    // memory once ALL live CTAs have passed this barrier; each warp then normalises the blocks it produced
+    const int64_t tiles = (p.n_dst + kTileRows - 1) / kTileRows;
+    const unsigned live_x = unsigned(tiles < int64_t(gridDim.x) ? tiles : int64_t(gridDim.x));
+    grid_barrier(p.bn_bar, live_x * gridDim.y * gridDim.z);
+    if (warp < kEpiWarps) {
+      const unsigned long long dkey = p.bn_drop.p > 0.f ? drop_key(p.bn_drop) : 0ull;
+      for (int64_t tile_i = blockIdx.x; tile_i * kTileRows < p.n_dst; tile_i += gridDim.x) {
+        const int64_t row0 = tile_i * kTileRows;
+        const int rows_left = int(p.n_dst - row0 < int64_t(kTileRows) ? p.n_dst - row0 : int64_t(kTileRows));
+        const int rb_live = (rows_left + kTileM - 1) / kTileM;
+        if (!SPLIT) {
+          for (int rb = 0; rb < rb_live; ++rb) {
+            const int wr0 = rb * kTileM + (warp & 3) * 32;
+            int rmax = rows_left - wr0;
+            if (rmax > 32) rmax = 32;
+            for (int col = (warp >> 2) * 32; col < p.n_tile; col += 64)
+              bn_finish_block(p, row0 + wr0, rmax, n0 + col, p.n_tile - col < 32 ? p.n_tile - col : 32, lane, dkey);
+          }
+        } else {
+          const int units = rb_live * 4 * ncc;
+          for (int j = warp; krank + ks * j < units; j += kEpiWarps) {
+            const int u = krank + ks * j;
+            const int cc = u % ncc, rq = (u / ncc) & 3, rb = u / (4 * ncc);
+            const int wr0 = rb * kTileM + rq * 32;
+            int rmax = rows_left - wr0;
+            if (rmax > 32) rmax = 32;
+            bn_finish_block(p, row0 + wr0, rmax, n0 + cc * 32, p.n_tile - cc * 32 < 32 ? p.n_tile - cc * 32 : 32, lane, dkey);
+          }
+        }
+      }
+    }
+  }
   WFSP_TRACE(9);
   if (p.trace != nullptr && tid == 0) {
     unsigned long long gt;
@@ -1152,6 +1277,11 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 int g_force_rblk = 0;  // tuning knob (wfsp_set_option "apply_row_blocks"): 0 = cost model
 int g_auto_ksplit = 4;  // wfsp_set_option "apply_k_split": 0 = never split the reduction over a cluster, else the largest split
+// wfsp_set_option "apply_bn_fuse": 1 = small launches finish the BatchNorm behind them inside the launch (grid barrier).
+// Measured on B200 and left OFF: at 64 events the fused launches take 22 / 29 us against 11.5 / 18.7 us for convolution
+// + stand-alone BatchNorm -- the few warps that own blocks fold the statistics serially, while the stand-alone kernel
+// spreads the same work over every SM (profiles/r2_experiments.md).
+int g_bn_fuse = 0;
 int g_split_wide = 0;    // wfsp_set_option "apply_split_wide": split launches take the widest column tiles (fewest MMA instructions)
 int g_split_stages = 4;  // wfsp_set_option "apply_split_stages": ring depth of split launches (each CTA walks few slices)
 
@@ -1195,6 +1325,7 @@ void set_force_rblk(int v) { g_force_rblk = v; }
 void set_auto_ksplit(int v) { g_auto_ksplit = v == 1 ? 8 : v; }
 void set_split_stages(int v) { g_split_stages = v; }
 void set_split_wide(int v) { g_split_wide = v; }
+void set_bn_fuse(int v) { g_bn_fuse = v; }
 unsigned long long* g_trace = nullptr;
 void set_trace(unsigned long long* p) { g_trace = p; }
 
@@ -1247,6 +1378,21 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
   const int64_t live = (n_dst_hint > 0 && n_dst_hint < n_dst) ? n_dst_hint : n_dst;
   const int64_t row_blocks = ceil_div<int64_t>(live, kTileM);
   const int iters_est = kvol * (a.kc_pad / kSliceK);
+  // BatchNorm inside the launch: small launches only (all CTAs co-resident, checked below); otherwise, or when the
+  // check fails, the convolution runs as usual and the stand-alone BatchNorm launch follows it right here
+  const wfsp_bn_fuse* bn = (ep != nullptr && ep->bn != nullptr && ep->bn_partials != nullptr) ? ep->bn : nullptr;
+  bool fuse_bn = bn != nullptr && g_bn_fuse && live <= 8192 && c_dst <= 512 && bn->barrier != nullptr;
+  auto unfused = [&]() -> int {
+    wfsp_conv_epilogue e2 = *ep;
+    e2.bn = nullptr;
+    if (int rc = conv_apply_umma_launch(act, n_src, c_red, wt, bias, nbr, kvol, dst, n_dst, c_dst, n_src_dev, n_dst_dev,
+                                        n_dst_hint, &e2, st))
+      return rc;
+    return wfsp_bn_relu_fwd_stats_ex(dst, n_dst, n_dst_dev, n_dst_hint, c_dst, ep->bn_partials, bn->gamma, bn->beta,
+                                     bn->running_mean, bn->running_var, bn->momentum, bn->eps, bn->relu, bn->y, bn->y_bf16,
+                                     bn->save_mean, bn->save_invstd, bn->dropout, reinterpret_cast<wfsp_stream_t>(st));
+  };
+  if (bn != nullptr && !fuse_bn) return unfused();
   ApplyParams p{};
   p.src = act; p.n_src = n_src; p.c_pad = a.c_pad; p.wt = wt; p.n_pad = a.n_pad; p.kc_pad = a.kc_pad;
   p.bias = bias; p.nbr = nbr; p.kvol = kvol; p.dst = dst; p.n_dst = n_dst; p.c_dst = c_dst;
@@ -1291,7 +1437,7 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
     // when the row blocks exceed one round -- small problems keep rblk = 1 and as many CTAs as possible.
     int best_r = 1;
     double best_cost = 1e300;
-    const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr;  // conv_apply_split_kernel: one row block per CTA
+    const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr || fuse_bn;  // conv_apply_split_kernel: one row block per CTA
     for (int r = 1; r <= (tile_loop_kernel ? 1 : kMaxRowBlocks); ++r) {
       if (r * p.acc_stride > 512) break;
       const int stage_b = r * kABytes + n_tile * 128;
@@ -1330,12 +1476,40 @@ int conv_apply_umma_launch(const __nv_bfloat16* act, int64_t n_src, int c_red, c
   // grid: the tiles of the EXPECTED live rows plus half as many again (the kernel loops over whatever lies beyond)
   const int64_t tile_rows = int64_t(kTileM) * p.rblk;
   int64_t grid_x = ceil_div<int64_t>(n_dst, tile_rows);
-  const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr;
+  const bool tile_loop_kernel = ksplit > 1 || p.bwd_part != nullptr || fuse_bn;
   if (tile_loop_kernel && live < n_dst) {
-    const int64_t want = ceil_div<int64_t>(live + live / 2, tile_rows);
+    // (a fused BatchNorm needs every CTA resident at once: one spare tile instead of half as many again)
+    const int64_t want = fuse_bn ? ceil_div<int64_t>(live, tile_rows) + 1 : ceil_div<int64_t>(live + live / 2, tile_rows);
     if (want < grid_x) grid_x = want;
   }
   const dim3 grid{unsigned(grid_x), unsigned(n_tiles), unsigned(ksplit)};
+  if (fuse_bn) {
+    // co-residency of the whole grid (the barrier spins): clusters for the split kernel, CTAs otherwise
+    int fit = 0;
+    if (ksplit > 1) {
+      WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_split_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = grid; qc.blockDim = dim3(kApplyThreads, 1, 1); qc.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = unsigned(ksplit);
+      qc.attrs = qa; qc.numAttrs = 1;
+      int clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&clusters, conv_apply_split_kernel<1, true>, &qc) != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+      fit = int64_t(clusters) >= grid_x * n_tiles ? 1 : 0;
+    } else {
+      WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_split_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_apply_split_kernel<1, false>, kApplyThreads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+      fit = int64_t(per_sm) * sm_count() >= grid_x * n_tiles ? 1 : 0;
+    }
+    if (!fit) return unfused();
+    p.bn_fuse = 1; p.bn_relu = bn->relu; p.bn_gamma = bn->gamma; p.bn_beta = bn->beta;
+    p.bn_rmean = bn->running_mean; p.bn_rvar = bn->running_var; p.bn_save_mean = bn->save_mean; p.bn_save_invstd = bn->save_invstd;
+    p.bn_eps = bn->eps; p.bn_momentum = bn->momentum; p.bn_y32 = bn->y; p.bn_y16 = static_cast<__nv_bfloat16*>(bn->y_bf16);
+    p.bn_bar = static_cast<unsigned*>(bn->barrier);
+    p.bn_drop = make_drop(bn->dropout);
+  }
   if (tile_loop_kernel && ksplit == 1) {
     WFSP_CHECK_CUDA(cudaFuncSetAttribute(conv_apply_split_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptIn));
     conv_apply_split_kernel<1, false><<<grid, kApplyThreads, smem, st>>>(p);

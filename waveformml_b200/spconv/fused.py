@@ -201,6 +201,20 @@ def _dense_geometry(t, idx=None):
 
 _drop_steps = {}
 last_drop_seed = 0
+_bn_barriers = {}
+
+
+def _bn_barrier(dev):
+    """Per-device counter pair of the grid barrier inside convolution launches that finish their BatchNorm themselves
+    (zero once, left consistent by every launch)."""
+    key = (dev.type, dev.index)
+    if key not in _bn_barriers:
+        _bn_barriers[key] = torch.zeros((2,), dtype=torch.int32, device=dev)
+    return _bn_barriers[key]
+
+
+def _ptr_int(t):
+    return None if t is None else t.data_ptr()
 
 
 def _drop_step(dev):
@@ -384,32 +398,43 @@ class FusedStackFunction(Function):
                 partials = None
                 if b.bn is not None and b.bn.training and n_dst > _STATS_FUSE_MIN_ROWS and cout <= 512:
                     partials = torch.empty((lib.wfsp_bn_partials_bytes(n_dst, cout),), dtype=torch.uint8, device=dev)
-                hint = 0
-                if n_dst:
-                    hint = Fsp.hints.get(n_dst_dev)
-                    ep = _lib.conv_epilogue(bn_partials=partials)
-                    _lib.check(lib.wfsp_conv_apply_bf16_ex(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
-                                                           ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
-                                                           _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
-                                                           hint, cout, ctypes.byref(ep), st()))
-                # ---- BatchNorm / ReLU -> next operand (bf16) or the stack's output (fp32)
+                hint = Fsp.hints.get(n_dst_dev) if n_dst else 0
+                # ---- BatchNorm / ReLU (/ Dropout) -> next operand (bf16) or the stack's output (fp32).  With the
+                # epilogue statistics the BatchNorm is handed to the convolution launch itself (wfsp_bn_fuse): small
+                # launches finish it behind a grid barrier, otherwise the library runs it right behind the convolution
                 y32 = y16 = mean = invstd = None
+                bn_in_conv = None
                 if b.bn is not None or b.relu:
                     if last:
                         y32 = torch.empty_like(xf)
                     else:
                         y16 = torch.empty((max(n_dst, 1), pitch8(cout)), dtype=torch.bfloat16, device=dev)
+                if b.bn is not None:
+                    bn = b.bn
+                    mean = torch.empty((cout,), dtype=torch.float32, device=dev)
+                    invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
+                    if n_dst and partials is not None:
+                        spec = _lib.dropout_spec(b.drop, drop_seed, _drop_step(dev), bi) if b.drop else None
+                        bn_in_conv = _lib.BnFuse()
+                        bn_in_conv.gamma, bn_in_conv.beta = _ptr_int(bn.weight), _ptr_int(bn.bias)
+                        bn_in_conv.running_mean, bn_in_conv.running_var = _ptr_int(bn.running_mean), _ptr_int(bn.running_var)
+                        bn_in_conv.momentum, bn_in_conv.eps, bn_in_conv.relu = float(bn.momentum), float(bn.eps), int(b.relu)
+                        bn_in_conv.y, bn_in_conv.y_bf16 = _ptr_int(y32), _ptr_int(y16)
+                        bn_in_conv.save_mean, bn_in_conv.save_invstd = _ptr_int(mean), _ptr_int(invstd)
+                        bn_in_conv._spec_keep = spec
+                        bn_in_conv.dropout = None if spec is None else ctypes.addressof(spec)
+                        bn_in_conv.barrier = _ptr_int(_bn_barrier(dev))
+                        bn_in_conv.n_rows_hint = hint
+                if n_dst:
+                    ep = _lib.conv_epilogue(bn_partials=partials, bn=bn_in_conv)
+                    _lib.check(lib.wfsp_conv_apply_bf16_ex(_lib.ptr(a16), cur.indices.shape[0], _lib.ptr(n_src_dev), cin,
+                                                           ctypes.c_void_p(wbuf.data_ptr() + offs[bi][0]), _lib.ptr(bias),
+                                                           _lib.ptr(nbr), kvol, _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev),
+                                                           hint, cout, ctypes.byref(ep), st()))
+                if b.bn is not None or b.relu:
                     if b.bn is not None:
-                        bn = b.bn
-                        mean = torch.empty((cout,), dtype=torch.float32, device=dev)
-                        invstd = torch.empty((cout,), dtype=torch.float32, device=dev)
-                        if n_dst and partials is not None:
-                            spec = _lib.dropout_spec(b.drop, drop_seed, _drop_step(dev), bi) if b.drop else None
-                            _lib.check(lib.wfsp_bn_relu_fwd_stats_ex(
-                                _lib.ptr(xf), n_dst, _lib.ptr(n_dst_dev), hint, cout, _lib.ptr(partials), _lib.ptr(bn.weight),
-                                _lib.ptr(bn.bias), _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var),
-                                float(bn.momentum), float(bn.eps), int(b.relu), _lib.ptr(y32), _lib.ptr(y16),
-                                _lib.ptr(mean), _lib.ptr(invstd), None if spec is None else ctypes.byref(spec), st()))
+                        if bn_in_conv is not None:
+                            pass  # done by (or right behind) the convolution launch
                         elif n_dst:
                             assert not b.drop, "Dropout needs the epilogue statistics path"
                             ws = _bn_ws(lib, n_dst, cout, dev)
