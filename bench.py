@@ -474,9 +474,9 @@ def time_e2e(wl, steps, flush, sync_all):
         step.prefetch(*wl.host[0])
 
         def one(i):
-            out = step.run()                       # consumes the pending prefetch
+            step.run()                             # consumes the pending prefetch
             step.prefetch(*wl.host[(i + 1) % nb])  # next batch: copy stream, overlaps this step
-            return float(out.item())
+            return step.loss_value()               # D2H of the loss is a node of the step; one stream sync here
     else:
         def one(i):
             c, w, y = (t.to(dev, non_blocking=True) for t in wl.host[i % nb])

@@ -168,6 +168,7 @@ def test_graph_replay_tracks_eager_training(cuda_device):
             le = float(s1.step(idx, feats, labels, B))
             s2.load(coords, wave, labels)
             lg = float(s2.run())
+            assert s2.loss_value() == lg  # the pinned copy written by the step itself
             assert abs(le - lg) < 2e-3 * max(abs(le), 1e-3), (le, lg)
         assert len(rows) > 1  # the graph really was reused across different row counts
         for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):

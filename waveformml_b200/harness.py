@@ -355,6 +355,7 @@ class GraphTrainStep(TrainStep):
                 "target": torch.zeros(tshape, dtype=torch.int64 if task == "psd" else torch.float32, device=dev),
                 "n_rows": torch.zeros((1,), dtype=torch.int32, device=dev),
                 "n_host": torch.zeros((1,), dtype=torch.int32).pin_memory() if dev.type == "cuda" else None,
+                "loss_host": torch.zeros((1,), dtype=torch.float32).pin_memory() if dev.type == "cuda" else None,
                 "graph": None, "loss": None, "dup_flags": [], "ready": None, "done": None})
         self.cur = 0  # the set the next run() replays
         self.tables = batcher.item_tables([0, row_capacity], [0], dev)
@@ -505,7 +506,20 @@ class GraphTrainStep(TrainStep):
                                      overlap_exchange=self.capture_update)
         if self.capture_update:
             self._update()
-        return loss.detach()
+        loss = loss.detach()
+        if st.get("loss_host") is not None:
+            # the loss lands in pinned host memory as part of the step (a copy node of the captured graph): the host
+            # reads it after one stream synchronisation, no separate blocking copy per step (loss_value())
+            st["loss_host"].copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    def loss_value(self):
+        """Loss of the last run() as a Python float: waits for the step, reads the pinned copy the step wrote."""
+        st = self.sets[self.cur]
+        torch.cuda.current_stream().synchronize()
+        if st.get("loss_host") is not None:
+            return float(st["loss_host"][0])
+        return float(self.loss_out.item())
 
     def _snapshot(self):
         import copy
