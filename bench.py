@@ -345,6 +345,53 @@ def conv_breakdown(model, idx, feats, batch_size, flush, reps=10):
     return rows, e
 
 
+def bn_breakdown(rows_c, flush, pk, reps=10):
+    """The HBM-bound passes of the step (BatchNorm + ReLU between the convolutions, SPConvBlocks.py:505-508) timed alone
+    with CUDA events, L2 flushed: achieved GB/s over ALGORITHMIC bytes (forward: 4 B read + 2 B bf16 written per
+    element; backward: x and dy read twice (reduction, then update) + 2 B written = 18 B per element)."""
+    from waveformml_b200 import _lib
+    from waveformml_b200.spconv.fused import pitch8
+    lib = _lib.load()
+    out = []
+    for name, n, c in rows_c:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        x = torch.randn(n, c, device=dev)
+        dy = torch.randn(n, c, device=dev)
+        gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        mean, invstd = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        y16 = torch.empty(n, pitch8(c), dtype=torch.bfloat16, device=dev)
+        part = torch.zeros(lib.wfsp_bn_partials_bytes(n, c), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.wfsp_bn_workspace_bytes(n, c), dtype=torch.uint8, device=dev)
+        dg, db = torch.empty(c, device=dev), torch.empty(c, device=dev)
+
+        def fwd():
+            _lib.check(lib.wfsp_bn_relu_fwd_stats(_lib.ptr(x), n, None, 0, c, _lib.ptr(part), _lib.ptr(gamma), _lib.ptr(beta),
+                                                  _lib.ptr(rm), _lib.ptr(rv), 0.1, 1e-5, 1, None, _lib.ptr(y16),
+                                                  _lib.ptr(mean), _lib.ptr(invstd), _lib.stream()))
+
+        def bwd():
+            _lib.check(lib.wfsp_bn_relu_bwd_x(_lib.ptr(x), _lib.ptr(dy), n, None, 0, c, _lib.ptr(gamma), _lib.ptr(beta),
+                                              _lib.ptr(mean), _lib.ptr(invstd), 1, None, _lib.ptr(y16), _lib.ptr(dg),
+                                              _lib.ptr(db), _lib.ptr(ws), ws.numel(), _lib.stream()))
+
+        for what, fn, bpe in (("BatchNorm+ReLU forward (fold + normalise)", fwd, 6), ("BatchNorm+ReLU backward (reduce + fold + update)", bwd, 18)):
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3)
+            sec = float(np.mean(ts))
+            by = float(n) * c * bpe
+            out.append({"name": "%s %s [%d x %d]" % (name, what, n, c), "ms": sec * 1e3, "algorithmic_bytes": by,
+                        "gbs": by / sec / 1e9, "frac_hbm": by / sec / 1e9 / pk["hbm_gbs"]})
+    return out
+
+
 def roofline_of(row, pk, ms_per_step, traffic_key, note=None):
     """roofline object for ONE isolated kernel launch (CUDA events, L2 flushed): the denominator is the BURST
     tensor peak (a kernel timed alone), `frac_sustained` rides along; HBM-bound launches use the copy bandwidth."""
@@ -684,6 +731,9 @@ def run_ours(args):
             ideal_ms = max(fl / (pk["tflops_burst"] * 1e12), by / (pk["hbm_gbs"] * 1e9)) * 1e3
             large["step_vs_ideal"] = {"conv_flops": fl, "conv_bytes": by, "ideal_ms": ideal_ms,
                                       "frac": ideal_ms / (l_ms / l_steps)}
+            # the HBM-bound passes between the convolutions, at the sizes of this workload's first two blocks
+            n0 = lw.rows  # full-grid events: 154 rows in, 108 rows out of the first 3x3 layer per event
+            large["hbm_kernels"] = bn_breakdown([("L0", n0, 252), ("L1", n0 * 108 // 154, 158)], flush, pk)
         line["large"] = large
     wl_cpu_model, wl_cpu_batch = wl.model, wl.batch
 
