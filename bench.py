@@ -493,6 +493,16 @@ class GpuWorkload:
         return int(c.numel() * c.element_size() + w.numel() * w.element_size() + y.numel() * y.element_size())
 
 
+def exchange_kind(wl, world):
+    if world == 1:
+        return "none (one GPU)"
+    opt = getattr(wl.step, "opt", None)
+    if getattr(opt, "p2p", None) is not None:
+        return ("wfsp_sgd_step_p2p -- reduce-scatter in rank order + SGD on the shard + all-gather of the parameters over "
+                "NVLink peer memory, one launch")
+    return "NCCL all-reduce of gradient buckets issued during backward (head first) + flat SGD"
+
+
 def timed_steps(fn, steps, flush, sync_all):
     """CUDA events on the launching stream around every step, L2 flushed before each; returns total ms."""
     evs = []
@@ -664,8 +674,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16" if args.math == "bf16" else "f32", "data": "synthetic",
         "config": config_of(args, world, wl.rows),
         "implementation": {
-            "parallelism": "dp%d (events sharded by rank, rank-local rulebooks and BatchNorm, NCCL all-reduce of the "
-                           "flat 4.2 MB gradient inside the captured step)" % world,
+            "parallelism": "dp%d (events sharded by rank, rank-local rulebooks and BatchNorm; gradient exchange inside the "
+                           "captured step: %s)" % (world, exchange_kind(wl, world)),
             "math": {"bf16": "bf16 operands / fp32 accumulate (tcgen05)", "fp32": "fp32 CUDA cores",
                      "bf16x3": "fp32-grade on tcgen05: hi/lo bf16 operand split, three products per pair, fp32 "
                                "accumulate"}[args.math],
