@@ -508,7 +508,7 @@ int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1, const flo
                      float* dw2, float* db2, void* workspace, size_t workspace_bytes,
                      wfsp_stream_t stream);
 /* The tail of wfsp_head_ce_fwd for ANY batch size, for callers that computed h1 = x w1^T + b1 themselves (one plain GEMM:
- * library): logits, mean cross-entropy, dlogits, dh1, dw2, db2 in ONE launch of ceil(batch / 32) CTAs; the batch
+ * library): logits, mean cross-entropy, dlogits, dh1, dw2, db2 in ONE launch of ceil(batch / 16) CTAs; the batch
  * reductions (loss, dw2, db2) are added in tile order by the last CTA to finish (deterministic).  *ticket: a device
  * counter that is zero before the call and is left zero (allocate once, reuse).  Workspace:
  * wfsp_head_tail_workspace_bytes(). */

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(256) head_l1_partial(const float* __restrict__
 // h1 = sum of the K-chunk partials + b1.  Four lanes per element take every fourth chunk and are combined by
 // shuffles in a fixed order (deterministic); consecutive lane groups = consecutive elements (coalesced).
 __global__ void __launch_bounds__(256) head_l1_reduce(const float* __restrict__ partial, int splits, const float* __restrict__ b1,
-                                                      int B, int H1, float* __restrict__ h1) {
+                                                      int B, int H1, float* __restrict__ h1, unsigned* __restrict__ tail_ticket) {
   const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t == 0 && tail_ticket != nullptr) *tail_ticket = 0u;  // the multi-CTA tail launched behind this kernel counts from zero
   const int i = t >> 2, q = t & 3;
   float s = 0.f;
   if (i < B * H1)
@@ -174,11 +175,11 @@ __global__ void __launch_bounds__(1024) head_tail(const float* __restrict__ w2, 
   }
 }
 
-// The same tail for ANY batch: CTA t owns batch rows [32 t, 32 t + 32).  Per-row results (logits, dlogits, dh1) are
+// The same tail for ANY batch: CTA t owns batch rows [16 t, 16 t + 16).  Per-row results (logits, dlogits, dh1) are
 // final per CTA; the batch reductions (loss, dW2, db2) go through per-tile partials that the LAST CTA to finish (ticket)
 // adds in tile order -- deterministic, one launch.  h1 = x w1^T + b1 comes from the caller (a plain GEMM: library).
 // dynamic smem: h1 [TB][H1+1] | w2 [C][H1+1] | dlogits [TB][C] | logits [TB][C];  part: [tiles][C*H1 + C + 1]
-constexpr int kTailRows = 32;
+constexpr int kTailRows = 16;
 __global__ void __launch_bounds__(256) head_tail_tiles(const float* __restrict__ w2, const float* __restrict__ b2,
                                                        const int64_t* __restrict__ labels, int B, int H1, int C,
                                                        const float* __restrict__ h1, float* __restrict__ logits,
@@ -368,9 +369,11 @@ __global__ void __launch_bounds__(256) head_bwd_small(const float* __restrict__ 
 
 using namespace wfsp;
 
+extern "C" size_t wfsp_head_tail_workspace_bytes(int batch, int h1, int n_class);
 extern "C" size_t wfsp_head_workspace_bytes(int batch, int k0, int h1) {
   const size_t splits = size_t((k0 + kKC - 1) / kKC);
-  return align_up(splits * size_t(batch) * h1 * sizeof(float), 256);
+  // split-K partials of Linear-1 | per-tile partials of the tail (for up to 64 classes) | the tail's ticket
+  return align_up(splits * size_t(batch) * h1 * sizeof(float), 256) + wfsp_head_tail_workspace_bytes(batch, h1, 64) + 256;
 }
 
 extern "C" int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -387,16 +390,21 @@ extern "C" int wfsp_head_ce_fwd(const float* x, const float* w1, const float* b1
   float* partial = static_cast<float*>(workspace);
   dim3 grid(unsigned(splits), unsigned((h1_dim + kHT - 1) / kHT), unsigned((batch + kBT - 1) / kBT));
   head_l1_partial<<<grid, 256, 0, st>>>(x, w1, batch, k0, h1_dim, partial);
-  head_l1_reduce<<<unsigned((batch * h1_dim * 4 + 255) / 256), 256, 0, st>>>(partial, splits, b1, batch, h1_dim, h1);
-  const size_t tail_smem = (size_t(batch) * (h1_dim + 1) + size_t(n_class) * (h1_dim + 1) + size_t(2) * batch * n_class) * sizeof(float);
-  if (tail_smem > size_t(200) * 1024) return set_error(WFSP_EUNSUPPORTED, "head batch %d too large for the fused tail", batch);
-  WFSP_CHECK_CUDA(cudaFuncSetAttribute(head_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  head_tail<<<1, 1024, tail_smem, st>>>(w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2);
+  // the tail runs as ceil(batch / 16) CTAs (logits / loss terms / dlogits / dh1 are per-row work; the batch reductions
+  // are folded by the last CTA in tile order): the one-CTA version was 12 us of four dependent phases at 64 events
+  char* w8 = static_cast<char*>(workspace);
+  const size_t off_tail = align_up(size_t(splits) * batch * h1_dim * sizeof(float), 256);
+  float* tail_part = reinterpret_cast<float*>(w8 + off_tail);
+  unsigned* ticket = reinterpret_cast<unsigned*>(w8 + off_tail + wfsp_head_tail_workspace_bytes(batch, h1_dim, 64));
+  head_l1_reduce<<<unsigned((batch * h1_dim * 4 + 255) / 256), 256, 0, st>>>(partial, splits, b1, batch, h1_dim, h1, ticket);
+  const size_t tail_smem = (size_t(kTailRows) * (h1_dim + 1) + size_t(n_class) * (h1_dim + 1) + size_t(2) * kTailRows * n_class) * sizeof(float);
+  WFSP_CHECK_CUDA(cudaFuncSetAttribute(head_tail_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  head_tail_tiles<<<unsigned((batch + kTailRows - 1) / kTailRows), 256, tail_smem, st>>>(
+      w2, b2, labels, batch, h1_dim, n_class, h1, logits, loss, dlogits, dh1, dw2, db2, tail_part, ticket);
   count_launches(3);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
 }
-
 
 extern "C" size_t wfsp_head_tail_workspace_bytes(int batch, int h1, int n_class) {
   const size_t tiles = size_t((batch + kTailRows - 1) / kTailRows);
