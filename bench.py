@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="events per GPU")
     ap.add_argument("--math", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--no-math-modes", action="store_true", help="skip the bf16x3 / fp32 figures of the default line")
+    ap.add_argument("--c3-batch", type=int, default=1024, help="events of the C3 (z-regression) block, 0 = skip")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: sync-free capacity-sized step replayed from a CUDA graph; eager: exact shapes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -637,6 +638,29 @@ def run_ours(args):
         extra["rotating"] = {"batches": args.rotate, "steps": rot_steps, "rows_min": min(rws), "rows_max": max(rws),
                              "hint_rows": rws[0], "ms_per_step": rot_ms / rot_steps,
                              "value": world * B / (rot_ms / rot_steps * 1e-3)}
+    # BASELINE.json configs[2] (C3): the z-position regression model (SingleEndedZCNN.json: SparseConv2d(300,150,3,1,1) .
+    # BN . ReLU . SparseConv2d(150,1,1) . ReLU . ToDense, masked-L1 segment loss) at 1024 events -- same captured-step
+    # machinery, same timing rules
+    if args.mode == "graph" and world == 1 and args.c3_batch > 0:
+        from waveformml_b200 import harness as _h, stacks as _st
+        from waveformml_b200.synth import make_events as _mk
+        cb = args.c3_batch
+        torch.manual_seed(0)
+        zmodel = _st.ZRegressor().to(dev).train()
+        zev = _mk(cb, n_samples=150, seed=4321)
+        zc, zw, zz = (torch.from_numpy(zev[k]).to(dev) for k in ("coords", "wave", "z"))
+        zstep = _h.GraphTrainStep(zmodel, "z", cb, cb * 10, 300)
+        zstep.load(zc, zw, zz)
+        zstep.capture()
+        for _ in range(3):
+            zstep.run()
+        z_steps = max(10, min(args.steps, 30))
+        z_ms = timed_steps(lambda i: zstep.run(), z_steps, flush, sync_all)
+        extra["c3"] = {"workload": "C3: z-position regression model (SingleEndedZCNN.json stack), masked-L1 segment loss, "
+                                   "synthetic clustered events", "events_per_gpu": cb, "rows_per_gpu": int(zc.shape[0]),
+                       "steps": z_steps, "ms_per_step": z_ms / z_steps, "value": cb / (z_ms / z_steps * 1e-3),
+                       "unit": "events/s", "gpu_launches_per_step": zstep.launches_per_replay}
+        del zstep, zmodel
     # the tight-tolerance mode on the same tensor-core kernels (WFSP_MATH_BF16X3: hi/lo bf16 operand split, fp32-grade
     # results) and, for reference, the CUDA-core fp32 mode it replaces -- same workload, same timing rules
     if args.mode == "graph" and args.math == "bf16" and world == 1 and not args.no_math_modes:

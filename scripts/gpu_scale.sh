@@ -3,9 +3,9 @@
 tag=$1; n=$2; shift 2
 port=$((29600 + n))
 if [ "$n" = "1" ]; then
-  timeout 300 python bench.py --gpus 1 --steps 50 --warmup 5 --large-batch 0 --no-breakdown --no-cpu-baseline --no-math-modes --rotate 1 --sustained 0 "$@" > gpurun_out/${tag}_${n}gpu.json 2> gpurun_out/${tag}_${n}gpu.err
+  timeout 300 python bench.py --gpus 1 --steps 50 --warmup 5 --large-batch 0 --no-breakdown --no-cpu-baseline --no-math-modes --c3-batch 0 --rotate 1 --sustained 0 "$@" > gpurun_out/${tag}_${n}gpu.json 2> gpurun_out/${tag}_${n}gpu.err
 else
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 50 --warmup 5 --large-batch 0 --no-breakdown --no-cpu-baseline --no-math-modes --rotate 1 --sustained 0 "$@" > gpurun_out/${tag}_${n}gpu.json 2> gpurun_out/${tag}_${n}gpu.err
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 50 --warmup 5 --large-batch 0 --no-breakdown --no-cpu-baseline --no-math-modes --c3-batch 0 --rotate 1 --sustained 0 "$@" > gpurun_out/${tag}_${n}gpu.json 2> gpurun_out/${tag}_${n}gpu.err
 fi
 python -c "
 import json,sys
