@@ -529,6 +529,26 @@ int wfsp_head_bwd(const float* x, const float* w1, const float* dh1, const float
                   int n_class, float* dx, float* dw1, float* db1, float* dw2, float* db2,
                   wfsp_stream_t stream);
 
+/* Masked L1 segment loss of the z / energy regression models (src/engineering/LitBase.py:124-174
+ * _calc_segment_loss; src/engineering/LitZ.py:89-107): the reference densifies a ones-mask and the per-hit target with
+ * SparseConvTensor.dense() and takes l1_loss(mask * prediction, target, "sum") / N.  Inactive cells contribute
+ * |0 - 0|, so the same value is the row-wise L1 between the dense prediction at every hit's cell and the hit's target:
+ * pred fp32 [batch, n_chan, h, w]; indices int32 [n_rows, 3] = (b, x, y); target fp32 [n_rows, target_chan] with
+ * target_chan = n_chan or 1 (broadcast over channels).  fwd: *loss (device scalar); chunk partials are added in a fixed
+ * order.  bwd: d_pred (ZEROED by the caller) gets sign(pred - target) * *grad_out / N at every hit's cell. */
+size_t wfsp_segment_l1_workspace_bytes(int64_t n_rows);
+int wfsp_segment_l1_fwd(const float* pred, const int32_t* indices, const float* target, int64_t n_rows,
+                        const int32_t* n_rows_dev, int n_chan, int target_chan, int batch, int h, int w,
+                        float* loss, void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+int wfsp_segment_l1_bwd(const float* pred, const int32_t* indices, const float* target, int64_t n_rows,
+                        const int32_t* n_rows_dev, int n_chan, int target_chan, int batch, int h, int w,
+                        const float* grad_out, float* d_pred, wfsp_stream_t stream);
+
+/* Column sums of the live rows of x [n_rows, c] (the bias gradient of a convolution on the graph path, where the
+ * buffer is capacity-sized and only *n_rows_dev rows are live); workspace: wfsp_bn_workspace_bytes(n_rows, c). */
+int wfsp_col_sum(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, float* out,
+                 void* workspace, size_t workspace_bytes, wfsp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (9) Window edges.  Replaces the reference's only native function, cffi_window_edges
  * (src/custom_functions/cffi.c:5-37, bound in src/custom_functions/__init__.py:5-35 and called from

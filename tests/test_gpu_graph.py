@@ -278,3 +278,34 @@ def test_two_backwards_accumulate_outside_write_through(cuda_device):
     step = harness.TrainStep(model, "psd")
     step.forward_backward(idx, feats, labels, B)
     assert _l2(step.grads.flat, once) < 1e-2  # bf16 math mode runs the head GEMMs of the harness step in TF32
+
+
+@pytest.mark.parametrize("n,cap,C,Ct", [(3000, 3000, 1, 1), (777, 1200, 2, 1), (500, 500, 3, 3)])
+def test_segment_l1_and_live_column_sums(cuda_device, n, cap, C, Ct):
+    """The gather form of the masked L1 segment loss (wfsp_segment_l1_*) equals the reference's dense form
+    (LitBase._calc_segment_loss) in value and gradient; wfsp_col_sum sums only the live rows of a capacity buffer."""
+    from waveformml_b200.spconv import functional as Fsp
+    dev = cuda_device
+    B = 64
+    g = torch.Generator().manual_seed(n)
+    cells = torch.randperm(B * 14 * 11, generator=g)[:cap]
+    idx = torch.stack([cells // 154, (cells % 154) // 11, cells % 11], 1).int().to(dev)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=dev) if cap != n else None
+    pred = torch.randn(B, C, 14, 11, generator=g).to(dev).requires_grad_(True)
+    tgt = torch.randn(cap, Ct, generator=g).to(dev)
+    tgt_in = tgt[:, 0] if Ct == 1 else tgt
+    loss = harness.segment_l1_loss(idx, pred, tgt_in, [14, 11], B, n_dev)
+    (loss * 1.7).backward()
+    # dense reference form on the live rows
+    p2 = pred.detach().clone().requires_grad_(True)
+    li = idx[:n].long()
+    mask = torch.zeros(B, C, 14, 11, device=dev)
+    mask[li[:, 0], :, li[:, 1], li[:, 2]] = 1.0
+    td = torch.zeros(B, Ct, 14, 11, device=dev)
+    td[li[:, 0], :, li[:, 1], li[:, 2]] = tgt[:n]
+    ref = torch.nn.functional.l1_loss(mask * p2, td.expand(B, C, 14, 11), reduction="sum") / n
+    (ref * 1.7).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    torch.testing.assert_close(pred.grad, p2.grad, rtol=1e-6, atol=1e-9)
+    x = torch.randn(cap, 150, generator=g).to(dev)
+    torch.testing.assert_close(Fsp.live_col_sum(x, n_dev), x[:n].sum(0), rtol=1e-4, atol=1e-4)

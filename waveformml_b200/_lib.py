@@ -79,6 +79,10 @@ SIGNATURES = {
     "wfsp_sgd_step_p2p": (_int, [_vp, _vp, _vp, _i64, _f32, _f32, _int, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _int, _int,
                                  _int, _vp]),
     "wfsp_sgd_p2p_wait": (_int, [_vp, _vp, _int, _vp]),
+    "wfsp_segment_l1_workspace_bytes": (_sz, [_i64]),
+    "wfsp_segment_l1_fwd": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _int, _int, _int, _int, _vp, _vp, _sz, _vp]),
+    "wfsp_segment_l1_bwd": (_int, [_vp, _vp, _vp, _i64, _vp, _int, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "wfsp_col_sum": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "wfsp_head_workspace_bytes": (_sz, [_int, _int, _int]),
     "wfsp_head_tail_workspace_bytes": (_sz, [_int, _int, _int]),
     "wfsp_head_ce_tail": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),

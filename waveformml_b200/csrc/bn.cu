@@ -997,6 +997,60 @@ extern "C" int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows,
 
 namespace wfsp {
 namespace {
+// column sums of the LIVE rows of x [cap, c] (bias gradient of a convolution on the graph path): per 256-row chunk
+// partials (row lanes combined in lane order), folded in chunk order by bn_bwd_finalize -- deterministic
+__global__ void __launch_bounds__(256) col_sum_partial(const float* __restrict__ x, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                                                       int c, float* __restrict__ part /* [chunks][2][c], slot 1 = 0 */) {
+  __shared__ float red[8][32];
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t r0 = int64_t(blockIdx.x) * kRowsBwd;
+  if (r0 >= n) return;
+  const int64_t r_end = r0 + kRowsBwd < n ? r0 + kRowsBwd : n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int ch0 = 0; ch0 < c; ch0 += 32) {
+    const int ch = ch0 + tx;
+    float s = 0.f;
+    if (ch < c)
+      for (int64_t r = r0 + ty; r < r_end; r += 8) s += x[r * c + ch];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && ch < c) {
+      float t = 0.f;
+      for (int l = 0; l < 8; ++l) t += red[l][tx];
+      part[(int64_t(blockIdx.x) * 2 + 0) * c + ch] = t;
+      part[(int64_t(blockIdx.x) * 2 + 1) * c + ch] = 0.f;
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+}  // namespace wfsp
+
+extern "C" int wfsp_col_sum(const float* x, int64_t n_rows, const int32_t* n_rows_dev, int c, float* out, void* workspace,
+                            size_t workspace_bytes, wfsp_stream_t stream) {
+  WFSP_REQUIRE(n_rows >= 0 && c >= 1 && out != nullptr, "bad column-sum arguments");
+  cudaStream_t st = as_stream(stream);
+  if (n_rows == 0) {
+    WFSP_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(c) * 4, st));
+    return WFSP_OK;
+  }
+  if (workspace == nullptr || workspace_bytes < wfsp_bn_workspace_bytes(n_rows, c))
+    return set_error(WFSP_EWORKSPACE, "column-sum workspace too small");
+  float* part = static_cast<float*>(workspace);
+  // the fold kernel of BatchNorm backward adds slot 0 into its "d_beta" output (= the column sums) and slot 1 (zeros)
+  // into its "d_gamma" output, which goes to the scratch area behind the partial list
+  float* unused = reinterpret_cast<float*>(static_cast<char*>(workspace) +
+                                           align_up(size_t(ceil_div<int64_t>(n_rows, kRowsBwd)) * 2 * c * sizeof(float), 256));
+  col_sum_partial<<<unsigned(ceil_div<int64_t>(n_rows, kRowsBwd)), 256, 0, st>>>(x, n_rows, n_rows_dev, c, part);
+  bn_bwd_finalize<<<ceil_div(c, kCh), dim3(kCh, kFinLanes), 0, st>>>(part, kRowsBwd, n_rows, n_rows_dev, c, unused, out, nullptr,
+                                                                    nullptr, -1);
+  count_launches(2);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
+namespace wfsp {
+namespace {
 __global__ void __launch_bounds__(256) dropout_factors_kernel(const DropSpec drop, int64_t total, float* __restrict__ out) {
   const unsigned long long key = drop_key(drop);
   for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256)

@@ -51,6 +51,21 @@ class LaunchHints:
 hints = LaunchHints()
 
 
+def live_col_sum(x, n_rows_dev):
+    """Column sums over the LIVE rows of a capacity-sized [cap, c] fp32 buffer (wfsp_col_sum): the bias gradient of a
+    convolution on the graph path -- a masked torch reduction would stream the whole capacity (157 696 x 150 floats for
+    the z-regression model at 1024 events: 80 us for 3 000 live rows)."""
+    lib = _lib.load()
+    x = x.contiguous()
+    n, c = x.shape
+    out = torch.empty((c,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((lib.wfsp_bn_workspace_bytes(max(n, 1), c),), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.wfsp_col_sum(_lib.ptr(x), n, _lib.ptr(n_rows_dev), c, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                    _lib.stream()))
+    return out
+
+
 def conv_apply(src, weight3, transpose_w, bias, nbr, n_dst, c_dst, math, n_src_dev=None, n_dst_dev=None):
     """dst[r] = bias + sum_k src[nbr[r,k]] @ (weight3[k] or weight3[k]^T)   (wfsp_conv_apply)"""
     lib = _lib.load()
@@ -145,8 +160,7 @@ class SparseConvFunction(Function):
             if n_dst_dev is None:
                 d_b = g.sum(0)
             else:  # graph path: only the live rows of the capacity-sized gradient count
-                live = (torch.arange(g.shape[0], device=g.device) < n_dst_dev).unsqueeze(1)
-                d_b = torch.where(live, g, torch.zeros((), device=g.device)).sum(0)
+                d_b = live_col_sum(g, n_dst_dev)
         return d_feats, d_w, d_b, None, None, None, None
 
 

@@ -549,8 +549,7 @@ class FusedStackFunction(Function):
                     if n_dst_dev is None:
                         grads[4 * bi + 1] = dx32.sum(0)
                     else:  # graph path: only the live rows of the capacity-sized gradient count
-                        live = (torch.arange(n_dst, device=dev) < n_dst_dev).unsqueeze(1)
-                        grads[4 * bi + 1] = torch.where(live, dx32, torch.zeros((), device=dev)).sum(0)
+                        grads[4 * bi + 1] = Fsp.live_col_sum(dx32, n_dst_dev)
                 # ---- wgrad
                 if ctx.needs_input_grad[4 + 4 * bi]:
                     dw, w_through = _grad_target(w_p, (kvol, cin, cout), dev)
