@@ -572,6 +572,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    for kv in os.environ.get("WFSP_OPTIONS", "").split(","):  # tuning knobs, e.g. WFSP_OPTIONS=apply_k_split=0
+        if kv:
+            k, v = kv.split("=")
+            _lib.check(lib.wfsp_set_option(k.encode(), int(v)))
     spconv.set_math_mode(args.math)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

@@ -33,6 +33,7 @@ int sm_count() {
 }
 
 void set_force_hash(int v);
+void set_small_rows(int v);
 void set_force_rblk(int v);
 void set_auto_ksplit(int v);
 void set_split_stages(int v);
@@ -102,6 +103,7 @@ extern "C" int wfsp_device_info(int* sm, int* major, int* minor) {
 // test hook: force the open-addressing hash table in the rulebook builder even for small grids
 extern "C" int wfsp_set_option(const char* name, int value) {
   if (strcmp(name, "rulebook_force_hash") == 0) { set_force_hash(value); return WFSP_OK; }
+  if (strcmp(name, "rulebook_small_rows") == 0) { set_small_rows(value); return WFSP_OK; }
   if (strcmp(name, "apply_row_blocks") == 0) { set_force_rblk(value); return WFSP_OK; }
   if (strcmp(name, "apply_k_split") == 0) { set_auto_ksplit(value); return WFSP_OK; }
   if (strcmp(name, "apply_split_stages") == 0) { set_split_stages(value); return WFSP_OK; }

@@ -23,6 +23,7 @@ namespace wfsp {
 
 static int g_force_hash = 0;
 void set_force_hash(int v) { g_force_hash = v; }
+void set_small_rows(int v);
 extern unsigned long long* g_trace;  // conv_umma.cu (wfsp_debug_trace)
 
 namespace {
@@ -368,7 +369,7 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 
 constexpr int kSmallBlock = 1024;
 constexpr int kSmallWarps = kSmallBlock / 32;
-constexpr int64_t kSmallMaxRows = 2048;   // live rows (two rounds): beyond this the multi-kernel phases win
+int64_t kSmallMaxRows = 2048;   // live rows (two rounds): beyond this the multi-kernel phases win (wfsp_set_option "rulebook_small_rows")
 constexpr int64_t kSmallMaxCap = 65536;    // capacity bound of the single-launch builder (its cost follows the LIVE count)
 
 template <bool SUBM, bool SMEM_TABLE>
@@ -836,6 +837,8 @@ extern "C" int wfsp_rulebook_tables(const int32_t* pairs, const int32_t* pair_nu
 // inputs (up to kSmallMaxRows expected live rows, direct table, kernel volume <= 256) take the single-launch
 // path; everything else runs the phase kernels above followed by rb_tables.  ndim 2: index rows (b, x, y);
 // ndim 3: (b, x, y, t).
+namespace wfsp { void set_small_rows(int v) { kSmallMaxRows = v; } }
+
 extern "C" int wfsp_rulebook_build_phased(int ndim, const int32_t* indices, int64_t n_in, const int32_t* n_in_dev,
                                           int64_t n_in_hint, int batch, const int* in_shape, const int* ksize,
                                           const int* stride, const int* pad, const int* dil, int subm,
