@@ -14,14 +14,14 @@ grep "step span" gpurun_out/r2_final_timeline_C2_b64.txt gpurun_out/r2_final_tim
 for cfg in "C2 64" "C5 1024"; do
   set -- $cfg
   TAG=r2_final_$1_b$2
-  CMD="python bench.py --workload $1 --batch $2 --large-batch 0 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --no-math-modes --rotate 1 --sustained 0"
+  CMD="python bench.py --workload $1 --batch $2 --large-batch 0 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --no-math-modes --c3-batch 0 --rotate 1 --sustained 0"
   $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -n 5 gpurun_out/${TAG}_plain.log; continue; }
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
   echo "launch list $TAG rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_(apply|wgrad)" -c 8 -o gpurun_out/${TAG}_conv_full -f $CMD > gpurun_out/${TAG}_ncu_conv.log 2>&1
   echo "full conv $TAG rc=$?"
 done
-CMD="python bench.py --workload C5 --batch 1024 --large-batch 0 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --no-math-modes --rotate 1 --sustained 0"
+CMD="python bench.py --workload C5 --batch 1024 --large-batch 0 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --no-math-modes --c3-batch 0 --rotate 1 --sustained 0"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:bn_stream" -c 9 -o gpurun_out/r2_final_C5_b1024_bn_full -f $CMD > gpurun_out/r2_final_C5_b1024_ncu_bn.log 2>&1
 echo "full bn rc=$?"
 ls -la gpurun_out/r2_final_* | awk '{print $5, $9}'

@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: per-kernel count, total
-and share.  Usage: launch_summary.py launches.csv [last_n_launches]"""
+and share.  Usage: launch_summary.py launches.csv [last_n_launches | until=SUBSTR]
+(until=SUBSTR keeps the launches before the first kernel whose name contains SUBSTR, e.g. the bench's C3 block)."""
 import csv, sys, collections, io
 path = sys.argv[1]
 lines = [l for l in open(path, errors="replace") if l.startswith('"')]
 rows = list(csv.DictReader(io.StringIO("".join(lines))))
 rows = [r for r in rows if r.get("Metric Name") == "gpu__time_duration.sum"]
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2].startswith("until="):
+    cut = next((i for i, r in enumerate(rows) if sys.argv[2][6:] in r["Kernel Name"]), len(rows))
+    rows = rows[:cut]
+elif len(sys.argv) > 2:
     rows = rows[-int(sys.argv[2]):]
 def dur_us(r):
     try:
