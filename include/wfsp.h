@@ -55,7 +55,7 @@ enum wfsp_math {
                           The tensor-core counterpart of WFSP_MATH_FP32 for the tight-tolerance mode.    */
 };
 
-#define WFSP_VERSION 201
+#define WFSP_VERSION 203
 #define WFSP_MAX_KVOL 1024
 
 int wfsp_version(void);
@@ -251,6 +251,14 @@ int wfsp_conv_wgrad(const float* a, int64_t n_a, const int32_t* n_a_dev, int c_a
 int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows,
                   const int32_t* n_rows_dev, int n_chan, int batch, int h, int w, float* dense,
                   int32_t* cell_table, wfsp_stream_t stream);
+
+/* The two halves of wfsp_to_dense.  The cell table (row of every dense cell, -1 = empty) depends on the
+ * coordinates only, so a caller that knows the output coordinates early (the rulebook of the last layer)
+ * builds it beside the convolutions; the scatter then is one launch behind the last layer. */
+int wfsp_dense_cell_table(const int32_t* indices, int64_t n_rows, const int32_t* n_rows_dev, int batch,
+                          int h, int w, int32_t* cell_table, wfsp_stream_t stream);
+int wfsp_to_dense_from_table(const float* feats, int n_chan, int batch, int h, int w,
+                             const int32_t* cell_table, float* dense, wfsp_stream_t stream);
 
 int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows,
                       const int32_t* n_rows_dev, int n_chan, int batch, int h, int w,
@@ -466,6 +474,11 @@ int wfsp_act_bwd(const float* x, const float* dy, int64_t n_rows, const int32_t*
 int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr,
                   float momentum, int nesterov, float weight_decay, float grad_scale,
                   wfsp_stream_t stream);
+/* zero_grads != 0: the gradient buffer is cleared in the same pass (optimizer.zero_grad() folded in), so a training
+ * step that accumulates into it needs no fill launch at its start. */
+int wfsp_sgd_step_ex(float* params, float* grads, float* momentum_buf, int64_t n, float lr,
+                     float momentum, int nesterov, float weight_decay, float grad_scale,
+                     int zero_grads, wfsp_stream_t stream);
 
 /* The same update for data-parallel training (one process per GPU), fused with the gradient exchange over NVLink peer
  * memory -- replaces NCCL all-reduce + optimiser step (src/utils/util.py:233-236: Lightning DDP).  The flat gradient

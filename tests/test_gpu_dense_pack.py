@@ -76,6 +76,38 @@ def test_to_dense_fwd_bwd(cuda_device, shape, C):
     assert torch.equal(nhwc.cpu(), ref.permute(0, 2, 3, 1))
 
 
+def test_to_dense_two_halves_equal_whole(cuda_device):
+    """wfsp_dense_cell_table (on another stream, as the fused stack builds it beside the convolutions) +
+    wfsp_to_dense_from_table == wfsp_to_dense, bit for bit, with duplicate coordinates (last row wins)."""
+    from waveformml_b200 import _lib
+    lib = _lib.load()
+    B, shape, C = 9, (14, 11), 45
+    ev = make_events(B, n_samples=1, seed=3)
+    idx = torch.from_numpy(ev["coords"])[:, [2, 0, 1]].contiguous()
+    idx = torch.cat([idx, idx[:5]]).contiguous()  # five duplicates
+    n = idx.shape[0]
+    feats = torch.randn(n, C)
+    ref = osp.to_dense_c(feats, idx, B, shape)
+    fg, ig = feats.to(cuda_device), idx.to(cuda_device)
+    whole = torch.empty((B, C) + shape, device=cuda_device)
+    halves = torch.empty_like(whole)
+    t1 = torch.empty((B * shape[0] * shape[1],), dtype=torch.int32, device=cuda_device)
+    t2 = torch.empty_like(t1)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=cuda_device)
+    torch.cuda.synchronize()
+    _lib.check(lib.wfsp_to_dense(_lib.ptr(fg), _lib.ptr(ig), n, _lib.ptr(n_dev), C, B, shape[0], shape[1], _lib.ptr(whole),
+                                 _lib.ptr(t1), _lib.stream()))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        _lib.check(lib.wfsp_dense_cell_table(_lib.ptr(ig), n, _lib.ptr(n_dev), B, shape[0], shape[1], _lib.ptr(t2),
+                                             _lib.stream()))
+    torch.cuda.current_stream().wait_stream(side)
+    _lib.check(lib.wfsp_to_dense_from_table(_lib.ptr(fg), C, B, shape[0], shape[1], _lib.ptr(t2), _lib.ptr(halves),
+                                            _lib.stream()))
+    assert torch.equal(t1.cpu(), t2.cpu())
+    assert torch.equal(whole.cpu(), ref) and torch.equal(halves.cpu(), ref)
+
+
 def test_to_dense_empty(cuda_device):
     d = spconv.SparseConvTensor(torch.zeros(0, 3, device=cuda_device), torch.zeros(0, 3, dtype=torch.int32, device=cuda_device),
                                 [14, 11], 2).dense()

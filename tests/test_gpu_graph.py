@@ -177,6 +177,41 @@ def test_graph_replay_tracks_eager_training(cuda_device):
         spconv.set_math_mode("bf16")
 
 
+def test_replay_after_foreign_gradient_writes(cuda_device):
+    """The captured step has no fill launch (the optimiser's pass leaves the gradient buffer cleared); gradients
+    written by anything else in between -- here an eager forward_backward on the same step object -- must not leak
+    into the next replay."""
+    spconv.set_math_mode("fp32")
+    try:
+        B = 16
+        torch.manual_seed(3)
+        m1 = stacks.PSDClassifier().to(cuda_device).train()
+        m2 = copy.deepcopy(m1)
+        s1 = harness.TrainStep(m1, "psd", lr=0.01, momentum=0.9)
+        s2 = harness.GraphTrainStep(m2, "psd", B, B * 10, 300, lr=0.01, momentum=0.9)
+        batches = [_psd_inputs(B, 300 + i, cuda_device) for i in range(3)]
+        s2.load(*batches[0])
+        s2.capture()
+        for i, (coords, wave, labels) in enumerate(batches):
+            idx, feats = batcher.pack_batch(coords, wave)
+            s1.step(idx, feats, labels, B)
+            if i == 1:  # gradients of some other batch land in the flat buffer between two replays
+                bn_state = copy.deepcopy([b.clone() for b in m2.buffers()])
+                oc, ow, ol = batches[2]
+                oi, of = batcher.pack_batch(oc, ow)
+                s2.forward_backward(oi, of, ol, B)
+                assert float(s2.grads.flat.abs().sum()) > 0
+                for b, saved in zip(m2.buffers(), bn_state):  # (the eager pass also moved the BatchNorm statistics)
+                    b.copy_(saved)
+            s2.load(coords, wave, labels)
+            s2.run()
+        for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+            assert _l2(b, a) < 1e-3, (k, _l2(b, a))
+        assert float(s2.grads.flat.abs().sum()) == 0.0  # left cleared by the optimiser's pass
+    finally:
+        spconv.set_math_mode("bf16")
+
+
 def test_graph_path_vs_oracle_bf16(cuda_device):
     """The captured bf16 step against the CPU oracle with bf16-rounded GEMM operands."""
     B = 24

@@ -162,10 +162,14 @@ def test_flat_sgd_matches_torch_nesterov(cuda_device):
         for p, r, g in zip(ours, ref, gs):
             p.grad.copy_(g)
             r.grad = (g * 0.5).clone()
-        opt.step(grad_scale=0.5)
+        opt.step(grad_scale=0.5, zero_grads=step % 2 == 1)  # (265 elements: vector body + a scalar tail)
         ropt.step()
         for p, r in zip(ours, ref):
             torch.testing.assert_close(p.detach(), r.detach(), rtol=1e-5, atol=1e-6)
+        if step % 2 == 1:
+            assert float(fg.flat.abs().sum()) == 0.0  # optimizer.zero_grad() folded into the update pass
+        else:
+            assert float(fg.flat.abs().sum()) > 0.0
     assert all(p.data_ptr() >= opt.flat_p.data_ptr() for p in ours)  # parameters live in the flat buffer
 
 

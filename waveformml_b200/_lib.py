@@ -47,6 +47,8 @@ SIGNATURES = {
     "wfsp_conv_wgrad": (_int, [_vp, _i64, _vp, _int, _vp, _i64, _vp, _int, _vp, _vp, _vp, _int, _i64, _i64, _vp, _int,
                                _int, _vp, _sz, _vp]),
     "wfsp_to_dense": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "wfsp_dense_cell_table": (_int, [_vp, _i64, _vp, _int, _int, _int, _vp, _vp]),
+    "wfsp_to_dense_from_table": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp]),
     "wfsp_to_dense_bwd": (_int, [_vp, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp]),
     "wfsp_bn_workspace_bytes": (_sz, [_i64, _int]),
     "wfsp_bn_relu_fwd": (_int, [_vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _int, _vp, _vp, _vp, _vp,
@@ -93,6 +95,7 @@ SIGNATURES = {
     "wfsp_window_edges_workspace_bytes": (_sz, [_i64]),
     "wfsp_window_edges": (_int, [_i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "wfsp_sgd_step": (_int, [_vp, _vp, _vp, _i64, _f32, _f32, _int, _f32, _f32, _vp]),
+    "wfsp_sgd_step_ex": (_int, [_vp, _vp, _vp, _i64, _f32, _f32, _int, _f32, _f32, _int, _vp]),
 }
 
 
@@ -156,7 +159,7 @@ class WfspError(RuntimeError):
     pass
 
 
-EXPECTED_VERSION = 201  # include/wfsp.h WFSP_VERSION: bumped with every change of the C ABI
+EXPECTED_VERSION = 203  # include/wfsp.h WFSP_VERSION: bumped with every change of the C ABI
 
 
 def load():

@@ -38,6 +38,7 @@ void set_force_rblk(int v);
 void set_auto_ksplit(int v);
 void set_split_stages(int v);
 void set_split_wide(int v);
+void set_prep_ctas(int v);
 void set_bn_stream(int v);
 void set_bn_fuse(int v);
 void set_trace(unsigned long long* p);
@@ -108,6 +109,7 @@ extern "C" int wfsp_set_option(const char* name, int value) {
   if (strcmp(name, "apply_k_split") == 0) { set_auto_ksplit(value); return WFSP_OK; }
   if (strcmp(name, "apply_split_stages") == 0) { set_split_stages(value); return WFSP_OK; }
   if (strcmp(name, "apply_split_wide") == 0) { set_split_wide(value); return WFSP_OK; }
+  if (strcmp(name, "prep_ctas") == 0) { set_prep_ctas(value); return WFSP_OK; }
   if (strcmp(name, "bn_stream") == 0) { set_bn_stream(value); return WFSP_OK; }
   if (strcmp(name, "apply_bn_fuse") == 0) { set_bn_fuse(value); return WFSP_OK; }
   return set_error(WFSP_EINVAL, "unknown option %s", name);

@@ -170,14 +170,36 @@ constexpr int kMaxPrepJobs = 16;
 struct PrepJob { const float* w; __nv_bfloat16* out; int kvol, c_red, c_dst, transpose_w; int block0, blocks; };
 struct PrepBatch { PrepJob job[kMaxPrepJobs]; int n; };
 
+// One 16-byte chunk (eight consecutive reduction channels of one output channel) per thread and iteration: one
+// index decomposition and one store per eight values.  The grid is kept BELOW one CTA per SM over all jobs: the launch
+// runs beside the first convolution of the step, whose CTAs take a whole SM's shared memory (226 KB + the 1 KB every
+// resident CTA reserves) -- a preparation launch that touched every SM kept them out until it had drained.
 __global__ void __launch_bounds__(256) prep_weights_batch_kernel(const PrepBatch b) {
   int j = 0;
   while (j + 1 < b.n && int(blockIdx.x) >= b.job[j + 1].block0) ++j;
   const PrepJob& q = b.job[j];
   const int n_pad = (q.c_dst + 15) / 16 * 16, kc_pad = (q.c_red + 63) / 64 * 64, num_kb = kc_pad / 64;
-  const int64_t total = int64_t(q.kvol) * n_pad * kc_pad;
-  for (int64_t i = (int64_t(blockIdx.x) - q.block0) * blockDim.x + threadIdx.x; i < total; i += int64_t(q.blocks) * blockDim.x)
-    q.out[i] = __float2bfloat16_rn(prep_weight_value(q.w, i, q.c_red, q.c_dst, q.transpose_w, n_pad, num_kb));
+  const int64_t chunks = int64_t(q.kvol) * n_pad * (kc_pad >> 3);
+  uint4* out = reinterpret_cast<uint4*>(q.out);
+  for (int64_t ci = (int64_t(blockIdx.x) - q.block0) * blockDim.x + threadIdx.x; ci < chunks; ci += int64_t(q.blocks) * blockDim.x) {
+    const int pc = int(ci & 7);
+    int64_t t = ci >> 3;
+    const int n = int(t % n_pad);
+    t /= n_pad;
+    const int kb = int(t % num_kb), k = int(t / num_kb);
+    const int c0 = kb * 64 + ((pc ^ (n & 7)) << 3);
+    const float* wk = q.w + int64_t(k) * q.c_red * q.c_dst;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      v[e] = (c < q.c_red && n < q.c_dst) ? (q.transpose_w ? wk[int64_t(n) * q.c_red + c] : wk[int64_t(c) * q.c_dst + n]) : 0.f;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    out[ci] = u;
+  }
 }
 
 int launch_cast(const CastJob& a, const CastJob* b, cudaStream_t st) {
@@ -1283,6 +1305,7 @@ int g_auto_ksplit = 4;  // wfsp_set_option "apply_k_split": 0 = never split the 
 // spreads the same work over every SM (profiles/r2_experiments.md).
 int g_bn_fuse = 0;
 int g_split_wide = 0;    // wfsp_set_option "apply_split_wide": split launches take the widest column tiles (fewest MMA instructions)
+int g_prep_ctas = 0;     // wfsp_set_option "prep_ctas": CTAs of one weight-preparation launch, 0 = SM count - 52
 int g_split_stages = 4;  // wfsp_set_option "apply_split_stages": ring depth of split launches (each CTA walks few slices)
 
 // column tiling of the destination channels: as few tiles as possible (<= 256 columns each) when
@@ -1325,6 +1348,7 @@ void set_force_rblk(int v) { g_force_rblk = v; }
 void set_auto_ksplit(int v) { g_auto_ksplit = v == 1 ? 8 : v; }
 void set_split_stages(int v) { g_split_stages = v; }
 void set_split_wide(int v) { g_split_wide = v; }
+void set_prep_ctas(int v) { g_prep_ctas = v; }
 void set_bn_fuse(int v) { g_bn_fuse = v; }
 unsigned long long* g_trace = nullptr;
 void set_trace(unsigned long long* p) { g_trace = p; }
@@ -1668,14 +1692,27 @@ int prep_weights_batch(const wfsp_prep_job* jobs, int n_jobs, cudaStream_t st) {
   for (int j0 = 0; j0 < n_jobs; j0 += kMaxPrepJobs) {
     PrepBatch b{};
     b.n = n_jobs - j0 < kMaxPrepJobs ? n_jobs - j0 : kMaxPrepJobs;
-    int blocks = 0;
+    int64_t chunks[kMaxPrepJobs], all = 0;
     for (int j = 0; j < b.n; ++j) {
       const wfsp_prep_job& q = jobs[j0 + j];
       if (q.weight == nullptr || q.out == nullptr || q.kvol < 1 || q.c_red < 1 || q.c_dst < 1)
         return set_error(WFSP_EINVAL, "bad weight-preparation job %d", j0 + j);
-      const int64_t total = int64_t(q.kvol) * round_up(q.c_dst, 16) * round_up(q.c_red, kSliceK);
-      int64_t nb = ceil_div<int64_t>(total, 256 * 4);
-      if (nb > 4 * sm_count()) nb = 4 * sm_count();
+      if ((reinterpret_cast<uintptr_t>(q.out) & 15) != 0)
+        return set_error(WFSP_EINVAL, "prepared-weight buffer of job %d is not 16-byte aligned", j0 + j);
+      chunks[j] = int64_t(q.kvol) * round_up(q.c_dst, 16) * (round_up(q.c_red, kSliceK) >> 3);
+      all += chunks[j];
+    }
+    // about one CTA per SM in total, shared out by size (at least one each, never more than the job has chunks for)
+    // (default: about a third of the SMs stay free -- a convolution CTA takes a whole SM's shared memory, so it
+    // cannot share one with even a single preparation CTA; 64-event step: first convolution at 14.5 instead of 18.7 us)
+    const int64_t budget = g_prep_ctas > 0 ? g_prep_ctas : (sm_count() > 104 ? sm_count() - 52 : sm_count() / 2 + 1);
+    int blocks = 0;
+    for (int j = 0; j < b.n; ++j) {
+      const wfsp_prep_job& q = jobs[j0 + j];
+      int64_t nb = (budget * chunks[j] + all / 2) / all;
+      const int64_t most = ceil_div<int64_t>(chunks[j], 256);
+      if (nb > most) nb = most;
+      if (nb < 1) nb = 1;
       b.job[j] = PrepJob{q.weight, static_cast<__nv_bfloat16*>(q.out), q.kvol, q.c_red, q.c_dst, q.transpose_w, blocks, int(nb)};
       blocks += int(nb);
     }

@@ -324,21 +324,41 @@ extern "C" int wfsp_batch_pack(const int32_t* coords_xye, const void* wave, int 
   return launch_pack_feats<float, __nv_bfloat16>(wave, n_rows, n_rows_dev, n_chan, scale, feats, feats_pitch, st);
 }
 
+extern "C" int wfsp_dense_cell_table(const int32_t* indices, int64_t n_rows, const int32_t* n_rows_dev, int batch, int h,
+                                     int w, int32_t* cell_table, wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_rows >= 0, "bad dense sizes");
+  cudaStream_t st = as_stream(stream);
+  const int64_t cells = int64_t(batch) * h * w;
+  if (cells == 0) return WFSP_OK;
+  WFSP_CHECK_CUDA(cudaMemsetAsync(cell_table, 0xff, size_t(cells) * 4, st));
+  if (n_rows > 0) {
+    dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, n_rows_dev, batch, h, w, cell_table);
+    count_launches(1);
+    WFSP_CHECK_LAUNCH();
+  }
+  return WFSP_OK;
+}
+
+extern "C" int wfsp_to_dense_from_table(const float* feats, int n_chan, int batch, int h, int w, const int32_t* cell_table,
+                                        float* dense, wfsp_stream_t stream) {
+  WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0, "bad dense sizes");
+  const int64_t cells = int64_t(batch) * h * w;
+  if (cells == 0 || n_chan == 0) return WFSP_OK;
+  dim3 grid(unsigned(ceil_div<int64_t>(cells, 32)), unsigned(ceil_div(n_chan, 32)));
+  dense_fwd_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(feats, n_chan, cell_table, cells, h * w, dense);
+  count_launches(1);
+  WFSP_CHECK_LAUNCH();
+  return WFSP_OK;
+}
+
 extern "C" int wfsp_to_dense(const float* feats, const int32_t* indices, int64_t n_rows, const int32_t* n_rows_dev,
                              int n_chan, int batch, int h, int w, float* dense, int32_t* cell_table,
                              wfsp_stream_t stream) {
-  WFSP_REQUIRE(batch >= 0 && h > 0 && w > 0 && n_chan >= 0 && n_rows >= 0, "bad dense sizes");
-  cudaStream_t st = as_stream(stream);
-  const int64_t cells = int64_t(batch) * h * w;
-  if (cells == 0 || n_chan == 0) return WFSP_OK;
-  WFSP_CHECK_CUDA(cudaMemsetAsync(cell_table, 0xff, size_t(cells) * 4, st));
-  if (n_rows > 0)
-    dense_mark_kernel<<<unsigned(ceil_div<int64_t>(n_rows, 256)), 256, 0, st>>>(indices, n_rows, n_rows_dev, batch, h, w, cell_table);
-  dim3 grid(unsigned(ceil_div<int64_t>(cells, 32)), unsigned(ceil_div(n_chan, 32)));
-  dense_fwd_kernel<<<grid, dim3(32, 8), 0, st>>>(feats, n_chan, cell_table, cells, h * w, dense);
-  count_launches(n_rows > 0 ? 2 : 1);
-  WFSP_CHECK_LAUNCH();
-  return WFSP_OK;
+  WFSP_REQUIRE(n_chan >= 0, "bad dense sizes");
+  if (n_chan == 0) return WFSP_OK;
+  const int rc = wfsp_dense_cell_table(indices, n_rows, n_rows_dev, batch, h, w, cell_table, stream);
+  if (rc != WFSP_OK) return rc;
+  return wfsp_to_dense_from_table(feats, n_chan, batch, h, w, cell_table, dense, stream);
 }
 
 extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, int64_t n_rows,
@@ -363,19 +383,49 @@ extern "C" int wfsp_to_dense_bwd(const float* d_dense, const int32_t* indices, i
 // grad_scale folds the 1 / world_size of the data-parallel mean into the update.
 namespace wfsp {
 namespace {
-__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+__device__ __forceinline__ float sgd_update(float pv, float gv_in, float& b, float lr, float momentum, int nesterov,
+                                            float weight_decay, float grad_scale) {
+  const float gv = gv_in * grad_scale + weight_decay * pv;
+  float step = gv;
+  if (momentum != 0.f) {
+    b = momentum * b + gv;
+    step = nesterov ? gv + momentum * b : b;
+  }
+  return pv - lr * step;
+}
+
+// One 16-byte vector of each buffer per thread and iteration, every load issued before the first store (a store
+// between the loads -- e.g. clearing g right after reading it -- holds the later loads back: the scalar version with the
+// clearing store took 24 us instead of 5.6).  ZERO: the gradient buffer is cleared in the same pass, so the next step
+// accumulates into a clean buffer without a fill launch at its start.  The last n % 4 elements go to one thread.
+template <bool ZERO>
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf,
                                                        int64_t n, float lr, float momentum, int nesterov, float weight_decay,
                                                        float grad_scale) {
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-    const float pv = p[i];
-    float gv = g[i] * grad_scale + weight_decay * pv;
-    float step = gv;
-    if (momentum != 0.f) {
-      const float b = momentum * buf[i] + gv;
-      buf[i] = b;
-      step = nesterov ? gv + momentum * b : b;
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* b4 = reinterpret_cast<float4*>(buf);
+  const bool mom = momentum != 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 pv = p4[i];
+    const float4 gv = g4[i];
+    float4 bv = mom ? b4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    pv.x = sgd_update(pv.x, gv.x, bv.x, lr, momentum, nesterov, weight_decay, grad_scale);
+    pv.y = sgd_update(pv.y, gv.y, bv.y, lr, momentum, nesterov, weight_decay, grad_scale);
+    pv.z = sgd_update(pv.z, gv.z, bv.z, lr, momentum, nesterov, weight_decay, grad_scale);
+    pv.w = sgd_update(pv.w, gv.w, bv.w, lr, momentum, nesterov, weight_decay, grad_scale);
+    p4[i] = pv;
+    if (mom) b4[i] = bv;
+    if (ZERO) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = n4 << 2; i < n; ++i) {
+      float b = mom ? buf[i] : 0.f;
+      p[i] = sgd_update(p[i], g[i], b, lr, momentum, nesterov, weight_decay, grad_scale);
+      if (mom) buf[i] = b;
+      if (ZERO) g[i] = 0.f;
     }
-    p[i] = pv - lr * step;
   }
 }
 struct StageJobs {
@@ -433,17 +483,29 @@ extern "C" int wfsp_stage_inputs(void* dst0, const void* src0, size_t bytes0, vo
   return WFSP_OK;
 }
 
-extern "C" int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
-                             int nesterov, float weight_decay, float grad_scale, wfsp_stream_t stream) {
+extern "C" int wfsp_sgd_step_ex(float* params, float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                                int nesterov, float weight_decay, float grad_scale, int zero_grads, wfsp_stream_t stream) {
   WFSP_REQUIRE(n >= 0 && params != nullptr && grads != nullptr, "bad optimiser arguments");
   WFSP_REQUIRE(momentum == 0.f || momentum_buf != nullptr, "momentum needs a buffer");
   if (n == 0) return WFSP_OK;
+  WFSP_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                 reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "flat buffers must be 16-byte aligned");
   int64_t blocks = wfsp::ceil_div<int64_t>(n, 256 * 4);
   const int64_t cap = int64_t(wfsp::sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  wfsp::sgd_flat_kernel<<<unsigned(blocks), 256, 0, wfsp::as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum,
-                                                                               nesterov, weight_decay, grad_scale);
+  if (zero_grads)
+    wfsp::sgd_flat_kernel<true><<<unsigned(blocks), 256, 0, wfsp::as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum,
+                                                                                       nesterov, weight_decay, grad_scale);
+  else
+    wfsp::sgd_flat_kernel<false><<<unsigned(blocks), 256, 0, wfsp::as_stream(stream)>>>(params, grads, momentum_buf, n, lr, momentum,
+                                                                                        nesterov, weight_decay, grad_scale);
   wfsp::count_launches(1);
   WFSP_CHECK_LAUNCH();
   return WFSP_OK;
+}
+
+extern "C" int wfsp_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                             int nesterov, float weight_decay, float grad_scale, wfsp_stream_t stream) {
+  return wfsp_sgd_step_ex(params, const_cast<float*>(grads), momentum_buf, n, lr, momentum, nesterov, weight_decay, grad_scale,
+                          0, stream);
 }

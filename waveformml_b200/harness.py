@@ -16,6 +16,8 @@ Two ways to run a step:
                   enqueued without any host readback -- row counts stay on the device, buffers are
                   capacity-sized -- captured once in a CUDA graph and replayed per batch.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -226,13 +228,15 @@ class FlatSGD:
                                              _lib.stream()))
         self.exchange_pending = False
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, zero_grads=False):
+        """zero_grads: the gradient buffer is cleared in the same pass (the next step needs no fill launch)."""
         from . import _lib
         lib = _lib.load()
         with torch.cuda.device(self.flat_p.device):
-            _lib.check(lib.wfsp_sgd_step(_lib.ptr(self.flat_p), _lib.ptr(self.grads.flat), _lib.ptr(self.buf),
-                                         self.flat_p.numel(), float(self.lr), float(self.momentum), int(self.nesterov),
-                                         float(self.weight_decay), float(grad_scale), _lib.stream()))
+            _lib.check(lib.wfsp_sgd_step_ex(_lib.ptr(self.flat_p), _lib.ptr(self.grads.flat), _lib.ptr(self.buf),
+                                            self.flat_p.numel(), float(self.lr), float(self.momentum), int(self.nesterov),
+                                            float(self.weight_decay), float(grad_scale), int(bool(zero_grads)),
+                                            _lib.stream()))
 
     def state_dict(self):
         return {"momentum_buffer": self.buf.clone()}
@@ -295,6 +299,12 @@ def segment_l1_loss(indices, predictions, target, spatial_size, batch_size, n_ro
     return nn.functional.l1_loss(pred, target_tensor, reduction="sum") / denom
 
 
+# Linear-1's weight gradient of the fused head on a side stream (WFSP_TOPOLOGY=0: on the main stream, for A/B runs)
+_HEAD_DEFER = os.environ.get("WFSP_TOPOLOGY", "1") != "0"
+# the flat optimiser clears the gradient buffer in its own pass (no fill launch at the start of the next step)
+_SGD_ZEROES = os.environ.get("WFSP_SGD_ZEROES", "1") != "0"
+
+
 class TrainStep:
     def __init__(self, model, task="psd", lr=0.02, momentum=0.98, nesterov=True, group=None, fused_head=True,
                  data_parallel=True):
@@ -312,14 +322,15 @@ class TrainStep:
     def _update(self):
         """gradient exchange + optimiser step"""
         import os
+        zero = bool(getattr(self, "_sgd_zeroes", False))  # GraphTrainStep: the optimiser leaves the gradients cleared
         if os.environ.get("WFSP_NO_EXCHANGE") == "1" and isinstance(self.opt, FlatSGD):
-            self.opt.step(1.0)  # measurement aid: independent replicas, no gradient exchange at all
+            self.opt.step(1.0, zero)  # measurement aid: independent replicas, no gradient exchange at all
         elif isinstance(self.opt, FlatSGD) and self.opt.p2p is not None:
             # exchange + update over NVLink peer memory, no NCCL collective; the graph path completes the closing
             # barrier at the start of the NEXT replay (other ranks' stragglers hide behind its input handling)
             self.opt.step_exchange(wait_now=not getattr(self, "_defer_exchange_wait", False))
         elif isinstance(self.opt, FlatSGD):
-            self.opt.step(self.grads.all_reduce_sum(self.group))
+            self.opt.step(self.grads.all_reduce_sum(self.group), zero)
         else:
             self.grads.all_reduce_mean(self.group)
             self.opt.step()
@@ -360,10 +371,14 @@ class TrainStep:
                 if (getattr(self, "_one", None) is None or self._one.device != loss.device or self._one.dtype != loss.dtype
                         or self._one.shape != loss.shape):
                     self._one = torch.ones(loss.shape, dtype=loss.dtype, device=loss.device)
+                _head.defer_weight_grad = self.grads.flat.is_cuda and _HEAD_DEFER
                 loss.backward(gradient=self._one)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
             spconv.fused.grads_ready_hook, _head.grads_ready_hook = None, None
+            _head.defer_weight_grad = False
+            _head.join_deferred()
+        self._grads_dirty = True
         return loss
 
     def _after_forward(self, loss):
@@ -523,7 +538,7 @@ class GraphTrainStep(TrainStep):
 
     def _body(self, st=None):
         st = self.sets[self.cur] if st is None else st
-        self._cur_set, self._loss_copied = st, None
+        self._cur_set, self._loss_copied, self._zeroed = st, None, None
         p2p = isinstance(self.opt, FlatSGD) and self.opt.p2p is not None and self.capture_update
         self._defer_exchange_wait = p2p
         if p2p:
@@ -538,21 +553,38 @@ class GraphTrainStep(TrainStep):
         if st["coords"].is_cuda:
             main = torch.cuda.current_stream()
             side = spconv.fused._side_stream(st["coords"].device, 2)
-            side.wait_stream(main)
+            # Layer 0's weight preparation (a 3 us launch on this stream) is the ONLY root of the captured step and
+            # every side branch forks behind it: roots of parallel branches start staggered by up to 7 us in an order
+            # that changes from replay to replay, and when the main chain came last the whole step was late.
             spconv.fused.prepare_stacks(self.model)
+            side.wait_stream(main)
+        feats_main = os.environ.get("WFSP_FEATS_MAIN", "0") == "1"
         idx, feats = batcher.pack_batch(st["coords"], st["wave"], scale=self.scale, n_rows=st["n_rows"],
                                         tables=self.tables, out_dtype=torch.bfloat16 if direct else torch.float32,
-                                        feats_stream=side)
+                                        feats_stream=None if feats_main else side)
         if side is not None:
-            with torch.cuda.stream(side):
-                self.grads.zero()  # off the main stream too: the first gradient is written long after the join below
-            feats_ready = torch.cuda.Event()
-            feats_ready.record(side)
-            feats._wfsp_ready = feats_ready  # the first consumer on the main stream waits for it (fused.py)
-        loss = self.forward_backward(idx, feats, st["target"], self.batch_size, st["n_rows"], zero=side is None,
+            if not feats_main:
+                feats_ready = torch.cuda.Event()
+                feats_ready.record(side)
+                feats._wfsp_ready = feats_ready  # the first consumer on the main stream waits for it (fused.py)
+            if getattr(self, "_grads_dirty", True):
+                with torch.cuda.stream(side):
+                    self.grads.zero()  # off the main stream too: the first gradient is written long after the join
+                self._zeroed = torch.cuda.Event()
+                self._zeroed.record(side)
+        # With the flat optimiser in the step, ITS pass leaves the gradient buffer cleared for the next step: no fill
+        # launch beside the first convolution (whose CTAs need whole SMs).  _grads_dirty tracks on the host whether
+        # anything else (an eager forward_backward, a step without update) has written gradients since: the next
+        # eager call / capture then zeroes explicitly, run() does so in front of a replay.
+        self._sgd_zeroes = (self.capture_update and side is not None and isinstance(self.opt, FlatSGD)
+                            and self.opt.p2p is None and _SGD_ZEROES)
+        loss = self.forward_backward(idx, feats, st["target"], self.batch_size, st["n_rows"],
+                                     zero=side is None and getattr(self, "_grads_dirty", True),
                                      overlap_exchange=self.capture_update)
         if self.capture_update:
             self._update()
+            if self._sgd_zeroes:
+                self._grads_dirty = False
         loss = loss.detach()
         if self._loss_copied is not None:
             torch.cuda.current_stream().wait_event(self._loss_copied)  # join the copy branch (it finished long ago)
@@ -564,6 +596,11 @@ class GraphTrainStep(TrainStep):
         # after one stream synchronisation: loss_value()).  Issued on a side branch as soon as the forward pass has
         # produced it -- at the end of the step it was 7 us of the critical path behind the optimiser.
         st = self._cur_set
+        if getattr(self, "_zeroed", None) is not None:
+            # the gradient buffers were zeroed on a side branch (off the first convolution's dependencies): joined
+            # here, in front of the first gradient write
+            torch.cuda.current_stream().wait_event(self._zeroed)
+            self._zeroed = None
         if st is None or st.get("loss_host") is None or not loss.is_cuda:
             return
         main = torch.cuda.current_stream()
@@ -641,7 +678,10 @@ class GraphTrainStep(TrainStep):
             hints.start("replay")
             del _ops.graph_dup_flags[:]
             try:
-                with torch.cuda.graph(st["graph"]):
+                prio = int(os.environ.get("WFSP_CAPTURE_PRIO", "0"))
+                kw = {"stream": torch.cuda.Stream(priority=prio)} if prio else {}
+                st["expects_clean"] = not getattr(self, "_grads_dirty", True)  # captured without a fill launch
+                with torch.cuda.graph(st["graph"], **kw):
                     st["loss"] = self._body(st)
             finally:
                 hints.stop()
@@ -662,6 +702,10 @@ class GraphTrainStep(TrainStep):
         st = self.sets[self.cur]
         if st["graph"] is None:
             self.capture()
+        if st.get("expects_clean") and getattr(self, "_grads_dirty", False):
+            # something outside the captured step wrote gradients since the optimiser last cleared them
+            self.grads.zero()
+            self._grads_dirty = False
         st["graph"].replay()
         if len(self.sets) > 1:
             st["done"] = torch.cuda.Event()

@@ -16,6 +16,18 @@ from .spconv.fused import _grad_target
 
 grads_ready_hook = None  # see spconv.fused.grads_ready_hook: called when the head's parameter gradients are final
 
+# Set by a caller that promises to call join_deferred() on the backward stream before the gradients are used
+# (harness.TrainStep.forward_backward): Linear-1's weight gradient then runs on a side stream, off the critical path.
+defer_weight_grad = False
+_deferred = []
+
+
+def join_deferred():
+    """Makes the current stream wait for every deferred weight-gradient product and releases its operands."""
+    while _deferred:
+        torch.cuda.current_stream().wait_event(_deferred.pop()[0])
+
+
 MAX_BATCH = 256   # up to here the first Linear runs as our split-K launch + a one-CTA tail; beyond, Linear-1 is a library
                   # GEMM (TF32 in bf16 math mode) and the tail (Linear-2, loss, small backward half) one multi-CTA launch
 _tickets = {}     # per device: the zero-initialised counter of wfsp_head_ce_tail (left zero by every call)
@@ -101,13 +113,30 @@ class HeadCEFunction(Function):
             # small half in one launch; the two large products are plain GEMMs -> cuBLAS
             _lib.check(lib.wfsp_head_bwd_small(_lib.ptr(dh1), _lib.ptr(dw2_in), _lib.ptr(db2_in), _lib.ptr(go), B, h1d, C,
                                                _lib.ptr(dh1s), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2), _lib.stream()))
-            torch.mm(dh1s.t(), x, out=dw1)
+            events = []
             if dx is not None:
                 torch.mm(dh1s, w1, out=dx)
+            if defer_weight_grad and dx is not None and w1_thr:  # (a gradient handed to autograd must be final on return)
+                # the gradient of the stack below waits for dx only: Linear-1's weight gradient follows on a side stream,
+                # beside the stack's backward pass (started behind dx: side by side the two small GEMMs slow each other)
+                from .spconv.fused import _side_stream
+                main, side = torch.cuda.current_stream(), _side_stream(dev, 5)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    torch.mm(dh1s.t(), x, out=dw1)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                # the operands stay referenced until join_deferred(): the allocator must not hand them out meanwhile
+                _deferred.append((done, dh1s, x, dw1))
+                events.append(done)
+            else:
+                torch.mm(dh1s.t(), x, out=dw1)
         if grads_ready_hook is not None and w1_thr and w2_thr and b1_thr and b2_thr:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
-            grads_ready_hook([q for q in (w1_p, b1_p, w2_p, b2_p) if q is not None], [ev])
+            grads_ready_hook([q for q in (w1_p, b1_p, w2_p, b2_p) if q is not None], events + [ev])
         return (dx, None if w1_thr else dw1, None if b1_thr else db1, None if w2_thr else dw2, None if b2_thr else db2,
                 None)
 

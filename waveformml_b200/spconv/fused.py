@@ -18,6 +18,7 @@ path (conv operands only), accumulation and BatchNorm stay fp32.  Anything the p
 modules, unknown modules) falls back to the per-layer path in SparseSequential.forward.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -36,6 +37,10 @@ _STATS_FUSE_MIN_ROWS = 0
 # kernels is not overlapped with the next tile's main loop (one CTA per SM), so the extra pass over x is exposed --
 # C5@1024: 3x3 dgrad 156 -> 451 us against 141 us of bn_bwd_partial saved; 64 events: dgrad +9 us against -2.5 us.
 _BWD_PARTS = False
+# Graph-topology choices of the fused stack, each measured on the 64-event step (WFSP_TOPOLOGY=0 switches them off for
+# an A/B run): ToDense's cell table built on the geometry branch; layer 0's weights prepared in a launch of their own.
+_EARLY_CELL_TABLE = os.environ.get("WFSP_TOPOLOGY", "1") != "0"
+_SPLIT_PREP = os.environ.get("WFSP_TOPOLOGY", "1") != "0"
 
 
 def set_fused(flag):
@@ -258,15 +263,33 @@ def _prep_weights(plan, params, need_in_grad, dev, fork):
         if d_off is not None:
             jobs.append(_lib.PrepJob(w.data_ptr(), wbuf.data_ptr() + d_off, kvol, cout, cin, 1))
     arr = (_lib.PrepJob * len(jobs))(*jobs)
-    # the weights do not depend on this step's data: prepared on a side stream, beside the batcher / the input cast
+    # Layer 0's forward layout: a short launch of its own on the CALLING stream (at the head of the step's main chain in
+    # harness.GraphTrainStep), so the first convolution has no cross-branch join in front of it -- roots of parallel
+    # graph branches start staggered by 1-3 us each and every join costs 2-4 us more.  Everything else is prepared on
+    # a side stream, beside the batcher / the input cast / the first layer.
+    split = _SPLIT_PREP and len(jobs) > 1
+    w0_ready = None
+    if split:
+        if any(b.drop for b in blocks):  # the first BatchNorm kernel must see this step's value
+            _drop_step(dev).add_(1)
+        _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), 1, st()))
+        w0_ready = torch.cuda.Event()
+        w0_ready.record(torch.cuda.current_stream())
     side2 = _side_stream(dev, 1)
     with torch.cuda.stream(side2):
-        side2.wait_event(fork)
-        if any(b.drop for b in blocks):  # before w_ready: the first BatchNorm kernel must see this step's value
-            _drop_step(dev).add_(1)
-        _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
+        # (split: behind layer 0's launch, which then is the step's only root -- see harness.GraphTrainStep._body)
+        side2.wait_event(w0_ready if split else fork)
+        if split:
+            rest = (_lib.PrepJob * (len(jobs) - 1))(*jobs[1:])
+            _lib.check(lib.wfsp_prep_weights(ctypes.cast(rest, ctypes.c_void_p), len(jobs) - 1, st()))
+        else:
+            if any(b.drop for b in blocks):  # before w_ready: the first BatchNorm kernel must see this step's value
+                _drop_step(dev).add_(1)
+            _lib.check(lib.wfsp_prep_weights(ctypes.cast(arr, ctypes.c_void_p), len(jobs), st()))
         w_ready = torch.cuda.Event()
         w_ready.record(side2)
+        if w0_ready is None:
+            w0_ready = w_ready
         # BatchNorm step counters: one multi-tensor add here instead of one launch per layer on the main stream
         counters = [b.bn.num_batches_tracked for b in blocks
                     if b.bn is not None and b.bn.training and b.bn.num_batches_tracked is not None]
@@ -274,7 +297,7 @@ def _prep_weights(plan, params, need_in_grad, dev, fork):
             torch._foreach_add_(counters, 1)
         side2_done = torch.cuda.Event()
         side2_done.record(side2)
-    return {"wbuf": wbuf, "offs": offs, "w_ready": w_ready, "done": side2_done, "need_in_grad": need_in_grad,
+    return {"wbuf": wbuf, "offs": offs, "w_ready": w_ready, "w0_ready": w0_ready, "done": side2_done, "need_in_grad": need_in_grad,
             "key": _param_key(params)}
 
 
@@ -359,6 +382,17 @@ class FusedStackFunction(Function):
                     nxt.indice_dict, nxt.grid = gcur.indice_dict, gcur.grid
                     geoms.append((rb, outids, out_shape, out_rows, gcur, nxt, ready))
                     gcur = nxt
+                # ToDense: the cell table (row of every dense cell) depends on the output coordinates only -- built
+                # here, beside the convolutions, so that only the scatter itself follows the last layer
+                dense_pre = None
+                if plan.to_dense and _EARLY_CELL_TABLE:
+                    dh, dw, didx = _dense_geometry(gcur)
+                    dtable = torch.empty((max(gcur.batch_size * dh * dw, 1),), dtype=torch.int32, device=dev)
+                    _lib.check(lib.wfsp_dense_cell_table(_lib.ptr(didx), didx.shape[0], _lib.ptr(gcur.n_rows),
+                                                         gcur.batch_size, dh, dw, _lib.ptr(dtable), st()))
+                    dready = torch.cuda.Event()
+                    dready.record(side)
+                    dense_pre = (dh, dw, didx, dtable, dready)
 
             backs = [g[0] for g in geoms if g[0] is not None and getattr(g[0], "_pending", None)]
             back_done = None
@@ -370,7 +404,7 @@ class FusedStackFunction(Function):
                         rb.finish()
                     back_done = torch.cuda.Event()
                     back_done.record(side3)
-            main.wait_event(w_ready)
+            main.wait_event(prep["w0_ready"])  # layer 0's weights; the rest is waited for in front of layer 1
             drop_seed = 0
             if any(b.drop for b in blocks):  # from torch's CPU generator: reproducible under torch.manual_seed
                 drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -379,6 +413,8 @@ class FusedStackFunction(Function):
                 conv = b.conv
                 rb, outids, out_shape, out_rows, cur, nxt, ready = geoms[bi]
                 main.wait_event(ready)
+                if bi == 1 and prep["w0_ready"] is not w_ready:
+                    main.wait_event(w_ready)
                 last = bi == len(blocks) - 1
                 kvol = 1 if rb is None else rb.kvol
                 cin, cout = conv.in_channels, conv.out_channels
@@ -469,12 +505,20 @@ class FusedStackFunction(Function):
             ctx.need_in_grad, ctx.in_dtype = need_in_grad, features.dtype
             ctx.final = cur
             if plan.to_dense:
-                h, w, ctx.dense_idx = _dense_geometry(cur)
                 n, c = out32.shape
-                dense = torch.empty((cur.batch_size, c, h, w), dtype=torch.float32, device=dev)
-                table = torch.empty((max(cur.batch_size * h * w, 1),), dtype=torch.int32, device=dev)
-                _lib.check(lib.wfsp_to_dense(_lib.ptr(out32), _lib.ptr(ctx.dense_idx), n, _lib.ptr(cur.n_rows),
-                                             c, cur.batch_size, h, w, _lib.ptr(dense), _lib.ptr(table), st()))
+                if dense_pre is not None:
+                    h, w, ctx.dense_idx, table, dready = dense_pre
+                    dense = torch.empty((cur.batch_size, c, h, w), dtype=torch.float32, device=dev)
+                    main.wait_event(dready)
+                    _lib.check(lib.wfsp_to_dense_from_table(_lib.ptr(out32), c, cur.batch_size, h, w, _lib.ptr(table),
+                                                            _lib.ptr(dense), st()))
+                    ctx.dense_table = table  # allocated on the side stream: kept until backward has run
+                else:
+                    h, w, ctx.dense_idx = _dense_geometry(cur)
+                    dense = torch.empty((cur.batch_size, c, h, w), dtype=torch.float32, device=dev)
+                    table = torch.empty((max(cur.batch_size * h * w, 1),), dtype=torch.int32, device=dev)
+                    _lib.check(lib.wfsp_to_dense(_lib.ptr(out32), _lib.ptr(ctx.dense_idx), n, _lib.ptr(cur.n_rows),
+                                                 c, cur.batch_size, h, w, _lib.ptr(dense), _lib.ptr(table), st()))
                 return dense.view(cur.batch_size, c, *cur.spatial_shape)
             return out32
 
