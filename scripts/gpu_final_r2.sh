@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-2 evidence in one GPU-box visit: smoke, both bench arms, timelines, ncu launch lists and full captures.
+# Round-2 evidence in one GPU-box visit: smoke, both bench arms, timelines, ncu launch lists and full captures
+# (FAST=1: without the --set full captures).
 mkdir -p gpurun_out
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
@@ -18,9 +19,12 @@ for cfg in "C2 64" "C5 1024"; do
   $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -n 5 gpurun_out/${TAG}_plain.log; continue; }
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
   echo "launch list $TAG rc=$?"
-  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_(apply|wgrad)" -c 8 -o gpurun_out/${TAG}_conv_full -f $CMD > gpurun_out/${TAG}_ncu_conv.log 2>&1
-  echo "full conv $TAG rc=$?"
+  if [ "$FAST" != "1" ]; then
+    timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_(apply|wgrad)" -c 8 -o gpurun_out/${TAG}_conv_full -f $CMD > gpurun_out/${TAG}_ncu_conv.log 2>&1
+    echo "full conv $TAG rc=$?"
+  fi
 done
+[ "$FAST" = "1" ] && exit 0  # (the --set full captures are only repeated when a conv / BatchNorm kernel changed)
 CMD="python bench.py --workload C5 --batch 1024 --large-batch 0 --steps 2 --warmup 3 --no-cpu-baseline --no-breakdown --no-math-modes --c3-batch 0 --rotate 1 --sustained 0"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:bn_stream" -c 9 -o gpurun_out/r2_final_C5_b1024_bn_full -f $CMD > gpurun_out/r2_final_C5_b1024_ncu_bn.log 2>&1
 echo "full bn rc=$?"
