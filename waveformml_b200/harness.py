@@ -319,10 +319,10 @@ class TrainStep:
             self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, nesterov=nesterov, foreach=True)
         self.criterion = nn.CrossEntropyLoss()
 
-    def _update(self):
-        """gradient exchange + optimiser step"""
+    def _update(self, zero_grads=False):
+        """gradient exchange + optimiser step (zero_grads: the flat optimiser also clears the gradient buffer)"""
         import os
-        zero = bool(getattr(self, "_sgd_zeroes", False))  # GraphTrainStep: the optimiser leaves the gradients cleared
+        zero = bool(zero_grads)
         if os.environ.get("WFSP_NO_EXCHANGE") == "1" and isinstance(self.opt, FlatSGD):
             self.opt.step(1.0, zero)  # measurement aid: independent replicas, no gradient exchange at all
         elif isinstance(self.opt, FlatSGD) and self.opt.p2p is not None:
@@ -582,7 +582,7 @@ class GraphTrainStep(TrainStep):
                                      zero=side is None and getattr(self, "_grads_dirty", True),
                                      overlap_exchange=self.capture_update)
         if self.capture_update:
-            self._update()
+            self._update(self._sgd_zeroes)
             if self._sgd_zeroes:
                 self._grads_dirty = False
         loss = loss.detach()
