@@ -558,6 +558,8 @@ class GraphTrainStep(TrainStep):
             # that changes from replay to replay, and when the main chain came last the whole step was late.
             spconv.fused.prepare_stacks(self.model)
             side.wait_stream(main)
+        # (measurement aid, profiles/r2_experiments.md: the waveform conversion on the main chain instead of a side
+        # branch -- no gain, off)
         feats_main = os.environ.get("WFSP_FEATS_MAIN", "0") == "1"
         idx, feats = batcher.pack_batch(st["coords"], st["wave"], scale=self.scale, n_rows=st["n_rows"],
                                         tables=self.tables, out_dtype=torch.bfloat16 if direct else torch.float32,
@@ -678,6 +680,7 @@ class GraphTrainStep(TrainStep):
             hints.start("replay")
             del _ops.graph_dup_flags[:]
             try:
+                # (measurement aid: capture the main chain on a high-priority stream -- no gain, off)
                 prio = int(os.environ.get("WFSP_CAPTURE_PRIO", "0"))
                 kw = {"stream": torch.cuda.Stream(priority=prio)} if prio else {}
                 st["expects_clean"] = not getattr(self, "_grads_dirty", True)  # captured without a fill launch
