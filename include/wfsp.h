@@ -307,12 +307,13 @@ int wfsp_bn_relu_bwd(const float* x, const float* dy, int64_t n_rows, const int3
 
 typedef struct wfsp_prep_job {
   const float* weight; /* fp32 [kvol, c_red, c_dst], or [kvol, c_dst, c_red] if transpose_w      */
-  void* out;           /* prepared bf16 weights, wfsp_prepared_weight_bytes(kvol, c_red, c_dst) */
+  void* out;           /* prepared bf16 weights, wfsp_prepared_weight_bytes(kvol, c_red, c_dst); 16-byte aligned */
   int kvol, c_red, c_dst, transpose_w;
 } wfsp_prep_job;
 
 size_t wfsp_prepared_weight_bytes(int kvol, int c_red, int c_dst);
-/* jobs_host: HOST array; one kernel launch per 16 jobs */
+/* jobs_host: HOST array; one kernel launch per 16 jobs (sized to leave about a third of the SMs free: it is meant
+ * to run beside the first convolution of a step, whose CTAs each need a whole SM) */
 int wfsp_prep_weights(const wfsp_prep_job* jobs_host, int n_jobs, wfsp_stream_t stream);
 
 /* fp32 [n_rows, c] -> bf16 [n_rows, WFSP_BF16_PITCH(c)] */
